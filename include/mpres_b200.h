@@ -1,0 +1,177 @@
+/*
+ * mpres_b200.h -- C-ABI of the B200-native mp_gemm / mp_gemv / mp_dot path.
+ *
+ * This is the drop-in boundary for the multiple-precision GEMM path of MPRES-BLAS (kisupov/mpres-blas
+ * v1.7.0).  Every entry point names the reference interface it replaces (paths relative to the
+ * reference root).  Plain pointers and sizes only; all mp_array_t / mp_collection_t members are DEVICE
+ * pointers exactly as in the reference (src/mparray.cuh:35-54), scalars (alpha, beta, r) are
+ * length-1 device arrays (tests/blas/performance/test_gemm_performance.cu:156-157).
+ *
+ * Return value of every function: 0 = ok, < 0 = invalid argument (the reference returns silently,
+ * src/blas/gemm.cuh:75-96), > 0 = cudaError_t.  There is no CPU fallback: if the CUDA library cannot
+ * run, calls fail.
+ */
+#ifndef MPRES_B200_H
+#define MPRES_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- data types, byte-identical to src/types.cuh ------------------------------------------------- */
+
+/* src/types.cuh:46-49 */
+typedef struct {
+    double frac;
+    long exp;
+} mpres_er_float_t;
+
+/* CUDA's int4 without the cuda headers (16-byte aligned in the reference; only ever used through a
+ * device pointer here) */
+typedef struct { int x, y, z, w; } mpres_int4;
+
+/* src/types.cuh:85-92 -- SoA array with scratch `buf` and device-resident length `len` */
+typedef struct {
+    int *digits;             /* [len * N], element-major: all residues of x0, all residues of x1, ... */
+    int *sign;               /* [len] */
+    int *exp;                /* [len] */
+    mpres_er_float_t *eval;  /* [2 * len]: lower bounds of all elements, then upper bounds */
+    mpres_int4 *buf;         /* [len] scratch of the reference's two-kernel additions; unused by this library */
+    int *len;                /* device scalar: ALLOCATED length (offset of the upper bounds) */
+} mpres_array_t;
+
+/* src/types.cuh:99-104 -- SoA array without buf/len; the length travels as an argument */
+typedef struct {
+    int *digits;
+    int *sign;
+    int *exp;
+    mpres_er_float_t *eval;
+} mpres_collection_t;
+
+/* src/blas/mblas_enum.cuh:25-29 */
+enum { MPRES_NO_TRANS = 111, MPRES_TRANS = 112, MPRES_CONJ_TRANS = 113 };
+
+/* Stage-2 strategy.  AUTO = exact-window fast path wherever its guard holds, reference-order
+ * fallback per element otherwise.  REFERENCE_ORDER = the k-loop of src/blas/gemm.cuh:46-49 step by
+ * step (mp_mul, mp_add, rounding after each), residue-parallel: bit-identical to the reference
+ * kernels including the interval evaluations.  FAST = fast path only (elements whose guard fails
+ * are reported through mpres_last_fallback_count). */
+enum { MPRES_MODE_AUTO = 0, MPRES_MODE_REFERENCE_ORDER = 1, MPRES_MODE_FAST = 2 };
+
+typedef struct mpres_ctx mpres_ctx;
+typedef void *mpres_stream_t; /* cudaStream_t */
+
+/* ---- lifecycle: replaces rns_const_init() + mp_const_init() (src/rns.cuh:324-442,
+ *      src/arith/arith_utils.cuh:44-85), which need GMP/MPFR and one precision per binary -------- */
+
+/* moduli_size selects one of the predefined sets of src/params/32-bit-n-double-moduli/
+ * (8, 16, 24, 32, 40, 48, 56, 64 or 128 moduli); constants are uploaded to `device`. */
+int mpres_init(mpres_ctx **ctx, int moduli_size, int device);
+/* any pairwise-coprime odd moduli < 2^31 (what overwriting src/params.h does in the reference) */
+int mpres_init_moduli(mpres_ctx **ctx, const int *moduli, int moduli_size, int device);
+int mpres_finalize(mpres_ctx *ctx);
+
+/* RNS_MODULI_SIZE, RNS_MODULI_PRODUCT_LOG2 (src/params.h:31-36), MP_PRECISION, MP_H, MP_J
+ * (src/arith/arith_utils.cuh:33-35) */
+int mpres_moduli_size(const mpres_ctx *ctx);
+int mpres_moduli_product_log2(const mpres_ctx *ctx);
+int mpres_precision(const mpres_ctx *ctx);
+int mpres_mp_h(const mpres_ctx *ctx);
+int mpres_mp_j(const mpres_ctx *ctx);
+int mpres_device(const mpres_ctx *ctx);
+/* sizeof(mp_float_t) for this moduli set = 4N + 40 (src/types.cuh:69-74) */
+size_t mpres_sizeof_mp_float(const mpres_ctx *ctx);
+/* Host copies of the constant tables, for tests: which = 0 RNS_MODULI, 1 RNS_PART_MODULI_PRODUCT_INVERSE,
+ * 2 RNS_POW2, 3 RNS_MODULI_PRODUCT_POW2_RESIDUES, 4 RNS_PART_MODULI_PRODUCT_POW2_RESIDUES,
+ * 5 RNS_POW2_INVERSE, 6 MRC_MULT_INV (int tables); 7 RNS_MODULI_RECIP_RD, 8 RNS_MODULI_RECIP_RU,
+ * 9 {RNS_EVAL_ACCURACY, UNIT.low.frac, UNIT.upp.frac, INV_UNIT.low.frac, INV_UNIT.upp.frac},
+ * 10 {RNS_EVAL_REF_FACTOR, UNIT.low.exp, UNIT.upp.exp, INV_UNIT.low.exp, INV_UNIT.upp.exp} as doubles.
+ * Returns the number of bytes written (<= cap) or < 0. */
+long mpres_get_constant(const mpres_ctx *ctx, int which, void *out, size_t cap);
+
+int mpres_set_mode(mpres_ctx *ctx, int mode);
+int mpres_get_mode(const mpres_ctx *ctx);
+/* number of result elements the last AUTO/FAST call routed to the reference-order fallback
+ * (synchronises the stream of that call) */
+long mpres_last_fallback_count(mpres_ctx *ctx);
+/* kernels launched by this library since init (all devices of this ctx) */
+long mpres_launch_count(const mpres_ctx *ctx);
+
+/* ---- containers: replace cuda::mp_array_init / clear / host2device / device2host
+ *      (src/mparray.cuh:35,59,76,125) and the mp_collection_* twins (src/mpcollection.cuh:35,54,69,117).
+ *      Host side is the reference's AoS mp_float_t[] (4N+40 bytes per element); copies are bulk. ---- */
+int mpres_array_init(mpres_ctx *ctx, mpres_array_t *arr, size_t size);
+int mpres_array_clear(mpres_ctx *ctx, mpres_array_t *arr);
+int mpres_array_host2device(mpres_ctx *ctx, mpres_array_t *dst, const void *host_mp_float, size_t size);
+int mpres_array_device2host(mpres_ctx *ctx, void *host_mp_float, const mpres_array_t *src, size_t size);
+int mpres_collection_init(mpres_ctx *ctx, mpres_collection_t *arr, size_t size);
+int mpres_collection_clear(mpres_ctx *ctx, mpres_collection_t *arr);
+int mpres_collection_host2device(mpres_ctx *ctx, mpres_collection_t *dst, const void *host_mp_float, size_t size);
+int mpres_collection_device2host(mpres_ctx *ctx, void *host_mp_float, const mpres_collection_t *src, size_t size);
+
+/* Device-side conversion (replaces the host string round trip of mp_set_mpfr / mp_set_d,
+ * src/arith/assign.cuh:54-127): element i of dst (from `offset`) := (-1)^sign[i] * L_i * 2^exp[i] with
+ * L_i the little-endian nlimbs x 32-bit integer at limbs[i * nlimbs]; trailing zero bits are trimmed
+ * and the interval evaluation computed like mp_set_mpfr does.  All pointers are device pointers. */
+int mpres_array_set_binary(mpres_ctx *ctx, mpres_array_t *dst, size_t offset, const int *sign, const int *exp,
+                           const uint32_t *limbs, int nlimbs, size_t count, mpres_stream_t stream);
+
+/* ---- BLAS entry points ---------------------------------------------------------------------------- */
+
+/* cuda::mp_gemm<blockDim1x, blockDim1y, gridDim2x, gridDim2y, blockDim3> (src/blas/gemm.cuh:69-70):
+ * C = alpha * op(A) * op(B) + beta * C, column-major.  The launch-shape template parameters of the
+ * reference have no equivalent here.  `buffer` (m*n scratch in the reference) may be NULL.  All four
+ * transpose combinations are accepted (the reference prints and returns for anything but N/N,
+ * gemm.cuh:114-125; semantics of src/blas/v2/gemm_v2.cuh:64-71). */
+int mpres_gemm(mpres_ctx *ctx, int transa, int transb, int m, int n, int k, const mpres_array_t *alpha,
+               const mpres_array_t *A, int lda, const mpres_array_t *B, int ldb, const mpres_array_t *beta,
+               mpres_array_t *C, int ldc, mpres_array_t *buffer, mpres_stream_t stream);
+
+/* cuda::mp_gemv<gridDim1, blockDim1, gridDim2, blockDim3> (src/blas/gemv.cuh:150-152):
+ * y = alpha * op(A) * x + beta * y.  buffer1 / buffer2 may be NULL (no m*n intermediate is built). */
+int mpres_gemv(mpres_ctx *ctx, int trans, int m, int n, const mpres_array_t *alpha, const mpres_array_t *A, int lda,
+               const mpres_array_t *x, int incx, const mpres_array_t *beta, mpres_array_t *y, int incy,
+               mpres_array_t *buffer1, mpres_array_t *buffer2, mpres_stream_t stream);
+
+/* cuda::mp_dot<gridDim1, blockDim1, gridDim2, gridDim3, blockDim3> (src/blas/dot.cuh:84-85):
+ * r[0] = sum x_i * y_i.  `buffer` (n scratch in the reference) may be NULL. */
+int mpres_dot(mpres_ctx *ctx, int n, const mpres_array_t *x, int incx, const mpres_array_t *y, int incy,
+              mpres_array_t *r, mpres_array_t *buffer, mpres_stream_t stream);
+
+/* The same three operations over mp_collection_t operands with explicit allocated lengths (the
+ * reference only uses mp_collection_t in its sparse kernels, src/sparse/mpmtx/*.cuh; north_star asks
+ * for the dense path over both containers). */
+int mpres_gemm_coll(mpres_ctx *ctx, int transa, int transb, int m, int n, int k,
+                    const mpres_collection_t *alpha, const mpres_collection_t *A, int lda, size_t lenA,
+                    const mpres_collection_t *B, int ldb, size_t lenB, const mpres_collection_t *beta,
+                    mpres_collection_t *C, int ldc, size_t lenC, mpres_stream_t stream);
+int mpres_gemv_coll(mpres_ctx *ctx, int trans, int m, int n, const mpres_collection_t *alpha,
+                    const mpres_collection_t *A, int lda, size_t lenA, const mpres_collection_t *x, int incx, size_t lenx,
+                    const mpres_collection_t *beta, mpres_collection_t *y, int incy, size_t leny, mpres_stream_t stream);
+int mpres_dot_coll(mpres_ctx *ctx, int n, const mpres_collection_t *x, int incx, size_t lenx,
+                   const mpres_collection_t *y, int incy, size_t leny, mpres_collection_t *r, mpres_stream_t stream);
+
+/* Partial DOT for segment sharding across GPUs: reduces x[0..n), y[0..n) to ONE packed
+ * mp_float_t (4N+40 bytes, AoS) at `partial` (device); mpres_reduce_partials sums `count` packed
+ * partials in index order (mp_add, src/arith/add.cuh:190-200) into r[0] -- run it on every rank after
+ * an all-gather of the partial bytes. */
+int mpres_dot_partial(mpres_ctx *ctx, int n, const mpres_array_t *x, int incx, const mpres_array_t *y, int incy,
+                      void *partial, mpres_stream_t stream);
+int mpres_reduce_partials(mpres_ctx *ctx, const void *partials, int count, mpres_array_t *r, mpres_stream_t stream);
+
+/* Element-wise probes of the scalar device routines, for parity tests against the reference's
+ * cuda::mp_mul / mp_add / rns_eval_compute[_fast] / mp_round (src/arith/mul.cuh:99-111,
+ * add.cuh:190-200, rns.cuh:797-933, arith_utils.cuh:184-193).  op: 0 mul, 1 add, 2 eval, 3 eval_fast,
+ * 4 round by bits[i].  x, y, r: device AoS mp_float_t arrays; bits: device ints. */
+int mpres_probe(mpres_ctx *ctx, int op, void *r, const void *x, const void *y, const int *bits, size_t n,
+                mpres_stream_t stream);
+
+const char *mpres_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPRES_B200_H */

@@ -1,0 +1,245 @@
+"""mpres-blas_b200 -- host-side mirror of the reference's operator interface for the
+mp_gemm / mp_gemv / mp_dot path, over the C-ABI of libmpres_b200.so (include/mpres_b200.h).
+
+The names follow the reference (cuda::mp_array_init, mp_array_host2device, mp_gemm, mp_gemv, mp_dot:
+src/mparray.cuh, src/blas/{gemm,gemv,dot}.cuh).  Host data is the reference's AoS mp_float_t[] as a
+numpy structured array (record_dtype).  There is NO CPU implementation behind these calls: if the
+CUDA library is missing or no GPU is present they raise.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmpres_b200.so")
+
+mblas_no_trans, mblas_trans, mblas_conj_trans = 111, 112, 113  # src/blas/mblas_enum.cuh:25-29
+MODE_AUTO, MODE_REFERENCE_ORDER, MODE_FAST = 0, 1, 2
+
+_lib = None
+
+
+class MpresError(RuntimeError):
+    pass
+
+
+class mp_array_t(ctypes.Structure):  # src/types.cuh:85-92
+    _fields_ = [("digits", ctypes.c_void_p), ("sign", ctypes.c_void_p), ("exp", ctypes.c_void_p),
+                ("eval", ctypes.c_void_p), ("buf", ctypes.c_void_p), ("len", ctypes.c_void_p)]
+
+
+class mp_collection_t(ctypes.Structure):  # src/types.cuh:99-104
+    _fields_ = [("digits", ctypes.c_void_p), ("sign", ctypes.c_void_p), ("exp", ctypes.c_void_p),
+                ("eval", ctypes.c_void_p)]
+
+
+EXPORTS = [
+    "mpres_init", "mpres_init_moduli", "mpres_finalize", "mpres_moduli_size", "mpres_moduli_product_log2",
+    "mpres_precision", "mpres_mp_h", "mpres_mp_j", "mpres_device", "mpres_sizeof_mp_float", "mpres_get_constant",
+    "mpres_set_mode", "mpres_get_mode", "mpres_last_fallback_count", "mpres_launch_count",
+    "mpres_array_init", "mpres_array_clear", "mpres_array_host2device", "mpres_array_device2host",
+    "mpres_collection_init", "mpres_collection_clear", "mpres_collection_host2device", "mpres_collection_device2host",
+    "mpres_array_set_binary", "mpres_gemm", "mpres_gemv", "mpres_dot", "mpres_gemm_coll", "mpres_gemv_coll",
+    "mpres_dot_coll", "mpres_dot_partial", "mpres_reduce_partials", "mpres_probe", "mpres_version",
+]
+
+
+def load_library():
+    """dlopen libmpres_b200.so; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MpresError("libmpres_b200.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+                         "there is no CPU fallback")
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.mpres_version.restype = ctypes.c_char_p
+    lib.mpres_sizeof_mp_float.restype = ctypes.c_size_t
+    for f in ("mpres_get_constant", "mpres_last_fallback_count", "mpres_launch_count"):
+        getattr(lib, f).restype = ctypes.c_long
+    _lib = lib
+    return lib
+
+
+def record_dtype(N):
+    """numpy view of the reference's AoS mp_float_t (src/types.cuh:69-74)."""
+    return np.dtype([("digits", np.int32, (N,)), ("sign", np.int32), ("exp", np.int32),
+                     ("eval", [("frac", np.float64), ("exp", np.int64)], (2,))])
+
+
+def _check(rc, what):
+    if rc != 0:
+        kind = "invalid argument" if rc < 0 else "CUDA error"
+        raise MpresError("%s failed: %s %d" % (what, kind, rc))
+
+
+def _vp(x):
+    return ctypes.c_void_p(x) if x is not None else None
+
+
+class Context:
+    """rns_const_init() + mp_const_init() for one moduli set on one device (src/rns.cuh:324,
+    src/arith/arith_utils.cuh:44)."""
+
+    def __init__(self, moduli_size=8, device=0, moduli=None):
+        self.lib = load_library()
+        self.h = ctypes.c_void_p()
+        if moduli is None:
+            _check(self.lib.mpres_init(ctypes.byref(self.h), int(moduli_size), int(device)), "mpres_init")
+        else:
+            arr = (ctypes.c_int * len(moduli))(*moduli)
+            _check(self.lib.mpres_init_moduli(ctypes.byref(self.h), arr, len(moduli), int(device)), "mpres_init_moduli")
+        self.N = self.lib.mpres_moduli_size(self.h)
+        self.dtype = record_dtype(self.N)
+        self.device = device
+
+    def close(self):
+        if self.h:
+            self.lib.mpres_finalize(self.h)
+            self.h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    precision = property(lambda s: s.lib.mpres_precision(s.h))
+    mp_h = property(lambda s: s.lib.mpres_mp_h(s.h))
+    mp_j = property(lambda s: s.lib.mpres_mp_j(s.h))
+    log2M = property(lambda s: s.lib.mpres_moduli_product_log2(s.h))
+    launch_count = property(lambda s: s.lib.mpres_launch_count(s.h))
+
+    def set_mode(self, mode):
+        _check(self.lib.mpres_set_mode(self.h, mode), "mpres_set_mode")
+
+    def last_fallback_count(self):
+        return self.lib.mpres_last_fallback_count(self.h)
+
+    def constant(self, which, dtype, count):
+        out = np.zeros(count, dtype=dtype)
+        n = self.lib.mpres_get_constant(self.h, which, out.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(out.nbytes))
+        if n < 0:
+            raise MpresError("mpres_get_constant(%d) -> %d" % (which, n))
+        return out[: n // out.itemsize]
+
+    # --- containers (src/mparray.cuh:35-165) ---
+    def mp_array_init(self, size):
+        a = MpArray(self, size)
+        return a
+
+    def mp_array_from_host(self, recs):
+        recs = np.ascontiguousarray(recs, dtype=self.dtype).reshape(-1)
+        a = MpArray(self, recs.size)
+        a.host2device(recs)
+        return a
+
+    def mp_collection_from_host(self, recs):
+        recs = np.ascontiguousarray(recs, dtype=self.dtype).reshape(-1)
+        a = MpCollection(self, recs.size)
+        a.host2device(recs)
+        return a
+
+
+class MpArray:
+    """mp_array_t in device memory (src/types.cuh:85-92)."""
+
+    def __init__(self, ctx, size):
+        self.ctx, self.size = ctx, int(size)
+        self.s = mp_array_t()
+        _check(ctx.lib.mpres_array_init(ctx.h, ctypes.byref(self.s), ctypes.c_size_t(self.size)), "mpres_array_init")
+
+    def host2device(self, recs):
+        recs = np.ascontiguousarray(recs, dtype=self.ctx.dtype).reshape(-1)
+        _check(self.ctx.lib.mpres_array_host2device(self.ctx.h, ctypes.byref(self.s), recs.ctypes.data_as(ctypes.c_void_p),
+                                                    ctypes.c_size_t(recs.size)), "mpres_array_host2device")
+
+    def device2host(self, size=None):
+        n = self.size if size is None else int(size)
+        out = np.zeros(n, dtype=self.ctx.dtype)
+        _check(self.ctx.lib.mpres_array_device2host(self.ctx.h, out.ctypes.data_as(ctypes.c_void_p), ctypes.byref(self.s),
+                                                    ctypes.c_size_t(n)), "mpres_array_device2host")
+        return out
+
+    def clear(self):
+        if self.s.digits:
+            self.ctx.lib.mpres_array_clear(self.ctx.h, ctypes.byref(self.s))
+
+    def __del__(self):
+        try:
+            if self.ctx.h:
+                self.clear()
+        except Exception:
+            pass
+
+
+class MpCollection:
+    """mp_collection_t in device memory (src/types.cuh:99-104)."""
+
+    def __init__(self, ctx, size):
+        self.ctx, self.size = ctx, int(size)
+        self.s = mp_collection_t()
+        _check(ctx.lib.mpres_collection_init(ctx.h, ctypes.byref(self.s), ctypes.c_size_t(self.size)), "mpres_collection_init")
+
+    def host2device(self, recs):
+        recs = np.ascontiguousarray(recs, dtype=self.ctx.dtype).reshape(-1)
+        _check(self.ctx.lib.mpres_collection_host2device(self.ctx.h, ctypes.byref(self.s), recs.ctypes.data_as(ctypes.c_void_p),
+                                                         ctypes.c_size_t(recs.size)), "mpres_collection_host2device")
+
+    def device2host(self):
+        out = np.zeros(self.size, dtype=self.ctx.dtype)
+        _check(self.ctx.lib.mpres_collection_device2host(self.ctx.h, out.ctypes.data_as(ctypes.c_void_p), ctypes.byref(self.s),
+                                                         ctypes.c_size_t(self.size)), "mpres_collection_device2host")
+        return out
+
+    def clear(self):
+        if self.s.digits:
+            self.ctx.lib.mpres_collection_clear(self.ctx.h, ctypes.byref(self.s))
+
+    def __del__(self):
+        try:
+            if self.ctx.h:
+                self.clear()
+        except Exception:
+            pass
+
+
+def _ref(a):
+    return ctypes.byref(a.s) if a is not None else None
+
+
+def mp_gemm(ctx, transa, transb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, buffer=None, stream=0):
+    """cuda::mp_gemm (src/blas/gemm.cuh:69-70): C = alpha*op(A)*op(B) + beta*C, column-major."""
+    if isinstance(A, MpCollection):
+        _check(ctx.lib.mpres_gemm_coll(ctx.h, transa, transb, m, n, k, _ref(alpha), _ref(A), lda, ctypes.c_size_t(A.size),
+                                       _ref(B), ldb, ctypes.c_size_t(B.size), _ref(beta), _ref(C), ldc, ctypes.c_size_t(C.size),
+                                       _vp(stream)), "mpres_gemm_coll")
+        return
+    _check(ctx.lib.mpres_gemm(ctx.h, transa, transb, m, n, k, _ref(alpha), _ref(A), lda, _ref(B), ldb, _ref(beta), _ref(C), ldc,
+                              _ref(buffer), _vp(stream)), "mpres_gemm")
+
+
+def mp_gemv(ctx, trans, m, n, alpha, A, lda, x, incx, beta, y, incy, buffer1=None, buffer2=None, stream=0):
+    """cuda::mp_gemv (src/blas/gemv.cuh:150-152): y = alpha*op(A)*x + beta*y."""
+    if isinstance(A, MpCollection):
+        _check(ctx.lib.mpres_gemv_coll(ctx.h, trans, m, n, _ref(alpha), _ref(A), lda, ctypes.c_size_t(A.size), _ref(x), incx,
+                                       ctypes.c_size_t(x.size), _ref(beta), _ref(y), incy, ctypes.c_size_t(y.size), _vp(stream)),
+               "mpres_gemv_coll")
+        return
+    _check(ctx.lib.mpres_gemv(ctx.h, trans, m, n, _ref(alpha), _ref(A), lda, _ref(x), incx, _ref(beta), _ref(y), incy,
+                              _ref(buffer1), _ref(buffer2), _vp(stream)), "mpres_gemv")
+
+
+def mp_dot(ctx, n, x, incx, y, incy, r, buffer=None, stream=0):
+    """cuda::mp_dot (src/blas/dot.cuh:84-85): r[0] = sum x_i*y_i."""
+    if isinstance(x, MpCollection):
+        _check(ctx.lib.mpres_dot_coll(ctx.h, n, _ref(x), incx, ctypes.c_size_t(x.size), _ref(y), incy, ctypes.c_size_t(y.size),
+                                      _ref(r), _vp(stream)), "mpres_dot_coll")
+        return
+    _check(ctx.lib.mpres_dot(ctx.h, n, _ref(x), incx, _ref(y), incy, _ref(r), _ref(buffer), _vp(stream)), "mpres_dot")
+
+
+def synchronize(ctx):
+    """cudaDeviceSynchronize through the library's fallback-counter read (it syncs the last stream)."""
+    return ctx.last_fallback_count()

@@ -1,0 +1,97 @@
+// ctx.hpp -- the library context and small host helpers shared by the kernel launchers.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "../../include/mpres_b200.h"
+#include "host_consts.hpp"
+#include "mp_device.cuh"
+
+using namespace mpres;
+
+struct mpres_ctx {
+    int device = 0;
+    int mode = MPRES_MODE_AUTO;
+    HostConsts hc;
+    DevConsts *dconsts = nullptr;
+    int *d_pow2 = nullptr, *d_inv_pow2 = nullptr, *d_mrc = nullptr;
+    std::atomic<long> launches{0};
+    // workspace pool (grown on demand, never freed per call)
+    void *ws[8] = {nullptr};
+    size_t ws_size[8] = {0};
+    int *d_counter = nullptr;      // fallback element counter of the last call
+    cudaStream_t last_stream = nullptr;
+    int sm_count = 148;
+    std::mutex mu;
+};
+
+#define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return (int) e_; } while (0)
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int ws_reserve(mpres_ctx *c, int slot, size_t bytes, void **out) {
+    if (c->ws_size[slot] < bytes) {
+        if (c->ws[slot]) { cudaDeviceSynchronize(); cudaFree(c->ws[slot]); c->ws[slot] = nullptr; c->ws_size[slot] = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        CUDA_TRY(cudaMalloc(&c->ws[slot], want));
+        c->ws_size[slot] = want;
+    }
+    *out = c->ws[slot];
+    return 0;
+}
+
+SoA view(const mpres_array_t *a) {
+    SoA v;
+    v.digits = a->digits; v.sign = a->sign; v.exp = a->exp; v.eval = (Er *) a->eval; v.len_ptr = a->len; v.len_val = 0;
+    return v;
+}
+SoA view(const mpres_collection_t *a, size_t len) {
+    SoA v;
+    v.digits = a->digits; v.sign = a->sign; v.exp = a->exp; v.eval = (Er *) a->eval; v.len_ptr = nullptr; v.len_val = (long long) len;
+    return v;
+}
+// carve an SoA of `len` elements out of one workspace slot
+int ws_soa(mpres_ctx *c, int slot, size_t len, SoA *out) {
+    const size_t N = c->hc.N;
+    size_t bytes = len * (4 * N + 4 + 4 + 32) + 64;
+    void *p;
+    int rc = ws_reserve(c, slot, bytes, &p);
+    if (rc) return rc;
+    char *b = (char *) p;
+    out->eval = (Er *) b; b += len * 32;
+    out->digits = (int *) b; b += len * 4 * N;
+    out->sign = (int *) b; b += len * 4;
+    out->exp = (int *) b;
+    out->len_ptr = nullptr;
+    out->len_val = (long long) len;
+    return 0;
+}
+
+inline int group_size(int N) { return N <= 8 ? 8 : N <= 16 ? 16 : 32; }
+
+}  // namespace
+
+// Dispatch on the (lanes per number, residues per lane) shape chosen from N.
+#define MPRES_DISPATCH(N_, ...)                                    \
+    do {                                                           \
+        if ((N_) <= 8) { constexpr int G = 8, R = 1; __VA_ARGS__; }        \
+        else if ((N_) <= 16) { constexpr int G = 16, R = 1; __VA_ARGS__; } \
+        else if ((N_) <= 32) { constexpr int G = 32, R = 1; __VA_ARGS__; } \
+        else if ((N_) <= 64) { constexpr int G = 32, R = 2; __VA_ARGS__; } \
+        else { constexpr int G = 32, R = 4; __VA_ARGS__; }                 \
+    } while (0)
+
+#define LAUNCHED(c) ((c)->launches.fetch_add(1, std::memory_order_relaxed))
+

@@ -1,0 +1,192 @@
+// host_consts.hpp -- every precomputed constant of the RNS floating-point format, derived from the
+// moduli alone with a small exact integer type (no GMP / MPFR on the product path).
+//
+// Replaces rns_const_init (reference src/rns.cuh:324-442) and mp_const_init
+// (src/arith/arith_utils.cuh:44-85); definitions are tabulated in SURVEY.md Appendix A.  Bit-for-bit
+// agreement with the reference's GMP/MPFR-derived values is enforced by tests/test_constants.py.
+#pragma once
+
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+namespace mpres {
+
+constexpr int kScalingThreshold = 30;        // RNS_P2_SCALING_THRESHOLD (src/params.h:42)
+constexpr double kEvalRelError = 0.0000001;  // RNS_EVAL_RELATIVE_ERROR (src/params.h:47)
+constexpr int kMaxModuli = 128;
+
+// Predefined moduli sets of src/params/32-bit-n-double-moduli/params.<N>_<n>double.h (data of the
+// number format).  Generated table, see moduli_sets.inc.
+struct ModuliSet { int n; const int *values; };
+#include "moduli_sets.inc"
+
+// Non-negative arbitrary-size integer, little-endian 32-bit limbs; just what the constants need.
+class BigUInt {
+public:
+    std::vector<uint32_t> limb;
+    BigUInt(uint64_t v = 0) { while (v) { limb.push_back((uint32_t) v); v >>= 32; } }
+    void mul_small(uint32_t f) {
+        uint64_t carry = 0;
+        for (auto &l : limb) { uint64_t t = (uint64_t) l * f + carry; l = (uint32_t) t; carry = t >> 32; }
+        if (carry) limb.push_back((uint32_t) carry);
+    }
+    // returns remainder, *this becomes the quotient
+    uint32_t div_small(uint32_t d) {
+        uint64_t rem = 0;
+        for (size_t i = limb.size(); i-- > 0;) {
+            uint64_t cur = (rem << 32) | limb[i];
+            limb[i] = (uint32_t) (cur / d);
+            rem = cur % d;
+        }
+        while (!limb.empty() && limb.back() == 0) limb.pop_back();
+        return (uint32_t) rem;
+    }
+    int bit_length() const {
+        if (limb.empty()) return 0;
+        return (int) (32 * (limb.size() - 1)) + (32 - __builtin_clz(limb.back()));
+    }
+    uint64_t low_bits(int j) const {  // value mod 2^j, j <= 63
+        uint64_t v = 0;
+        if (!limb.empty()) v = limb[0];
+        if (limb.size() > 1) v |= (uint64_t) limb[1] << 32;
+        return j >= 64 ? v : v & ((1ull << j) - 1);
+    }
+    uint64_t top_bits(int count) const {  // the `count` (<= 64) most significant bits
+        int L = bit_length();
+        uint64_t v = 0;
+        for (int b = L - 1; b >= L - count && b >= 0; --b) v = (v << 1) | ((limb[b / 32] >> (b % 32)) & 1u);
+        return v;
+    }
+    bool any_bits_below(int pos) const {  // any set bit at positions [0, pos)
+        for (int b = 0; b < pos; ++b) if ((limb[b / 32] >> (b % 32)) & 1u) return true;
+        return false;
+    }
+};
+
+inline int64_t inverse_mod(int64_t x, int64_t m) {  // extended Euclid; gcd(x, m) must be 1
+    int64_t a = ((x % m) + m) % m, b = m, u = 1, v = 0;
+    while (b) { int64_t q = a / b, t = a - q * b; a = b; b = t; t = u - q * v; u = v; v = t; }
+    return a == 1 ? ((u % m) + m) % m : 0;
+}
+
+struct ErHost { double frac; long exp; };
+
+struct HostConsts {
+    int N = 0, log2M = 0, mp_precision = 0, mp_h = 0, mp_j = 0, ref_factor = 0;
+    double accuracy = 0;
+    ErHost unit_low{}, unit_upp{}, inv_low{}, inv_upp{};
+    std::vector<int> moduli, part_inverse, pow2, m_pow2, mi_pow2, pow2_inv, mrc_inv, inv_pow2_ext;
+    std::vector<double> recip_rd, recip_ru;
+    std::vector<uint64_t> barrett;  // floor((2^64 - 1) / m_i)
+};
+
+// returns 0 on success, negative on unusable moduli
+inline int compute_constants(const int *mods, int N, HostConsts &c) {
+    if (N < 2 || N > kMaxModuli) return -1;
+    for (int i = 0; i < N; ++i) {
+        if (mods[i] < 3 || (mods[i] & 1) == 0) return -2;  // power-of-two scaling needs odd moduli
+        for (int j = 0; j < i; ++j) if (std::__gcd(mods[i], mods[j]) != 1) return -3;
+    }
+    c.N = N;
+    c.moduli.assign(mods, mods + N);
+    BigUInt M(1);
+    for (int i = 0; i < N; ++i) M.mul_small((uint32_t) mods[i]);
+    const int L = M.bit_length();
+    if (L <= 64) return -4;
+    c.log2M = L - 1;  // RNS_MODULI_PRODUCT_LOG2
+
+    // w_i = (M / m_i)^-1 mod m_i                                        rns.cuh:339-346
+    c.part_inverse.resize(N);
+    for (int i = 0; i < N; ++i) {
+        int64_t p = 1;
+        for (int j = 0; j < N; ++j) if (j != i) p = p * (mods[j] % mods[i]) % mods[i];
+        c.part_inverse[i] = (int) inverse_mod(p, mods[i]);
+    }
+    // 2^j mod m_i, j = 0..log2M                                          rns.cuh:352-358
+    c.pow2.resize((size_t) (c.log2M + 1) * N);
+    c.inv_pow2_ext.resize((size_t) (c.log2M + 1) * N);
+    for (int i = 0; i < N; ++i) {
+        int64_t v = 1, iv = 1, half = (mods[i] + 1) / 2;
+        for (int j = 0; j <= c.log2M; ++j) {
+            c.pow2[(size_t) j * N + i] = (int) v;
+            c.inv_pow2_ext[(size_t) j * N + i] = (int) iv;
+            v = v * 2 % mods[i];
+            iv = iv * half % mods[i];
+        }
+    }
+    // M mod 2^j, M_i mod 2^j, (2^j)^-1 mod m_i for j = 1..30             rns.cuh:360-382
+    c.m_pow2.resize(kScalingThreshold);
+    c.mi_pow2.resize((size_t) kScalingThreshold * N);
+    c.pow2_inv.resize((size_t) kScalingThreshold * N);
+    for (int j = 0; j < kScalingThreshold; ++j) c.m_pow2[j] = (int) M.low_bits(j + 1);
+    for (int i = 0; i < N; ++i) {
+        BigUInt Mi = M;
+        Mi.div_small((uint32_t) mods[i]);
+        for (int j = 0; j < kScalingThreshold; ++j) {
+            c.mi_pow2[(size_t) j * N + i] = (int) Mi.low_bits(j + 1);
+            c.pow2_inv[(size_t) j * N + i] = c.inv_pow2_ext[(size_t) (j + 1) * N + i];
+        }
+    }
+    // interval-evaluation constants                                       rns.cuh:385-410
+    c.accuracy = 4 * std::pow(2.0, 1 - 53) * N * std::log2((double) N) * (1 + kEvalRelError / 2) / kEvalRelError;
+    c.ref_factor = (int) std::floor(std::log2(1 / (2 * c.accuracy)));
+    // The reference divides by M rounded DOWN to 53 bits (mpfr_init default precision, rns.cuh:336).
+    const uint64_t mant = M.top_bits(53);  // in [2^52, 2^53)
+    const int s = L - 53;
+    {
+        unsigned __int128 num = (unsigned __int128) 1 << 105;
+        uint64_t q = (uint64_t) (num / mant);
+        bool inexact = (num % mant) != 0;
+        auto pack = [&](uint64_t qq) {
+            ErHost e;
+            if (qq == (1ull << 53)) { e.frac = 0.5; e.exp = -52 - s + 1; }
+            else { e.frac = (double) qq / 9007199254740992.0; e.exp = -52 - s; }
+            return e;  // mpfr_get_d_2exp convention: frac in [0.5, 1)
+        };
+        c.unit_low = pack(q);
+        c.unit_upp = pack(q + (inexact ? 1 : 0));
+    }
+    // (M-1)/M = 1 - 1/M: for log2 M > 54 the 53-bit roundings are 1 - 2^-53 (down) and 1.0 (up)
+    c.inv_low = {1.0 - std::ldexp(1.0, -53), 0};
+    c.inv_upp = {0.5, 1};
+    // 1/m_i widened by the reference's host emulation of directed rounding   rns.cuh:412-415,
+    // dinterval.cuh:142-154, bitwise.cuh:51-61
+    c.recip_rd.resize(N);
+    c.recip_ru.resize(N);
+    {
+        const double eps = std::ldexp(1.0, -53), phi1 = eps * (1 + 2 * eps), eta = std::ldexp(1.0, -1074);
+        for (int i = 0; i < N; ++i) {
+            volatile double q = 1.0 / (double) mods[i];
+            volatile double e = phi1 * std::fabs(q);
+            e = e + eta;
+            c.recip_rd[i] = q - e;
+            c.recip_ru[i] = q + e;
+        }
+    }
+    // m_i^-1 mod m_j for j > i                                            rns.cuh:417-426
+    c.mrc_inv.assign((size_t) N * N, 0);
+    for (int i = 0; i < N; ++i)
+        for (int j = i + 1; j < N; ++j) c.mrc_inv[(size_t) i * N + j] = (int) inverse_mod(mods[i], mods[j]);
+    c.barrett.resize(N);
+    for (int i = 0; i < N; ++i) c.barrett[i] = ~0ull / (uint64_t) mods[i];
+    // MP_PRECISION, MP_H, MP_J on the 53-bit truncated M                  arith_utils.cuh:44-61
+    c.mp_precision = (L - 1) / 2 - 1;
+    {
+        // smallest h with 4^h >= Md  (Md = mant * 2^s)
+        int h = (L + 1) / 2;             // 4^h >= 2^L > Md
+        // 4^(h-1) >= Md  <=>  2h-2 >= L, or 2h-2 == L-1 and Md == 2^(L-1)
+        while (true) {
+            int e = 2 * (h - 1);
+            bool ge = e >= L || (e == L - 1 && mant == (1ull << 52));
+            if (!ge) break;
+            --h;
+        }
+        c.mp_h = -h;
+    }
+    c.mp_j = -1;
+    return 0;
+}
+
+}  // namespace mpres

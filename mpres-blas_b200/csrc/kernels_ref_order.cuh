@@ -1,0 +1,247 @@
+// kernels_ref_order.cuh -- "reference-order" kernels: the reference's per-step semantics (mp_mul,
+// mp_add, rounding after every operation, same summation order where it is fixed by the algorithm),
+// executed residue-parallel by lane groups.  They are (a) the bit-exact parity mode against the
+// reference kernels and (b) the per-element fallback of the exact-window fast path.
+#pragma once
+
+#include "mp_device.cuh"
+
+namespace mpres {
+
+// op(X)(row, col) of a column-major matrix with leading dimension ld
+__device__ __forceinline__ long long mat_index(bool trans, long long row, long long col, long long ld) {
+    return trans ? col + row * ld : row + col * ld;
+}
+
+// ---- element-wise probes (tests) -------------------------------------------------------------------
+template <int G, int R>
+__global__ void k_probe(const DevConsts *Cp, int op, char *r, const char *x, const char *y, const int *bits, long long n) {
+    const DevConsts &C = *Cp;
+    Lane<R> L;
+    lane_init<G, R>(C, L);
+    const long long grp = ((long long) blockIdx.x * blockDim.x + threadIdx.x) / G;
+    if (grp >= n) return;
+    Num<R> a, b, out;
+    load_rec<G, R>(C, L, x, grp, a);
+    if (op == 0) { load_rec<G, R>(C, L, y, grp, b); mp_mul<G, R, true>(C, L, out, a, b); }
+    else if (op == 1) { load_rec<G, R>(C, L, y, grp, b); mp_add<G, R, true>(C, L, out, a, b); }
+    else if (op == 2) { out = a; eval_compute<G, R, false>(C, L, out.d, out.lo, out.up); }
+    else if (op == 3) { out = a; eval_compute<G, R, true>(C, L, out.d, out.lo, out.up); }
+    else { out = a; mp_round<G, R>(C, L, out, bits[grp]); }
+    store_rec<G, R>(C, L, r, grp, out);
+}
+
+// ---- GEMM stage: S = op(A) * op(B), reference order (src/blas/gemm.cuh:39-58) ----------------------
+// One lane group per element of S; groups are laid out along rows so that neighbouring groups read
+// neighbouring elements of a column of A.  `todo` (optional) lists the elements to compute
+// (fallback of the fast path): todo[t] = row + col * m.
+template <int G, int R>
+__global__ void k_gemm_ref_order(const DevConsts *Cp, bool ta, bool tb, int m, int n, int k, SoA A, int lda, SoA B, int ldb,
+                                 SoA S, int lds, const long long *todo, const int *todo_count) {
+    const DevConsts &C = *Cp;
+    Lane<R> L;
+    lane_init<G, R>(C, L);
+    long long grp = ((long long) blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const long long ngrp = (long long) gridDim.x * blockDim.x / G;
+    const long long total = todo ? (long long) *todo_count : (long long) m * n;
+    for (; grp < total; grp += ngrp) {
+        const long long e = todo ? todo[grp] : grp;
+        const int row = (int) (e % m), col = (int) (e / m);
+        Num<R> sum, prod, a, b;
+        num_zero(sum);
+        for (int l = 0; l < k; ++l) {
+            load_num<G, R>(C, L, A, mat_index(ta, row, l, lda), a);
+            load_num<G, R>(C, L, B, mat_index(tb, l, col, ldb), b);
+            mp_mul<G, R, true>(C, L, prod, a, b);
+            mp_add<G, R, true>(C, L, sum, sum, prod);
+        }
+        store_num<G, R>(C, L, S, row + (long long) col * lds, sum);
+    }
+}
+
+// ---- GEMM epilogue: C = alpha * S + beta * C with the reference's three roundings
+//      (src/blas/gemm.cuh:142-166: K2-K4 on buffer, K2-K4 on C, K5-K6-K4) fused into one pass -------
+template <int G, int R>
+__global__ void k_gemm_epilogue(const DevConsts *Cp, int m, int n, SoA alpha, SoA beta, SoA S, int lds, SoA Cm, int ldc) {
+    const DevConsts &C = *Cp;
+    Lane<R> L;
+    lane_init<G, R>(C, L);
+    long long grp = ((long long) blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const long long ngrp = (long long) gridDim.x * blockDim.x / G;
+    Num<R> al, be;
+    load_num<G, R>(C, L, alpha, 0, al);
+    load_num<G, R>(C, L, beta, 0, be);
+    for (; grp < (long long) m * n; grp += ngrp) {
+        const int row = (int) (grp % m), col = (int) (grp / m);
+        Num<R> s, c, t1, t2;
+        load_num<G, R>(C, L, S, row + (long long) col * lds, s);
+        load_num<G, R>(C, L, Cm, row + (long long) col * ldc, c);
+        mp_mul<G, R, true>(C, L, t1, s, al);
+        mp_mul<G, R, true>(C, L, t2, c, be);
+        mp_add<G, R, true>(C, L, c, t2, t1);
+        store_num<G, R>(C, L, Cm, row + (long long) col * ldc, c);
+    }
+}
+
+// ---- vector scale: r[i] = round(x[ix] * s[0]) (src/mpvector.cuh:139-216 + 669-714) -----------------
+__device__ __forceinline__ long long inc_index(long long i, long long n, int inc) {
+    return inc > 0 ? i * inc : (-n + i + 1) * (long long) inc;   // BLAS convention, mpvector.cuh:68-70
+}
+template <int G, int R>
+__global__ void k_vec_scale(const DevConsts *Cp, long long n, SoA r, int incr, SoA x, int incx, SoA s) {
+    const DevConsts &C = *Cp;
+    Lane<R> L;
+    lane_init<G, R>(C, L);
+    long long grp = ((long long) blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const long long ngrp = (long long) gridDim.x * blockDim.x / G;
+    Num<R> sc;
+    load_num<G, R>(C, L, s, 0, sc);
+    for (; grp < n; grp += ngrp) {
+        Num<R> a, t;
+        load_num<G, R>(C, L, x, inc_index(grp, n, incx), a);
+        mp_mul<G, R, true>(C, L, t, a, sc);
+        store_num<G, R>(C, L, r, inc_index(grp, n, incr), t);
+    }
+}
+
+// ---- GEMV, reference order: y[o] = y[o] + sum_q op(A)(o, q) * ax[q]  (src/blas/gemv.cuh:199-218) ----
+// y already holds round(beta * y) and ax = round(alpha * x).  One group per output element.
+template <int G, int R>
+__global__ void k_gemv_ref_order(const DevConsts *Cp, bool trans, int m, int n, SoA A, int lda, SoA ax, SoA y, int incy) {
+    const DevConsts &C = *Cp;
+    Lane<R> L;
+    lane_init<G, R>(C, L);
+    const int leny = trans ? n : m, lenx = trans ? m : n;
+    long long grp = ((long long) blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const long long ngrp = (long long) gridDim.x * blockDim.x / G;
+    for (; grp < leny; grp += ngrp) {
+        Num<R> sum, prod, a, b;
+        num_zero(sum);
+        for (int q = 0; q < lenx; ++q) {
+            load_num<G, R>(C, L, A, trans ? q + grp * lda : grp + (long long) q * lda, a);
+            load_num<G, R>(C, L, ax, q, b);
+            mp_mul<G, R, true>(C, L, prod, a, b);
+            mp_add<G, R, true>(C, L, sum, sum, prod);
+        }
+        const long long iy = inc_index(grp, leny, incy);
+        load_num<G, R>(C, L, y, iy, a);
+        mp_add<G, R, true>(C, L, a, a, sum);
+        store_num<G, R>(C, L, y, iy, a);
+    }
+}
+
+// ---- DOT, reference order: per-group serial mul/add over a strided slice, partials as AoS records
+//      (structure of src/mpreduct.cuh:38-74 with groups in place of threads) --------------------------
+template <int G, int R>
+__global__ void k_dot_partial(const DevConsts *Cp, long long n, SoA x, int incx, SoA y, int incy, char *partials) {
+    const DevConsts &C = *Cp;
+    Lane<R> L;
+    lane_init<G, R>(C, L);
+    const long long grp = ((long long) blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const long long ngrp = (long long) gridDim.x * blockDim.x / G;
+    Num<R> sum, prod, a, b;
+    num_zero(sum);
+    for (long long i = grp; i < n; i += ngrp) {
+        load_num<G, R>(C, L, x, inc_index(i, n, incx), a);
+        load_num<G, R>(C, L, y, inc_index(i, n, incy), b);
+        mp_mul<G, R, true>(C, L, prod, a, b);
+        mp_add<G, R, true>(C, L, sum, sum, prod);
+    }
+    store_rec<G, R>(C, L, partials, grp, sum);
+}
+
+// Sum `count` AoS records in index order with one group, result to SoA out[out_idx] or AoS record.
+template <int G, int R>
+__global__ void k_reduce_records(const DevConsts *Cp, const char *recs, long long count, SoA out, long long out_idx, char *out_rec) {
+    const DevConsts &C = *Cp;
+    Lane<R> L;
+    lane_init<G, R>(C, L);
+    if (threadIdx.x >= G || blockIdx.x > 0) return;
+    Num<R> sum, a;
+    num_zero(sum);
+    for (long long i = 0; i < count; ++i) {
+        load_rec<G, R>(C, L, recs, i, a);
+        mp_add<G, R, true>(C, L, sum, sum, a);
+    }
+    if (out_rec) store_rec<G, R>(C, L, out_rec, 0, sum);
+    else store_num<G, R>(C, L, out, out_idx, sum);
+}
+
+// Pairwise tree over AoS records held by the groups of ONE block: rec[g] += rec[g + stride].
+template <int G, int R>
+__global__ void k_tree_records(const DevConsts *Cp, char *recs, long long count, SoA out, long long out_idx, char *out_rec) {
+    const DevConsts &C = *Cp;
+    Lane<R> L;
+    lane_init<G, R>(C, L);
+    const int grp = threadIdx.x / G, ngrp = blockDim.x / G;
+    // fold the tail onto the first ngrp records, then tree
+    Num<R> sum, a;
+    if (grp < count) {
+        load_rec<G, R>(C, L, recs, grp, sum);
+        for (long long i = grp + ngrp; i < count; i += ngrp) {
+            load_rec<G, R>(C, L, recs, i, a);
+            mp_add<G, R, true>(C, L, sum, sum, a);
+        }
+        store_rec<G, R>(C, L, recs, grp, sum);
+    }
+    __syncthreads();
+    long long live = count < ngrp ? count : ngrp;
+    int p = 1;
+    while (p < live) p <<= 1;
+    for (int s = p >> 1; s >= 1; s >>= 1) {
+        if (grp < s && grp + s < live) {
+            load_rec<G, R>(C, L, recs, grp, sum);
+            load_rec<G, R>(C, L, recs, grp + s, a);
+            mp_add<G, R, true>(C, L, sum, sum, a);
+            store_rec<G, R>(C, L, recs, grp, sum);
+        }
+        __syncthreads();
+    }
+    if (grp == 0) {
+        load_rec<G, R>(C, L, recs, 0, sum);
+        if (count <= 0) num_zero(sum);
+        if (out_rec) store_rec<G, R>(C, L, out_rec, 0, sum);
+        else store_num<G, R>(C, L, out, out_idx, sum);
+    }
+}
+
+// ---- device-side conversion from binary significands (replaces mp_set_mpfr, assign.cuh:86-127) -----
+// One group per element.  limbs: little-endian 32-bit words.
+template <int G, int R>
+__global__ void k_set_binary(const DevConsts *Cp, SoA dst, long long offset, const int *sign, const int *exp,
+                             const uint32_t *limbs, int nlimbs, long long count) {
+    const DevConsts &C = *Cp;
+    Lane<R> L;
+    lane_init<G, R>(C, L);
+    long long grp = ((long long) blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const long long ngrp = (long long) gridDim.x * blockDim.x / G;
+    for (; grp < count; grp += ngrp) {
+        const uint32_t *w = limbs + grp * nlimbs;
+        int top = nlimbs;
+        while (top > 0 && w[top - 1] == 0) --top;
+        Num<R> x;
+        num_zero(x);
+        if (top > 0) {
+            int tz = 0;
+            while (w[tz >> 5] == 0) tz += 32;
+            tz += __ffs(w[tz >> 5]) - 1;
+            const int ws = tz >> 5, bs = tz & 31;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                unsigned long long acc = 0;
+                for (int l = top - 1 - ws; l >= 0; --l) {
+                    uint32_t lo = w[l + ws], hi = (l + ws + 1 < top) ? w[l + ws + 1] : 0u;
+                    uint32_t v = bs ? ((lo >> bs) | (hi << (32 - bs))) : lo;
+                    acc = ((acc << 32) | v) % (unsigned long long) (unsigned) L.m[r];
+                }
+                x.d[r] = L.act[r] ? (int) acc : 0;
+            }
+            x.sign = sign[grp] ? 1 : 0;
+            x.exp = exp[grp] + tz;
+            eval_compute<G, R, false>(C, L, x.d, x.lo, x.up);
+        }
+        store_num<G, R>(C, L, dst, offset + grp, x);
+    }
+}
+
+}  // namespace mpres

@@ -1,0 +1,547 @@
+// mpres_b200.cu -- C-ABI (include/mpres_b200.h) over the sm_100a kernels.
+//
+// Host logic mirrors the argument checks and call structure of the reference's host templates
+// (src/blas/gemm.cuh:69-167, src/blas/gemv.cuh:150-268, src/blas/dot.cuh:84-107) but every numeric
+// step runs in this library's own kernels.  There is no CPU path.
+#include "../../include/mpres_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "ctx.hpp"
+#include "kernels_ref_order.cuh"
+#include "kernels_fast.cuh"
+
+// a constants-only context (device < 0) cannot compute
+#define NEED_DEVICE(c) do { if ((c) && (c)->device < 0) return -100; } while (0)
+
+static_assert(sizeof(mpres_er_float_t) == 16 && sizeof(Er) == 16, "er_float_t layout (src/types.cuh:46-49)");
+
+extern "C" {
+
+const char *mpres_version(void) { return "mpres-b200 0.1 (sm_100a)"; }
+
+int mpres_init_moduli(mpres_ctx **out, const int *moduli, int n, int device) {
+    if (!out || !moduli) return -1;
+    if (device < 0) {
+        // constants-only context (no device): lets the constant tables be checked on a CPU-only box.
+        // Every compute entry point rejects it -- there is no CPU arithmetic in this library.
+        mpres_ctx *c = new mpres_ctx();
+        c->device = -1;
+        int rc = compute_constants(moduli, n, c->hc);
+        if (rc) { delete c; return rc - 10; }
+        *out = c;
+        return 0;
+    }
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (device >= ndev) return -2;
+    mpres_ctx *c = new mpres_ctx();
+    c->device = device;
+    int rc = compute_constants(moduli, n, c->hc);
+    if (rc) { delete c; return rc - 10; }
+    DeviceGuard g(device);
+    const HostConsts &h = c->hc;
+    DevConsts *d = new DevConsts();
+    memset(d, 0, sizeof(*d));
+    d->N = h.N; d->log2M = h.log2M; d->mp_h = h.mp_h; d->mp_j = h.mp_j; d->ref_factor = h.ref_factor;
+    d->accuracy = h.accuracy;
+    d->unit_low = {h.unit_low.frac, h.unit_low.exp}; d->unit_upp = {h.unit_upp.frac, h.unit_upp.exp};
+    d->inv_low = {h.inv_low.frac, h.inv_low.exp}; d->inv_upp = {h.inv_upp.frac, h.inv_upp.exp};
+    for (int i = 0; i < h.N; ++i) {
+        d->moduli[i] = h.moduli[i]; d->part_inverse[i] = h.part_inverse[i]; d->barrett[i] = h.barrett[i];
+        d->recip_rd[i] = h.recip_rd[i]; d->recip_ru[i] = h.recip_ru[i];
+    }
+    for (int j = 0; j < kThresh; ++j) {
+        d->m_pow2[j] = h.m_pow2[j];
+        for (int i = 0; i < h.N; ++i) {
+            d->mi_pow2[j][i] = h.mi_pow2[(size_t) j * h.N + i];
+            d->pow2_inv[j][i] = h.pow2_inv[(size_t) j * h.N + i];
+        }
+    }
+    cudaError_t e;
+    auto up = [&](int **dst, const std::vector<int> &src) {
+        e = cudaMalloc(dst, src.size() * sizeof(int));
+        if (e == cudaSuccess) e = cudaMemcpy(*dst, src.data(), src.size() * sizeof(int), cudaMemcpyHostToDevice);
+        return e;
+    };
+    if (up(&c->d_pow2, h.pow2) != cudaSuccess || up(&c->d_inv_pow2, h.inv_pow2_ext) != cudaSuccess ||
+        up(&c->d_mrc, h.mrc_inv) != cudaSuccess) { delete d; delete c; return (int) e; }
+    d->pow2 = c->d_pow2; d->inv_pow2 = c->d_inv_pow2; d->mrc_inv = c->d_mrc;
+    e = cudaMalloc(&c->dconsts, sizeof(DevConsts));
+    if (e == cudaSuccess) e = cudaMemcpy(c->dconsts, d, sizeof(DevConsts), cudaMemcpyHostToDevice);
+    delete d;
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_counter, 4 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(c->d_counter, 0, 4 * sizeof(int));
+    if (e != cudaSuccess) { delete c; return (int) e; }
+    cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    *out = c;
+    return 0;
+}
+
+int mpres_init(mpres_ctx **out, int moduli_size, int device) {
+    for (const ModuliSet &s : kModuliSets)
+        if (s.n == moduli_size) return mpres_init_moduli(out, s.values, s.n, device);
+    return -3;
+}
+
+int mpres_finalize(mpres_ctx *c) {
+    if (!c) return -1;
+    if (c->device < 0) { delete c; return 0; }
+    DeviceGuard g(c->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < 8; ++i) if (c->ws[i]) cudaFree(c->ws[i]);
+    cudaFree(c->d_pow2); cudaFree(c->d_inv_pow2); cudaFree(c->d_mrc); cudaFree(c->dconsts); cudaFree(c->d_counter);
+    delete c;
+    return 0;
+}
+
+int mpres_moduli_size(const mpres_ctx *c) { return c ? c->hc.N : -1; }
+int mpres_moduli_product_log2(const mpres_ctx *c) { return c ? c->hc.log2M : -1; }
+int mpres_precision(const mpres_ctx *c) { return c ? c->hc.mp_precision : -1; }
+int mpres_mp_h(const mpres_ctx *c) { return c ? c->hc.mp_h : 0; }
+int mpres_mp_j(const mpres_ctx *c) { return c ? c->hc.mp_j : 0; }
+int mpres_device(const mpres_ctx *c) { return c ? c->device : -1; }
+size_t mpres_sizeof_mp_float(const mpres_ctx *c) { return c ? 4 * (size_t) c->hc.N + 40 : 0; }
+int mpres_set_mode(mpres_ctx *c, int mode) { if (!c || mode < 0 || mode > 2) return -1; c->mode = mode; return 0; }
+int mpres_get_mode(const mpres_ctx *c) { return c ? c->mode : -1; }
+long mpres_launch_count(const mpres_ctx *c) { return c ? c->launches.load() : -1; }
+
+long mpres_last_fallback_count(mpres_ctx *c) {
+    if (!c || c->device < 0) return -1;
+    DeviceGuard g(c->device);
+    int v = 0;
+    if (cudaStreamSynchronize(c->last_stream) != cudaSuccess) return -2;
+    if (cudaMemcpy(&v, c->d_counter, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+    return v;
+}
+
+long mpres_get_constant(const mpres_ctx *c, int which, void *out, size_t cap) {
+    if (!c || !out) return -1;
+    const HostConsts &h = c->hc;
+    const void *src = nullptr;
+    size_t bytes = 0;
+    double tmp[5];
+    switch (which) {
+        case 0: src = h.moduli.data(); bytes = h.moduli.size() * 4; break;
+        case 1: src = h.part_inverse.data(); bytes = h.part_inverse.size() * 4; break;
+        case 2: src = h.pow2.data(); bytes = h.pow2.size() * 4; break;
+        case 3: src = h.m_pow2.data(); bytes = h.m_pow2.size() * 4; break;
+        case 4: src = h.mi_pow2.data(); bytes = h.mi_pow2.size() * 4; break;
+        case 5: src = h.pow2_inv.data(); bytes = h.pow2_inv.size() * 4; break;
+        case 6: src = h.mrc_inv.data(); bytes = h.mrc_inv.size() * 4; break;
+        case 7: src = h.recip_rd.data(); bytes = h.recip_rd.size() * 8; break;
+        case 8: src = h.recip_ru.data(); bytes = h.recip_ru.size() * 8; break;
+        case 9: tmp[0] = h.accuracy; tmp[1] = h.unit_low.frac; tmp[2] = h.unit_upp.frac; tmp[3] = h.inv_low.frac; tmp[4] = h.inv_upp.frac;
+                src = tmp; bytes = sizeof(tmp); break;
+        case 10: tmp[0] = h.ref_factor; tmp[1] = (double) h.unit_low.exp; tmp[2] = (double) h.unit_upp.exp; tmp[3] = (double) h.inv_low.exp; tmp[4] = (double) h.inv_upp.exp;
+                src = tmp; bytes = sizeof(tmp); break;
+        default: return -2;
+    }
+    if (bytes > cap) return -3;
+    memcpy(out, src, bytes);
+    return (long) bytes;
+}
+
+/* ---- containers ---------------------------------------------------------------------------------- */
+
+static int soa_alloc(mpres_ctx *c, int **digits, int **sign, int **exp, mpres_er_float_t **eval, size_t size) {
+    const size_t n = size ? size : 1;
+    CUDA_TRY(cudaMalloc(digits, n * c->hc.N * sizeof(int)));
+    CUDA_TRY(cudaMalloc(sign, n * sizeof(int)));
+    CUDA_TRY(cudaMalloc(exp, n * sizeof(int)));
+    CUDA_TRY(cudaMalloc(eval, 2 * n * sizeof(mpres_er_float_t)));
+    return 0;
+}
+
+int mpres_array_init(mpres_ctx *c, mpres_array_t *a, size_t size) {
+    NEED_DEVICE(c);
+    if (!c || !a) return -1;
+    DeviceGuard g(c->device);
+    memset(a, 0, sizeof(*a));
+    int rc = soa_alloc(c, &a->digits, &a->sign, &a->exp, &a->eval, size);
+    if (rc) return rc;
+    CUDA_TRY(cudaMalloc(&a->buf, (size ? size : 1) * sizeof(mpres_int4)));
+    CUDA_TRY(cudaMalloc(&a->len, sizeof(int)));
+    int len = (int) size;
+    CUDA_TRY(cudaMemcpy(a->len, &len, sizeof(int), cudaMemcpyHostToDevice));
+    return 0;
+}
+int mpres_array_clear(mpres_ctx *c, mpres_array_t *a) {
+    NEED_DEVICE(c);
+    if (!c || !a) return -1;
+    DeviceGuard g(c->device);
+    cudaFree(a->digits); cudaFree(a->sign); cudaFree(a->exp); cudaFree(a->eval); cudaFree(a->buf); cudaFree(a->len);
+    memset(a, 0, sizeof(*a));
+    return 0;
+}
+int mpres_collection_init(mpres_ctx *c, mpres_collection_t *a, size_t size) {
+    NEED_DEVICE(c);
+    if (!c || !a) return -1;
+    DeviceGuard g(c->device);
+    memset(a, 0, sizeof(*a));
+    return soa_alloc(c, &a->digits, &a->sign, &a->exp, &a->eval, size);
+}
+int mpres_collection_clear(mpres_ctx *c, mpres_collection_t *a) {
+    NEED_DEVICE(c);
+    if (!c || !a) return -1;
+    DeviceGuard g(c->device);
+    cudaFree(a->digits); cudaFree(a->sign); cudaFree(a->exp); cudaFree(a->eval);
+    memset(a, 0, sizeof(*a));
+    return 0;
+}
+
+// AoS records <-> SoA on the device: one staging copy of the raw records, one kernel.
+__global__ void k_aos_to_soa(int N, const char *recs, long long n, int *digits, int *sign, int *exp, Er *eval, long long len) {
+    const long long rs = 4ll * N + 40;
+    for (long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x; t < n * (N + 6); t += (long long) gridDim.x * blockDim.x) {
+        const long long i = t / (N + 6);
+        const int f = (int) (t % (N + 6));
+        const char *p = recs + i * rs;
+        if (f < N) digits[i * N + f] = ((const int *) p)[f];
+        else if (f == N) sign[i] = ((const int *) p)[N];
+        else if (f == N + 1) exp[i] = ((const int *) p)[N + 1];
+        else {
+            const int q = f - N - 2;  // 0..3: lo.frac, lo.exp, up.frac, up.exp as 8-byte words
+            const long long *src = (const long long *) (p + 4 * N + 8);
+            long long *dst = (long long *) (eval + (q < 2 ? i : i + len));
+            dst[q & 1] = src[q];
+        }
+    }
+}
+__global__ void k_soa_to_aos(int N, char *recs, long long n, const int *digits, const int *sign, const int *exp, const Er *eval, long long len) {
+    const long long rs = 4ll * N + 40;
+    for (long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x; t < n * (N + 6); t += (long long) gridDim.x * blockDim.x) {
+        const long long i = t / (N + 6);
+        const int f = (int) (t % (N + 6));
+        char *p = recs + i * rs;
+        if (f < N) ((int *) p)[f] = digits[i * N + f];
+        else if (f == N) ((int *) p)[N] = sign[i];
+        else if (f == N + 1) ((int *) p)[N + 1] = exp[i];
+        else {
+            const int q = f - N - 2;
+            long long *dst = (long long *) (p + 4 * N + 8);
+            const long long *src = (const long long *) (eval + (q < 2 ? i : i + len));
+            dst[q] = src[q & 1];
+        }
+    }
+}
+
+static int h2d_common(mpres_ctx *c, int *digits, int *sign, int *exp, mpres_er_float_t *eval, size_t len, const void *host, size_t size) {
+    if (!c || !host) return -1;
+    if (size == 0) return 0;
+    DeviceGuard g(c->device);
+    std::lock_guard<std::mutex> lk(c->mu);
+    const size_t rs = 4 * (size_t) c->hc.N + 40;
+    void *stage;
+    int rc = ws_reserve(c, 7, size * rs, &stage);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpy(stage, host, size * rs, cudaMemcpyHostToDevice));
+    k_aos_to_soa<<<c->sm_count * 8, 256>>>(c->hc.N, (const char *) stage, (long long) size, digits, sign, exp, (Er *) eval, (long long) len);
+    LAUNCHED(c);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaDeviceSynchronize());
+    return 0;
+}
+static int d2h_common(mpres_ctx *c, void *host, const int *digits, const int *sign, const int *exp, const mpres_er_float_t *eval, size_t len, size_t size) {
+    if (!c || !host) return -1;
+    if (size == 0) return 0;
+    DeviceGuard g(c->device);
+    std::lock_guard<std::mutex> lk(c->mu);
+    const size_t rs = 4 * (size_t) c->hc.N + 40;
+    void *stage;
+    int rc = ws_reserve(c, 7, size * rs, &stage);
+    if (rc) return rc;
+    k_soa_to_aos<<<c->sm_count * 8, 256>>>(c->hc.N, (char *) stage, (long long) size, digits, sign, exp, (const Er *) eval, (long long) len);
+    LAUNCHED(c);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(host, stage, size * rs, cudaMemcpyDeviceToHost));
+    return 0;
+}
+static int read_len(const mpres_array_t *a, size_t *len) {
+    int l = 0;
+    CUDA_TRY(cudaMemcpy(&l, a->len, sizeof(int), cudaMemcpyDeviceToHost));
+    *len = (size_t) l;
+    return 0;
+}
+
+int mpres_array_host2device(mpres_ctx *c, mpres_array_t *dst, const void *host, size_t size) {
+    NEED_DEVICE(c);
+    if (!c || !dst) return -1;
+    DeviceGuard g(c->device);
+    size_t len;
+    int rc = read_len(dst, &len);
+    if (rc) return rc;
+    if (size > len) return -2;
+    return h2d_common(c, dst->digits, dst->sign, dst->exp, dst->eval, len, host, size);
+}
+int mpres_array_device2host(mpres_ctx *c, void *host, const mpres_array_t *src, size_t size) {
+    NEED_DEVICE(c);
+    if (!c || !src) return -1;
+    DeviceGuard g(c->device);
+    size_t len;
+    int rc = read_len(src, &len);
+    if (rc) return rc;
+    if (size > len) return -2;
+    return d2h_common(c, host, src->digits, src->sign, src->exp, src->eval, len, size);
+}
+int mpres_collection_host2device(mpres_ctx *c, mpres_collection_t *dst, const void *host, size_t size) {
+    NEED_DEVICE(c);
+    if (!c || !dst) return -1;
+    return h2d_common(c, dst->digits, dst->sign, dst->exp, dst->eval, size, host, size);
+}
+int mpres_collection_device2host(mpres_ctx *c, void *host, const mpres_collection_t *src, size_t size) {
+    NEED_DEVICE(c);
+    if (!c || !src) return -1;
+    return d2h_common(c, host, src->digits, src->sign, src->exp, src->eval, size, size);
+}
+
+int mpres_array_set_binary(mpres_ctx *c, mpres_array_t *dst, size_t offset, const int *sign, const int *exp,
+                           const uint32_t *limbs, int nlimbs, size_t count, mpres_stream_t stream) {
+    NEED_DEVICE(c);
+    if (!c || !dst || !sign || !exp || !limbs || nlimbs < 1) return -1;
+    if (count == 0) return 0;
+    DeviceGuard g(c->device);
+    cudaStream_t st = (cudaStream_t) stream;
+    const int N = c->hc.N;
+    MPRES_DISPATCH(N, {
+        long long groups = (long long) count;
+        int block = 256;
+        long long blocks = std::min<long long>((groups * G + block - 1) / block, (long long) c->sm_count * 16);
+        k_set_binary<G, R><<<(unsigned) blocks, block, 0, st>>>(c->dconsts, view(dst), (long long) offset, sign, exp, limbs, nlimbs, (long long) count);
+    });
+    LAUNCHED(c);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int mpres_probe(mpres_ctx *c, int op, void *r, const void *x, const void *y, const int *bits, size_t n, mpres_stream_t stream) {
+    NEED_DEVICE(c);
+    if (!c || !r || !x || op < 0 || op > 4) return -1;
+    if ((op <= 1 && !y) || (op == 4 && !bits)) return -1;
+    if (n == 0) return 0;
+    DeviceGuard g(c->device);
+    cudaStream_t st = (cudaStream_t) stream;
+    MPRES_DISPATCH(c->hc.N, {
+        int block = 128;
+        long long blocks = ((long long) n * G + block - 1) / block;
+        k_probe<G, R><<<(unsigned) blocks, block, 0, st>>>(c->dconsts, op, (char *) r, (const char *) x, (const char *) y, bits, (long long) n);
+    });
+    LAUNCHED(c);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+/* ---- GEMM ------------------------------------------------------------------------------------------ */
+
+static int gemm_impl(mpres_ctx *c, int transa, int transb, int m, int n, int k, SoA alpha, SoA A, int lda, SoA B, int ldb,
+                     SoA beta, SoA Cm, int ldc, const SoA *buffer, cudaStream_t st) {
+    // argument checks of src/blas/gemm.cuh:75-96 (the reference returns silently)
+    if (m <= 0 || n <= 0 || k <= 0) return 0;
+    const bool ta = transa != MPRES_NO_TRANS, tb = transb != MPRES_NO_TRANS;
+    if (transa != MPRES_NO_TRANS && transa != MPRES_TRANS && transa != MPRES_CONJ_TRANS) return -2;
+    if (transb != MPRES_NO_TRANS && transb != MPRES_TRANS && transb != MPRES_CONJ_TRANS) return -2;
+    if (lda < std::max(1, ta ? k : m)) return -3;
+    if (ldb < std::max(1, tb ? n : k)) return -4;
+    if (ldc < std::max(1, m)) return -5;
+    DeviceGuard g(c->device);
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->last_stream = st;
+    const int N = c->hc.N;
+    SoA S;
+    int lds = m;
+    if (buffer) S = *buffer;
+    else { int rc = ws_soa(c, 0, (size_t) m * n, &S); if (rc) return rc; }
+    CUDA_TRY(cudaMemsetAsync(c->d_counter, 0, 4 * sizeof(int), st));
+
+    bool done = false;
+    if (c->mode != MPRES_MODE_REFERENCE_ORDER) {
+        int rc = gemm_fast(c, ta, tb, m, n, k, A, lda, B, ldb, S, lds, st, &done);
+        if (rc) return rc;
+    }
+    if (!done) {
+        MPRES_DISPATCH(N, {
+            int block = 128;
+            long long groups = (long long) m * n;
+            long long blocks = std::min<long long>((groups * G + block - 1) / block, (long long) c->sm_count * 64);
+            k_gemm_ref_order<G, R><<<(unsigned) blocks, block, 0, st>>>(c->dconsts, ta, tb, m, n, k, A, lda, B, ldb, S, lds, nullptr, nullptr);
+        });
+        LAUNCHED(c);
+        CUDA_TRY(cudaGetLastError());
+    }
+    MPRES_DISPATCH(N, {
+        int block = 128;
+        long long groups = (long long) m * n;
+        long long blocks = std::min<long long>((groups * G + block - 1) / block, (long long) c->sm_count * 32);
+        k_gemm_epilogue<G, R><<<(unsigned) blocks, block, 0, st>>>(c->dconsts, m, n, alpha, beta, S, lds, Cm, ldc);
+    });
+    LAUNCHED(c);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int mpres_gemm(mpres_ctx *c, int transa, int transb, int m, int n, int k, const mpres_array_t *alpha,
+               const mpres_array_t *A, int lda, const mpres_array_t *B, int ldb, const mpres_array_t *beta,
+               mpres_array_t *Cm, int ldc, mpres_array_t *buffer, mpres_stream_t stream) {
+    NEED_DEVICE(c);
+    if (!c || !alpha || !A || !B || !beta || !Cm) return -1;
+    SoA buf;
+    if (buffer && buffer->digits) buf = view(buffer);
+    return gemm_impl(c, transa, transb, m, n, k, view(alpha), view(A), lda, view(B), ldb, view(beta), view(Cm), ldc,
+                     (buffer && buffer->digits) ? &buf : nullptr, (cudaStream_t) stream);
+}
+int mpres_gemm_coll(mpres_ctx *c, int transa, int transb, int m, int n, int k, const mpres_collection_t *alpha,
+                    const mpres_collection_t *A, int lda, size_t lenA, const mpres_collection_t *B, int ldb, size_t lenB,
+                    const mpres_collection_t *beta, mpres_collection_t *Cm, int ldc, size_t lenC, mpres_stream_t stream) {
+    NEED_DEVICE(c);
+    if (!c || !alpha || !A || !B || !beta || !Cm) return -1;
+    return gemm_impl(c, transa, transb, m, n, k, view(alpha, 1), view(A, lenA), lda, view(B, lenB), ldb, view(beta, 1),
+                     view(Cm, lenC), ldc, nullptr, (cudaStream_t) stream);
+}
+
+/* ---- GEMV ------------------------------------------------------------------------------------------ */
+
+static int gemv_impl(mpres_ctx *c, int trans, int m, int n, SoA alpha, SoA A, int lda, SoA x, int incx, SoA beta, SoA y, int incy,
+                     cudaStream_t st) {
+    // src/blas/gemv.cuh:155-161
+    if (m <= 0 || n <= 0) return 0;
+    if (incx == 0 || incy == 0 || lda < std::max(1, m)) return -3;
+    if (trans != MPRES_NO_TRANS && trans != MPRES_TRANS && trans != MPRES_CONJ_TRANS) return -2;
+    const bool tr = trans != MPRES_NO_TRANS;
+    DeviceGuard g(c->device);
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->last_stream = st;
+    const int N = c->hc.N;
+    const int lenx = tr ? m : n, leny = tr ? n : m;
+    SoA ax;
+    int rc = ws_soa(c, 1, (size_t) lenx, &ax);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemsetAsync(c->d_counter, 0, 4 * sizeof(int), st));
+    MPRES_DISPATCH(N, {
+        int block = 128;
+        auto nb = [&](long long groups) { return (unsigned) std::min<long long>((groups * G + block - 1) / block, (long long) c->sm_count * 32); };
+        // buffer1 = round(alpha * x), y = round(beta * y)          gemv.cuh:175-190
+        k_vec_scale<G, R><<<nb(lenx), block, 0, st>>>(c->dconsts, lenx, ax, 1, x, incx, alpha);
+        k_vec_scale<G, R><<<nb(leny), block, 0, st>>>(c->dconsts, leny, y, incy, y, incy, beta);
+    });
+    LAUNCHED(c); LAUNCHED(c);
+    CUDA_TRY(cudaGetLastError());
+    bool done = false;
+    if (c->mode != MPRES_MODE_REFERENCE_ORDER) {
+        rc = gemv_fast(c, tr, m, n, A, lda, ax, y, incy, st, &done);
+        if (rc) return rc;
+    }
+    if (!done) {
+        MPRES_DISPATCH(N, {
+            int block = 128;
+            long long blocks = std::min<long long>(((long long) leny * G + block - 1) / block, (long long) c->sm_count * 64);
+            k_gemv_ref_order<G, R><<<(unsigned) blocks, block, 0, st>>>(c->dconsts, tr, m, n, A, lda, ax, y, incy);
+        });
+        LAUNCHED(c);
+        CUDA_TRY(cudaGetLastError());
+    }
+    return 0;
+}
+
+int mpres_gemv(mpres_ctx *c, int trans, int m, int n, const mpres_array_t *alpha, const mpres_array_t *A, int lda,
+               const mpres_array_t *x, int incx, const mpres_array_t *beta, mpres_array_t *y, int incy,
+               mpres_array_t *buffer1, mpres_array_t *buffer2, mpres_stream_t stream) {
+    NEED_DEVICE(c);
+    (void) buffer1; (void) buffer2;
+    if (!c || !alpha || !A || !x || !beta || !y) return -1;
+    return gemv_impl(c, trans, m, n, view(alpha), view(A), lda, view(x), incx, view(beta), view(y), incy, (cudaStream_t) stream);
+}
+int mpres_gemv_coll(mpres_ctx *c, int trans, int m, int n, const mpres_collection_t *alpha, const mpres_collection_t *A, int lda,
+                    size_t lenA, const mpres_collection_t *x, int incx, size_t lenx, const mpres_collection_t *beta,
+                    mpres_collection_t *y, int incy, size_t leny, mpres_stream_t stream) {
+    NEED_DEVICE(c);
+    if (!c || !alpha || !A || !x || !beta || !y) return -1;
+    return gemv_impl(c, trans, m, n, view(alpha, 1), view(A, lenA), lda, view(x, lenx), incx, view(beta, 1), view(y, leny), incy,
+                     (cudaStream_t) stream);
+}
+
+/* ---- DOT ------------------------------------------------------------------------------------------- */
+
+// partial (device AoS record) := sum x_i * y_i
+static int dot_to_record(mpres_ctx *c, int n, SoA x, int incx, SoA y, int incy, char *rec_out, SoA out, cudaStream_t st) {
+    const int N = c->hc.N;
+    const size_t rs = 4 * (size_t) N + 40;
+    bool done = false;
+    int rc;
+    CUDA_TRY(cudaMemsetAsync(c->d_counter, 0, 4 * sizeof(int), st));
+    if (c->mode != MPRES_MODE_REFERENCE_ORDER) {
+        rc = dot_fast(c, n, x, incx, y, incy, rec_out, out, st, &done);
+        if (rc) return rc;
+    }
+    if (done) return 0;
+    MPRES_DISPATCH(N, {
+        const int block = 128;
+        const long long gpb = block / G;
+        long long blocks = std::min<long long>(((long long) n + gpb - 1) / gpb, (long long) c->sm_count * 8);
+        const long long groups = blocks * gpb;
+        void *parts;
+        rc = ws_reserve(c, 2, (size_t) groups * rs, &parts);
+        if (rc) return rc;
+        k_dot_partial<G, R><<<(unsigned) blocks, block, 0, st>>>(c->dconsts, n, x, incx, y, incy, (char *) parts);
+        k_tree_records<G, R><<<1, 256, 0, st>>>(c->dconsts, (char *) parts, groups, out, 0, rec_out);
+    });
+    LAUNCHED(c); LAUNCHED(c);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int mpres_dot(mpres_ctx *c, int n, const mpres_array_t *x, int incx, const mpres_array_t *y, int incy, mpres_array_t *r,
+              mpres_array_t *buffer, mpres_stream_t stream) {
+    NEED_DEVICE(c);
+    (void) buffer;
+    if (!c || !x || !y || !r) return -1;
+    if (n <= 0) return 0;  // src/blas/dot.cuh:88-90
+    if (incx == 0 || incy == 0) return -3;
+    DeviceGuard g(c->device);
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->last_stream = (cudaStream_t) stream;
+    return dot_to_record(c, n, view(x), incx, view(y), incy, nullptr, view(r), (cudaStream_t) stream);
+}
+int mpres_dot_coll(mpres_ctx *c, int n, const mpres_collection_t *x, int incx, size_t lenx, const mpres_collection_t *y, int incy,
+                   size_t leny, mpres_collection_t *r, mpres_stream_t stream) {
+    NEED_DEVICE(c);
+    if (!c || !x || !y || !r) return -1;
+    if (n <= 0) return 0;
+    if (incx == 0 || incy == 0) return -3;
+    DeviceGuard g(c->device);
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->last_stream = (cudaStream_t) stream;
+    return dot_to_record(c, n, view(x, lenx), incx, view(y, leny), incy, nullptr, view(r, 1), (cudaStream_t) stream);
+}
+int mpres_dot_partial(mpres_ctx *c, int n, const mpres_array_t *x, int incx, const mpres_array_t *y, int incy, void *partial,
+                      mpres_stream_t stream) {
+    NEED_DEVICE(c);
+    if (!c || !x || !y || !partial) return -1;
+    if (incx == 0 || incy == 0) return -3;
+    DeviceGuard g(c->device);
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->last_stream = (cudaStream_t) stream;
+    if (n <= 0) { CUDA_TRY(cudaMemsetAsync(partial, 0, 4 * (size_t) c->hc.N + 40, (cudaStream_t) stream)); return 0; }
+    SoA dummy{};
+    return dot_to_record(c, n, view(x), incx, view(y), incy, (char *) partial, dummy, (cudaStream_t) stream);
+}
+int mpres_reduce_partials(mpres_ctx *c, const void *partials, int count, mpres_array_t *r, mpres_stream_t stream) {
+    NEED_DEVICE(c);
+    if (!c || !partials || !r || count < 0) return -1;
+    DeviceGuard g(c->device);
+    cudaStream_t st = (cudaStream_t) stream;
+    MPRES_DISPATCH(c->hc.N, {
+        k_reduce_records<G, R><<<1, G, 0, st>>>(c->dconsts, (const char *) partials, count, view(r), 0, nullptr);
+    });
+    LAUNCHED(c);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"
