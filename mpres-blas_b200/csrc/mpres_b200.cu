@@ -354,27 +354,26 @@ static int gemm_impl(mpres_ctx *c, int transa, int transb, int m, int n, int k, 
     std::lock_guard<std::mutex> lk(c->mu);
     c->last_stream = st;
     const int N = c->hc.N;
+    CUDA_TRY(cudaMemsetAsync(c->d_counter, 0, 4 * sizeof(int), st));
+
+    if (c->mode != MPRES_MODE_REFERENCE_ORDER) {
+        bool done = false;
+        int rc = gemm_fast_full(c, ta, tb, m, n, k, A, lda, B, ldb, alpha, beta, Cm, ldc, st, &done);
+        if (rc) return rc;
+        if (done) return 0;
+    }
     SoA S;
     int lds = m;
     if (buffer) S = *buffer;
     else { int rc = ws_soa(c, 0, (size_t) m * n, &S); if (rc) return rc; }
-    CUDA_TRY(cudaMemsetAsync(c->d_counter, 0, 4 * sizeof(int), st));
-
-    bool done = false;
-    if (c->mode != MPRES_MODE_REFERENCE_ORDER) {
-        int rc = gemm_fast(c, ta, tb, m, n, k, A, lda, B, ldb, S, lds, st, &done);
-        if (rc) return rc;
-    }
-    if (!done) {
-        MPRES_DISPATCH(N, {
-            int block = 128;
-            long long groups = (long long) m * n;
-            long long blocks = std::min<long long>((groups * G + block - 1) / block, (long long) c->sm_count * 64);
-            k_gemm_ref_order<G, R><<<(unsigned) blocks, block, 0, st>>>(c->dconsts, ta, tb, m, n, k, A, lda, B, ldb, S, lds, nullptr, nullptr);
-        });
-        LAUNCHED(c);
-        CUDA_TRY(cudaGetLastError());
-    }
+    MPRES_DISPATCH(N, {
+        int block = 128;
+        long long groups = (long long) m * n;
+        long long blocks = std::min<long long>((groups * G + block - 1) / block, (long long) c->sm_count * 64);
+        k_gemm_ref_order<G, R><<<(unsigned) blocks, block, 0, st>>>(c->dconsts, ta, tb, m, n, k, A, lda, B, ldb, S, lds, nullptr, nullptr);
+    });
+    LAUNCHED(c);
+    CUDA_TRY(cudaGetLastError());
     MPRES_DISPATCH(N, {
         int block = 128;
         long long groups = (long long) m * n;

@@ -80,3 +80,104 @@ def test_dot_and_gemv_reference_order(pkg, N):
             r, _ = oracle.RefLib(N, gpu=True).gpu_gemv(trans, m, nn, alpha, A, xv, beta, yv)
             assert diff_fields(got, r, ("digits", "sign", "exp")).size == 0
     ctx.close()
+
+
+def _transpose_recs(X, rows, cols):
+    """column-major rows x cols -> column-major cols x rows"""
+    return np.ascontiguousarray(X.reshape(cols, rows).T).reshape(-1)
+
+
+@pytest.mark.parametrize("N,shape", [(8, (33, 17, 41)), (8, (200, 150, 300)), (16, (130, 70, 129)), (32, (64, 64, 256)), (24, (40, 40, 40))])
+def test_gemm_fast_path_bit_exact_quarter_precision(pkg, N, shape):
+    """p/4-bit inputs (the reference's benchmark convention): nothing rounds inside the k-loop, so the
+    exact-window fast path must give the reference's digits, sign and exponent bit for bit, with no
+    element routed to the fallback."""
+    ctx = pkg.Context(N, 0)
+    orc = get_oracle(N, oracle.DEVICE)
+    bits = orc.precision // 4
+    m, n, k = shape
+    A = random_records(N, m * k, bits, 21)
+    B = random_records(N, k * n, bits, 22)
+    C = random_records(N, m * n, bits, 23)
+    alpha = random_records(N, 1, bits, 24)
+    beta = random_records(N, 1, bits, 25)
+    got = _gemm(pkg, ctx, m, n, k, alpha, A, B, beta, C, pkg.MODE_AUTO)
+    assert ctx.last_fallback_count() == 0
+    ref_order = _gemm(pkg, ctx, m, n, k, alpha, A, B, beta, C, pkg.MODE_REFERENCE_ORDER)
+    bad = diff_fields(got, ref_order, ("digits", "sign", "exp"))
+    assert bad.size == 0, "%d/%d differ from reference order, first %d\n%s\n%s" % (bad.size, m * n, bad[0], got[bad[0]], ref_order[bad[0]])
+    if oracle.have_ref(N) and m * n * k < 3000000:
+        r, _, _ = oracle.RefLib(N, gpu=True).gpu_gemm(m, n, k, alpha, A, B, beta, C)
+        assert diff_fields(got, r, ("digits", "sign", "exp")).size == 0
+    ctx.close()
+
+
+def test_gemm_fast_path_transposes(pkg):
+    N = 8
+    ctx = pkg.Context(N, 0)
+    orc = get_oracle(N, oracle.DEVICE)
+    bits = orc.precision // 4
+    m, n, k = 37, 29, 53
+    A = random_records(N, m * k, bits, 31)
+    B = random_records(N, k * n, bits, 32)
+    C = random_records(N, m * n, bits, 33)
+    alpha = random_records(N, 1, bits, 34)
+    beta = random_records(N, 1, bits, 35)
+    want = _gemm(pkg, ctx, m, n, k, alpha, A, B, beta, C, pkg.MODE_REFERENCE_ORDER)
+    At, Bt = _transpose_recs(A, m, k), _transpose_recs(B, k, n)
+    for mode in (pkg.MODE_AUTO, pkg.MODE_REFERENCE_ORDER):
+        for ta, tb, a_, b_ in ((112, 111, At, B), (111, 112, A, Bt), (112, 112, At, Bt)):
+            got = _gemm(pkg, ctx, m, n, k, alpha, a_, b_, beta, C, mode, ta, tb)
+            assert diff_fields(got, want, ("digits", "sign", "exp")).size == 0, (mode, ta, tb)
+    ctx.close()
+
+
+@pytest.mark.parametrize("N", [8, 32])
+def test_gemm_full_precision_inputs(pkg, N):
+    """p-bit inputs: every product needs a rounding in the reference, the exact window does not fit in
+    M.  AUTO must route those elements to the reference-order fallback (bit-exact again)."""
+    ctx = pkg.Context(N, 0)
+    orc = get_oracle(N, oracle.DEVICE)
+    bits = orc.precision
+    m, n, k = 24, 20, 50
+    A = random_records(N, m * k, bits, 41)
+    B = random_records(N, k * n, bits, 42)
+    C = random_records(N, m * n, bits, 43)
+    alpha = random_records(N, 1, bits, 44)
+    beta = random_records(N, 1, bits, 45)
+    got = _gemm(pkg, ctx, m, n, k, alpha, A, B, beta, C, pkg.MODE_AUTO)
+    assert ctx.last_fallback_count() == m * n
+    want = _gemm(pkg, ctx, m, n, k, alpha, A, B, beta, C, pkg.MODE_REFERENCE_ORDER)
+    assert diff_fields(got, want).size == 0
+    ctx.close()
+
+
+def test_gemm_mixed_width_accuracy(pkg):
+    """half-precision-width inputs: the reference rounds some partial sums, the fast path rounds once.
+    Results must agree with the exact rational result within the reference's error model
+    (test_dot_accuracy.cu:59-72): |err| <= gamma_k * sum |a||b| with u = 4/sqrt(M)."""
+    from fractions import Fraction
+    N = 8
+    ctx = pkg.Context(N, 0)
+    orc = get_oracle(N, oracle.DEVICE)
+    bits = orc.precision // 2 - 8
+    m, n, k = 12, 10, 64
+    A = random_records(N, m * k, bits, 51)
+    B = random_records(N, k * n, bits, 52)
+    C = random_records(N, m * n, bits, 53)
+    alpha = random_records(N, 1, bits, 54)
+    beta = random_records(N, 1, bits, 55)
+    got = _gemm(pkg, ctx, m, n, k, alpha, A, B, beta, C, pkg.MODE_AUTO)
+    u = unit_roundoff(orc)
+    gam = (k + 3) * u / (1 - (k + 3) * u)
+    fa = [orc.to_fraction(x) for x in A]
+    fb = [orc.to_fraction(x) for x in B]
+    fc = [orc.to_fraction(x) for x in C]
+    al, be = orc.to_fraction(alpha[0]), orc.to_fraction(beta[0])
+    for j in range(n):
+        for i in range(m):
+            exact = al * sum(fa[i + l * m] * fb[l + j * k] for l in range(k)) + be * fc[i + j * m]
+            bound = gam * (abs(al) * sum(abs(fa[i + l * m] * fb[l + j * k]) for l in range(k)) + abs(be * fc[i + j * m]))
+            err = abs(orc.to_fraction(got[i + j * m]) - exact)
+            assert err <= bound, (i, j, float(err), float(bound))
+    ctx.close()
