@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the mp_gemm hot path (BASELINE.json metric) on 1..8 B200.
+
+    python bench.py --gpus N --steps K --warmup W            our CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  the reference's CPU path (oracle/_ref)
+
+One step = one C = alpha*A*B + beta*C over synthetic uniform(-1,1) matrices with p/4-bit significands
+(the reference's own benchmark convention, tests/blas/performance/test_gemm_performance.cu:65-69).
+Default workload: m = n = k = 4096 with the 32-moduli / 424-bit set (BASELINE config 3).  On N > 1 GPUs
+A and C are split into N row blocks (one process per GPU), B is broadcast from rank 0 over NCCL inside
+every timed step; total work is fixed ("strong" scaling).
+
+Prints ONE JSON line (rank 0).  metric = MP-GFLOP/s = 2*m*n*k / seconds / 1e9 (one mp-flop = one
+multiple-precision add or mul, tests/arith/peak/test_mp_arith_peak.cuh:86-87).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (m, n, k, moduli)
+    "gemm4096_424bit": (4096, 4096, 4096, 32),
+    "gemm1024_106bit": (1024, 1024, 1024, 8),
+    "gemm2048_106bit": (2048, 2048, 2048, 8),
+    "gemm2048_212bit": (2048, 2048, 2048, 16),
+    "gemm2048_318bit": (2048, 2048, 2048, 24),
+    "gemm2048_424bit": (2048, 2048, 2048, 32),
+    "gemm2048_530bit": (2048, 2048, 2048, 40),
+    "gemm2048_636bit": (2048, 2048, 2048, 48),
+    "gemm2048_742bit": (2048, 2048, 2048, 56),
+    "gemm2048_848bit": (2048, 2048, 2048, 64),
+}
+# measured on this pool's B200 by tools/mma_bench.cu (profiles/r01_pipe_rates.json)
+R_MAC_IMAD_WIDE = 8.54e12        # residue-MAC/s through IMAD.WIDE.U32: the INT32 roofline of SURVEY 8(d)
+PEAK_INT8_LEGACY_MMA = 1.139e15  # int8 op/s (2 per MAC) through mma.sync m16n8k32 (IMMA.16832)
+CPU_SAMPLE = (64, 256)             # block of C timed on the host cores (full k)
+FALLBACK_BF16_TFLOPS = 1590.0    # /opt/skills/guides/B200_PROFILING.md fallback (MEASURED_PEAKS.json absent)
+
+
+def read_measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d.get("bf16_tflops", FALLBACK_BF16_TFLOPS)), "measured"
+        except Exception:
+            pass
+    return FALLBACK_BF16_TFLOPS, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+                for nme, v in zip(names, r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w": statistics.median(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_reference_leg(N, m_s, n_s, k, bits, seed=7):
+    """The reference's own CPU implementation (host mp_mul/mp_add over mp_float_t, compiled unmodified into
+    oracle/_ref) -- or the C port (oracle/) where no _ref binary exists -- on a bounded sample: an
+    m_s x n_s block of C with the full inner dimension k, all host threads."""
+    import numpy as np
+    import oracle
+    from oracle import gen
+    orc = oracle.Oracle(N, oracle.HOST)
+
+    def recs(count, sd):
+        return orc.random_records(count, bits, sd)
+    A, B, C = recs(m_s * k, seed), recs(k * n_s, seed + 1), recs(m_s * n_s, seed + 2)
+    al, be = recs(1, seed + 3), recs(1, seed + 4)
+    if oracle.have_ref(N):
+        ref = oracle.RefLib(N)
+        t0 = time.perf_counter()
+        _, nt = ref.host_gemm(m_s, n_s, k, al, A, B, be, C)
+        dt = time.perf_counter() - t0
+        kind = "reference"
+    else:
+        t0 = time.perf_counter()
+        orc.gemm(m_s, n_s, k, al, A, B, be, C)
+        dt = time.perf_counter() - t0
+        nt = os.cpu_count()
+        kind = "port"
+    gflops = 2.0 * m_s * n_s * k / dt / 1e9
+    return {"value": gflops, "unit": "MP-GFLOP/s", "cores": int(nt), "kind": kind, "seconds": dt,
+            "sample": "%dx%d block of C with full k=%d (%d-bit inputs), %s host mp_mul+mp_add, OpenMP" % (m_s, n_s, k, bits,
+                      "reference" if kind == "reference" else "oracle-port")}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="gemm4096_424bit", choices=sorted(WORKLOADS))
+    ap.add_argument("--mode", default="auto", choices=["auto", "reference_order", "fast"])
+    ap.add_argument("--full-precision-inputs", action="store_true", help="p-bit significands instead of p/4")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    args = ap.parse_args()
+
+    m, n, k, N = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    import oracle  # only for the precision table and the CPU legs (never on the measured GPU path)
+    from oracle import constants
+    precision = constants.compute(oracle.moduli_sets()[N])["mp_precision"]
+    bits = precision if args.full_precision_inputs else precision // 4
+    config = {"workload": args.workload, "op": "mp_gemm", "m": m, "n": n, "k": k, "moduli": N, "precision_bits": precision,
+              "input_significand_bits": bits, "sharding": "A,C row blocks x%d, B broadcast (NCCL) inside the step" % world if world > 1 else "single GPU",
+              "l2": "operands (%.2f GB per matrix) exceed the 126 MB L2; no flush needed" % (m * k * (4 * N + 40) / 1e9), "mode": args.mode,
+              "step": "C <- C0 (device copy of the pristine p/4-bit C), [B broadcast], C = alpha*A*B + beta*C"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        ms_s, ns_s = CPU_SAMPLE
+        vals, last = [], None
+        for i in range(args.warmup + args.steps):
+            last = cpu_reference_leg(N, ms_s, ns_s, k, bits, seed=7 + i)
+            if i >= args.warmup:
+                vals.append(last)
+        v = statistics.mean(x["value"] for x in vals) if vals else last["value"]
+        secs = statistics.mean(x["seconds"] for x in vals) if vals else last["seconds"]
+        cb = dict(last); cb["value"] = v
+        print(json.dumps({"impl": "reference", "metric": "mp_gemm MP-GFLOP/s", "value": v, "unit": "MP-GFLOP/s", "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs * 1e3, "higher_is_better": True,
+                          "scaling": "strong", "vs_baseline": None, "dtype": "int32 residues (host mp_float_t arithmetic)",
+                          "data": "synthetic", "config": config, "cpu_baseline": cb,
+                          "e2e": {"value": v, "unit": "MP-GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import _pkg
+    pkg = _pkg.load()
+    from mpres_blas_b200 import torch_arrays as ta
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU path in this library")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = pkg.Context(N, local_rank)
+    ctx.set_mode({"auto": pkg.MODE_AUTO, "reference_order": pkg.MODE_REFERENCE_ORDER, "fast": pkg.MODE_FAST}[args.mode])
+    assert m % world == 0
+    mr = m // world                       # rows of A and C owned by this rank
+    A = ta.TorchMpArray(ctx, mr * k)
+    B = ta.TorchMpArray(ctx, k * n)
+    C = ta.TorchMpArray(ctx, mr * n)
+    C0 = ta.TorchMpArray(ctx, mr * n)     # pristine p/4-bit C, copied into C at the start of every step
+    alpha, beta = ta.TorchMpArray(ctx, 1), ta.TorchMpArray(ctx, 1)
+    ta.random_fill(ctx, A, bits, 1000 + rank)
+    ta.random_fill(ctx, C0, bits, 2000 + rank)
+    ta.random_fill(ctx, alpha, bits, 31)
+    ta.random_fill(ctx, beta, bits, 32)
+    if rank == 0:
+        ta.random_fill(ctx, B, bits, 33)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        for dst, src in zip(C.tensors(), C0.tensors()):   # fresh C every step (device-to-device, ~1 ms at 4096^2)
+            dst.copy_(src, non_blocking=True)
+        if world > 1:
+            for t in B.tensors():
+                dist.broadcast(t, src=0)
+        pkg.mp_gemm(ctx, pkg.mblas_no_trans, pkg.mblas_no_trans, mr, n, k, alpha, A, mr, B, k, beta, C, mr, None, stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    ctx.set_profiling(True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = ctx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    launches = ctx.launch_count - launches0
+    fallback = ctx.last_fallback_count()
+    try:
+        stage_ms, s2_launches = ctx.last_stage_ms()
+    except Exception:
+        stage_ms, s2_launches = None, 0
+    ctx.set_profiling(False)
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = 2.0 * m * n * k / (ms_step * 1e-3) / 1e9
+
+    # ---- end-to-end through the C-ABI with host buffers ------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        rs = 4 * N + 40
+        hA = torch.empty(mr * k * rs, dtype=torch.uint8).pin_memory()
+        hB = torch.empty(k * n * rs, dtype=torch.uint8).pin_memory()
+        hC = torch.empty(mr * n * rs, dtype=torch.uint8).pin_memory()
+        hOut = torch.empty(mr * n * rs, dtype=torch.uint8).pin_memory()
+        hal, hbe = torch.empty(rs, dtype=torch.uint8).pin_memory(), torch.empty(rs, dtype=torch.uint8).pin_memory()
+        if world > 1:
+            for t in B.tensors():
+                dist.broadcast(t, src=0)
+        A.device2host_ptr(hA.data_ptr(), mr * k); B.device2host_ptr(hB.data_ptr(), k * n)
+        C0.device2host_ptr(hC.data_ptr(), mr * n)
+        alpha.device2host_ptr(hal.data_ptr(), 1); beta.device2host_ptr(hbe.data_ptr(), 1)
+
+        def e2e_step():
+            A.host2device_ptr(hA.data_ptr(), mr * k)
+            B.host2device_ptr(hB.data_ptr(), k * n)
+            C.host2device_ptr(hC.data_ptr(), mr * n)
+            alpha.host2device_ptr(hal.data_ptr(), 1); beta.host2device_ptr(hbe.data_ptr(), 1)
+            pkg.mp_gemm(ctx, pkg.mblas_no_trans, pkg.mblas_no_trans, mr, n, k, alpha, A, mr, B, k, beta, C, mr, None, stream)
+            C.device2host_ptr(hOut.data_ptr(), mr * n)
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        barrier()
+        dt = (time.perf_counter() - t0) / args.e2e_steps
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        h2d = (mr * k + k * n + mr * n + 2) * rs
+        d2h = mr * n * rs
+        e2e = {"value": 2.0 * m * n * k / dt / 1e9, "unit": "MP-GFLOP/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
+               "ms_per_step": dt * 1e3, "steps": args.e2e_steps,
+               "path": "mpres_array_host2device(A,B,C,alpha,beta) + mpres_gemm + mpres_array_device2host(C), pinned host AoS mp_float_t[]"}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (stage 2, k_limb_gemm) ----------------------------------------
+    bf16_peak, peak_src = read_measured_peaks()
+    roof, int32_roof = None, None
+    if stage_ms and s2_launches:
+        t2 = stage_ms[1] * 1e-3                       # all stage-2 launches of one mp_gemm call on this rank
+        limb_macs = 16.0 * mr * n * k * N             # int8 MACs: 16 limb products per residue MAC
+        ops = 2.0 * limb_macs
+        achieved = ops / t2 / 1e12
+        peak = 2.0 * bf16_peak                        # dense int8 = 2 x dense bf16 on the same tensor cores
+        roof = {"bound": "tensor", "kernel": "k_limb_gemm<0>+<1> (int8 IMMA limb GEMM)", "achieved": achieved, "peak": peak, "unit": "TOP/s (int8)",
+                "frac": achieved / peak, "peak_source": "2 x bf16 %s peak of %s TFLOP/s (int8 dense = 2 x bf16 dense)" % (peak_src, bf16_peak),
+                "traffic": None, "launches_per_step": s2_launches, "avg_launch_ms": stage_ms[1] / s2_launches,
+                "frac_of_legacy_mma_peak": ops / t2 / PEAK_INT8_LEGACY_MMA,
+                "legacy_mma_peak_note": "mma.sync IMMA.16832 ceiling measured by tools/mma_bench.cu = 1139 TOP/s",
+                "stage_ms": {"stage1_align": stage_ms[0], "stage2_limb_gemm": stage_ms[1], "stage3_normalise_epilogue": stage_ms[2]}}
+        int32_roof = {"definition": "SURVEY 8(d): m*n*k*N residue-MACs / t / R_mac, R_mac = measured IMAD.WIDE.U32 rate",
+                      "R_mac_per_s": R_MAC_IMAD_WIDE, "residue_macs_per_s_stage2": mr * n * k * N / t2,
+                      "frac_stage2": mr * n * k * N / t2 / R_MAC_IMAD_WIDE,
+                      "frac_whole_step": (m / world) * n * k * N / (ms_step * 1e-3) / R_MAC_IMAD_WIDE}
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_reference_leg(N, CPU_SAMPLE[0], CPU_SAMPLE[1], k, bits)
+    line = {"metric": "mp_gemm MP-GFLOP/s", "value": value, "unit": "MP-GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u8 limbs of int32 RNS residues, s32 accumulate (f64 interval bounds)", "data": "synthetic", "config": config,
+            "gpu_launches": int(launches), "fallback_elements_last_step": int(fallback), "clocks": clocks,
+            "roofline": roof, "int32_roofline": int32_roof, "cpu_baseline": cpu, "e2e": e2e}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

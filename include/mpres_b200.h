@@ -97,8 +97,13 @@ int mpres_get_mode(const mpres_ctx *ctx);
 /* number of result elements the last AUTO/FAST call routed to the reference-order fallback
  * (synchronises the stream of that call) */
 long mpres_last_fallback_count(mpres_ctx *ctx);
-/* kernels launched by this library since init (all devices of this ctx) */
+/* kernels launched by this library since init */
 long mpres_launch_count(const mpres_ctx *ctx);
+/* Optional per-stage timing of the fast mp_gemm path with CUDA events on the caller's stream (what
+ * the reference's tests do around whole calls with tests/timers.cuh:57-76).  ms[0] = stage 1
+ * alignment, ms[1] = stage 2 per-modulus multiply-accumulate, ms[2] = stage 3 normalisation + epilogue. */
+int mpres_set_profiling(mpres_ctx *ctx, int on);
+int mpres_last_stage_ms(mpres_ctx *ctx, float *ms, int *stage2_launches);
 
 /* ---- containers: replace cuda::mp_array_init / clear / host2device / device2host
  *      (src/mparray.cuh:35,59,76,125) and the mp_collection_* twins (src/mpcollection.cuh:35,54,69,117).

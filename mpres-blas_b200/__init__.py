@@ -38,6 +38,7 @@ EXPORTS = [
     "mpres_init", "mpres_init_moduli", "mpres_finalize", "mpres_moduli_size", "mpres_moduli_product_log2",
     "mpres_precision", "mpres_mp_h", "mpres_mp_j", "mpres_device", "mpres_sizeof_mp_float", "mpres_get_constant",
     "mpres_set_mode", "mpres_get_mode", "mpres_last_fallback_count", "mpres_launch_count",
+    "mpres_set_profiling", "mpres_last_stage_ms",
     "mpres_array_init", "mpres_array_clear", "mpres_array_host2device", "mpres_array_device2host",
     "mpres_collection_init", "mpres_collection_clear", "mpres_collection_host2device", "mpres_collection_device2host",
     "mpres_array_set_binary", "mpres_gemm", "mpres_gemv", "mpres_dot", "mpres_gemm_coll", "mpres_gemv_coll",
@@ -113,6 +114,15 @@ class Context:
 
     def set_mode(self, mode):
         _check(self.lib.mpres_set_mode(self.h, mode), "mpres_set_mode")
+
+    def set_profiling(self, on):
+        _check(self.lib.mpres_set_profiling(self.h, 1 if on else 0), "mpres_set_profiling")
+
+    def last_stage_ms(self):
+        ms = (ctypes.c_float * 3)()
+        n = ctypes.c_int()
+        _check(self.lib.mpres_last_stage_ms(self.h, ms, ctypes.byref(n)), "mpres_last_stage_ms")
+        return [ms[0], ms[1], ms[2]], n.value
 
     def last_fallback_count(self):
         return self.lib.mpres_last_fallback_count(self.h)

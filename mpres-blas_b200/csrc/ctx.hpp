@@ -28,6 +28,11 @@ struct mpres_ctx {
     int *d_counter = nullptr;      // fallback element counter of the last call
     cudaStream_t last_stream = nullptr;
     int sm_count = 148;
+    // optional per-stage timing (events recorded on the caller's stream)
+    bool profiling = false;
+    cudaEvent_t ev[6] = {nullptr};
+    bool ev_valid = false;
+    int last_stage2_launches = 0;
     std::mutex mu;
 };
 

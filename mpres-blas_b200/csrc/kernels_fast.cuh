@@ -337,6 +337,74 @@ __global__ void __launch_bounds__(256, 1) k_limb_gemm(const DevConsts *Cp, const
             }
 }
 
+// Sign and interval evaluation of an exact sum S known only through its residues X = S mod M, given
+// |S| < 2^bound <= M/4.  Instead of the reference's generic refinement (src/rns.cuh:911-921: up to
+// log2(M)/49 rounds, each with a log2 and a ceil) the known bound gives the magnification directly:
+// X * 2^K mod M has its fractional value in (0, 1/8) for S > 0 and in (7/8, 1) for S < 0.  Further
+// rounds (only after heavy cancellation) magnify by what the current upper bound allows.
+// Returns 0 for S == 0, else +1 / -1, with [lo, up] enclosing |S| / M.
+template <int G, int R>
+__device__ __forceinline__ int sign_eval_window(const DevConsts &C, const Lane<R> &L, const int (&x)[R], int bound, Er &lo, Er &up) {
+    int nzbits = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) nzbits |= x[r];
+    if (gor<G>(nzbits) == 0) { lo.frac = 0; lo.exp = 0; up.frac = 0; up.exp = 0; return 0; }
+    int K = C.log2M - bound - 3;
+    K = K < 0 ? 0 : K;
+    int s[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        int c = mulmod(x[r], L.w[r], L.m[r], L.mu[r]);
+        s[r] = L.act[r] ? mulmod(c, __ldg(C.pow2 + (long long) K * C.N + L.idx[r]), L.m[r], L.mu[r]) : 0;
+    }
+    for (int iter = 0; iter < 200; ++iter) {
+        double fl[R], fu[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            fl[r] = __dmul_rd((double) s[r], L.rrd[r]);
+            fu[r] = __dmul_ru((double) s[r], L.rru[r]);
+        }
+        const double suml = gsum_dir<G, R, false>(fl), sumu = gsum_dir<G, R, true>(fu);
+        const double wl = floor(suml), wu = floor(sumu);
+        const double dl = __dsub_rd(suml, wl), du = __dsub_ru(sumu, wu);   // exact
+        double dist;   // upper bound of the distance of the fraction to the nearest integer
+        if (wl == wu) {
+            if (du < 0.25 && dl >= C.accuracy) {
+                lo = er_from_double(dl); up = er_from_double(du);
+                lo.exp -= K; up.exp -= K;
+                return 1;
+            }
+            const double ml = __dsub_rd(1.0, du), mh = __dsub_ru(1.0, dl);
+            if (dl > 0.75 && ml >= C.accuracy) {
+                lo = er_from_double(ml); up = er_from_double(mh);
+                lo.exp -= K; up.exp -= K;
+                return -1;
+            }
+            if (du >= 0.25 && dl <= 0.75) {   // outside both windows: the guard did not hold (MODE_FAST only)
+                lo = er_from_double(dl); up = er_from_double(du);
+                lo.exp -= K; up.exp -= K;
+                return 1;
+            }
+            dist = du < 0.25 ? du : mh;
+        } else {
+            dist = __dadd_ru(du, __dsub_ru(1.0, dl));   // straddles an integer
+        }
+        // |frac| <= dist < 2^(e+1): magnify by -(e+1) - 3 bits, keeping the value below 1/8
+        int e = (int) (((unsigned long long) __double_as_longlong(dist) >> 52) & 0x7ff) - 1023;
+        int kk = -(e + 1) - 3;
+        kk = kk < 1 ? 1 : (kk > 60 ? 60 : kk);
+        if (K + kk > C.log2M) kk = C.log2M - K;
+        if (kk <= 0) break;
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            s[r] = L.act[r] ? mulmod(s[r], __ldg(C.pow2 + (long long) kk * C.N + L.idx[r]), L.m[r], L.mu[r]) : 0;
+        K += kk;
+    }
+    // not resolvable by magnification (cannot happen for |S| >= 1): fall back to the generic evaluation
+    eval_compute<G, R, false>(C, L, x, lo, up);
+    return (lo.frac != 0 && lo.exp >= -1) ? -1 : 1;
+}
+
 // ---- stage 3: normalise + alpha/beta epilogue ------------------------------------------------------
 // One lane group per C entry; a block covers kNormTile consecutive rows of one column so the
 // per-modulus planes are read as contiguous runs and transposed through shared memory (256 / G rows).
@@ -380,22 +448,22 @@ __global__ void __launch_bounds__(256) k_normalize_epilogue(const DevConsts *Cp,
             d = d > C.log2M ? C.log2M : d;   // only reachable in MODE_FAST with a failed guard
 #pragma unroll
             for (int r = 0; r < R; ++r) s.d[r] = L.act[r] ? sm_res[L.idx[r] * (kNormTile + 1) + grp] : 0;
-            // sign: |sum| < M/4, so a residue value above M/2 is a negative sum
+            long long bound = (long long) ra.win + cb.win + lgk;
+            bound = bound > C.log2M - 2 ? C.log2M - 2 : bound;
             Er lo, up;
-            eval_compute<G, R, false>(C, L, s.d, lo, up);
-            const bool neg = lo.frac != 0 && lo.exp >= -1;
-            const bool zero = up.frac == 0;
-            if (!zero) {
+            const int sg = sign_eval_window<G, R>(C, L, s.d, (int) bound, lo, up);
+            if (sg != 0) {
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     int v = s.d[r];
-                    if (neg && v) v = L.m[r] - v;
+                    if (sg < 0 && v) v = L.m[r] - v;
                     // exact division by 2^d (every term carries at least d trailing zero bits)
                     s.d[r] = L.act[r] ? mulmod(v, __ldg(C.inv_pow2 + (long long) d * N + L.idx[r]), L.m[r], L.mu[r]) : 0;
                 }
-                s.sign = neg ? 1 : 0;
+                s.sign = sg < 0 ? 1 : 0;
                 s.exp = ra.emin + cb.emin + d;
-                eval_compute<G, R, true>(C, L, s.d, s.lo, s.up);
+                s.lo = lo; s.up = up;
+                s.lo.exp -= d; s.up.exp -= d;
                 round_if_needed<G, R>(C, L, s);
             }
         }
@@ -481,6 +549,8 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
     // element (o, l) index strides: op(A)(i, l) and op(B)(l, j)
     const long long soA = ta ? lda : 1, slA = ta ? 1 : lda;
     const long long soB = tb ? 1 : ldb, slB = tb ? ldb : 1;
+    auto mark = [&](int i) { if (c->profiling) { if (!c->ev[i]) cudaEventCreate(&c->ev[i]); cudaEventRecord(c->ev[i], st); } };
+    mark(0);
     k_outer_info<<<(unsigned) ((m * 32ll + 255) / 256), 256, 0, st>>>(c->dconsts, A, soA, slA, m, k, IA);
     k_outer_info<<<(unsigned) ((n * 32ll + 255) / 256), 256, 0, st>>>(c->dconsts, B, soB, slB, n, k, IB);
     const size_t smem_align = (size_t) N * 4 * (kRun + 4);
@@ -495,6 +565,7 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
     k_align_planes<<<dim3((unsigned) n_p, (unsigned) (k_p / kRun)), 256, smem_align, st>>>(c->dconsts, B, soB, slB, n, k, IB, (uint8_t *) pPB, SB, n_p, k_p);
     k_minplus<<<dim3((unsigned) (m_p / kMpT), (unsigned) (n_p / kMpT)), 256, 0, st>>>(SA, SB, D, k_p, m_p, n_p);
     dim3 grid((unsigned) (n_p / kBN), (unsigned) (m_p / kBM), (unsigned) N);
+    mark(1);
     int gemm_launches = 0;
     for (long long kb = 0; kb < k_p; kb += 8064) {
         const int kl = (int) std::min<long long>(8064, k_p - kb);
@@ -502,6 +573,7 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
         k_limb_gemm<1><<<grid, 256, kGemmSmem, st>>>(c->dconsts, (const uint8_t *) pPA, (const uint8_t *) pPB, (int *) pS, m_p, n_p, k_p, kb, kl, true);
         gemm_launches += 2;
     }
+    mark(2);
     const bool allow_fb = c->mode == MPRES_MODE_AUTO;
     MPRES_DISPATCH(N, {
         constexpr int kNormTile = 256 / G;
@@ -511,6 +583,9 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
         if (allow_fb)
             k_gemm_todo<G, R><<<c->sm_count * 8, 128, 0, st>>>(c->dconsts, ta, tb, m, n, k, A, lda, B, ldb, alpha, beta, Cm, ldc, todo, c->d_counter);
     });
+    mark(3);
+    c->ev_valid = c->profiling;
+    c->last_stage2_launches = gemm_launches;
     for (int i = 0; i < (allow_fb ? 7 : 6) + gemm_launches; ++i) LAUNCHED(c);
     CUDA_TRY(cudaGetLastError());
     *done = true;

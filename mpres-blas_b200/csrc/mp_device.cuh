@@ -464,11 +464,11 @@ __device__ __forceinline__ void scaling_step(const DevConsts &C, const Lane<R> &
     for (int r = 0; r < R; ++r)
         if (L.act[r]) part += ((long long) C.mi_pow2[j - 1][L.idx[r]] * (long long) c[r]) & (pow2j - 1);
     long long residue = gsum_ll<G>(part);
-    residue = (residue - (long long) k * (long long) C.m_pow2[j - 1]) % pow2j;
-    if (residue < 0) residue += pow2j;
+    // (a mod 2^j) made non-negative == two's-complement masking
+    residue = (residue - (long long) k * (long long) C.m_pow2[j - 1]) & (pow2j - 1);
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        int mult = (int) (residue % L.m[r]);
+        int mult = reduce64((unsigned long long) residue, L.m[r], L.mu[r]);
         mult = submod(x[r], mult, L.m[r]);
         x[r] = L.act[r] ? mulmod(mult, C.pow2_inv[j - 1][L.idx[r]], L.m[r], L.mu[r]) : 0;
     }

@@ -122,6 +122,20 @@ long mpres_last_fallback_count(mpres_ctx *c) {
     return v;
 }
 
+int mpres_set_profiling(mpres_ctx *c, int on) { if (!c) return -1; c->profiling = on != 0; c->ev_valid = false; return 0; }
+
+// ms[0..2] = stage 1 (alignment), stage 2 (limb GEMM launches), stage 3 (normalise + epilogue + fallback)
+// of the last fast-path mp_gemm; launches = number of stage-2 kernel launches.  Synchronises.
+int mpres_last_stage_ms(mpres_ctx *c, float *ms, int *launches) {
+    if (!c || !ms) return -1;
+    if (!c->ev_valid) return -2;
+    DeviceGuard g(c->device);
+    CUDA_TRY(cudaEventSynchronize(c->ev[3]));
+    for (int i = 0; i < 3; ++i) CUDA_TRY(cudaEventElapsedTime(&ms[i], c->ev[i], c->ev[i + 1]));
+    if (launches) *launches = c->last_stage2_launches;
+    return 0;
+}
+
 long mpres_get_constant(const mpres_ctx *c, int which, void *out, size_t cap) {
     if (!c || !out) return -1;
     const HostConsts &h = c->hc;

@@ -100,6 +100,12 @@ class Oracle:
             self.lib.orc_mp_set(self.ctx, _ip(out[i:i + 1]), int(signs[i]), _ip(limbs), nl, int(exps[i]))
         return out
 
+    def random_records(self, count, bits, seed):
+        """bulk synthetic records (C, OpenMP) for the CPU-baseline legs"""
+        out = self.empty(count)
+        self.lib.orc_random_fill(self.ctx, _ip(out), ctypes.c_long(count), int(bits), ctypes.c_uint64(seed))
+        return out
+
     def _bin(self, fn, x, y):
         x = np.ascontiguousarray(x)
         y = np.ascontiguousarray(y)

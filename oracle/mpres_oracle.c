@@ -458,6 +458,43 @@ void orc_mp_set(const orc_ctx *c, void *r, int sign, const uint32_t *limbs, int 
     orc_eval_compute(c, &EVAL(c, r)[0], &EVAL(c, r)[1], DIG(r));
 }
 
+static uint64_t splitmix64(uint64_t *st) {
+    uint64_t z = (*st += 0x9e3779b97f4a7c15ull);
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+void orc_random_fill(const orc_ctx *c, void *recs, long n, int bits, uint64_t seed) {
+    int nl = (bits + 31) / 32;
+    if (nl > 150) nl = 150;
+    #pragma omp parallel for schedule(static)
+    for (long i = 0; i < n; i++) {
+        uint64_t st = seed * 0x100000001b3ull + (uint64_t) i * 0x9e3779b97f4a7c15ull + 1;
+        double z = (double) (splitmix64(&st) >> 11) * 0x1p-53, u = (double) (splitmix64(&st) >> 11) * 0x1p-52 - 1.0;
+        double v = z * fabs(u);
+        if (v < 0x1p-200) v = 0x1p-200;
+        int e;
+        double mant = frexp(v, &e);
+        uint64_t top = (uint64_t) (mant * 0x1p53);
+        uint32_t w[160];
+        for (int j = 0; j < nl; j++) w[j] = (uint32_t) splitmix64(&st);
+        int sh = bits - 53;
+        if (sh >= 0) {
+            for (int j = 0; j < nl; j++) {
+                int lo_bit = 32 * j;
+                uint32_t keep = lo_bit + 32 <= sh ? 0xffffffffu : (lo_bit < sh ? ((1u << (sh - lo_bit)) - 1u) : 0u);
+                int s = sh - lo_bit;
+                uint32_t hi = s >= 32 ? 0u : (s >= 0 ? (uint32_t) (top << s) : (-s < 64 ? (uint32_t) (top >> (-s)) : 0u));
+                w[j] = hi | (w[j] & keep);
+            }
+        } else {
+            uint64_t t = top >> (-sh);
+            for (int j = 0; j < nl; j++) w[j] = j < 2 ? (uint32_t) (t >> (32 * j)) : 0u;
+        }
+        orc_mp_set(c, REC(c, recs, i), u < 0, w, nl, e - bits);
+    }
+}
+
 /* ---------------- vector and BLAS-level restatements ---------------------------------------------- */
 static void set_zero(const orc_ctx *c, void *r) { memset(r, 0, orc_record_size(c)); } /* MP_ZERO, arith_utils.cuh:64-72 */
 

@@ -51,6 +51,10 @@ int orc_mrc_compare(const orc_ctx *c, const int *x, const int *y);
  * mp_set_mpfr (assign.cuh:95-111) and evaluates with the full rns_eval_compute */
 void orc_mp_set(const orc_ctx *c, void *r, int sign, const uint32_t *limbs, int nlimbs, int exp);
 
+/* bulk synthetic records for CPU-baseline timing: uniform(-1,1) magnitudes, `bits`-bit significands
+ * (top 53 bits from a double product as in tests/tsthelper.cuh:63-65, low bits uniform), OpenMP */
+void orc_random_fill(const orc_ctx *c, void *recs, long n, int bits, uint64_t seed);
+
 /* vector / BLAS-level restatements (reference-order summation) */
 void orc_mul_vec(const orc_ctx *c, void *r, const void *x, const void *y, long n);
 void orc_add_vec(const orc_ctx *c, void *r, const void *x, const void *y, long n);
