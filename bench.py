@@ -179,7 +179,7 @@ def main():
     import torch
     import _pkg
     pkg = _pkg.load()
-    from mpres_blas_b200 import torch_arrays as ta
+    from mpres_blas_b200 import parallel, torch_arrays as ta
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU path in this library")
     torch.cuda.set_device(local_rank)
@@ -207,10 +207,8 @@ def main():
     def step():
         for dst, src in zip(C.tensors(), C0.tensors()):   # fresh C every step (device-to-device, ~1 ms at 4096^2)
             dst.copy_(src, non_blocking=True)
-        if world > 1:
-            for t in B.tensors():
-                dist.broadcast(t, src=0)
-        pkg.mp_gemm(ctx, pkg.mblas_no_trans, pkg.mblas_no_trans, mr, n, k, alpha, A, mr, B, k, beta, C, mr, None, stream)
+        parallel.gemm_row_sharded(dist, B.tensors(), lambda: pkg.mp_gemm(
+            ctx, pkg.mblas_no_trans, pkg.mblas_no_trans, mr, n, k, alpha, A, mr, B, k, beta, C, mr, None, stream))
 
     def barrier():
         torch.cuda.synchronize()

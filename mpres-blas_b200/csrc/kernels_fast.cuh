@@ -254,17 +254,21 @@ __global__ void __launch_bounds__(256, 1) k_limb_gemm(const DevConsts *Cp, const
     for (int u = 0; u < NACC; ++u) cu[u] = (unsigned long long) (unsigned) Cp->pow2[(long long) (8 * (UBASE + u)) * Cp->N + q];
 
     const int nslab = k_len / kBK;   // host keeps k_len <= 8064 so that 4 pairs * 255^2 * k_len < 2^31
+    // Per-thread copy assignment, fixed across slabs: 16-byte chunk c = tid & 3 of rows r0 and r0 + 64 of
+    // every A limb tile and of row r0 of every B limb tile.
+    const int cpc = threadIdx.x & 3, cpr = threadIdx.x >> 2;
+    const uint8_t *gA = Aq + ((long long) i0 + cpr) * k_p + k_begin + cpc * 16;
+    const uint8_t *gB = Bq + ((long long) j0 + cpr) * k_p + k_begin + cpc * 16;
+    const long long limbA = m_p * k_p, limbB = n_p * k_p, half = 64 * k_p;
+    const int dsw = swz(cpr, cpc);
     auto load_slab = [&](int slab, int stage) {
-        uint8_t *sA = smem + stage * kStageBytes, *sB = sA + kStageBytesA;
-        const long long kb = k_begin + (long long) slab * kBK;
-        // A: NL limbs x 128 rows x 4 chunks; B: NL limbs x 64 rows x 4 chunks
-        for (int t = threadIdx.x; t < NL * kBM * 4; t += 256) {
-            const int c = t & 3, row = (t >> 2) & (kBM - 1), lb = LIMB0 + (t >> 9);
-            cp_async16(sA + lb * kBM * kBK + swz(row, c), Aq + ((long long) lb * m_p + i0 + row) * k_p + kb + c * 16);
-        }
-        for (int t = threadIdx.x; t < NL * kBN * 4; t += 256) {
-            const int c = t & 3, row = (t >> 2) & (kBN - 1), lb = LIMB0 + (t >> 8);
-            cp_async16(sB + lb * kBN * kBK + swz(row, c), Bq + ((long long) lb * n_p + j0 + row) * k_p + kb + c * 16);
+        uint8_t *sA = smem + stage * kStageBytes + dsw, *sB = smem + stage * kStageBytes + kStageBytesA + dsw;
+        const long long kb = (long long) slab * kBK;
+#pragma unroll
+        for (int lb = LIMB0; lb < 4; ++lb) {
+            cp_async16(sA + lb * kBM * kBK, gA + lb * limbA + kb);
+            cp_async16(sA + lb * kBM * kBK + 64 * kBK, gA + lb * limbA + half + kb);
+            cp_async16(sB + lb * kBN * kBK, gB + lb * limbB + kb);
         }
     };
 
