@@ -225,11 +225,16 @@ def main():
     launches0 = ctx.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    use_profiler_range = os.environ.get("MPRES_BENCH_PROFILER_RANGE") == "1"   # ncu --profile-from-start off
+    if use_profiler_range:
+        torch.cuda.profiler.start()
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
     barrier()
+    if use_profiler_range:
+        torch.cuda.profiler.stop()
     clocks = sampler.stop()
     ms_total = e0.elapsed_time(e1)
     launches = ctx.launch_count - launches0
