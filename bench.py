@@ -138,6 +138,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="gemm4096_424bit", choices=sorted(WORKLOADS))
     ap.add_argument("--mode", default="auto", choices=["auto", "reference_order", "fast"])
+    ap.add_argument("--stage2", default="umma", choices=["umma", "umma_unstacked", "mma_sync"], help="stage-2 kernel (A/B measurement)")
     ap.add_argument("--full-precision-inputs", action="store_true", help="p-bit significands instead of p/4")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -189,6 +190,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = pkg.Context(N, local_rank)
     ctx.set_mode({"auto": pkg.MODE_AUTO, "reference_order": pkg.MODE_REFERENCE_ORDER, "fast": pkg.MODE_FAST}[args.mode])
+    ctx.set_stage2_kernel({"umma": pkg.STAGE2_UMMA, "umma_unstacked": pkg.STAGE2_UMMA_UNSTACKED, "mma_sync": pkg.STAGE2_MMA_SYNC}[args.stage2])
+    config["stage2_kernel"] = args.stage2
     assert m % world == 0
     mr = m // world                       # rows of A and C owned by this rank
     A = ta.TorchMpArray(ctx, mr * k)

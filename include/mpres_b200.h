@@ -60,6 +60,7 @@ enum { MPRES_NO_TRANS = 111, MPRES_TRANS = 112, MPRES_CONJ_TRANS = 113 };
  * kernels including the interval evaluations.  FAST = fast path only (elements whose guard fails
  * are reported through mpres_last_fallback_count). */
 enum { MPRES_MODE_AUTO = 0, MPRES_MODE_REFERENCE_ORDER = 1, MPRES_MODE_FAST = 2 };
+enum { MPRES_STAGE2_UMMA = 0, MPRES_STAGE2_UMMA_UNSTACKED = 1, MPRES_STAGE2_MMA_SYNC = 2 };
 
 typedef struct mpres_ctx mpres_ctx;
 typedef void *mpres_stream_t; /* cudaStream_t */
@@ -94,6 +95,10 @@ long mpres_get_constant(const mpres_ctx *ctx, int which, void *out, size_t cap);
 
 int mpres_set_mode(mpres_ctx *ctx, int mode);
 int mpres_get_mode(const mpres_ctx *ctx);
+/* Stage-2 kernel of the fast path: UMMA = tcgen05.mma kind::i8 with TMA-fed limb tiles (default),
+ * UMMA_UNSTACKED = the same kernel issuing one MMA per limb pair, MMA_SYNC = the legacy warp-level
+ * int8 MMA kernel.  All three produce identical residues; the switch exists for A/B measurement. */
+int mpres_set_stage2_kernel(mpres_ctx *ctx, int kind);
 /* number of result elements the last AUTO/FAST call routed to the reference-order fallback
  * (synchronises the stream of that call) */
 long mpres_last_fallback_count(mpres_ctx *ctx);

@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libmpres_b200.so")
 
 mblas_no_trans, mblas_trans, mblas_conj_trans = 111, 112, 113  # src/blas/mblas_enum.cuh:25-29
 MODE_AUTO, MODE_REFERENCE_ORDER, MODE_FAST = 0, 1, 2
+STAGE2_UMMA, STAGE2_UMMA_UNSTACKED, STAGE2_MMA_SYNC = 0, 1, 2
 
 _lib = None
 
@@ -37,7 +38,7 @@ class mp_collection_t(ctypes.Structure):  # src/types.cuh:99-104
 EXPORTS = [
     "mpres_init", "mpres_init_moduli", "mpres_finalize", "mpres_moduli_size", "mpres_moduli_product_log2",
     "mpres_precision", "mpres_mp_h", "mpres_mp_j", "mpres_device", "mpres_sizeof_mp_float", "mpres_get_constant",
-    "mpres_set_mode", "mpres_get_mode", "mpres_last_fallback_count", "mpres_launch_count",
+    "mpres_set_mode", "mpres_get_mode", "mpres_set_stage2_kernel", "mpres_last_fallback_count", "mpres_launch_count",
     "mpres_set_profiling", "mpres_last_stage_ms",
     "mpres_array_init", "mpres_array_clear", "mpres_array_host2device", "mpres_array_device2host",
     "mpres_collection_init", "mpres_collection_clear", "mpres_collection_host2device", "mpres_collection_device2host",
@@ -114,6 +115,9 @@ class Context:
 
     def set_mode(self, mode):
         _check(self.lib.mpres_set_mode(self.h, mode), "mpres_set_mode")
+
+    def set_stage2_kernel(self, kind):
+        _check(self.lib.mpres_set_stage2_kernel(self.h, kind), "mpres_set_stage2_kernel")
 
     def set_profiling(self, on):
         _check(self.lib.mpres_set_profiling(self.h, 1 if on else 0), "mpres_set_profiling")

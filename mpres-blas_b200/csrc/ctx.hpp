@@ -18,6 +18,7 @@ using namespace mpres;
 struct mpres_ctx {
     int device = 0;
     int mode = MPRES_MODE_AUTO;
+    int stage2 = MPRES_STAGE2_UMMA;   // which stage-2 kernel the fast path launches
     HostConsts hc;
     DevConsts *dconsts = nullptr;
     int *d_pow2 = nullptr, *d_inv_pow2 = nullptr, *d_mrc = nullptr;

@@ -36,6 +36,7 @@
 
 #include "ctx.hpp"
 #include "kernels_ref_order.cuh"
+#include "kernels_umma.cuh"
 
 namespace mpres {
 
@@ -573,9 +574,15 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
     int gemm_launches = 0;
     for (long long kb = 0; kb < k_p; kb += 8064) {
         const int kl = (int) std::min<long long>(8064, k_p - kb);
-        k_limb_gemm<0><<<grid, 256, kGemmSmem, st>>>(c->dconsts, (const uint8_t *) pPA, (const uint8_t *) pPB, (int *) pS, m_p, n_p, k_p, kb, kl, kb > 0);
-        k_limb_gemm<1><<<grid, 256, kGemmSmem, st>>>(c->dconsts, (const uint8_t *) pPA, (const uint8_t *) pPB, (int *) pS, m_p, n_p, k_p, kb, kl, true);
-        gemm_launches += 2;
+        if (c->stage2 == MPRES_STAGE2_MMA_SYNC) {
+            k_limb_gemm<0><<<grid, 256, kGemmSmem, st>>>(c->dconsts, (const uint8_t *) pPA, (const uint8_t *) pPB, (int *) pS, m_p, n_p, k_p, kb, kl, kb > 0);
+            k_limb_gemm<1><<<grid, 256, kGemmSmem, st>>>(c->dconsts, (const uint8_t *) pPA, (const uint8_t *) pPB, (int *) pS, m_p, n_p, k_p, kb, kl, true);
+            gemm_launches += 2;
+        } else {
+            if ((rc = launch_limb_umma(c, c->stage2 == MPRES_STAGE2_UMMA, (const uint8_t *) pPA, (const uint8_t *) pPB, (int *) pS, m_p, n_p, k_p, kb, kl,
+                                       kb > 0, st))) return rc;
+            gemm_launches += 1;
+        }
     }
     mark(2);
     const bool allow_fb = c->mode == MPRES_MODE_AUTO;

@@ -111,6 +111,7 @@ int mpres_device(const mpres_ctx *c) { return c ? c->device : -1; }
 size_t mpres_sizeof_mp_float(const mpres_ctx *c) { return c ? 4 * (size_t) c->hc.N + 40 : 0; }
 int mpres_set_mode(mpres_ctx *c, int mode) { if (!c || mode < 0 || mode > 2) return -1; c->mode = mode; return 0; }
 int mpres_get_mode(const mpres_ctx *c) { return c ? c->mode : -1; }
+int mpres_set_stage2_kernel(mpres_ctx *c, int kind) { if (!c || kind < 0 || kind > 2) return -1; c->stage2 = kind; return 0; }
 long mpres_launch_count(const mpres_ctx *c) { return c ? c->launches.load() : -1; }
 
 long mpres_last_fallback_count(mpres_ctx *c) {

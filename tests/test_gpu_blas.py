@@ -181,3 +181,26 @@ def test_gemm_mixed_width_accuracy(pkg):
             err = abs(orc.to_fraction(got[i + j * m]) - exact)
             assert err <= bound, (i, j, float(err), float(bound))
     ctx.close()
+
+
+@pytest.mark.parametrize("N,shape", [(8, (200, 150, 300)), (32, (130, 70, 129)), (8, (20, 10, 8300)), (16, (256, 128, 1024))])
+def test_gemm_stage2_kernels_agree(pkg, N, shape):
+    """The three stage-2 kernels (tcgen05 stacked / unstacked, legacy mma.sync) give the same result as
+    the reference-order k-loop, bit for bit; k = 8300 crosses the 8064-byte accumulation chunk."""
+    ctx = pkg.Context(N, 0)
+    orc = get_oracle(N, oracle.DEVICE)
+    bits = orc.precision // 4
+    m, n, k = shape
+    A = random_records(N, m * k, bits, 61)
+    B = random_records(N, k * n, bits, 62)
+    C = random_records(N, m * n, bits, 63)
+    alpha = random_records(N, 1, bits, 64)
+    beta = random_records(N, 1, bits, 65)
+    want = _gemm(pkg, ctx, m, n, k, alpha, A, B, beta, C, pkg.MODE_REFERENCE_ORDER)
+    for kind in (pkg.STAGE2_UMMA, pkg.STAGE2_UMMA_UNSTACKED, pkg.STAGE2_MMA_SYNC):
+        ctx.set_stage2_kernel(kind)
+        got = _gemm(pkg, ctx, m, n, k, alpha, A, B, beta, C, pkg.MODE_AUTO)
+        assert ctx.last_fallback_count() == 0
+        bad = diff_fields(got, want, ("digits", "sign", "exp"))
+        assert bad.size == 0, "stage2 kernel %d: %d/%d differ, first %d" % (kind, bad.size, m * n, bad[0])
+    ctx.close()
