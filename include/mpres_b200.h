@@ -99,6 +99,15 @@ int mpres_get_mode(const mpres_ctx *ctx);
  * UMMA_UNSTACKED = the same kernel issuing one MMA per limb pair, MMA_SYNC = the legacy warp-level
  * int8 MMA kernel.  All three produce identical residues; the switch exists for A/B measurement. */
 int mpres_set_stage2_kernel(mpres_ctx *ctx, int kind);
+/* Stage-3 kernel of the fast path: 0 = entry-per-thread normalisation with a residue-parallel list
+ * kernel for the entries that need refinement / rounding / sign resolution (default), 1 = the
+ * residue-parallel tile kernel for every entry.  Identical results (including interval evaluations). */
+int mpres_set_stage3_kernel(mpres_ctx *ctx, int kind);
+/* Stage-1 alignment kernel: 0 = vectorised (four residues per work item, default), 1 = one residue per thread. */
+int mpres_set_stage1_kernel(mpres_ctx *ctx, int kind);
+/* number of result elements of the last fast-path call that the entry-per-thread normalisation kernel
+ * handed to the residue-parallel list kernel (diagnostic; synchronises) */
+long mpres_last_slow_count(mpres_ctx *ctx);
 /* number of result elements the last AUTO/FAST call routed to the reference-order fallback
  * (synchronises the stream of that call) */
 long mpres_last_fallback_count(mpres_ctx *ctx);

@@ -33,6 +33,7 @@
 #include <stdint.h>
 
 #include <climits>
+#include <type_traits>
 
 #include "ctx.hpp"
 #include "kernels_ref_order.cuh"
@@ -145,50 +146,125 @@ __global__ void __launch_bounds__(256) k_align_planes(const DevConsts *Cp, SoA X
     }
 }
 
+// ---- stage 1b, vectorised: four residues per work item ------------------------------------------------
+// Same output as k_align_planes for N % 4 == 0.  A thread owns a fixed group of four moduli (constants in
+// registers) and walks entries; the exponent / sign / interval fields are read once per four residues, digits
+// and the 2^s table row as 128-bit loads.  Bytes are staged in shared memory as [limb][q][l] (pitch 33 words:
+// the eight modulus groups of a warp hit eight different banks, the four entries of a warp the same word)
+// and leave as full 128-byte rows.
+__global__ void __launch_bounds__(256) k_align_planes4(const DevConsts *Cp, SoA X, long long so, long long sl, int outer, int inner,
+                                                       const OuterInfo *info, uint8_t *planes, int16_t *shifts,
+                                                       long long outer_p, long long inner_p) {
+    extern __shared__ uint8_t sm_stage[];   // [4][N][kRun + 4]
+    const DevConsts &C = *Cp;
+    const int N = C.N;
+    const int Q4 = N >> 2;                  // modulus groups
+    const int EP = 256 / Q4;                // entries per pass
+    const int o = blockIdx.x;
+    const int l0 = blockIdx.y * kRun;
+    constexpr int pitch = kRun + 4;
+    const long long len = X.len();
+    const bool line_ok = o < outer;
+    const OuterInfo oi = line_ok ? info[o] : OuterInfo{0, -1};
+    const int q4 = threadIdx.x % Q4, slot = threadIdx.x / Q4;
+    if (slot < EP) {
+        const int4 mq = *(const int4 *) (C.moduli + 4 * q4);
+        const int mv[4] = {mq.x, mq.y, mq.z, mq.w};
+        unsigned long long mu[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) mu[e] = C.barrett[4 * q4 + e];
+        const int log2M = C.log2M;
+        for (int ll = slot; ll < kRun; ll += EP) {
+            const int l = l0 + ll;
+            unsigned r[4] = {0u, 0u, 0u, 0u};
+            int sh16 = kShiftSentinel;
+            if (line_ok && l < inner) {
+                const long long idx = (long long) o * so + (long long) l * sl;
+                if (X.eval[idx + len].frac != 0) {
+                    long long sh = (long long) X.exp[idx] - oi.emin;
+                    const int s = sh > kShiftMax ? kShiftMax : (int) sh;
+                    sh16 = s;
+                    if (s <= log2M) {   // s > log2M: the line fails the window guard anyway
+                        const int4 dg = __ldg((const int4 *) (X.digits + idx * N) + q4);
+                        const int4 pw = __ldg((const int4 *) (C.pow2 + (long long) s * N) + q4);
+                        const int dv[4] = {dg.x, dg.y, dg.z, dg.w}, pv[4] = {pw.x, pw.y, pw.z, pw.w};
+                        const int neg = X.sign[idx];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            int v = mulmod(dv[e], pv[e], mv[e], mu[e]);
+                            if (neg && v) v = mv[e] - v;
+                            r[e] = (unsigned) v;
+                        }
+                    }
+                }
+            }
+            if (q4 == 0) shifts[(long long) o * inner_p + l] = (int16_t) sh16;
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) sm_stage[(b * N + 4 * q4 + e) * pitch + ll] = (uint8_t) (r[e] >> (8 * b));
+        }
+    }
+    __syncthreads();
+    // write out: shared row (b, q) -> plane row (q, b), kRun contiguous bytes, one warp per row
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int row = warp; row < 4 * N; row += 8) {
+        const int b = row / N, q = row - b * N;
+        const uint32_t v = *(const uint32_t *) (sm_stage + row * pitch + lane * 4);
+        *(uint32_t *) (planes + ((long long) (q * 4 + b) * outer_p + o) * inner_p + l0 + lane * 4) = v;
+    }
+}
+
 // ---- stage 1c: (min,+) product of the shift planes ------------------------------------------------
 // delta[j][i] = min_l (SA[i][l] + SB[j][l]); int16 SIMD pairs (DPX add-min on sm_90+).
-constexpr int kMpT = 64;   // output tile 64 x 64, 256 threads, 4 x 4 outputs each
+// CTA tile 128 (i) x 64 (j), 256 threads, 8 x 4 outputs per thread; the shift words of a K slab sit in
+// shared memory as [word][row] so that a thread's 8 + 4 operands are three 128-bit loads per 32 add-mins.
+constexpr int kMpTI = 128, kMpTJ = 64;
 constexpr int kMpK = 64;   // shift entries per stage (32 words)
 __global__ void __launch_bounds__(256) k_minplus(const int16_t *SA, const int16_t *SB, int16_t *delta, long long inner_p,
                                                  long long m_p, long long n_p) {
-    __shared__ uint32_t sa[kMpK / 2][kMpT + 1];
-    __shared__ uint32_t sb[kMpK / 2][kMpT + 1];
-    const int i0 = blockIdx.x * kMpT, j0 = blockIdx.y * kMpT;
-    const int ti = (threadIdx.x & 15) * 4, tj = (threadIdx.x >> 4) * 4;
-    uint32_t acc[4][4];
+    __shared__ __align__(16) uint32_t sa[kMpK / 2][kMpTI + 4];
+    __shared__ __align__(16) uint32_t sb[kMpK / 2][kMpTJ + 4];
+    const int i0 = blockIdx.x * kMpTI, j0 = blockIdx.y * kMpTJ;
+    const int ti = (threadIdx.x & 15) * 8, tj = (threadIdx.x >> 4) * 4;
+    uint32_t acc[8][4];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < 8; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b) acc[a][b] = 0x7fff7fffu;
     const uint32_t *A32 = (const uint32_t *) SA, *B32 = (const uint32_t *) SB;
     const long long wpl = inner_p / 2;   // words per line
     for (long long w0 = 0; w0 < wpl; w0 += kMpK / 2) {
-        for (int t = threadIdx.x; t < kMpT * (kMpK / 2); t += 256) {
+        for (int t = threadIdx.x; t < kMpTI * (kMpK / 2); t += 256) {
             const int row = t / (kMpK / 2), w = t - row * (kMpK / 2);
             sa[w][row] = A32[(long long) (i0 + row) * wpl + w0 + w];
+        }
+        for (int t = threadIdx.x; t < kMpTJ * (kMpK / 2); t += 256) {
+            const int row = t / (kMpK / 2), w = t - row * (kMpK / 2);
             sb[w][row] = B32[(long long) (j0 + row) * wpl + w0 + w];
         }
         __syncthreads();
 #pragma unroll 4
         for (int w = 0; w < kMpK / 2; ++w) {
-            uint32_t av[4], bv[4];
+            const uint4 a0 = *(const uint4 *) &sa[w][ti], a1 = *(const uint4 *) &sa[w][ti + 4], b0 = *(const uint4 *) &sb[w][tj];
+            const uint32_t av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, bv[4] = {b0.x, b0.y, b0.z, b0.w};
 #pragma unroll
-            for (int a = 0; a < 4; ++a) { av[a] = sa[w][ti + a]; bv[a] = sb[w][tj + a]; }
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
+            for (int a = 0; a < 8; ++a)
 #pragma unroll
                 for (int b = 0; b < 4; ++b) acc[a][b] = __viaddmin_s16x2(av[a], bv[b], acc[a][b]);
         }
         __syncthreads();
     }
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int b = 0; b < 4; ++b) {
+        __align__(16) short out[8];
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
+        for (int a = 0; a < 8; ++a) {
             int lo = (int) (short) (acc[a][b] & 0xffffu), hi = (int) (short) (acc[a][b] >> 16);
-            int v = lo < hi ? lo : hi;
-            delta[(long long) (j0 + tj + b) * m_p + i0 + ti + a] = (int16_t) v;
+            out[a] = (short) (lo < hi ? lo : hi);
         }
+        *(uint4 *) (delta + (long long) (j0 + tj + b) * m_p + i0 + ti) = *(const uint4 *) out;
+    }
 }
 
 // ---- stage 2: per-modulus limb GEMM on the int8 tensor cores ---------------------------------------
@@ -342,147 +418,11 @@ __global__ void __launch_bounds__(256, 1) k_limb_gemm(const DevConsts *Cp, const
             }
 }
 
-// Sign and interval evaluation of an exact sum S known only through its residues X = S mod M, given
-// |S| < 2^bound <= M/4.  Instead of the reference's generic refinement (src/rns.cuh:911-921: up to
-// log2(M)/49 rounds, each with a log2 and a ceil) the known bound gives the magnification directly:
-// X * 2^K mod M has its fractional value in (0, 1/8) for S > 0 and in (7/8, 1) for S < 0.  Further
-// rounds (only after heavy cancellation) magnify by what the current upper bound allows.
-// Returns 0 for S == 0, else +1 / -1, with [lo, up] enclosing |S| / M.
-template <int G, int R>
-__device__ __forceinline__ int sign_eval_window(const DevConsts &C, const Lane<R> &L, const int (&x)[R], int bound, Er &lo, Er &up) {
-    int nzbits = 0;
-#pragma unroll
-    for (int r = 0; r < R; ++r) nzbits |= x[r];
-    if (gor<G>(nzbits) == 0) { lo.frac = 0; lo.exp = 0; up.frac = 0; up.exp = 0; return 0; }
-    int K = C.log2M - bound - 3;
-    K = K < 0 ? 0 : K;
-    int s[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        int c = mulmod(x[r], L.w[r], L.m[r], L.mu[r]);
-        s[r] = L.act[r] ? mulmod(c, __ldg(C.pow2 + (long long) K * C.N + L.idx[r]), L.m[r], L.mu[r]) : 0;
-    }
-    for (int iter = 0; iter < 200; ++iter) {
-        double fl[R], fu[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            fl[r] = __dmul_rd((double) s[r], L.rrd[r]);
-            fu[r] = __dmul_ru((double) s[r], L.rru[r]);
-        }
-        const double suml = gsum_dir<G, R, false>(fl), sumu = gsum_dir<G, R, true>(fu);
-        const double wl = floor(suml), wu = floor(sumu);
-        const double dl = __dsub_rd(suml, wl), du = __dsub_ru(sumu, wu);   // exact
-        double dist;   // upper bound of the distance of the fraction to the nearest integer
-        if (wl == wu) {
-            if (du < 0.25 && dl >= C.accuracy) {
-                lo = er_from_double(dl); up = er_from_double(du);
-                lo.exp -= K; up.exp -= K;
-                return 1;
-            }
-            const double ml = __dsub_rd(1.0, du), mh = __dsub_ru(1.0, dl);
-            if (dl > 0.75 && ml >= C.accuracy) {
-                lo = er_from_double(ml); up = er_from_double(mh);
-                lo.exp -= K; up.exp -= K;
-                return -1;
-            }
-            if (du >= 0.25 && dl <= 0.75) {   // outside both windows: the guard did not hold (MODE_FAST only)
-                lo = er_from_double(dl); up = er_from_double(du);
-                lo.exp -= K; up.exp -= K;
-                return 1;
-            }
-            dist = du < 0.25 ? du : mh;
-        } else {
-            dist = __dadd_ru(du, __dsub_ru(1.0, dl));   // straddles an integer
-        }
-        // |frac| <= dist < 2^(e+1): magnify by -(e+1) - 3 bits, keeping the value below 1/8
-        int e = (int) (((unsigned long long) __double_as_longlong(dist) >> 52) & 0x7ff) - 1023;
-        int kk = -(e + 1) - 3;
-        kk = kk < 1 ? 1 : (kk > 60 ? 60 : kk);
-        if (K + kk > C.log2M) kk = C.log2M - K;
-        if (kk <= 0) break;
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-            s[r] = L.act[r] ? mulmod(s[r], __ldg(C.pow2 + (long long) kk * C.N + L.idx[r]), L.m[r], L.mu[r]) : 0;
-        K += kk;
-    }
-    // not resolvable by magnification (cannot happen for |S| >= 1): fall back to the generic evaluation
-    eval_compute<G, R, false>(C, L, x, lo, up);
-    return (lo.frac != 0 && lo.exp >= -1) ? -1 : 1;
-}
+}  // namespace mpres
 
-// ---- stage 3: normalise + alpha/beta epilogue ------------------------------------------------------
-// One lane group per C entry; a block covers kNormTile consecutive rows of one column so the
-// per-modulus planes are read as contiguous runs and transposed through shared memory (256 / G rows).
-template <int G, int R>
-__global__ void __launch_bounds__(256) k_normalize_epilogue(const DevConsts *Cp, int m, int n, int k, const int *S, const int16_t *delta,
-                                                 long long m_p, long long n_p, const OuterInfo *ia, const OuterInfo *ib,
-                                                 SoA alpha, SoA beta, SoA Cm, int ldc, long long *todo, int *todo_count, bool fallback_allowed) {
-    extern __shared__ int sm_res[];   // [N][kNormTile + 1]
-    constexpr int kNormTile = 256 / G;
-    const DevConsts &C = *Cp;
-    const int N = C.N;
-    Lane<R> L;
-    lane_init<G, R>(C, L);
-    const int tiles = (m + kNormTile - 1) / kNormTile;
-    const int col = blockIdx.x / tiles;
-    const int row0 = (blockIdx.x - col * tiles) * kNormTile;
-    for (int t = threadIdx.x; t < N * kNormTile; t += blockDim.x) {
-        const int q = t / kNormTile, r = t - q * kNormTile;
-        sm_res[q * (kNormTile + 1) + r] = S[((long long) q * n_p + col) * m_p + row0 + r];
-    }
-    __syncthreads();
-    const int grp = threadIdx.x / G;
-    const int row = row0 + grp;
-    if (row >= m) return;
-    const OuterInfo ra = ia[row], cb = ib[col];
-    int lgk = 0;
-    while ((1 << lgk) < k) ++lgk;
-    Num<R> s;
-    num_zero(s);
-    if (ra.win >= 0 && cb.win >= 0) {
-        if ((long long) ra.win + cb.win + lgk > (long long) C.log2M - 2) {
-            // window guard failed: exact accumulation not guaranteed -> reference-order recomputation
-            if ((threadIdx.x & (G - 1)) == 0) {
-                int pos = atomicAdd(todo_count, 1);
-                if (fallback_allowed) todo[pos] = row + (long long) col * m;
-            }
-            if (fallback_allowed) return;
-        }
-        int d = delta[(long long) col * m_p + row];
-        if (d < kShiftSentinel) {
-            d = d > C.log2M ? C.log2M : d;   // only reachable in MODE_FAST with a failed guard
-#pragma unroll
-            for (int r = 0; r < R; ++r) s.d[r] = L.act[r] ? sm_res[L.idx[r] * (kNormTile + 1) + grp] : 0;
-            long long bound = (long long) ra.win + cb.win + lgk;
-            bound = bound > C.log2M - 2 ? C.log2M - 2 : bound;
-            Er lo, up;
-            const int sg = sign_eval_window<G, R>(C, L, s.d, (int) bound, lo, up);
-            if (sg != 0) {
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    int v = s.d[r];
-                    if (sg < 0 && v) v = L.m[r] - v;
-                    // exact division by 2^d (every term carries at least d trailing zero bits)
-                    s.d[r] = L.act[r] ? mulmod(v, __ldg(C.inv_pow2 + (long long) d * N + L.idx[r]), L.m[r], L.mu[r]) : 0;
-                }
-                s.sign = sg < 0 ? 1 : 0;
-                s.exp = ra.emin + cb.emin + d;
-                s.lo = lo; s.up = up;
-                s.lo.exp -= d; s.up.exp -= d;
-                round_if_needed<G, R>(C, L, s);
-            }
-        }
-    }
-    Num<R> al, be, c, t1, t2;
-    load_num<G, R>(C, L, alpha, 0, al);
-    load_num<G, R>(C, L, beta, 0, be);
-    const long long ic = row + (long long) col * ldc;
-    load_num<G, R>(C, L, Cm, ic, c);
-    mp_mul<G, R, true>(C, L, t1, s, al);
-    mp_mul<G, R, true>(C, L, t2, c, be);
-    mp_add<G, R, true>(C, L, c, t2, t1);
-    store_num<G, R>(C, L, Cm, ic, c);
-}
+#include "kernels_norm.cuh"
+
+namespace mpres {
 
 // reference-order recomputation of the elements in `todo`, epilogue fused
 template <int G, int R>
@@ -536,20 +476,21 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
     const size_t bytesS = (size_t) N * n_p * m_p * 4;
     const size_t bytesSA = (size_t) m_p * k_p * 2, bytesSB = (size_t) n_p * k_p * 2, bytesD = (size_t) n_p * m_p * 2;
     const size_t bytesInfo = (size_t) (m_p + n_p) * sizeof(OuterInfo);
-    const size_t bytesTodo = (size_t) m * n * sizeof(long long);
+    const size_t bytesTodo = (size_t) m * n * sizeof(long long);   // per list: reference-order todo, stage-3 slow list
     void *pPA, *pPB, *pS, *pMisc;
     int rc;
     if ((rc = ws_reserve(c, 3, bytesPA, &pPA))) return rc;
     if ((rc = ws_reserve(c, 4, bytesPB, &pPB))) return rc;
     if ((rc = ws_reserve(c, 5, bytesS, &pS))) return rc;
-    if ((rc = ws_reserve(c, 6, bytesSA + bytesSB + bytesD + bytesInfo + bytesTodo + 1024, &pMisc))) return rc;
+    if ((rc = ws_reserve(c, 6, bytesSA + bytesSB + bytesD + bytesInfo + 2 * bytesTodo + 1024, &pMisc))) return rc;
     char *pm = (char *) pMisc;
     int16_t *SA = (int16_t *) pm; pm += bytesSA;
     int16_t *SB = (int16_t *) pm; pm += bytesSB;
     int16_t *D = (int16_t *) pm; pm += (bytesD + 15) / 16 * 16;
     OuterInfo *IA = (OuterInfo *) pm; pm += (size_t) m_p * sizeof(OuterInfo);
     OuterInfo *IB = (OuterInfo *) pm; pm += (size_t) n_p * sizeof(OuterInfo);
-    long long *todo = (long long *) pm;
+    long long *todo = (long long *) pm; pm += bytesTodo;
+    long long *slow = (long long *) pm;
 
     // element (o, l) index strides: op(A)(i, l) and op(B)(l, j)
     const long long soA = ta ? lda : 1, slA = ta ? 1 : lda;
@@ -562,13 +503,19 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
     static bool attr_done = false;
     if (!attr_done) {
         cudaFuncSetAttribute(k_align_planes, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 4 * (kRun + 4));
+        cudaFuncSetAttribute(k_align_planes4, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 4 * (kRun + 4));
         cudaFuncSetAttribute(k_limb_gemm<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
         cudaFuncSetAttribute(k_limb_gemm<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
         attr_done = true;
     }
-    k_align_planes<<<dim3((unsigned) m_p, (unsigned) (k_p / kRun)), 256, smem_align, st>>>(c->dconsts, A, soA, slA, m, k, IA, (uint8_t *) pPA, SA, m_p, k_p);
-    k_align_planes<<<dim3((unsigned) n_p, (unsigned) (k_p / kRun)), 256, smem_align, st>>>(c->dconsts, B, soB, slB, n, k, IB, (uint8_t *) pPB, SB, n_p, k_p);
-    k_minplus<<<dim3((unsigned) (m_p / kMpT), (unsigned) (n_p / kMpT)), 256, 0, st>>>(SA, SB, D, k_p, m_p, n_p);
+    if (N % 4 == 0 && N <= 128 && c->stage1 == 0) {
+        k_align_planes4<<<dim3((unsigned) m_p, (unsigned) (k_p / kRun)), 256, smem_align, st>>>(c->dconsts, A, soA, slA, m, k, IA, (uint8_t *) pPA, SA, m_p, k_p);
+        k_align_planes4<<<dim3((unsigned) n_p, (unsigned) (k_p / kRun)), 256, smem_align, st>>>(c->dconsts, B, soB, slB, n, k, IB, (uint8_t *) pPB, SB, n_p, k_p);
+    } else {
+        k_align_planes<<<dim3((unsigned) m_p, (unsigned) (k_p / kRun)), 256, smem_align, st>>>(c->dconsts, A, soA, slA, m, k, IA, (uint8_t *) pPA, SA, m_p, k_p);
+        k_align_planes<<<dim3((unsigned) n_p, (unsigned) (k_p / kRun)), 256, smem_align, st>>>(c->dconsts, B, soB, slB, n, k, IB, (uint8_t *) pPB, SB, n_p, k_p);
+    }
+    k_minplus<<<dim3((unsigned) (m_p / kMpTI), (unsigned) (n_p / kMpTJ)), 256, 0, st>>>(SA, SB, D, k_p, m_p, n_p);
     dim3 grid((unsigned) (n_p / kBN), (unsigned) (m_p / kBM), (unsigned) N);
     mark(1);
     int gemm_launches = 0;
@@ -586,18 +533,48 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
     }
     mark(2);
     const bool allow_fb = c->mode == MPRES_MODE_AUTO;
+    int stage3_launches = 0;
+    auto norm_fast = [&](auto tag) {
+        constexpr int NQ = decltype(tag)::value;
+        const unsigned g3 = (unsigned) ((long long) ((m + kNormFastThreads - 1) / kNormFastThreads) * n);
+        k_norm_fast<NQ><<<g3, kNormFastThreads, (size_t) kNormFastThreads * (NQ + 1) * sizeof(int), st>>>(c->dconsts, m, n, k, (const int *) pS, D, m_p, n_p, IA, IB, alpha, beta, Cm, ldc,
+                                                         todo, c->d_counter, slow, c->d_counter + 1, allow_fb);
+    };
+    bool have_fast = c->stage3 == 0;
+    if (have_fast) {
+        switch (N) {
+            case 8: norm_fast(std::integral_constant<int, 8>{}); break;
+            case 16: norm_fast(std::integral_constant<int, 16>{}); break;
+            case 24: norm_fast(std::integral_constant<int, 24>{}); break;
+            case 32: norm_fast(std::integral_constant<int, 32>{}); break;
+            case 40: norm_fast(std::integral_constant<int, 40>{}); break;
+            case 48: norm_fast(std::integral_constant<int, 48>{}); break;
+            case 56: norm_fast(std::integral_constant<int, 56>{}); break;
+            case 64: norm_fast(std::integral_constant<int, 64>{}); break;
+            default: have_fast = false;
+        }
+    }
     MPRES_DISPATCH(N, {
-        constexpr int kNormTile = 256 / G;
-        const unsigned g3 = (unsigned) ((long long) ((m + kNormTile - 1) / kNormTile) * n);
-        k_normalize_epilogue<G, R><<<g3, 256, (size_t) N * (kNormTile + 1) * 4, st>>>(
-            c->dconsts, m, n, k, (const int *) pS, D, m_p, n_p, IA, IB, alpha, beta, Cm, ldc, todo, c->d_counter, allow_fb);
-        if (allow_fb)
+        if (have_fast) {
+            k_norm_list<G, R><<<c->sm_count * 8, 256, 0, st>>>(c->dconsts, m, n, k, (const int *) pS, D, m_p, n_p, IA, IB, alpha, beta, Cm, ldc,
+                                                              slow, c->d_counter + 1);
+            stage3_launches = 2;
+        } else {
+            constexpr int kNormTile = 256 / G;
+            const unsigned g3 = (unsigned) ((long long) ((m + kNormTile - 1) / kNormTile) * n);
+            k_normalize_epilogue<G, R><<<g3, 256, (size_t) N * (kNormTile + 1) * 4, st>>>(
+                c->dconsts, m, n, k, (const int *) pS, D, m_p, n_p, IA, IB, alpha, beta, Cm, ldc, todo, c->d_counter, allow_fb);
+            stage3_launches = 1;
+        }
+        if (allow_fb) {
             k_gemm_todo<G, R><<<c->sm_count * 8, 128, 0, st>>>(c->dconsts, ta, tb, m, n, k, A, lda, B, ldb, alpha, beta, Cm, ldc, todo, c->d_counter);
+            ++stage3_launches;
+        }
     });
     mark(3);
     c->ev_valid = c->profiling;
     c->last_stage2_launches = gemm_launches;
-    for (int i = 0; i < (allow_fb ? 7 : 6) + gemm_launches; ++i) LAUNCHED(c);
+    for (int i = 0; i < 5 + stage3_launches + gemm_launches; ++i) LAUNCHED(c);
     CUDA_TRY(cudaGetLastError());
     *done = true;
     return 0;

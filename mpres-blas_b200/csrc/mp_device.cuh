@@ -524,12 +524,15 @@ __device__ __forceinline__ void mp_mul(const DevConsts &C, const Lane<R> &L, Num
     if (ROUND) round_if_needed<G, R>(C, L, r);
 }
 
-// STYLE 0: scalar cuda::mp_add (sign resolved by mixed-radix comparison when the interval straddles
-// zero, add.cuh:165-170).  ROUND adds the trailing rounding of add.cuh:197-199.
-template <int G, int R, bool ROUND>
-__device__ __forceinline__ void mp_add(const DevConsts &C, const Lane<R> &L, Num<R> &res, const Num<R> &xin, const Num<R> &yin) {
-    Er xl = xin.lo, xu = xin.up, yl = yin.lo, yu = yin.up;
-    int ex = xin.exp, ey = yin.exp, sx = xin.sign, sy = yin.sign;
+// Exponent/sign/interval part of cuda::mp_add (src/arith/add.cuh:126-170), shared by the residue-parallel
+// mp_add below and by the entry-per-thread normalisation kernel: alignment shifts, zeroing flags,
+// masked signs and the interval of the signed sum (before the result sign is applied).
+struct AddEsi {
+    int gamma, theta, nzx, nzy, sx, sy, ex, ey;
+    Er lo, up;
+};
+__device__ __forceinline__ AddEsi add_esi(const DevConsts &C, Er xl, Er xu, Er yl, Er yu, int ex, int ey, int sx, int sy) {
+    AddEsi p;
     const int dexp = ex - ey;
     int gamma = dexp > 0 ? dexp : 0;
     int theta = dexp < 0 ? -dexp : 0;
@@ -544,9 +547,21 @@ __device__ __forceinline__ void mp_add(const DevConsts &C, const Lane<R> &L, Num
     const int fx = (1 - 2 * sx) * nzx, fy = (1 - 2 * sy) * nzy;
     xl.exp += gamma; xu.exp += gamma; yl.exp += theta; yu.exp += theta;
     xl.frac *= fx; xu.frac *= fx; yl.frac *= fy; yu.frac *= fy;
+    p.lo = er_add_dir<false>(sx ? xu : xl, sy ? yu : yl);
+    p.up = er_add_dir<true>(sx ? xl : xu, sy ? yl : yu);
+    p.gamma = gamma; p.theta = theta; p.nzx = nzx; p.nzy = nzy; p.sx = sx; p.sy = sy; p.ex = ex; p.ey = ey;
+    return p;
+}
+
+// STYLE 0: scalar cuda::mp_add (sign resolved by mixed-radix comparison when the interval straddles
+// zero, add.cuh:165-170).  ROUND adds the trailing rounding of add.cuh:197-199.
+template <int G, int R, bool ROUND>
+__device__ __forceinline__ void mp_add(const DevConsts &C, const Lane<R> &L, Num<R> &res, const Num<R> &xin, const Num<R> &yin) {
+    const AddEsi p = add_esi(C, xin.lo, xin.up, yin.lo, yin.up, xin.exp, yin.exp, xin.sign, yin.sign);
+    const int gamma = p.gamma, theta = p.theta, nzx = p.nzx, nzy = p.nzy, sx = p.sx, sy = p.sy, ex = p.ex, ey = p.ey;
     Num<R> t;
-    t.lo = er_add_dir<false>(sx ? xu : xl, sy ? yu : yl);
-    t.up = er_add_dir<true>(sx ? xl : xu, sy ? yl : yu);
+    t.lo = p.lo;
+    t.up = p.up;
     // shifted operands (needed for the digits and, rarely, for the sign)
     int ax[R], ay[R];
 #pragma unroll

@@ -112,6 +112,8 @@ size_t mpres_sizeof_mp_float(const mpres_ctx *c) { return c ? 4 * (size_t) c->hc
 int mpres_set_mode(mpres_ctx *c, int mode) { if (!c || mode < 0 || mode > 2) return -1; c->mode = mode; return 0; }
 int mpres_get_mode(const mpres_ctx *c) { return c ? c->mode : -1; }
 int mpres_set_stage2_kernel(mpres_ctx *c, int kind) { if (!c || kind < 0 || kind > 2) return -1; c->stage2 = kind; return 0; }
+int mpres_set_stage3_kernel(mpres_ctx *c, int kind) { if (!c || kind < 0 || kind > 1) return -1; c->stage3 = kind; return 0; }
+int mpres_set_stage1_kernel(mpres_ctx *c, int kind) { if (!c || kind < 0 || kind > 1) return -1; c->stage1 = kind; return 0; }
 long mpres_launch_count(const mpres_ctx *c) { return c ? c->launches.load() : -1; }
 
 long mpres_last_fallback_count(mpres_ctx *c) {
@@ -120,6 +122,15 @@ long mpres_last_fallback_count(mpres_ctx *c) {
     int v = 0;
     if (cudaStreamSynchronize(c->last_stream) != cudaSuccess) return -2;
     if (cudaMemcpy(&v, c->d_counter, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+    return v;
+}
+
+long mpres_last_slow_count(mpres_ctx *c) {
+    if (!c || c->device < 0) return -1;
+    DeviceGuard g(c->device);
+    int v = 0;
+    if (cudaStreamSynchronize(c->last_stream) != cudaSuccess) return -2;
+    if (cudaMemcpy(&v, c->d_counter + 1, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
     return v;
 }
 

@@ -204,3 +204,91 @@ def test_gemm_stage2_kernels_agree(pkg, N, shape):
         bad = diff_fields(got, want, ("digits", "sign", "exp"))
         assert bad.size == 0, "stage2 kernel %d: %d/%d differ, first %d" % (kind, bad.size, m * n, bad[0])
     ctx.close()
+
+
+def _special_case_inputs(N, m, n, k, bits, seed):
+    """random matrices with the special cases of the normalisation stage mixed in: a zero row of A, a
+    zero column of B, zero entries of C, rows scaled by large powers of two (alignment shifts in the
+    alpha*S + beta*C addition), an exactly cancelling row."""
+    orc = get_oracle(N, oracle.DEVICE)
+    A = random_records(N, m * k, bits, seed)
+    B = random_records(N, k * n, bits, seed + 1)
+    C = random_records(N, m * n, bits, seed + 2)
+    zero = orc.set_ints([0], [0], [0])[0]
+    A2 = A.reshape(k, m).copy()      # column-major m x k: A2[l, i]
+    B2 = B.reshape(n, k).copy()      # B2[j, l]
+    C2 = C.reshape(n, m).copy()
+    A2[:, 1] = zero                  # zero row of A
+    B2[2, :] = zero                  # zero column of B
+    C2[0, :] = zero                  # zero column of C
+    C2[3, 5] = zero
+    A2[:, 4]["exp"] += 37            # row scaled up: alpha*S dominates beta*C
+    A2[:, 6]["exp"] -= 45            # row scaled down
+    C2[:, 7]["exp"] -= 300           # beta*C negligible: far alignment shift / zeroing
+    if k >= 2:                       # S(8, :) == 0 with non-zero terms
+        A2[1, 8] = A2[0, 8]
+        A2[1, 8]["sign"] ^= 1
+        A2[2:, 8] = zero
+        B2[:, 1] = B2[:, 0]
+    return A2.reshape(-1), B2.reshape(-1), C2.reshape(-1)
+
+
+@pytest.mark.parametrize("N,bits_div,shape", [(8, 4, (140, 20, 60)), (32, 4, (130, 9, 40)), (8, 2, (40, 12, 50)), (16, 3, (70, 10, 33)),
+                                              (24, 4, (33, 5, 20)), (64, 4, (20, 6, 24))])
+def test_gemm_stage3_kernels_identical(pkg, N, bits_div, shape):
+    """The entry-per-thread normalisation kernel (+ list kernel) and the residue-parallel tile kernel give
+    identical records -- digits, sign, exponent AND interval evaluations -- on inputs that exercise the
+    special cases (zeros, far exponents, exact cancellation, roundings)."""
+    ctx = pkg.Context(N, 0)
+    orc = get_oracle(N, oracle.DEVICE)
+    bits = orc.precision // bits_div - (8 if bits_div == 2 else 0)
+    m, n, k = shape
+    A, B, C = _special_case_inputs(N, m, n, k, bits, 71)
+    alpha = random_records(N, 1, bits, 74)
+    beta = random_records(N, 1, bits, 75)
+    out = []
+    for kind in (1, 0):
+        ctx.set_stage3_kernel(kind)
+        out.append(_gemm(pkg, ctx, m, n, k, alpha, A, B, beta, C, pkg.MODE_FAST))
+    bad = diff_fields(out[0], out[1])
+    assert bad.size == 0, "%d/%d entries differ, first %d\n%s\n%s" % (bad.size, m * n, bad[0], out[0][bad[0]], out[1][bad[0]])
+    if bits_div == 4:
+        want = _gemm(pkg, ctx, m, n, k, alpha, A, B, beta, C, pkg.MODE_REFERENCE_ORDER)
+        # Bit-identical except where an exact zero takes part (zero row / column / cancelling row): there the
+        # reference's exponent depends on the zero's own exponent (DESIGN.md section 7 "zeros") -- value-equal.
+        bad = diff_fields(out[1], want, ("digits", "sign", "exp"))
+        for e in bad:
+            row, col = e % m, e // m
+            assert row in (1, 8) or col == 2, "entry (%d, %d) differs from the reference order\n%s\n%s" % (row, col, out[1][e], want[e])
+            assert orc.to_fraction(out[1][e]) == orc.to_fraction(want[e]), (row, col)
+    # beta == 0 and alpha == 0
+    zero = orc.set_ints([0], [0], [0])
+    for al, be in ((alpha, zero), (zero, beta)):
+        res = []
+        for kind in (1, 0):
+            ctx.set_stage3_kernel(kind)
+            res.append(_gemm(pkg, ctx, m, n, k, al, A, B, be, C, pkg.MODE_FAST))
+        assert diff_fields(res[0], res[1]).size == 0
+    ctx.close()
+
+
+@pytest.mark.parametrize("N,shape,ta,tb", [(8, (150, 70, 200), 111, 111), (24, (40, 33, 140), 112, 111), (32, (129, 65, 130), 111, 112), (64, (20, 10, 130), 112, 112)])
+def test_gemm_stage1_kernels_identical(pkg, N, shape, ta, tb):
+    """vectorised alignment kernel == one-residue-per-thread alignment kernel (whole-result comparison)"""
+    ctx = pkg.Context(N, 0)
+    orc = get_oracle(N, oracle.DEVICE)
+    bits = orc.precision // 4
+    m, n, k = shape
+    A, B, C = _special_case_inputs(N, m, n, k, bits, 81)
+    if ta != 111:
+        A = _transpose_recs(A, m, k)
+    if tb != 111:
+        B = _transpose_recs(B, k, n)
+    alpha = random_records(N, 1, bits, 84)
+    beta = random_records(N, 1, bits, 85)
+    out = []
+    for kind in (1, 0):
+        ctx.set_stage1_kernel(kind)
+        out.append(_gemm(pkg, ctx, m, n, k, alpha, A, B, beta, C, pkg.MODE_AUTO, ta, tb))
+    assert diff_fields(out[0], out[1]).size == 0
+    ctx.close()
