@@ -103,6 +103,12 @@ int mpres_set_stage2_kernel(mpres_ctx *ctx, int kind);
  * kernel for the entries that need refinement / rounding / sign resolution (default), 1 = the
  * residue-parallel tile kernel for every entry.  Identical results (including interval evaluations). */
 int mpres_set_stage3_kernel(mpres_ctx *ctx, int kind);
+/* Reduced-base fast path (default on): stages 1 and 2 run on the first n' moduli only, n' the smallest
+ * multiple of four whose product exceeds four times the largest exact sum (from the per-row / per-column
+ * magnitude windows); the remaining residues follow by mixed-radix base extension.  Results are identical
+ * to the full-base path.  mpres_last_base_size returns n' of the last call (synchronises). */
+int mpres_set_reduced_base(mpres_ctx *ctx, int on);
+long mpres_last_base_size(mpres_ctx *ctx);
 /* Stage-1 alignment kernel: 0 = vectorised (four residues per work item, default), 1 = one residue per thread. */
 int mpres_set_stage1_kernel(mpres_ctx *ctx, int kind);
 /* number of result elements of the last fast-path call that the entry-per-thread normalisation kernel

@@ -19,11 +19,12 @@ struct mpres_ctx {
     int device = 0;
     int mode = MPRES_MODE_AUTO;
     int stage2 = MPRES_STAGE2_UMMA;   // which stage-2 kernel the fast path launches
+    int reduced_base = 1;             // 1: run stages 1-2 on as many moduli as the exact sums need, then extend the base
     int stage1 = 0;                   // 0: vectorised alignment kernel, 1: round-1 kernel
     int stage3 = 0;                   // 0: entry-per-thread kernel + list, 1: residue-parallel tile kernel
     HostConsts hc;
     DevConsts *dconsts = nullptr;
-    int *d_pow2 = nullptr, *d_inv_pow2 = nullptr, *d_mrc = nullptr;
+    int *d_pow2 = nullptr, *d_inv_pow2 = nullptr, *d_mrc = nullptr, *d_prefix = nullptr;
     std::atomic<long> launches{0};
     // workspace pool (grown on demand, never freed per call)
     void *ws[8] = {nullptr};

@@ -78,6 +78,9 @@ struct HostConsts {
     double accuracy = 0;
     ErHost unit_low{}, unit_upp{}, inv_low{}, inv_upp{};
     std::vector<int> moduli, part_inverse, pow2, m_pow2, mi_pow2, pow2_inv, mrc_inv, inv_pow2_ext;
+    // reduced-base fast path (not in the reference): floor(log2(m_0 * ... * m_{n-1})) for n = 0..N and
+    // prefix_mod[i * N + q] = (m_0 * ... * m_{i-1}) mod m_q for i = 0..N
+    std::vector<int> prefix_log2, prefix_mod;
     std::vector<double> recip_rd, recip_ru;
     std::vector<uint64_t> barrett;  // floor((2^64 - 1) / m_i)
 };
@@ -186,6 +189,22 @@ inline int compute_constants(const int *mods, int N, HostConsts &c) {
         c.mp_h = -h;
     }
     c.mp_j = -1;
+    // prefix products of the moduli: sizes (for choosing how many moduli an exact sum needs) and residues
+    // (mixed-radix weights for the base extension)
+    c.prefix_log2.assign(N + 1, 0);
+    c.prefix_mod.assign((size_t) (N + 1) * N, 0);
+    {
+        BigUInt P(1);
+        std::vector<int64_t> r(N, 1);
+        for (int i = 0; i <= N; ++i) {
+            c.prefix_log2[i] = P.bit_length() - 1;
+            for (int q = 0; q < N; ++q) c.prefix_mod[(size_t) i * N + q] = (int) (r[q] % mods[q]);
+            if (i < N) {
+                P.mul_small((uint32_t) mods[i]);
+                for (int q = 0; q < N; ++q) r[q] = r[q] % mods[q] * (mods[i] % mods[q]) % mods[q];
+            }
+        }
+    }
     return 0;
 }
 

@@ -88,6 +88,38 @@ __global__ void k_outer_info(const DevConsts *Cp, SoA X, long long so, long long
     }
 }
 
+// ---- stage 1a': how many moduli the exact sums need ---------------------------------------------------
+// Every exact sum satisfies |S| < 2^(win_a + win_b + ceil(log2 k)); the first n' moduli determine it when
+// their product M' obeys |S| < M'/4.  n' = smallest such count, rounded up to a multiple of four (the
+// alignment kernel works on groups of four moduli), or N.  Stages 1b and 2 then skip the moduli q >= n' and
+// k_base_extend reconstructs their residues.  One block.
+__global__ void __launch_bounds__(256) k_choose_base(const DevConsts *Cp, const OuterInfo *ia, int m, const OuterInfo *ib, int n, int k,
+                                                     int enabled, int *nprime) {
+    __shared__ int sa[256], sb[256];
+    int wa = -1, wb = -1;
+    for (int i = threadIdx.x; i < m; i += 256) wa = max(wa, ia[i].win);
+    for (int j = threadIdx.x; j < n; j += 256) wb = max(wb, ib[j].win);
+    sa[threadIdx.x] = wa; sb[threadIdx.x] = wb;
+    __syncthreads();
+    for (int o = 128; o >= 1; o >>= 1) {
+        if (threadIdx.x < o) { sa[threadIdx.x] = max(sa[threadIdx.x], sa[threadIdx.x + o]); sb[threadIdx.x] = max(sb[threadIdx.x], sb[threadIdx.x + o]); }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const int N = Cp->N;
+        int np = N;
+        if (enabled && (N & 3) == 0) {
+            int lgk = 0;
+            while ((1 << lgk) < k) ++lgk;
+            const long long need = (sa[0] < 0 || sb[0] < 0) ? 0 : (long long) sa[0] + sb[0] + lgk + 2;
+            for (int c = 1; c <= N; ++c)
+                if ((long long) Cp->prefix_log2[c] >= need) { np = c; break; }
+            np = min(N, (np + 3) & ~3);
+        }
+        *nprime = np;
+    }
+}
+
 // ---- stage 1b: pre-shifted signed residues as u8 limb planes + shift plane -------------------------
 // planes: [q][limb][outer_p][inner_p] bytes (inner contiguous); shifts: [outer_p][inner_p] int16.
 // One block handles one line `o` and a run of kRun inner positions.
@@ -154,7 +186,7 @@ __global__ void __launch_bounds__(256) k_align_planes(const DevConsts *Cp, SoA X
 // and leave as full 128-byte rows.
 __global__ void __launch_bounds__(256) k_align_planes4(const DevConsts *Cp, SoA X, long long so, long long sl, int outer, int inner,
                                                        const OuterInfo *info, uint8_t *planes, int16_t *shifts,
-                                                       long long outer_p, long long inner_p) {
+                                                       long long outer_p, long long inner_p, const int *nprime) {
     extern __shared__ uint8_t sm_stage[];   // [4][N][kRun + 4]
     const DevConsts &C = *Cp;
     const int N = C.N;
@@ -167,7 +199,8 @@ __global__ void __launch_bounds__(256) k_align_planes4(const DevConsts *Cp, SoA 
     const bool line_ok = o < outer;
     const OuterInfo oi = line_ok ? info[o] : OuterInfo{0, -1};
     const int q4 = threadIdx.x % Q4, slot = threadIdx.x / Q4;
-    if (slot < EP) {
+    const int np = *nprime;                 // moduli q >= np are not needed (reduced base): multiple of 4
+    if (slot < EP && 4 * q4 < np) {
         const int4 mq = *(const int4 *) (C.moduli + 4 * q4);
         const int mv[4] = {mq.x, mq.y, mq.z, mq.w};
         unsigned long long mu[4];
@@ -210,6 +243,7 @@ __global__ void __launch_bounds__(256) k_align_planes4(const DevConsts *Cp, SoA 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int row = warp; row < 4 * N; row += 8) {
         const int b = row / N, q = row - b * N;
+        if (q >= np) continue;
         const uint32_t v = *(const uint32_t *) (sm_stage + row * pitch + lane * 4);
         *(uint32_t *) (planes + ((long long) (q * 4 + b) * outer_p + o) * inner_p + l0 + lane * 4) = v;
     }
@@ -302,8 +336,10 @@ __device__ __forceinline__ int swz(int row, int c) { return row * kBK + ((c ^ ((
 
 template <int PASS>
 __global__ void __launch_bounds__(256, 1) k_limb_gemm(const DevConsts *Cp, const uint8_t *PA, const uint8_t *PB, int *S,
-                                                      long long m_p, long long n_p, long long k_p, long long k_begin, int k_len, bool add_to_S) {
+                                                      long long m_p, long long n_p, long long k_p, long long k_begin, int k_len, bool add_to_S,
+                                                      const int *nprime) {
     extern __shared__ __align__(128) uint8_t smem[];
+    if ((int) blockIdx.z >= *nprime) return;   // modulus outside the reduced base
     constexpr int NACC = PASS == 0 ? 4 : 3;
     constexpr int UBASE = PASS == 0 ? 0 : 4;
     constexpr int LIMB0 = PASS == 0 ? 0 : 1;     // PASS 1 never touches limb 0
@@ -499,18 +535,20 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
     mark(0);
     k_outer_info<<<(unsigned) ((m * 32ll + 255) / 256), 256, 0, st>>>(c->dconsts, A, soA, slA, m, k, IA);
     k_outer_info<<<(unsigned) ((n * 32ll + 255) / 256), 256, 0, st>>>(c->dconsts, B, soB, slB, n, k, IB);
+    k_choose_base<<<1, 256, 0, st>>>(c->dconsts, IA, m, IB, n, k, c->reduced_base, c->d_counter + 2);
     const size_t smem_align = (size_t) N * 4 * (kRun + 4);
     static bool attr_done = false;
     if (!attr_done) {
         cudaFuncSetAttribute(k_align_planes, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 4 * (kRun + 4));
         cudaFuncSetAttribute(k_align_planes4, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 4 * (kRun + 4));
+        cudaFuncSetAttribute(k_base_extend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) base_extend_smem(128));
         cudaFuncSetAttribute(k_limb_gemm<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
         cudaFuncSetAttribute(k_limb_gemm<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
         attr_done = true;
     }
     if (N % 4 == 0 && N <= 128 && c->stage1 == 0) {
-        k_align_planes4<<<dim3((unsigned) m_p, (unsigned) (k_p / kRun)), 256, smem_align, st>>>(c->dconsts, A, soA, slA, m, k, IA, (uint8_t *) pPA, SA, m_p, k_p);
-        k_align_planes4<<<dim3((unsigned) n_p, (unsigned) (k_p / kRun)), 256, smem_align, st>>>(c->dconsts, B, soB, slB, n, k, IB, (uint8_t *) pPB, SB, n_p, k_p);
+        k_align_planes4<<<dim3((unsigned) m_p, (unsigned) (k_p / kRun)), 256, smem_align, st>>>(c->dconsts, A, soA, slA, m, k, IA, (uint8_t *) pPA, SA, m_p, k_p, c->d_counter + 2);
+        k_align_planes4<<<dim3((unsigned) n_p, (unsigned) (k_p / kRun)), 256, smem_align, st>>>(c->dconsts, B, soB, slB, n, k, IB, (uint8_t *) pPB, SB, n_p, k_p, c->d_counter + 2);
     } else {
         k_align_planes<<<dim3((unsigned) m_p, (unsigned) (k_p / kRun)), 256, smem_align, st>>>(c->dconsts, A, soA, slA, m, k, IA, (uint8_t *) pPA, SA, m_p, k_p);
         k_align_planes<<<dim3((unsigned) n_p, (unsigned) (k_p / kRun)), 256, smem_align, st>>>(c->dconsts, B, soB, slB, n, k, IB, (uint8_t *) pPB, SB, n_p, k_p);
@@ -522,8 +560,8 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
     for (long long kb = 0; kb < k_p; kb += 8064) {
         const int kl = (int) std::min<long long>(8064, k_p - kb);
         if (c->stage2 == MPRES_STAGE2_MMA_SYNC) {
-            k_limb_gemm<0><<<grid, 256, kGemmSmem, st>>>(c->dconsts, (const uint8_t *) pPA, (const uint8_t *) pPB, (int *) pS, m_p, n_p, k_p, kb, kl, kb > 0);
-            k_limb_gemm<1><<<grid, 256, kGemmSmem, st>>>(c->dconsts, (const uint8_t *) pPA, (const uint8_t *) pPB, (int *) pS, m_p, n_p, k_p, kb, kl, true);
+            k_limb_gemm<0><<<grid, 256, kGemmSmem, st>>>(c->dconsts, (const uint8_t *) pPA, (const uint8_t *) pPB, (int *) pS, m_p, n_p, k_p, kb, kl, kb > 0, c->d_counter + 2);
+            k_limb_gemm<1><<<grid, 256, kGemmSmem, st>>>(c->dconsts, (const uint8_t *) pPA, (const uint8_t *) pPB, (int *) pS, m_p, n_p, k_p, kb, kl, true, c->d_counter + 2);
             gemm_launches += 2;
         } else {
             if ((rc = launch_limb_umma(c, c->stage2 == MPRES_STAGE2_UMMA, (const uint8_t *) pPA, (const uint8_t *) pPB, (int *) pS, m_p, n_p, k_p, kb, kl,
@@ -534,6 +572,11 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
     mark(2);
     const bool allow_fb = c->mode == MPRES_MODE_AUTO;
     int stage3_launches = 0;
+    if (c->reduced_base && N % 4 == 0) {
+        const unsigned gx = (unsigned) ((long long) ((m + kExtThreads - 1) / kExtThreads) * n);
+        k_base_extend<<<gx, kExtThreads, base_extend_smem(N), st>>>(c->dconsts, m, n, (int *) pS, m_p, n_p, c->d_counter + 2);
+        ++stage3_launches;
+    }
     auto norm_fast = [&](auto tag) {
         constexpr int NQ = decltype(tag)::value;
         const unsigned g3 = (unsigned) ((long long) ((m + kNormFastThreads - 1) / kNormFastThreads) * n);
@@ -574,7 +617,7 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
     mark(3);
     c->ev_valid = c->profiling;
     c->last_stage2_launches = gemm_launches;
-    for (int i = 0; i < 5 + stage3_launches + gemm_launches; ++i) LAUNCHED(c);
+    for (int i = 0; i < 6 + stage3_launches + gemm_launches; ++i) LAUNCHED(c);
     CUDA_TRY(cudaGetLastError());
     *done = true;
     return 0;

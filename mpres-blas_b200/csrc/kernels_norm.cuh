@@ -135,6 +135,67 @@ __device__ __forceinline__ int ceil_log2(int k) {
     return lgk;
 }
 
+// ---- base extension (reduced-base fast path) -----------------------------------------------------------
+// Stage 2 produced S mod m_q for the first np moduli only.  |S| < M'/4 with M' = m_0 ... m_{np-1}, so the
+// mixed-radix digits a_i of X = S mod M' (X = sum a_i m_0...m_{i-1}, src/rns.cuh:570-582 is the reference's
+// mixed-radix conversion) determine S: the top digit tells the sign (X/M' lies in [0,1/4) or (3/4,1)) and
+//      S mod m_q = sum_i a_i (m_0...m_{i-1} mod m_q) - [S < 0] (M' mod m_q)          for q >= np.
+// One thread per entry; digits live in shared memory ([i][thread], conflict-free), the triangular inverse
+// table and the weight table are staged per block.  Writes the planes q >= np of S.
+constexpr int kExtThreads = 128;
+inline size_t base_extend_smem(int N) { return (size_t) N * kExtThreads * sizeof(int) + (size_t) 2 * N * N * sizeof(int) + (size_t) N * 16; }
+
+__global__ void __launch_bounds__(kExtThreads) k_base_extend(const DevConsts *Cp, int m, int n, int *S, long long m_p, long long n_p, const int *nprime) {
+    extern __shared__ __align__(16) unsigned char ext_smem[];
+    const DevConsts &C = *Cp;
+    const int N = C.N;
+    const int np = *nprime;
+    if (np >= N) return;
+    unsigned long long *s_mu = (unsigned long long *) ext_smem;      // [N]
+    int *s_m = (int *) (s_mu + N);                                     // [N]
+    int *s_inv = s_m + N;                                              // [np][np]   m_i^-1 mod m_j
+    int *s_w = s_inv + np * np;                                        // [np + 1][N - np]  prefix weights
+    int *xs = s_w + (np + 1) * (N - np);                               // [np][kExtThreads]
+    for (int t = threadIdx.x; t < N; t += kExtThreads) { s_mu[t] = C.barrett[t]; s_m[t] = C.moduli[t]; }
+    for (int t = threadIdx.x; t < np * np; t += kExtThreads) s_inv[t] = C.mrc_inv[(t / np) * N + t % np];
+    for (int t = threadIdx.x; t < (np + 1) * (N - np); t += kExtThreads) s_w[t] = C.prefix_mod[(t / (N - np)) * N + np + t % (N - np)];
+    __syncthreads();
+    const int tiles = (m + kExtThreads - 1) / kExtThreads;
+    const int col = blockIdx.x / tiles;
+    const int row = (blockIdx.x - col * tiles) * kExtThreads + threadIdx.x;
+    if (row >= m) return;
+    int *Sp = S + (long long) col * m_p + row;
+    const long long plane = n_p * m_p;
+    int *xt = xs + threadIdx.x;
+    for (int i = 0; i < np; ++i) xt[i * kExtThreads] = Sp[i * plane];
+    // mixed-radix conversion: after step i every element j > i holds (x_j - a_i) / m_i mod m_j
+    for (int i = 0; i < np - 1; ++i) {
+        const int ai = xt[i * kExtThreads];
+        for (int j = i + 1; j < np; ++j) {
+            const int mj = s_m[j];
+            int a = ai >= mj ? ai - mj : ai;       // moduli of one set differ by less than a factor two ...
+            if (a >= mj) a %= mj;                  // ... but stay correct for any set
+            int t = xt[j * kExtThreads] - a;
+            t = t < 0 ? t + mj : t;
+            xt[j * kExtThreads] = mulmod(t, s_inv[i * np + j], mj, s_mu[j]);
+        }
+    }
+    const int top = xt[(np - 1) * kExtThreads];
+    const bool neg = 2ll * top >= (long long) s_m[np - 1];
+    for (int q = np; q < N; ++q) {
+        const int mq = s_m[q];
+        const unsigned long long muq = s_mu[q];
+        unsigned long long acc = 0;
+        for (int i = 0; i < np; ++i) {
+            acc += (unsigned long long) (unsigned) xt[i * kExtThreads] * (unsigned) s_w[i * (N - np) + q - np];
+            if ((i & 3) == 3) acc = (unsigned long long) (unsigned) reduce64(acc, mq, muq);   // any moduli < 2^31: 4 terms < 2^64
+        }
+        int r = reduce64(acc, mq, muq);
+        if (neg) { r -= s_w[np * (N - np) + q - np]; r = r < 0 ? r + mq : r; }
+        Sp[q * plane] = r;
+    }
+}
+
 // ---- round-1 tile kernel: every entry residue-parallel ---------------------------------------------
 // One lane group per C entry; a block covers kNormTile consecutive rows of one column so the
 // per-modulus planes are read as contiguous runs and transposed through shared memory (256 / G rows).

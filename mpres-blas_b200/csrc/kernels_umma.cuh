@@ -131,8 +131,9 @@ __host__ __device__ constexpr uint32_t idesc_u8(int M, int N) {
 template <bool STACKED>
 __global__ void __launch_bounds__(kUThreads, 1)
 k_limb_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const DevConsts *Cp, int *S,
-            long long m_p, long long n_p, int k_byte0, int nk, int add_to_S) {
+            long long m_p, long long n_p, int k_byte0, int nk, int add_to_S, const int *nprime) {
     extern __shared__ uint8_t smem_raw[];
+    if ((int) blockIdx.z >= *nprime) return;   // modulus outside the reduced base (whole CTA leaves before any setup)
     uint8_t *smem = (uint8_t *) (((uintptr_t) smem_raw + 1023) & ~(uintptr_t) 1023);
     uint64_t *full = (uint64_t *) (smem + kUStages * kUStageBytes);
     uint64_t *empty = full + kUStages;
@@ -296,8 +297,8 @@ inline int launch_limb_umma(mpres_ctx *c, bool stacked, const uint8_t *PA, const
     }
     dim3 grid((unsigned) (n_p / mpres::kUN), (unsigned) (m_p / mpres::kUM), (unsigned) N);
     if (stacked)
-        mpres::k_limb_umma<true><<<grid, mpres::kUThreads, mpres::kUSmem, st>>>(tmA, tmB, c->dconsts, S, m_p, n_p, (int) k_begin, k_len / mpres::kUK, add_to_S ? 1 : 0);
+        mpres::k_limb_umma<true><<<grid, mpres::kUThreads, mpres::kUSmem, st>>>(tmA, tmB, c->dconsts, S, m_p, n_p, (int) k_begin, k_len / mpres::kUK, add_to_S ? 1 : 0, c->d_counter + 2);
     else
-        mpres::k_limb_umma<false><<<grid, mpres::kUThreads, mpres::kUSmem, st>>>(tmA, tmB, c->dconsts, S, m_p, n_p, (int) k_begin, k_len / mpres::kUK, add_to_S ? 1 : 0);
+        mpres::k_limb_umma<false><<<grid, mpres::kUThreads, mpres::kUSmem, st>>>(tmA, tmB, c->dconsts, S, m_p, n_p, (int) k_begin, k_len / mpres::kUK, add_to_S ? 1 : 0, c->d_counter + 2);
     return 0;
 }

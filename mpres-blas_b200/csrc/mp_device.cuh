@@ -47,6 +47,8 @@ struct DevConsts {
     const int *pow2;      // [log2M+1][N]   2^j mod m_i
     const int *inv_pow2;  // [log2M+1][N]   2^-j mod m_i
     const int *mrc_inv;   // [N][N]         m_i^-1 mod m_j (j > i)
+    const int *prefix_mod;  // [N+1][N]     (m_0 ... m_{i-1}) mod m_q
+    int prefix_log2[kMaxN + 1];   // floor(log2(m_0 ... m_{n-1}))
 };
 
 // SoA view of mp_array_t / mp_collection_t (src/types.cuh:85-104).  `len` is the ALLOCATED length:

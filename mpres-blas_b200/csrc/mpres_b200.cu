@@ -72,8 +72,9 @@ int mpres_init_moduli(mpres_ctx **out, const int *moduli, int n, int device) {
         return e;
     };
     if (up(&c->d_pow2, h.pow2) != cudaSuccess || up(&c->d_inv_pow2, h.inv_pow2_ext) != cudaSuccess ||
-        up(&c->d_mrc, h.mrc_inv) != cudaSuccess) { delete d; delete c; return (int) e; }
-    d->pow2 = c->d_pow2; d->inv_pow2 = c->d_inv_pow2; d->mrc_inv = c->d_mrc;
+        up(&c->d_mrc, h.mrc_inv) != cudaSuccess || up(&c->d_prefix, h.prefix_mod) != cudaSuccess) { delete d; delete c; return (int) e; }
+    d->pow2 = c->d_pow2; d->inv_pow2 = c->d_inv_pow2; d->mrc_inv = c->d_mrc; d->prefix_mod = c->d_prefix;
+    for (int i = 0; i <= h.N; ++i) d->prefix_log2[i] = h.prefix_log2[i];
     e = cudaMalloc(&c->dconsts, sizeof(DevConsts));
     if (e == cudaSuccess) e = cudaMemcpy(c->dconsts, d, sizeof(DevConsts), cudaMemcpyHostToDevice);
     delete d;
@@ -97,7 +98,7 @@ int mpres_finalize(mpres_ctx *c) {
     DeviceGuard g(c->device);
     cudaDeviceSynchronize();
     for (int i = 0; i < 8; ++i) if (c->ws[i]) cudaFree(c->ws[i]);
-    cudaFree(c->d_pow2); cudaFree(c->d_inv_pow2); cudaFree(c->d_mrc); cudaFree(c->dconsts); cudaFree(c->d_counter);
+    cudaFree(c->d_pow2); cudaFree(c->d_inv_pow2); cudaFree(c->d_mrc); cudaFree(c->d_prefix); cudaFree(c->dconsts); cudaFree(c->d_counter);
     delete c;
     return 0;
 }
@@ -113,6 +114,15 @@ int mpres_set_mode(mpres_ctx *c, int mode) { if (!c || mode < 0 || mode > 2) ret
 int mpres_get_mode(const mpres_ctx *c) { return c ? c->mode : -1; }
 int mpres_set_stage2_kernel(mpres_ctx *c, int kind) { if (!c || kind < 0 || kind > 2) return -1; c->stage2 = kind; return 0; }
 int mpres_set_stage3_kernel(mpres_ctx *c, int kind) { if (!c || kind < 0 || kind > 1) return -1; c->stage3 = kind; return 0; }
+int mpres_set_reduced_base(mpres_ctx *c, int on) { if (!c) return -1; c->reduced_base = on != 0; return 0; }
+long mpres_last_base_size(mpres_ctx *c) {
+    if (!c || c->device < 0) return -1;
+    DeviceGuard g(c->device);
+    int v = 0;
+    if (cudaStreamSynchronize(c->last_stream) != cudaSuccess) return -2;
+    if (cudaMemcpy(&v, c->d_counter + 2, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+    return v;
+}
 int mpres_set_stage1_kernel(mpres_ctx *c, int kind) { if (!c || kind < 0 || kind > 1) return -1; c->stage1 = kind; return 0; }
 long mpres_launch_count(const mpres_ctx *c) { return c ? c->launches.load() : -1; }
 

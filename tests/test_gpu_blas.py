@@ -292,3 +292,28 @@ def test_gemm_stage1_kernels_identical(pkg, N, shape, ta, tb):
         out.append(_gemm(pkg, ctx, m, n, k, alpha, A, B, beta, C, pkg.MODE_AUTO, ta, tb))
     assert diff_fields(out[0], out[1]).size == 0
     ctx.close()
+
+
+@pytest.mark.parametrize("N,bits_div,shape", [(8, 4, (140, 20, 60)), (32, 4, (130, 70, 129)), (32, 8, (64, 64, 300)), (16, 2, (40, 12, 50)),
+                                              (24, 4, (33, 5, 20)), (64, 4, (20, 6, 24)), (64, 16, (130, 20, 64))])
+def test_gemm_reduced_base_identical(pkg, N, bits_div, shape):
+    """Stages 1-2 on the first n' moduli + mixed-radix base extension == stages 1-2 on all N moduli,
+    record for record (digits, sign, exp, eval), including zero lines, far exponents and cancellation."""
+    ctx = pkg.Context(N, 0)
+    orc = get_oracle(N, oracle.DEVICE)
+    bits = orc.precision // bits_div - (8 if bits_div == 2 else 0)
+    m, n, k = shape
+    A, B, C = _special_case_inputs(N, m, n, k, bits, 91)
+    alpha = random_records(N, 1, bits, 94)
+    beta = random_records(N, 1, bits, 95)
+    out, base = [], []
+    for on in (False, True):
+        ctx.set_reduced_base(on)
+        out.append(_gemm(pkg, ctx, m, n, k, alpha, A, B, beta, C, pkg.MODE_AUTO))
+        base.append(ctx.last_base_size())
+    bad = diff_fields(out[0], out[1])
+    assert bad.size == 0, "%d/%d entries differ, first %d\n%s\n%s" % (bad.size, m * n, bad[0], out[0][bad[0]], out[1][bad[0]])
+    assert base[0] == N and 4 <= base[1] <= N and base[1] % 4 == 0
+    if bits_div >= 4 and N >= 16:
+        assert base[1] < N, "p/%d-bit inputs must not need all %d moduli (got %d)" % (bits_div, N, base[1])
+    ctx.close()
