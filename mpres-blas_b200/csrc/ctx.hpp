@@ -24,7 +24,7 @@ struct mpres_ctx {
     int stage3 = 0;                   // 0: entry-per-thread kernel + list, 1: residue-parallel tile kernel
     HostConsts hc;
     DevConsts *dconsts = nullptr;
-    int *d_pow2 = nullptr, *d_inv_pow2 = nullptr, *d_mrc = nullptr, *d_prefix = nullptr;
+    int *d_pow2 = nullptr, *d_inv_pow2 = nullptr, *d_mrc = nullptr, *d_prefix = nullptr, *d_ext_w = nullptr, *d_ext_t = nullptr, *d_wpow2 = nullptr;
     std::atomic<long> launches{0};
     // workspace pool (grown on demand, never freed per call)
     void *ws[8] = {nullptr};

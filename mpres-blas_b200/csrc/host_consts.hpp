@@ -81,6 +81,11 @@ struct HostConsts {
     // reduced-base fast path (not in the reference): floor(log2(m_0 * ... * m_{n-1})) for n = 0..N and
     // prefix_mod[i * N + q] = (m_0 * ... * m_{i-1}) mod m_q for i = 0..N
     std::vector<int> prefix_log2, prefix_mod;
+    // CRT base extension from the first c moduli (c = 1..N-1), M' = m_0 ... m_{c-1}, M'_i = M' / m_i:
+    //   ext_w[c * N + i] = (M'_i)^-1 mod m_i  (i < c),   ext_t[(c * N + q) * N + i] = M'_i mod m_q  (i < c)
+    std::vector<int> ext_w, ext_t;
+    std::vector<int> wpow2;   // [log2M+1][N]  w_i * 2^j mod m_i (interval evaluation of a magnified number in one multiplication)
+    int ext_lazy = 0;   // 1 if N * max(m)^2 < 2^63: the extension sums need no intermediate reduction
     std::vector<double> recip_rd, recip_ru;
     std::vector<uint64_t> barrett;  // floor((2^64 - 1) / m_i)
 };
@@ -204,6 +209,28 @@ inline int compute_constants(const int *mods, int N, HostConsts &c) {
                 for (int q = 0; q < N; ++q) r[q] = r[q] % mods[q] * (mods[i] % mods[q]) % mods[q];
             }
         }
+    }
+    c.wpow2.resize((size_t) (c.log2M + 1) * N);
+    for (int j = 0; j <= c.log2M; ++j)
+        for (int i = 0; i < N; ++i) c.wpow2[(size_t) j * N + i] = (int) ((int64_t) c.pow2[(size_t) j * N + i] * c.part_inverse[i] % mods[i]);
+    c.ext_w.assign((size_t) N * N, 0);
+    c.ext_t.assign((size_t) N * N * N, 0);
+    {
+        std::vector<int64_t> suf(N + 1);
+        for (int cc = 1; cc < N; ++cc)
+            for (int q = 0; q < N; ++q) {
+                const int64_t mq = mods[q];
+                suf[cc] = 1;
+                for (int i = cc - 1; i >= 0; --i) suf[i] = suf[i + 1] * (mods[i] % mq) % mq;   // m_i ... m_{cc-1}
+                for (int i = 0; i < cc; ++i) {
+                    const int64_t t = (int64_t) c.prefix_mod[(size_t) i * N + q] * suf[i + 1] % mq;
+                    c.ext_t[((size_t) cc * N + q) * N + i] = (int) t;
+                    if (q == i) c.ext_w[(size_t) cc * N + i] = (int) inverse_mod(t, mq);
+                }
+            }
+        int64_t mx = 0;
+        for (int i = 0; i < N; ++i) mx = mods[i] > mx ? mods[i] : mx;
+        c.ext_lazy = ((long double) N * (long double) mx * (long double) mx < 9.0e18L) ? 1 : 0;
     }
     return 0;
 }

@@ -90,9 +90,10 @@ __global__ void k_outer_info(const DevConsts *Cp, SoA X, long long so, long long
 
 // ---- stage 1a': how many moduli the exact sums need ---------------------------------------------------
 // Every exact sum satisfies |S| < 2^(win_a + win_b + ceil(log2 k)); the first n' moduli determine it when
-// their product M' obeys |S| < M'/4.  n' = smallest such count, rounded up to a multiple of four (the
-// alignment kernel works on groups of four moduli), or N.  Stages 1b and 2 then skip the moduli q >= n' and
-// k_base_extend reconstructs their residues.  One block.
+// their product M' obeys |S| < M'/4.  n' = smallest such count (or N when more than kMaxReducedBase would be
+// needed).  Stage 1b then aligns the first ceil4(n') moduli (it works on groups of four), stage 2 multiplies
+// n' of them and k_base_extend reconstructs the residues q >= n'.  One block.
+constexpr int kMaxReducedBase = 48;
 __global__ void __launch_bounds__(256) k_choose_base(const DevConsts *Cp, const OuterInfo *ia, int m, const OuterInfo *ib, int n, int k,
                                                      int enabled, int *nprime) {
     __shared__ int sa[256], sb[256];
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(256) k_choose_base(const DevConsts *Cp, const 
             const long long need = (sa[0] < 0 || sb[0] < 0) ? 0 : (long long) sa[0] + sb[0] + lgk + 2;
             for (int c = 1; c <= N; ++c)
                 if ((long long) Cp->prefix_log2[c] >= need) { np = c; break; }
-            np = min(N, (np + 3) & ~3);
+            if (np > kMaxReducedBase) np = N;
         }
         *nprime = np;
     }
@@ -190,7 +191,8 @@ __global__ void __launch_bounds__(256) k_align_planes4(const DevConsts *Cp, SoA 
     extern __shared__ uint8_t sm_stage[];   // [4][N][kRun + 4]
     const DevConsts &C = *Cp;
     const int N = C.N;
-    const int Q4 = N >> 2;                  // modulus groups
+    const int np = min(N, (*nprime + 3) & ~3);   // moduli q >= np are not needed (reduced base)
+    const int Q4 = np >> 2;                 // active modulus groups
     const int EP = 256 / Q4;                // entries per pass
     const int o = blockIdx.x;
     const int l0 = blockIdx.y * kRun;
@@ -199,8 +201,7 @@ __global__ void __launch_bounds__(256) k_align_planes4(const DevConsts *Cp, SoA 
     const bool line_ok = o < outer;
     const OuterInfo oi = line_ok ? info[o] : OuterInfo{0, -1};
     const int q4 = threadIdx.x % Q4, slot = threadIdx.x / Q4;
-    const int np = *nprime;                 // moduli q >= np are not needed (reduced base): multiple of 4
-    if (slot < EP && 4 * q4 < np) {
+    if (slot < EP) {
         const int4 mq = *(const int4 *) (C.moduli + 4 * q4);
         const int mv[4] = {mq.x, mq.y, mq.z, mq.w};
         unsigned long long mu[4];
@@ -241,9 +242,9 @@ __global__ void __launch_bounds__(256) k_align_planes4(const DevConsts *Cp, SoA 
     __syncthreads();
     // write out: shared row (b, q) -> plane row (q, b), kRun contiguous bytes, one warp per row
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int row = warp; row < 4 * N; row += 8) {
-        const int b = row / N, q = row - b * N;
-        if (q >= np) continue;
+    for (int r = warp; r < 4 * np; r += 8) {
+        const int b = r / np, q = r - b * np;
+        const int row = b * N + q;
         const uint32_t v = *(const uint32_t *) (sm_stage + row * pitch + lane * 4);
         *(uint32_t *) (planes + ((long long) (q * 4 + b) * outer_p + o) * inner_p + l0 + lane * 4) = v;
     }
@@ -260,7 +261,9 @@ __global__ void __launch_bounds__(256) k_minplus(const int16_t *SA, const int16_
     __shared__ __align__(16) uint32_t sa[kMpK / 2][kMpTI + 4];
     __shared__ __align__(16) uint32_t sb[kMpK / 2][kMpTJ + 4];
     const int i0 = blockIdx.x * kMpTI, j0 = blockIdx.y * kMpTJ;
-    const int ti = (threadIdx.x & 15) * 8, tj = (threadIdx.x >> 4) * 4;
+    // rows of a thread: 4 l .. 4 l + 3 and 64 + 4 l .. 64 + 4 l + 3 (l = thread & 15): the eight lanes of a
+    // 128-bit shared-memory phase then cover 32 distinct banks
+    const int ti = (threadIdx.x & 15) * 4, tj = (threadIdx.x >> 4) * 4;
     uint32_t acc[8][4];
 #pragma unroll
     for (int a = 0; a < 8; ++a)
@@ -280,7 +283,7 @@ __global__ void __launch_bounds__(256) k_minplus(const int16_t *SA, const int16_
         __syncthreads();
 #pragma unroll 4
         for (int w = 0; w < kMpK / 2; ++w) {
-            const uint4 a0 = *(const uint4 *) &sa[w][ti], a1 = *(const uint4 *) &sa[w][ti + 4], b0 = *(const uint4 *) &sb[w][tj];
+            const uint4 a0 = *(const uint4 *) &sa[w][ti], a1 = *(const uint4 *) &sa[w][64 + ti], b0 = *(const uint4 *) &sb[w][tj];
             const uint32_t av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, bv[4] = {b0.x, b0.y, b0.z, b0.w};
 #pragma unroll
             for (int a = 0; a < 8; ++a)
@@ -297,7 +300,10 @@ __global__ void __launch_bounds__(256) k_minplus(const int16_t *SA, const int16_
             int lo = (int) (short) (acc[a][b] & 0xffffu), hi = (int) (short) (acc[a][b] >> 16);
             out[a] = (short) (lo < hi ? lo : hi);
         }
-        *(uint4 *) (delta + (long long) (j0 + tj + b) * m_p + i0 + ti) = *(const uint4 *) out;
+        const uint2 *o2 = (const uint2 *) out;
+        int16_t *drow = delta + (long long) (j0 + tj + b) * m_p + i0;
+        *(uint2 *) (drow + ti) = o2[0];
+        *(uint2 *) (drow + 64 + ti) = o2[1];
     }
 }
 
@@ -512,13 +518,14 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
     const size_t bytesS = (size_t) N * n_p * m_p * 4;
     const size_t bytesSA = (size_t) m_p * k_p * 2, bytesSB = (size_t) n_p * k_p * 2, bytesD = (size_t) n_p * m_p * 2;
     const size_t bytesInfo = (size_t) (m_p + n_p) * sizeof(OuterInfo);
+    const size_t bytesTab = (size_t) (3 * c->hc.log2M + 2) * N * sizeof(int);   // alpha * 2^j, beta * 2^j (stage 3)
     const size_t bytesTodo = (size_t) m * n * sizeof(long long);   // per list: reference-order todo, stage-3 slow list
     void *pPA, *pPB, *pS, *pMisc;
     int rc;
     if ((rc = ws_reserve(c, 3, bytesPA, &pPA))) return rc;
     if ((rc = ws_reserve(c, 4, bytesPB, &pPB))) return rc;
     if ((rc = ws_reserve(c, 5, bytesS, &pS))) return rc;
-    if ((rc = ws_reserve(c, 6, bytesSA + bytesSB + bytesD + bytesInfo + 2 * bytesTodo + 1024, &pMisc))) return rc;
+    if ((rc = ws_reserve(c, 6, bytesSA + bytesSB + bytesD + bytesInfo + 2 * bytesTodo + bytesTab + 1024, &pMisc))) return rc;
     char *pm = (char *) pMisc;
     int16_t *SA = (int16_t *) pm; pm += bytesSA;
     int16_t *SB = (int16_t *) pm; pm += bytesSB;
@@ -526,7 +533,8 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
     OuterInfo *IA = (OuterInfo *) pm; pm += (size_t) m_p * sizeof(OuterInfo);
     OuterInfo *IB = (OuterInfo *) pm; pm += (size_t) n_p * sizeof(OuterInfo);
     long long *todo = (long long *) pm; pm += bytesTodo;
-    long long *slow = (long long *) pm;
+    long long *slow = (long long *) pm; pm += bytesTodo;
+    int *scal_tab = (int *) pm;
 
     // element (o, l) index strides: op(A)(i, l) and op(B)(l, j)
     const long long soA = ta ? lda : 1, slA = ta ? 1 : lda;
@@ -580,8 +588,11 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
     auto norm_fast = [&](auto tag) {
         constexpr int NQ = decltype(tag)::value;
         const unsigned g3 = (unsigned) ((long long) ((m + kNormFastThreads - 1) / kNormFastThreads) * n);
+        const int rowsT = 3 * c->hc.log2M + 2;
+        k_scalar_tables<<<(rowsT * NQ + 255) / 256, 256, 0, st>>>(c->dconsts, alpha, beta, scal_tab);
         k_norm_fast<NQ><<<g3, kNormFastThreads, (size_t) kNormFastThreads * (NQ + 1) * sizeof(int), st>>>(c->dconsts, m, n, k, (const int *) pS, D, m_p, n_p, IA, IB, alpha, beta, Cm, ldc,
-                                                         todo, c->d_counter, slow, c->d_counter + 1, allow_fb);
+                                                         scal_tab, todo, c->d_counter, slow, c->d_counter + 1, allow_fb);
+        ++stage3_launches;
     };
     bool have_fast = c->stage3 == 0;
     if (have_fast) {

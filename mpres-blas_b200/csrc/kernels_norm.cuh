@@ -136,29 +136,75 @@ __device__ __forceinline__ int ceil_log2(int k) {
 }
 
 // ---- base extension (reduced-base fast path) -----------------------------------------------------------
-// Stage 2 produced S mod m_q for the first np moduli only.  |S| < M'/4 with M' = m_0 ... m_{np-1}, so the
-// mixed-radix digits a_i of X = S mod M' (X = sum a_i m_0...m_{i-1}, src/rns.cuh:570-582 is the reference's
-// mixed-radix conversion) determine S: the top digit tells the sign (X/M' lies in [0,1/4) or (3/4,1)) and
-//      S mod m_q = sum_i a_i (m_0...m_{i-1} mod m_q) - [S < 0] (M' mod m_q)          for q >= np.
-// One thread per entry; digits live in shared memory ([i][thread], conflict-free), the triangular inverse
-// table and the weight table are staged per block.  Writes the planes q >= np of S.
+// Stage 2 produced S mod m_q for the first np moduli only.  With M' = m_0 ... m_{np-1}, M'_i = M'/m_i and
+// xi_i = x_i (M'_i)^-1 mod m_i, the Chinese remainder theorem gives  S = sum_i xi_i M'_i - R M'  for an
+// integer R.  Because |S| < M'/4 (k_choose_base), R is the integer NEAREST to sum_i xi_i / m_i -- a double
+// sum (error < np 2^-52) decides it with a margin of 1/4, whatever the sign and however small S is.  Hence
+//      S mod m_q = ( sum_i xi_i (M'_i mod m_q) + R (m_q - M' mod m_q) ) mod m_q          for q >= np.
+// (The reference has no base extension; its rank-based CRT reconstruction in rns_scale2pow,
+// src/rns.cuh:1061-1124, is the same identity with a floor instead of the nearest integer.)
+// One thread per entry, the xi_i in registers, tables staged per block.  Writes the planes q >= np of S.
 constexpr int kExtThreads = 128;
-inline size_t base_extend_smem(int N) { return (size_t) N * kExtThreads * sizeof(int) + (size_t) 2 * N * N * sizeof(int) + (size_t) N * 16; }
+inline size_t base_extend_smem(int N) { return (size_t) N * N * sizeof(int) + (size_t) N * 40; }
 
-__global__ void __launch_bounds__(kExtThreads) k_base_extend(const DevConsts *Cp, int m, int n, int *S, long long m_p, long long n_p, const int *nprime) {
+template <int NP>
+__device__ __forceinline__ void base_extend_body(int np, int N, bool lazy, int *Sp, long long plane, const int *s_m, const unsigned long long *s_mu,
+                                                 const int *s_w, const double *s_rcp, const int *s_negmp, const int *s_t) {
+    unsigned xi[NP];
+    double sum = 0.0;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        xi[i] = 0;
+        if (i < np) {
+            xi[i] = (unsigned) mulmod(Sp[i * plane], s_w[i], s_m[i], s_mu[i]);
+            sum += (double) xi[i] * s_rcp[i];
+        }
+    }
+    const unsigned R = (unsigned) __double2int_rn(sum);
+    for (int q = np; q < N; ++q) {
+        const int mq = s_m[q];
+        const unsigned long long muq = s_mu[q];
+        const int4 *t4 = (const int4 *) (s_t + (q - np) * NP);
+        unsigned long long acc = 0;
+#pragma unroll
+        for (int i4 = 0; i4 < NP / 4; ++i4) {
+            const int4 t = t4[i4];
+            acc += (unsigned long long) xi[4 * i4] * (unsigned) t.x;
+            acc += (unsigned long long) xi[4 * i4 + 1] * (unsigned) t.y;
+            acc += (unsigned long long) xi[4 * i4 + 2] * (unsigned) t.z;
+            acc += (unsigned long long) xi[4 * i4 + 3] * (unsigned) t.w;
+            if (!lazy) acc = (unsigned long long) (unsigned) reduce64(acc, mq, muq);   // moduli up to 2^31: four terms fit
+        }
+        if (!lazy) acc = (unsigned long long) (unsigned) reduce64(acc, mq, muq);
+        acc += (unsigned long long) R * (unsigned) s_negmp[q];
+        Sp[q * plane] = reduce64(acc, mq, muq);
+    }
+}
+
+__global__ void __launch_bounds__(kExtThreads, 6) k_base_extend(const DevConsts *Cp, int m, int n, int *S, long long m_p, long long n_p, const int *nprime) {
     extern __shared__ __align__(16) unsigned char ext_smem[];
     const DevConsts &C = *Cp;
     const int N = C.N;
     const int np = *nprime;
     if (np >= N) return;
+    const int np4 = (np + 3) & ~3;
     unsigned long long *s_mu = (unsigned long long *) ext_smem;      // [N]
-    int *s_m = (int *) (s_mu + N);                                     // [N]
-    int *s_inv = s_m + N;                                              // [np][np]   m_i^-1 mod m_j
-    int *s_w = s_inv + np * np;                                        // [np + 1][N - np]  prefix weights
-    int *xs = s_w + (np + 1) * (N - np);                               // [np][kExtThreads]
-    for (int t = threadIdx.x; t < N; t += kExtThreads) { s_mu[t] = C.barrett[t]; s_m[t] = C.moduli[t]; }
-    for (int t = threadIdx.x; t < np * np; t += kExtThreads) s_inv[t] = C.mrc_inv[(t / np) * N + t % np];
-    for (int t = threadIdx.x; t < (np + 1) * (N - np); t += kExtThreads) s_w[t] = C.prefix_mod[(t / (N - np)) * N + np + t % (N - np)];
+    double *s_rcp = (double *) (s_mu + N);                             // [N]   1 / m_i
+    int *s_m = (int *) (s_rcp + N);                                    // [N]
+    int *s_w = s_m + N;                                                // [N]   (M'_i)^-1 mod m_i
+    int *s_negmp = s_w + N;                                            // [N]   m_q - M' mod m_q
+    int *s_t = s_negmp + N + ((4 - ((3 * N) & 3)) & 3);               // [N - np][np4]  M'_i mod m_q, 16-byte aligned
+    for (int t = threadIdx.x; t < N; t += kExtThreads) {
+        const int mq = C.moduli[t];
+        s_mu[t] = C.barrett[t]; s_m[t] = mq; s_rcp[t] = 1.0 / (double) mq;
+        s_w[t] = C.ext_w[np * N + t];
+        const int mp = C.prefix_mod[np * N + t];
+        s_negmp[t] = mp ? mq - mp : 0;
+    }
+    for (int t = threadIdx.x; t < (N - np) * np4; t += kExtThreads) {
+        const int q = np + t / np4, i = t % np4;
+        s_t[t] = i < np ? C.ext_t[((long long) np * N + q) * N + i] : 0;
+    }
     __syncthreads();
     const int tiles = (m + kExtThreads - 1) / kExtThreads;
     const int col = blockIdx.x / tiles;
@@ -166,33 +212,21 @@ __global__ void __launch_bounds__(kExtThreads) k_base_extend(const DevConsts *Cp
     if (row >= m) return;
     int *Sp = S + (long long) col * m_p + row;
     const long long plane = n_p * m_p;
-    int *xt = xs + threadIdx.x;
-    for (int i = 0; i < np; ++i) xt[i * kExtThreads] = Sp[i * plane];
-    // mixed-radix conversion: after step i every element j > i holds (x_j - a_i) / m_i mod m_j
-    for (int i = 0; i < np - 1; ++i) {
-        const int ai = xt[i * kExtThreads];
-        for (int j = i + 1; j < np; ++j) {
-            const int mj = s_m[j];
-            int a = ai >= mj ? ai - mj : ai;       // moduli of one set differ by less than a factor two ...
-            if (a >= mj) a %= mj;                  // ... but stay correct for any set
-            int t = xt[j * kExtThreads] - a;
-            t = t < 0 ? t + mj : t;
-            xt[j * kExtThreads] = mulmod(t, s_inv[i * np + j], mj, s_mu[j]);
-        }
-    }
-    const int top = xt[(np - 1) * kExtThreads];
-    const bool neg = 2ll * top >= (long long) s_m[np - 1];
-    for (int q = np; q < N; ++q) {
-        const int mq = s_m[q];
-        const unsigned long long muq = s_mu[q];
-        unsigned long long acc = 0;
-        for (int i = 0; i < np; ++i) {
-            acc += (unsigned long long) (unsigned) xt[i * kExtThreads] * (unsigned) s_w[i * (N - np) + q - np];
-            if ((i & 3) == 3) acc = (unsigned long long) (unsigned) reduce64(acc, mq, muq);   // any moduli < 2^31: 4 terms < 2^64
-        }
-        int r = reduce64(acc, mq, muq);
-        if (neg) { r -= s_w[np * (N - np) + q - np]; r = r < 0 ? r + mq : r; }
-        Sp[q * plane] = r;
+    const bool lazy = C.ext_lazy != 0;
+    switch (np4) {
+        case 4: base_extend_body<4>(np, N, lazy, Sp, plane, s_m, s_mu, s_w, s_rcp, s_negmp, s_t); break;
+        case 8: base_extend_body<8>(np, N, lazy, Sp, plane, s_m, s_mu, s_w, s_rcp, s_negmp, s_t); break;
+        case 12: base_extend_body<12>(np, N, lazy, Sp, plane, s_m, s_mu, s_w, s_rcp, s_negmp, s_t); break;
+        case 16: base_extend_body<16>(np, N, lazy, Sp, plane, s_m, s_mu, s_w, s_rcp, s_negmp, s_t); break;
+        case 20: base_extend_body<20>(np, N, lazy, Sp, plane, s_m, s_mu, s_w, s_rcp, s_negmp, s_t); break;
+        case 24: base_extend_body<24>(np, N, lazy, Sp, plane, s_m, s_mu, s_w, s_rcp, s_negmp, s_t); break;
+        case 28: base_extend_body<28>(np, N, lazy, Sp, plane, s_m, s_mu, s_w, s_rcp, s_negmp, s_t); break;
+        case 32: base_extend_body<32>(np, N, lazy, Sp, plane, s_m, s_mu, s_w, s_rcp, s_negmp, s_t); break;
+        case 36: base_extend_body<36>(np, N, lazy, Sp, plane, s_m, s_mu, s_w, s_rcp, s_negmp, s_t); break;
+        case 40: base_extend_body<40>(np, N, lazy, Sp, plane, s_m, s_mu, s_w, s_rcp, s_negmp, s_t); break;
+        case 44: base_extend_body<44>(np, N, lazy, Sp, plane, s_m, s_mu, s_w, s_rcp, s_negmp, s_t); break;
+        case 48: base_extend_body<48>(np, N, lazy, Sp, plane, s_m, s_mu, s_w, s_rcp, s_negmp, s_t); break;
+        default: break;   // k_choose_base never selects a reduced base above kMaxReducedBase
     }
 }
 
@@ -279,12 +313,31 @@ __global__ void __launch_bounds__(256) k_norm_list(const DevConsts *Cp, int m, i
 
 // ---- entry-per-thread kernel ---------------------------------------------------------------------------
 struct QConst {          // per-modulus constants, broadcast from shared memory
-    int m, w;
+    int m, pad;
     unsigned long long mu;
     double rrd, rru;
-    int al, be;          // digits of alpha and beta
-    int pad[2];
 };
+
+// Per-call tables for k_norm_fast: alpha * 2^j mod m_q for j = -log2M .. log2M (row j + log2M) and
+// beta * 2^j mod m_q for j = 0 .. log2M (rows 2 log2M + 1 + j).  They turn "multiply by the scalar, then by
+// the alignment power of two" (mp_mul followed by the shift inside mp_add) into one modular multiplication.
+__global__ void k_scalar_tables(const DevConsts *Cp, SoA alpha, SoA beta, int *tab) {
+    const DevConsts &C = *Cp;
+    const int N = C.N, L = C.log2M;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (3 * L + 2) * N) return;
+    const int row = t / N, q = t - row * N;
+    const int m = C.moduli[q];
+    const unsigned long long mu = C.barrett[q];
+    int v;
+    if (row <= 2 * L) {
+        const int j = row - L;
+        v = mulmod(alpha.digits[q], j >= 0 ? C.pow2[(long long) j * N + q] : C.inv_pow2[(long long) (-j) * N + q], m, mu);
+    } else {
+        v = mulmod(beta.digits[q], C.pow2[(long long) (row - 2 * L - 1) * N + q], m, mu);
+    }
+    tab[t] = v;
+}
 struct ScalarEsi { int sign, exp; Er lo, up; };
 
 __host__ __device__ constexpr int pow2ceil_c(int n) { int p = 1; while (p < n) p <<= 1; return p; }
@@ -294,9 +347,9 @@ __host__ __device__ constexpr int trailing_ones_c(int q) { int t = 0; while (q &
 constexpr int kNormFastThreads = 128;
 
 template <int NQ>
-__global__ void __launch_bounds__(kNormFastThreads) k_norm_fast(const DevConsts *Cp, int m, int n, int k, const int *S, const int16_t *delta,
+__global__ void __launch_bounds__(kNormFastThreads, 6) k_norm_fast(const DevConsts *Cp, int m, int n, int k, const int *S, const int16_t *delta,
                                                                 long long m_p, long long n_p, const OuterInfo *ia, const OuterInfo *ib,
-                                                                SoA alpha, SoA beta, SoA Cm, int ldc, long long *todo, int *todo_count,
+                                                                SoA alpha, SoA beta, SoA Cm, int ldc, const int *scal_tab, long long *todo, int *todo_count,
                                                                 long long *slow, int *slow_count, bool fallback_allowed) {
     constexpr int P = pow2ceil_c(NQ), LOGP = log2_c(P);
     constexpr int CP = NQ + 1;              // pitch of the staged C digits (conflict-free per-thread rows)
@@ -307,8 +360,7 @@ __global__ void __launch_bounds__(kNormFastThreads) k_norm_fast(const DevConsts 
     const DevConsts &C = *Cp;
     for (int q = threadIdx.x; q < NQ; q += blockDim.x) {
         QConst c;
-        c.m = C.moduli[q]; c.w = C.part_inverse[q]; c.mu = C.barrett[q]; c.rrd = C.recip_rd[q]; c.rru = C.recip_ru[q];
-        c.al = alpha.digits[q]; c.be = beta.digits[q]; c.pad[0] = c.pad[1] = 0;
+        c.m = C.moduli[q]; c.pad = 0; c.mu = C.barrett[q]; c.rrd = C.recip_rd[q]; c.rru = C.recip_ru[q];
         qc[q] = c;
     }
     if (threadIdx.x == 0) { s_al.sign = alpha.sign[0]; s_al.exp = alpha.exp[0]; s_al.lo = alpha.eval[0]; s_al.up = alpha.eval[alpha.len()]; }
@@ -340,21 +392,20 @@ __global__ void __launch_bounds__(kNormFastThreads) k_norm_fast(const DevConsts 
         int K = log2M - (int) bound - 3;
         K = K < 0 ? 0 : K;
         // ---- pass 1 over the moduli: residues, magnified fractions, directed sums (balanced tree) ----
-        int x[NQ];
         int nz = 0;
         double stl[LOGP + 1], stu[LOGP + 1];
+        const int *Sp = S + (long long) col * m_p + row;
+        const long long plane = n_p * m_p;
         {
-            const int *Sp = S + (long long) col * m_p + row;
-            const long long plane = n_p * m_p;
-            const int *p2 = C.pow2 + (long long) K * NQ;
+            const int *p2 = C.wpow2 + (long long) K * NQ;   // w_q 2^K mod m_q
 #pragma unroll
             for (int q = 0; q < P; ++q) {
                 double vl = 0.0, vu = 0.0;
                 if (q < NQ) {
                     const QConst c = qc[q];
-                    x[q] = __ldg(Sp + q * plane);
-                    nz |= x[q];
-                    const int sq = mulmod(mulmod(x[q], c.w, c.m, c.mu), __ldg(p2 + q), c.m, c.mu);
+                    const int xq = __ldg(Sp + q * plane);
+                    nz |= xq;
+                    const int sq = mulmod(xq, __ldg(p2 + q), c.m, c.mu);
                     vl = __dmul_rd((double) sq, c.rrd);
                     vu = __dmul_ru((double) sq, c.rru);
                 }
@@ -398,17 +449,17 @@ __global__ void __launch_bounds__(kNormFastThreads) k_norm_fast(const DevConsts 
         if (sign) { rlo.frac = -p.up.frac; rlo.exp = p.up.exp; rup.frac = -p.lo.frac; rup.exp = p.lo.exp; }
         if (rup.frac != 0 && rup.exp >= mp_h) { to_slow = true; break; }    // result needs a rounding
         // ---- pass 2 over the moduli: digits ----
-        const int ysh = p.theta - d;    // alpha*S carries 2^(theta - d)
-        const int *ty = ysh >= 0 ? C.pow2 + (long long) ysh * NQ : C.inv_pow2 + (long long) (-ysh) * NQ;
-        const int *tx = C.pow2 + (long long) p.gamma * NQ;
+        const int *ty = scal_tab + (long long) (p.theta - d + log2M) * NQ;          // alpha 2^(theta - d)
+        const int *tx = scal_tab + (long long) (2 * log2M + 1 + p.gamma) * NQ;      // beta 2^gamma
         int *mycd = cds + threadIdx.x * CP;
-#pragma unroll
-        for (int q = 0; q < NQ; ++q) {
+        const int *sp2 = Sp;
+#pragma unroll 8
+        for (int q = 0; q < NQ; ++q, sp2 += plane) {
             const QConst c = qc[q];
-            int v = x[q];
+            int v = __ldg(sp2);
             if (sg < 0 && v) v = c.m - v;
-            const int ay = p.nzy ? mulmod(mulmod(v, c.al, c.m, c.mu), __ldg(ty + q), c.m, c.mu) : 0;
-            const int ax = p.nzx ? mulmod(mulmod(mycd[q], c.be, c.m, c.mu), __ldg(tx + q), c.m, c.mu) : 0;
+            const int ay = p.nzy ? mulmod(v, __ldg(ty + q), c.m, c.mu) : 0;
+            const int ax = p.nzx ? mulmod(mycd[q], __ldg(tx + q), c.m, c.mu) : 0;
             const int a = p.sx ? (ax ? c.m - ax : 0) : ax;
             const int b = p.sy ? (ay ? c.m - ay : 0) : ay;
             int r = a + b - c.m;

@@ -49,6 +49,10 @@ struct DevConsts {
     const int *mrc_inv;   // [N][N]         m_i^-1 mod m_j (j > i)
     const int *prefix_mod;  // [N+1][N]     (m_0 ... m_{i-1}) mod m_q
     int prefix_log2[kMaxN + 1];   // floor(log2(m_0 ... m_{n-1}))
+    const int *ext_w;     // [N][N]       CRT base extension from the first c moduli: (M'/m_i)^-1 mod m_i
+    const int *ext_t;     // [N][N][N]    [c][q][i] = (M'/m_i) mod m_q
+    int ext_lazy, pad2;
+    const int *wpow2;     // [log2M+1][N] w_i * 2^j mod m_i
 };
 
 // SoA view of mp_array_t / mp_collection_t (src/types.cuh:85-104).  `len` is the ALLOCATED length:

@@ -72,8 +72,9 @@ int mpres_init_moduli(mpres_ctx **out, const int *moduli, int n, int device) {
         return e;
     };
     if (up(&c->d_pow2, h.pow2) != cudaSuccess || up(&c->d_inv_pow2, h.inv_pow2_ext) != cudaSuccess ||
-        up(&c->d_mrc, h.mrc_inv) != cudaSuccess || up(&c->d_prefix, h.prefix_mod) != cudaSuccess) { delete d; delete c; return (int) e; }
-    d->pow2 = c->d_pow2; d->inv_pow2 = c->d_inv_pow2; d->mrc_inv = c->d_mrc; d->prefix_mod = c->d_prefix;
+        up(&c->d_mrc, h.mrc_inv) != cudaSuccess || up(&c->d_prefix, h.prefix_mod) != cudaSuccess ||
+        up(&c->d_ext_w, h.ext_w) != cudaSuccess || up(&c->d_ext_t, h.ext_t) != cudaSuccess || up(&c->d_wpow2, h.wpow2) != cudaSuccess) { delete d; delete c; return (int) e; }
+    d->pow2 = c->d_pow2; d->inv_pow2 = c->d_inv_pow2; d->mrc_inv = c->d_mrc; d->prefix_mod = c->d_prefix; d->ext_w = c->d_ext_w; d->ext_t = c->d_ext_t; d->ext_lazy = h.ext_lazy; d->wpow2 = c->d_wpow2;
     for (int i = 0; i <= h.N; ++i) d->prefix_log2[i] = h.prefix_log2[i];
     e = cudaMalloc(&c->dconsts, sizeof(DevConsts));
     if (e == cudaSuccess) e = cudaMemcpy(c->dconsts, d, sizeof(DevConsts), cudaMemcpyHostToDevice);
@@ -98,7 +99,7 @@ int mpres_finalize(mpres_ctx *c) {
     DeviceGuard g(c->device);
     cudaDeviceSynchronize();
     for (int i = 0; i < 8; ++i) if (c->ws[i]) cudaFree(c->ws[i]);
-    cudaFree(c->d_pow2); cudaFree(c->d_inv_pow2); cudaFree(c->d_mrc); cudaFree(c->d_prefix); cudaFree(c->dconsts); cudaFree(c->d_counter);
+    cudaFree(c->d_pow2); cudaFree(c->d_inv_pow2); cudaFree(c->d_mrc); cudaFree(c->d_prefix); cudaFree(c->d_ext_w); cudaFree(c->d_ext_t); cudaFree(c->d_wpow2); cudaFree(c->dconsts); cudaFree(c->d_counter);
     delete c;
     return 0;
 }

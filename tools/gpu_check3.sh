@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 rm -f gpurun_out/summary.txt
 timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/t_gpu_all.log 2>&1; echo "all gpu tests rc=$?" >> gpurun_out/summary.txt
-timeout 600 python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/bench_r4.json 2> gpurun_out/bench_r4.err; echo "bench rc=$?" >> gpurun_out/summary.txt
+timeout 600 python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/bench_r5.json 2> gpurun_out/bench_r5.err; echo "bench rc=$?" >> gpurun_out/summary.txt
 MPRES_BENCH_PROFILER_RANGE=1 timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1; echo "ncu launches rc=$?" >> gpurun_out/summary.txt
-MPRES_BENCH_PROFILER_RANGE=1 timeout 1200 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:'k_limb_umma|k_norm_fast|k_align_planes4|k_minplus|k_norm_list|k_base_extend' -c 7 -o gpurun_out/prof_r4 -f python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?" >> gpurun_out/summary.txt
-cat gpurun_out/summary.txt; tail -15 gpurun_out/t_gpu_all.log; cat gpurun_out/bench_r4.json
+MPRES_BENCH_PROFILER_RANGE=1 timeout 1200 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:'k_limb_umma|k_norm_fast|k_align_planes4|k_minplus|k_norm_list|k_base_extend' -c 7 -o gpurun_out/prof_r5 -f python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?" >> gpurun_out/summary.txt
+cat gpurun_out/summary.txt; tail -15 gpurun_out/t_gpu_all.log; cat gpurun_out/bench_r5.json
