@@ -111,6 +111,9 @@ int mpres_set_reduced_base(mpres_ctx *ctx, int on);
 long mpres_last_base_size(mpres_ctx *ctx);
 /* Stage-1 alignment kernel: 0 = vectorised (four residues per work item, default), 1 = one residue per thread. */
 int mpres_set_stage1_kernel(mpres_ctx *ctx, int kind);
+/* Tile configuration of the single-pass mp_gemv / mp_dot kernels: 0 = 8 columns (4 row tiles) per stage, 2-deep
+ * ring (default); 1 = 4 columns (2 row tiles), 3-deep; 2 = 8 columns (4 row tiles), 3-deep.  Identical results. */
+int mpres_set_vec_config(mpres_ctx *ctx, int cfg);
 /* number of result elements of the last fast-path call that the entry-per-thread normalisation kernel
  * handed to the residue-parallel list kernel (diagnostic; synchronises) */
 long mpres_last_slow_count(mpres_ctx *ctx);

@@ -22,9 +22,10 @@ struct mpres_ctx {
     int reduced_base = 1;             // 1: run stages 1-2 on as many moduli as the exact sums need, then extend the base
     int stage1 = 0;                   // 0: vectorised alignment kernel, 1: round-1 kernel
     int stage3 = 0;                   // 0: entry-per-thread kernel + list, 1: residue-parallel tile kernel
+    int vec_config = 0;               // tile configuration of the mp_gemv / mp_dot kernels (A/B measurement)
     HostConsts hc;
     DevConsts *dconsts = nullptr;
-    int *d_pow2 = nullptr, *d_inv_pow2 = nullptr, *d_mrc = nullptr, *d_prefix = nullptr, *d_ext_w = nullptr, *d_ext_t = nullptr, *d_wpow2 = nullptr;
+    int *d_pow2 = nullptr, *d_inv_pow2 = nullptr, *d_mrc = nullptr, *d_prefix = nullptr, *d_ext_w = nullptr, *d_ext_t = nullptr, *d_wpow2 = nullptr, *d_spow2 = nullptr;
     std::atomic<long> launches{0};
     // workspace pool (grown on demand, never freed per call)
     void *ws[8] = {nullptr};

@@ -84,6 +84,7 @@ struct HostConsts {
     // CRT base extension from the first c moduli (c = 1..N-1), M' = m_0 ... m_{c-1}, M'_i = M' / m_i:
     //   ext_w[c * N + i] = (M'_i)^-1 mod m_i  (i < c),   ext_t[(c * N + q) * N + i] = M'_i mod m_q  (i < c)
     std::vector<int> ext_w, ext_t;
+    std::vector<int> spow2;   // [2 (log2M+1) + 1][N]  row 2s: 2^s, row 2s+1: -2^s, last row: zeros (mp_gemv / mp_dot term multipliers)
     std::vector<int> wpow2;   // [log2M+1][N]  w_i * 2^j mod m_i (interval evaluation of a magnified number in one multiplication)
     int ext_lazy = 0;   // 1 if N * max(m)^2 < 2^63: the extension sums need no intermediate reduction
     std::vector<double> recip_rd, recip_ru;
@@ -210,6 +211,13 @@ inline int compute_constants(const int *mods, int N, HostConsts &c) {
             }
         }
     }
+    c.spow2.assign((size_t) (2 * (c.log2M + 1) + 1) * N, 0);
+    for (int j = 0; j <= c.log2M; ++j)
+        for (int i = 0; i < N; ++i) {
+            const int v = c.pow2[(size_t) j * N + i];
+            c.spow2[(size_t) (2 * j) * N + i] = v;
+            c.spow2[(size_t) (2 * j + 1) * N + i] = v ? mods[i] - v : 0;
+        }
     c.wpow2.resize((size_t) (c.log2M + 1) * N);
     for (int j = 0; j <= c.log2M; ++j)
         for (int i = 0; i < N; ++i) c.wpow2[(size_t) j * N + i] = (int) ((int64_t) c.pow2[(size_t) j * N + i] * c.part_inverse[i] % mods[i]);

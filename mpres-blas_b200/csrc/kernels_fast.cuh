@@ -634,5 +634,4 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
     return 0;
 }
 
-inline int gemv_fast(mpres_ctx *, bool, int, int, SoA, int, SoA, SoA, int, cudaStream_t, bool *done) { *done = false; return 0; }
-inline int dot_fast(mpres_ctx *, int, SoA, int, SoA, int, char *, SoA, cudaStream_t, bool *done) { *done = false; return 0; }
+#include "kernels_vec.cuh"

@@ -107,14 +107,17 @@ __global__ void k_vec_scale(const DevConsts *Cp, long long n, SoA r, int incr, S
 // ---- GEMV, reference order: y[o] = y[o] + sum_q op(A)(o, q) * ax[q]  (src/blas/gemv.cuh:199-218) ----
 // y already holds round(beta * y) and ax = round(alpha * x).  One group per output element.
 template <int G, int R>
-__global__ void k_gemv_ref_order(const DevConsts *Cp, bool trans, int m, int n, SoA A, int lda, SoA ax, SoA y, int incy) {
+__global__ void k_gemv_ref_order(const DevConsts *Cp, bool trans, int m, int n, SoA A, int lda, SoA ax, SoA y, int incy,
+                                 const int *todo, const int *todo_count) {
     const DevConsts &C = *Cp;
     Lane<R> L;
     lane_init<G, R>(C, L);
     const int leny = trans ? n : m, lenx = trans ? m : n;
-    long long grp = ((long long) blockIdx.x * blockDim.x + threadIdx.x) / G;
+    long long it = ((long long) blockIdx.x * blockDim.x + threadIdx.x) / G;
     const long long ngrp = (long long) gridDim.x * blockDim.x / G;
-    for (; grp < leny; grp += ngrp) {
+    const long long total = todo ? (long long) *todo_count : (long long) leny;   // todo: outputs the fast path handed back
+    for (; it < total; it += ngrp) {
+        const long long grp = todo ? (long long) todo[it] : it;
         Num<R> sum, prod, a, b;
         num_zero(sum);
         for (int q = 0; q < lenx; ++q) {
@@ -133,7 +136,8 @@ __global__ void k_gemv_ref_order(const DevConsts *Cp, bool trans, int m, int n, 
 // ---- DOT, reference order: per-group serial mul/add over a strided slice, partials as AoS records
 //      (structure of src/mpreduct.cuh:38-74 with groups in place of threads) --------------------------
 template <int G, int R>
-__global__ void k_dot_partial(const DevConsts *Cp, long long n, SoA x, int incx, SoA y, int incy, char *partials) {
+__global__ void k_dot_partial(const DevConsts *Cp, long long n, SoA x, int incx, SoA y, int incy, char *partials, const int *gate) {
+    if (gate && *gate == 0) return;   // the fast path produced the result
     const DevConsts &C = *Cp;
     Lane<R> L;
     lane_init<G, R>(C, L);
@@ -169,7 +173,8 @@ __global__ void k_reduce_records(const DevConsts *Cp, const char *recs, long lon
 
 // Pairwise tree over AoS records held by the groups of ONE block: rec[g] += rec[g + stride].
 template <int G, int R>
-__global__ void k_tree_records(const DevConsts *Cp, char *recs, long long count, SoA out, long long out_idx, char *out_rec) {
+__global__ void k_tree_records(const DevConsts *Cp, char *recs, long long count, SoA out, long long out_idx, char *out_rec, const int *gate) {
+    if (gate && *gate == 0) return;
     const DevConsts &C = *Cp;
     Lane<R> L;
     lane_init<G, R>(C, L);

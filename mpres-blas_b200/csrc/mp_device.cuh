@@ -53,6 +53,7 @@ struct DevConsts {
     const int *ext_t;     // [N][N][N]    [c][q][i] = (M'/m_i) mod m_q
     int ext_lazy, pad2;
     const int *wpow2;     // [log2M+1][N] w_i * 2^j mod m_i
+    const int *spow2;     // [2 (log2M+1) + 1][N]  +2^s, -2^s interleaved; last row zeros
 };
 
 // SoA view of mp_array_t / mp_collection_t (src/types.cuh:85-104).  `len` is the ALLOCATED length:

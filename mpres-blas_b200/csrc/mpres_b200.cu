@@ -73,8 +73,8 @@ int mpres_init_moduli(mpres_ctx **out, const int *moduli, int n, int device) {
     };
     if (up(&c->d_pow2, h.pow2) != cudaSuccess || up(&c->d_inv_pow2, h.inv_pow2_ext) != cudaSuccess ||
         up(&c->d_mrc, h.mrc_inv) != cudaSuccess || up(&c->d_prefix, h.prefix_mod) != cudaSuccess ||
-        up(&c->d_ext_w, h.ext_w) != cudaSuccess || up(&c->d_ext_t, h.ext_t) != cudaSuccess || up(&c->d_wpow2, h.wpow2) != cudaSuccess) { delete d; delete c; return (int) e; }
-    d->pow2 = c->d_pow2; d->inv_pow2 = c->d_inv_pow2; d->mrc_inv = c->d_mrc; d->prefix_mod = c->d_prefix; d->ext_w = c->d_ext_w; d->ext_t = c->d_ext_t; d->ext_lazy = h.ext_lazy; d->wpow2 = c->d_wpow2;
+        up(&c->d_ext_w, h.ext_w) != cudaSuccess || up(&c->d_ext_t, h.ext_t) != cudaSuccess || up(&c->d_wpow2, h.wpow2) != cudaSuccess || up(&c->d_spow2, h.spow2) != cudaSuccess) { delete d; delete c; return (int) e; }
+    d->pow2 = c->d_pow2; d->inv_pow2 = c->d_inv_pow2; d->mrc_inv = c->d_mrc; d->prefix_mod = c->d_prefix; d->ext_w = c->d_ext_w; d->ext_t = c->d_ext_t; d->ext_lazy = h.ext_lazy; d->wpow2 = c->d_wpow2; d->spow2 = c->d_spow2;
     for (int i = 0; i <= h.N; ++i) d->prefix_log2[i] = h.prefix_log2[i];
     e = cudaMalloc(&c->dconsts, sizeof(DevConsts));
     if (e == cudaSuccess) e = cudaMemcpy(c->dconsts, d, sizeof(DevConsts), cudaMemcpyHostToDevice);
@@ -99,7 +99,7 @@ int mpres_finalize(mpres_ctx *c) {
     DeviceGuard g(c->device);
     cudaDeviceSynchronize();
     for (int i = 0; i < 8; ++i) if (c->ws[i]) cudaFree(c->ws[i]);
-    cudaFree(c->d_pow2); cudaFree(c->d_inv_pow2); cudaFree(c->d_mrc); cudaFree(c->d_prefix); cudaFree(c->d_ext_w); cudaFree(c->d_ext_t); cudaFree(c->d_wpow2); cudaFree(c->dconsts); cudaFree(c->d_counter);
+    cudaFree(c->d_pow2); cudaFree(c->d_inv_pow2); cudaFree(c->d_mrc); cudaFree(c->d_prefix); cudaFree(c->d_ext_w); cudaFree(c->d_ext_t); cudaFree(c->d_wpow2); cudaFree(c->d_spow2); cudaFree(c->dconsts); cudaFree(c->d_counter);
     delete c;
     return 0;
 }
@@ -124,6 +124,7 @@ long mpres_last_base_size(mpres_ctx *c) {
     if (cudaMemcpy(&v, c->d_counter + 2, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
     return v;
 }
+int mpres_set_vec_config(mpres_ctx *c, int cfg) { if (!c || cfg < 0 || cfg > 2) return -1; c->vec_config = cfg; return 0; }
 int mpres_set_stage1_kernel(mpres_ctx *c, int kind) { if (!c || kind < 0 || kind > 1) return -1; c->stage1 = kind; return 0; }
 long mpres_launch_count(const mpres_ctx *c) { return c ? c->launches.load() : -1; }
 
@@ -459,6 +460,8 @@ static int gemv_impl(mpres_ctx *c, int trans, int m, int n, SoA alpha, SoA A, in
     int rc = ws_soa(c, 1, (size_t) lenx, &ax);
     if (rc) return rc;
     CUDA_TRY(cudaMemsetAsync(c->d_counter, 0, 4 * sizeof(int), st));
+    c->ev_valid = false;
+    mv_mark(c, 0, st);
     MPRES_DISPATCH(N, {
         int block = 128;
         auto nb = [&](long long groups) { return (unsigned) std::min<long long>((groups * G + block - 1) / block, (long long) c->sm_count * 32); };
@@ -477,7 +480,7 @@ static int gemv_impl(mpres_ctx *c, int trans, int m, int n, SoA alpha, SoA A, in
         MPRES_DISPATCH(N, {
             int block = 128;
             long long blocks = std::min<long long>(((long long) leny * G + block - 1) / block, (long long) c->sm_count * 64);
-            k_gemv_ref_order<G, R><<<(unsigned) blocks, block, 0, st>>>(c->dconsts, tr, m, n, A, lda, ax, y, incy);
+            k_gemv_ref_order<G, R><<<(unsigned) blocks, block, 0, st>>>(c->dconsts, tr, m, n, A, lda, ax, y, incy, nullptr, nullptr);
         });
         LAUNCHED(c);
         CUDA_TRY(cudaGetLastError());
@@ -508,14 +511,17 @@ int mpres_gemv_coll(mpres_ctx *c, int trans, int m, int n, const mpres_collectio
 static int dot_to_record(mpres_ctx *c, int n, SoA x, int incx, SoA y, int incy, char *rec_out, SoA out, cudaStream_t st) {
     const int N = c->hc.N;
     const size_t rs = 4 * (size_t) N + 40;
-    bool done = false;
+    bool done = false, tried = false;
     int rc;
     CUDA_TRY(cudaMemsetAsync(c->d_counter, 0, 4 * sizeof(int), st));
+    c->ev_valid = false;
     if (c->mode != MPRES_MODE_REFERENCE_ORDER) {
-        rc = dot_fast(c, n, x, incx, y, incy, rec_out, out, st, &done);
+        rc = dot_fast(c, n, x, incx, y, incy, rec_out, out, st, &done, &tried);
         if (rc) return rc;
     }
     if (done) return 0;
+    // reference order: always in REFERENCE_ORDER mode; in AUTO mode gated on the fast path's guard counter
+    const int *gate = tried ? c->d_counter : nullptr;
     MPRES_DISPATCH(N, {
         const int block = 128;
         const long long gpb = block / G;
@@ -524,8 +530,8 @@ static int dot_to_record(mpres_ctx *c, int n, SoA x, int incx, SoA y, int incy, 
         void *parts;
         rc = ws_reserve(c, 2, (size_t) groups * rs, &parts);
         if (rc) return rc;
-        k_dot_partial<G, R><<<(unsigned) blocks, block, 0, st>>>(c->dconsts, n, x, incx, y, incy, (char *) parts);
-        k_tree_records<G, R><<<1, 256, 0, st>>>(c->dconsts, (char *) parts, groups, out, 0, rec_out);
+        k_dot_partial<G, R><<<(unsigned) blocks, block, 0, st>>>(c->dconsts, n, x, incx, y, incy, (char *) parts, gate);
+        k_tree_records<G, R><<<1, 256, 0, st>>>(c->dconsts, (char *) parts, groups, out, 0, rec_out, gate);
     });
     LAUNCHED(c); LAUNCHED(c);
     CUDA_TRY(cudaGetLastError());
