@@ -138,7 +138,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="gemm4096_424bit", choices=sorted(WORKLOADS))
     ap.add_argument("--mode", default="auto", choices=["auto", "reference_order", "fast"])
-    ap.add_argument("--stage2", default="umma", choices=["umma", "umma_unstacked", "mma_sync"], help="stage-2 kernel (A/B measurement)")
+    ap.add_argument("--stage2", default="small", choices=["small", "umma", "umma_unstacked", "mma_sync"], help="stage-2 kernel (A/B measurement)")
+    ap.add_argument("--stage3", type=int, default=0, choices=[0, 1, 2, 3], help="stage-3 kernel variant (mpres_set_stage3_kernel; A/B measurement)")
     ap.add_argument("--full-precision-inputs", action="store_true", help="p-bit significands instead of p/4")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -190,8 +191,10 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = pkg.Context(N, local_rank)
     ctx.set_mode({"auto": pkg.MODE_AUTO, "reference_order": pkg.MODE_REFERENCE_ORDER, "fast": pkg.MODE_FAST}[args.mode])
-    ctx.set_stage2_kernel({"umma": pkg.STAGE2_UMMA, "umma_unstacked": pkg.STAGE2_UMMA_UNSTACKED, "mma_sync": pkg.STAGE2_MMA_SYNC}[args.stage2])
+    ctx.set_stage2_kernel({"small": pkg.STAGE2_SMALL, "umma": pkg.STAGE2_UMMA, "umma_unstacked": pkg.STAGE2_UMMA_UNSTACKED, "mma_sync": pkg.STAGE2_MMA_SYNC}[args.stage2])
     config["stage2_kernel"] = args.stage2
+    ctx.set_stage3_kernel(args.stage3)
+    config["stage3_kernel"] = args.stage3
     assert m % world == 0
     mr = m // world                       # rows of A and C owned by this rank
     A = ta.TorchMpArray(ctx, mr * k)
@@ -244,6 +247,7 @@ def main():
     fallback = ctx.last_fallback_count()
     slow_listed = ctx.last_slow_count()
     base_size = ctx.last_base_size()          # moduli stages 1-2 actually ran on (reduced-base fast path)
+    small_P, small_nin = ctx.last_small_base()   # one-byte moduli of the small-modulus stage 2 (0: not used)
     try:
         stage_ms, s2_launches = ctx.last_stage_ms()
     except Exception:
@@ -307,16 +311,21 @@ def main():
     if stage_ms and s2_launches:
         t2 = stage_ms[1] * 1e-3                       # all stage-2 launches of one mp_gemm call on this rank
         nb = base_size if 0 < base_size <= N else N
-        limb_macs = 16.0 * mr * n * k * nb            # int8 MACs the kernel executes: 16 limb products per residue MAC, nb moduli
+        if small_P > 0:
+            limb_macs = 1.0 * mr * n * k * small_P    # one u8 x u8 MAC per one-byte modulus
+        else:
+            limb_macs = 16.0 * mr * n * k * nb        # int8 MACs the kernel executes: 16 limb products per residue MAC, nb moduli
         ops = 2.0 * limb_macs
         achieved = ops / t2 / 1e12
         peak = 2.0 * bf16_peak                        # dense int8 = 2 x dense bf16 on the same tensor cores
-        kname = {"umma": "k_limb_umma<stacked> (tcgen05.mma kind::i8, TMA, TMEM)", "umma_unstacked": "k_limb_umma<unstacked>",
+        kname = {"small": "k_small_umma (tcgen05.mma kind::i8 per one-byte modulus, TMA, TMEM)" if small_P > 0 else "k_limb_umma<stacked> (small base not selected)",
+                 "umma": "k_limb_umma<stacked> (tcgen05.mma kind::i8, TMA, TMEM)", "umma_unstacked": "k_limb_umma<unstacked>",
                  "mma_sync": "k_limb_gemm<0>+<1> (legacy mma.sync IMMA)"}[args.stage2]
         roof = {"bound": "tensor", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "TOP/s (int8)",
                 "frac": achieved / peak, "peak_source": "2 x bf16 %s peak of %s TFLOP/s (int8 dense = 2 x bf16 dense)" % (peak_src, bf16_peak),
                 "traffic": None, "launches_per_step": s2_launches, "avg_launch_ms": stage_ms[1] / s2_launches,
-                "algorithmic_ops_per_launch": ops / s2_launches, "moduli_in_stage2": nb, "moduli_total": N,
+                "algorithmic_ops_per_launch": ops / s2_launches, "moduli_in_stage2": small_P if small_P > 0 else nb, "moduli_total": N,
+                "small_base": {"one_byte_moduli": small_P, "input_residues_read": small_nin},
                 "frac_of_nominal_int8_peak_4500": achieved / 4500.0,
                 "stage_ms": {"stage1_align": stage_ms[0], "stage2_limb_gemm": stage_ms[1], "stage3_extend_normalise_epilogue": stage_ms[2]}}
         int32_roof = {"definition": "SURVEY 8(d): m*n*k*N residue-MACs / t / R_mac, R_mac = measured IMAD.WIDE.U32 rate (all N moduli counted: "
@@ -330,7 +339,7 @@ def main():
     line = {"metric": "mp_gemm MP-GFLOP/s", "value": value, "unit": "MP-GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u8 limbs of int32 RNS residues, s32 accumulate (f64 interval bounds)", "data": "synthetic", "config": config,
-            "gpu_launches": int(launches), "fallback_elements_last_step": int(fallback), "stage3_listed_elements_last_step": int(slow_listed), "reduced_base_moduli": int(base_size), "clocks": clocks,
+            "gpu_launches": int(launches), "fallback_elements_last_step": int(fallback), "stage3_listed_elements_last_step": int(slow_listed), "reduced_base_moduli": int(base_size), "small_base_moduli": int(small_P), "clocks": clocks,
             "roofline": roof, "int32_roofline": int32_roof, "cpu_baseline": cpu, "e2e": e2e}
     print(json.dumps(line))
     if dist is not None:

@@ -60,7 +60,7 @@ enum { MPRES_NO_TRANS = 111, MPRES_TRANS = 112, MPRES_CONJ_TRANS = 113 };
  * kernels including the interval evaluations.  FAST = fast path only (elements whose guard fails
  * are reported through mpres_last_fallback_count). */
 enum { MPRES_MODE_AUTO = 0, MPRES_MODE_REFERENCE_ORDER = 1, MPRES_MODE_FAST = 2 };
-enum { MPRES_STAGE2_UMMA = 0, MPRES_STAGE2_UMMA_UNSTACKED = 1, MPRES_STAGE2_MMA_SYNC = 2 };
+enum { MPRES_STAGE2_UMMA = 0, MPRES_STAGE2_UMMA_UNSTACKED = 1, MPRES_STAGE2_MMA_SYNC = 2, MPRES_STAGE2_SMALL = 3 };
 
 typedef struct mpres_ctx mpres_ctx;
 typedef void *mpres_stream_t; /* cudaStream_t */
@@ -95,13 +95,29 @@ long mpres_get_constant(const mpres_ctx *ctx, int which, void *out, size_t cap);
 
 int mpres_set_mode(mpres_ctx *ctx, int mode);
 int mpres_get_mode(const mpres_ctx *ctx);
-/* Stage-2 kernel of the fast path: UMMA = tcgen05.mma kind::i8 with TMA-fed limb tiles (default),
- * UMMA_UNSTACKED = the same kernel issuing one MMA per limb pair, MMA_SYNC = the legacy warp-level
- * int8 MMA kernel.  All three produce identical residues; the switch exists for A/B measurement. */
+/* Stage-2 kernel of the fast path.  SMALL (default) = the exact sums are accumulated modulo one-byte moduli
+ * (256, 251, 243, ...): one tcgen05.mma kind::i8 GEMM per modulus, inputs converted through their binary
+ * representation, results returned to the moduli of the number format by a CRT base extension; chosen per call
+ * when the sums fit the small base (about 360 bits), otherwise the call runs as UMMA.  UMMA = tcgen05.mma
+ * kind::i8 over four byte limbs of the format's own moduli with TMA-fed limb tiles, UMMA_UNSTACKED = the same
+ * kernel issuing one MMA per limb pair, MMA_SYNC = the legacy warp-level int8 MMA kernel.  All four produce
+ * identical residues; the switch exists for A/B measurement. */
 int mpres_set_stage2_kernel(mpres_ctx *ctx, int kind);
+/* Small-modulus base the last fast-path call used: *moduli = how many one-byte moduli (0: the call ran on the
+ * format's own moduli), *input_moduli = how many residues of each operand entry its conversion read.  Synchronises. */
+int mpres_last_small_base(mpres_ctx *ctx, int *moduli, int *input_moduli);
+/* the index-th one-byte modulus (0 when out of range or when the small base is unavailable for this moduli set) */
+int mpres_small_modulus(const mpres_ctx *ctx, int index);
+/* Test probe: copy `bytes` at `offset` of internal workspace `slot` to the host after synchronising the last stream
+ * (slots of the fast mp_gemm path: 3/4 limb planes of A/B, 5 residue planes of the sums, 8/9 one-byte planes of A/B,
+ * 10 one-byte planes of the sums).  Returns the bytes copied or < 0. */
+long mpres_debug_read_workspace(mpres_ctx *ctx, int slot, size_t offset, void *host, size_t bytes);
 /* Stage-3 kernel of the fast path: 0 = entry-per-thread normalisation with a residue-parallel list
  * kernel for the entries that need refinement / rounding / sign resolution (default), 1 = the
- * residue-parallel tile kernel for every entry.  Identical results (including interval evaluations). */
+ * residue-parallel tile kernel for every entry, 2 = like 0 but with the generic 64-bit modular products
+ * instead of the 32-bit Barrett step used when every modulus has the same bit length <= 27, 3 = like 0 but,
+ * on the small-modulus path, with the base extension as a separate kernel that writes the residue planes
+ * (default: fused into the normalisation kernel).  Identical results (including interval evaluations). */
 int mpres_set_stage3_kernel(mpres_ctx *ctx, int kind);
 /* Reduced-base fast path (default on): stages 1 and 2 run on the first n' moduli only, n' the smallest
  * multiple of four whose product exceeds four times the largest exact sum (from the per-row / per-column

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libmpres_b200.so")
 
 mblas_no_trans, mblas_trans, mblas_conj_trans = 111, 112, 113  # src/blas/mblas_enum.cuh:25-29
 MODE_AUTO, MODE_REFERENCE_ORDER, MODE_FAST = 0, 1, 2
-STAGE2_UMMA, STAGE2_UMMA_UNSTACKED, STAGE2_MMA_SYNC = 0, 1, 2
+STAGE2_UMMA, STAGE2_UMMA_UNSTACKED, STAGE2_MMA_SYNC, STAGE2_SMALL = 0, 1, 2, 3
 
 _lib = None
 
@@ -39,7 +39,7 @@ EXPORTS = [
     "mpres_init", "mpres_init_moduli", "mpres_finalize", "mpres_moduli_size", "mpres_moduli_product_log2",
     "mpres_precision", "mpres_mp_h", "mpres_mp_j", "mpres_device", "mpres_sizeof_mp_float", "mpres_get_constant",
     "mpres_set_mode", "mpres_get_mode", "mpres_set_stage2_kernel", "mpres_set_stage3_kernel", "mpres_set_stage1_kernel", "mpres_set_reduced_base", "mpres_last_base_size", "mpres_last_slow_count", "mpres_last_fallback_count", "mpres_launch_count",
-    "mpres_set_profiling", "mpres_last_stage_ms", "mpres_set_vec_config",
+    "mpres_set_profiling", "mpres_last_stage_ms", "mpres_set_vec_config", "mpres_last_small_base", "mpres_small_modulus", "mpres_debug_read_workspace",
     "mpres_array_init", "mpres_array_clear", "mpres_array_host2device", "mpres_array_device2host",
     "mpres_collection_init", "mpres_collection_clear", "mpres_collection_host2device", "mpres_collection_device2host",
     "mpres_array_set_binary", "mpres_gemm", "mpres_gemv", "mpres_dot", "mpres_gemm_coll", "mpres_gemv_coll",
@@ -58,7 +58,7 @@ def load_library():
     lib = ctypes.CDLL(LIB_PATH)
     lib.mpres_version.restype = ctypes.c_char_p
     lib.mpres_sizeof_mp_float.restype = ctypes.c_size_t
-    for f in ("mpres_get_constant", "mpres_last_fallback_count", "mpres_launch_count", "mpres_last_slow_count", "mpres_last_base_size"):
+    for f in ("mpres_get_constant", "mpres_last_fallback_count", "mpres_launch_count", "mpres_last_slow_count", "mpres_last_base_size", "mpres_debug_read_workspace"):
         getattr(lib, f).restype = ctypes.c_long
     _lib = lib
     return lib
@@ -124,6 +124,22 @@ class Context:
 
     def last_base_size(self):
         return self.lib.mpres_last_base_size(self.h)
+
+    def last_small_base(self):
+        """(one-byte moduli, residues read per operand entry) of the last fast-path call; (0, 0) if it ran on the format's moduli"""
+        a, b = ctypes.c_int(), ctypes.c_int()
+        _check(self.lib.mpres_last_small_base(self.h, ctypes.byref(a), ctypes.byref(b)), "mpres_last_small_base")
+        return a.value, b.value
+
+    def small_moduli(self, count):
+        return [self.lib.mpres_small_modulus(self.h, i) for i in range(count)]
+
+    def debug_read_workspace(self, slot, offset, nbytes):
+        out = np.zeros(nbytes, dtype=np.uint8)
+        n = self.lib.mpres_debug_read_workspace(self.h, int(slot), ctypes.c_size_t(offset), out.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(nbytes))
+        if n < 0:
+            raise MpresError("mpres_debug_read_workspace(%d) -> %d" % (slot, n))
+        return out
 
     def set_stage1_kernel(self, kind):
         _check(self.lib.mpres_set_stage1_kernel(self.h, kind), "mpres_set_stage1_kernel")

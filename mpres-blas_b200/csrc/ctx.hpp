@@ -13,23 +13,50 @@
 #include "host_consts.hpp"
 #include "mp_device.cuh"
 
+namespace mpres {
+
+// device tables of the small-modulus stage 2 (host_consts.hpp: SmallConsts; kernels_small.cuh)
+struct SmallDev {
+    int usable, ext_cols, red_shift, pad;
+    int p[64];                     // moduli (1 beyond kSmallMax)
+    unsigned mu[64];               // floor(2^32 / p)
+    float rcp[64];                 // 1 / p
+    int prefix_log2[kSmallMax + 2];
+    int in_log2_milli[kSmallNinMax + 1];
+    int pad2;
+    double log2M_up;
+    const uint8_t *inv;            // [kSmallMax + 1][64]
+    const uint8_t *ext_b;          // [kSmallMax + 1][ext_cols][64]
+    const uint32_t *cw;            // [64][16]
+    const uint8_t *pws;            // [2 (kSmallShiftMax + 1)][64]
+    const uint32_t *in_mi;         // [kSmallNinMax + 1][16][16]
+    const uint32_t *in_negmp;      // [kSmallNinMax + 1][16]
+    const uint32_t *red_mu;        // [N]
+};
+
+}  // namespace mpres
+
 using namespace mpres;
 
 struct mpres_ctx {
     int device = 0;
     int mode = MPRES_MODE_AUTO;
-    int stage2 = MPRES_STAGE2_UMMA;   // which stage-2 kernel the fast path launches
+    int stage2 = MPRES_STAGE2_SMALL;  // which stage-2 kernel the fast path launches
     int reduced_base = 1;             // 1: run stages 1-2 on as many moduli as the exact sums need, then extend the base
     int stage1 = 0;                   // 0: vectorised alignment kernel, 1: round-1 kernel
     int stage3 = 0;                   // 0: entry-per-thread kernel + list, 1: residue-parallel tile kernel
+    int fuse_ext = 1;                 // small-modulus path: base extension fused into the entry-per-thread normalisation kernel
+    int norm32 = 1;                   // entry-per-thread kernel: 32-bit Barrett products where every modulus has the same bit length <= 27
     int vec_config = 0;               // tile configuration of the mp_gemv / mp_dot kernels (A/B measurement)
     HostConsts hc;
+    SmallConsts sc;                   // small-modulus base of the tensor-core stage 2
+    void *d_small[8] = {nullptr};     // device copies of its tables (SmallDev first)
     DevConsts *dconsts = nullptr;
     int *d_pow2 = nullptr, *d_inv_pow2 = nullptr, *d_mrc = nullptr, *d_prefix = nullptr, *d_ext_w = nullptr, *d_ext_t = nullptr, *d_wpow2 = nullptr, *d_spow2 = nullptr;
     std::atomic<long> launches{0};
     // workspace pool (grown on demand, never freed per call)
-    void *ws[8] = {nullptr};
-    size_t ws_size[8] = {0};
+    void *ws[12] = {nullptr};
+    size_t ws_size[12] = {0};
     int *d_counter = nullptr;      // fallback element counter of the last call
     cudaStream_t last_stream = nullptr;
     int sm_count = 148;

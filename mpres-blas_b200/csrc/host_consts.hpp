@@ -6,6 +6,7 @@
 // agreement with the reference's GMP/MPFR-derived values is enforced by tests/test_constants.py.
 #pragma once
 
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -241,6 +242,150 @@ inline int compute_constants(const int *mods, int N, HostConsts &c) {
         c.ext_lazy = ((long double) N * (long double) mx * (long double) mx < 9.0e18L) ? 1 : 0;
     }
     return 0;
+}
+
+
+// ---- small-modulus base of the tensor-core stage 2 (not in the reference) ------------------------------
+// The exact per-entry sums S of the fast mp_gemm path are integers with |S| < 2^need.  Any set of pairwise
+// coprime moduli whose product exceeds 4 * 2^need determines them, so stage 2 runs on moduli that fit ONE
+// unsigned byte (256, 251, 243 = 3^5, 241, ...): one int8 tensor-core GEMM carries ~7.6 bits of S, against
+// sixteen limb x limb GEMMs per 26.6-bit reference modulus (1.7 bits per GEMM).  The inputs reach that base
+// through their binary representation (CRT over the first n_in reference moduli, exact because the
+// significands are known to be small), the outputs return to the reference moduli by a CRT base extension.
+constexpr int kSmallMax = 54;          // small moduli available (product ~ 2^362)
+constexpr int kSmallK = 64;            // K extent of the base-extension MMA: residues, rank, zero padding
+constexpr int kSmallNinMax = 16;       // reference moduli the input conversion may read
+constexpr int kSmallShiftMax = 400;    // alignment shifts the +-2^s table covers (> log2 of the product)
+static const int kSmallModuli[kSmallMax] = {
+    256, 251, 243, 241, 239, 233, 229, 227, 223, 211, 199, 197, 193, 191, 181, 179, 173, 169, 167, 163, 157, 151, 149, 139, 137, 131, 127,
+    125, 121, 113, 109, 107, 103, 101, 97,  89,  83,  79,  73,  71,  67,  61,  59,  53,  49,  47,  43,  41,  37,  31,  29,  23,  19,  17};
+
+struct SmallConsts {
+    bool usable = false;                 // N % 4 == 0, every reference modulus below 2^27
+    int ext_cols = 0;                    // columns of the extension operand: 128 per block of 32 reference moduli
+    int red_shift = 0;                   // > 0: all reference moduli have the same bit length k >= 24 (fast reduction of the extension sums)
+    std::vector<int> prefix_log2;        // [kSmallMax + 1]  floor(log2(p_0 ... p_{c-1}))
+    std::vector<uint8_t> inv;            // [kSmallMax + 1][64]   (M'_c / p_i)^-1 mod p_i, i < c
+    std::vector<uint8_t> ext_b;          // [kSmallMax + 1][ext_cols][64]  limbs of (M'_c / p_i) mod m_q (K index i < c) and of
+                                         //                                m_q - M'_c mod m_q (K index 63, multiplies the rank)
+    std::vector<uint32_t> cw;            // [kSmallMax][16]  byte b of word w = 256^(4 w + b) mod p_j
+    std::vector<uint8_t> pws;            // [2 (kSmallShiftMax + 1)][64]  row 2 s: 2^s mod p_j, row 2 s + 1: -2^s mod p_j
+    std::vector<uint32_t> in_mi;         // [kSmallNinMax + 1][16][16]  words of (m_0 ... m_{c-1}) / m_i
+    std::vector<uint32_t> in_negmp;      // [kSmallNinMax + 1][16]      words of 2^(32 c) - m_0 ... m_{c-1}
+    std::vector<int> in_log2_milli;      // [kSmallNinMax + 1]  floor(1024 log2(m_0 ... m_{c-1})) - 1
+    std::vector<uint32_t> red_mu;        // [N]  floor(2^(2 k) / m_q), k = red_shift (Barrett constant of the extension sums)
+    double log2M_up = 0;                 // log2(M), rounded up a little
+};
+
+// column of the extension operand that holds limb `limb` of reference modulus q (see k_ext_small: a thread of the
+// m16n8k32 accumulator fragment owns columns 2t, 2t+1 of an 8-column tile; limbs 0,1 and 2,3 of one modulus sit at the
+// same position of two neighbouring tiles)
+inline int small_ext_col(int q, int limb) { return (q >> 5) * 128 + ((q & 31) >> 2) * 16 + (limb >> 1) * 8 + (q & 3) * 2 + (limb & 1); }
+
+inline double biguint_log2(const BigUInt &v) {
+    const int L = v.bit_length();
+    if (L == 0) return 0;
+    const int take = L < 53 ? L : 53;
+    return std::log2((double) v.top_bits(take)) + (double) (L - take);
+}
+
+inline void compute_small_consts(const HostConsts &c, SmallConsts &s) {
+    const int N = c.N, P = kSmallMax;
+    int mx = 0, kmin = 32, kmax = 0;
+    for (int i = 0; i < N; ++i) {
+        mx = std::max(mx, c.moduli[i]);
+        const int k = 32 - __builtin_clz((unsigned) c.moduli[i]);
+        kmin = std::min(kmin, k); kmax = std::max(kmax, k);
+    }
+    s.usable = (N % 4 == 0) && mx < (1 << 27) && N >= 4;
+    if (!s.usable) return;
+    s.red_shift = (kmin == kmax && kmin >= 24) ? kmin : 0;
+    s.red_mu.assign(N, 0);
+    if (s.red_shift)
+        for (int i = 0; i < N; ++i) s.red_mu[i] = (uint32_t) ((1ull << (2 * s.red_shift)) / (uint64_t) c.moduli[i]);
+    s.ext_cols = ((N + 31) / 32) * 128;
+    s.prefix_log2.assign(P + 1, 0);
+    {
+        BigUInt prod(1);
+        for (int cc = 0; cc <= P; ++cc) {
+            s.prefix_log2[cc] = prod.bit_length() - 1;
+            if (cc < P) prod.mul_small((uint32_t) kSmallModuli[cc]);
+        }
+    }
+    s.inv.assign((size_t) (P + 1) * 64, 0);
+    s.ext_b.assign((size_t) (P + 1) * s.ext_cols * 64, 0);
+    for (int cc = 1; cc <= P; ++cc) {
+        for (int i = 0; i < cc; ++i) {
+            const int pi = kSmallModuli[i];
+            int64_t prod = 1;
+            for (int j = 0; j < cc; ++j) if (j != i) prod = prod * (kSmallModuli[j] % pi) % pi;
+            s.inv[(size_t) cc * 64 + i] = (uint8_t) inverse_mod(prod, pi);
+        }
+        std::vector<int64_t> pre(cc + 1), suf(cc + 1);
+        for (int q = 0; q < N; ++q) {
+            const int64_t mq = c.moduli[q];
+            pre[0] = 1;
+            for (int i = 0; i < cc; ++i) pre[i + 1] = pre[i] * (kSmallModuli[i] % mq) % mq;
+            suf[cc] = 1;
+            for (int i = cc - 1; i >= 0; --i) suf[i] = suf[i + 1] * (kSmallModuli[i] % mq) % mq;
+            for (int i = 0; i <= cc; ++i) {
+                uint32_t v;
+                if (i < cc) v = (uint32_t) (pre[i] * suf[i + 1] % mq);
+                else { const int64_t mp = pre[cc]; v = (uint32_t) (mp ? mq - mp : 0); }
+                const int kidx = i < cc ? i : kSmallK - 1;   // the rank sits in the last K slot
+                for (int limb = 0; limb < 4; ++limb)
+                    s.ext_b[((size_t) cc * s.ext_cols + small_ext_col(q, limb)) * 64 + kidx] = (uint8_t) (v >> (8 * limb));
+            }
+        }
+    }
+    s.cw.assign((size_t) P * 16, 0);
+    for (int j = 0; j < P; ++j) {
+        const int p = kSmallModuli[j];
+        int v = 1 % p;
+        for (int b = 0; b < 64; ++b) {
+            s.cw[(size_t) j * 16 + b / 4] |= (uint32_t) v << (8 * (b % 4));
+            v = v * 256 % p;
+        }
+    }
+    s.pws.assign((size_t) 2 * (kSmallShiftMax + 1) * 64, 0);
+    for (int j = 0; j < P; ++j) {
+        const int p = kSmallModuli[j];
+        int v = 1 % p;
+        for (int sh = 0; sh <= kSmallShiftMax; ++sh) {
+            s.pws[(size_t) (2 * sh) * 64 + j] = (uint8_t) v;
+            s.pws[(size_t) (2 * sh + 1) * 64 + j] = (uint8_t) (v ? p - v : 0);
+            v = v * 2 % p;
+        }
+    }
+    s.in_mi.assign((size_t) (kSmallNinMax + 1) * 16 * 16, 0);
+    s.in_negmp.assign((size_t) (kSmallNinMax + 1) * 16, 0);
+    s.in_log2_milli.assign(kSmallNinMax + 1, -1);
+    for (int cc = 1; cc <= kSmallNinMax && cc < N; ++cc) {
+        BigUInt prod(1);
+        for (int i = 0; i < cc; ++i) prod.mul_small((uint32_t) c.moduli[i]);
+        s.in_log2_milli[cc] = (int) std::floor(1024.0 * biguint_log2(prod)) - 1;
+        // 2^(32 cc) - prod, cc words
+        {
+            uint64_t borrow = 0;
+            for (int w = 0; w < cc; ++w) {
+                const uint64_t pw = w < (int) prod.limb.size() ? prod.limb[w] : 0;
+                const uint64_t sub = pw + borrow;
+                const uint32_t r = (uint32_t) (0ull - sub);
+                borrow = (sub != 0) ? 1 : 0;
+                s.in_negmp[(size_t) cc * 16 + w] = r;
+            }
+        }
+        for (int i = 0; i < cc; ++i) {
+            BigUInt mi = prod;
+            mi.div_small((uint32_t) c.moduli[i]);
+            for (int w = 0; w < cc && w < (int) mi.limb.size(); ++w) s.in_mi[((size_t) cc * 16 + i) * 16 + w] = mi.limb[w];
+        }
+    }
+    {
+        BigUInt M(1);
+        for (int i = 0; i < N; ++i) M.mul_small((uint32_t) c.moduli[i]);
+        s.log2M_up = biguint_log2(M) + 1e-9;
+    }
 }
 
 }  // namespace mpres

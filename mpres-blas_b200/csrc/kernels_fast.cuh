@@ -47,6 +47,8 @@ constexpr int kShiftMax = 8000;        // larger shifts cannot pass the window g
 struct OuterInfo {   // per row of op(A) / column of op(B)
     int emin;        // min exponent over non-zero entries (0 if none)
     int win;         // max over non-zero entries of (e - emin + bit bound of X); <0 if the line is all zero
+    int xb;          // upper bound of 1024 log2(X) over the non-zero entries (significand size, for the small-modulus path)
+    int pad;
 };
 
 // ---- stage 1a: exponent base and magnitude window of every line -----------------------------------
@@ -59,6 +61,7 @@ __global__ void k_outer_info(const DevConsts *Cp, SoA X, long long so, long long
     const long long len = X.len();
     int emin = INT_MAX;
     long long top = LLONG_MIN;
+    double lx = -1.0e300;   // max of log2(upper bound of X / M)
     for (int l = lane; l < inner; l += 32) {
         const long long idx = warp * so + l * sl;
         const Er up = X.eval[idx + len];
@@ -68,6 +71,8 @@ __global__ void k_outer_info(const DevConsts *Cp, SoA X, long long so, long long
             // X/M < 2^(up.exp+1) and M < 2^(log2M+1)  =>  X < 2^(log2M + up.exp + 2)
             long long t = (long long) e + up.exp;
             top = t > top ? t : top;
+            const long long ue = up.exp > 100000 ? 100000 : (up.exp < -100000 ? -100000 : up.exp);
+            lx = fmax(lx, (double) ue + log2(fabs(up.frac)));
         }
     }
 #pragma unroll
@@ -75,14 +80,19 @@ __global__ void k_outer_info(const DevConsts *Cp, SoA X, long long so, long long
         emin = min(emin, __shfl_xor_sync(0xffffffffu, emin, o));
         long long t = __shfl_xor_sync(0xffffffffu, top, o);
         top = t > top ? t : top;
+        lx = fmax(lx, __shfl_xor_sync(0xffffffffu, lx, o));
     }
     if (lane == 0) {
         OuterInfo r;
-        if (emin == INT_MAX) { r.emin = 0; r.win = -1; }
+        r.pad = 0;
+        if (emin == INT_MAX) { r.emin = 0; r.win = -1; r.xb = 0; }
         else {
             long long w = top - emin + log2M + 2;
             r.emin = emin;
             r.win = w > 1000000 ? 1000000 : (w < 0 ? 0 : (int) w);
+            // X <= up * M:  1024 log2 X <= 1024 (lx + log2 M), rounded up with a margin
+            const double b = (lx + (Cp->small ? Cp->small->log2M_up : (double) (log2M + 1))) * 1024.0;
+            r.xb = b > 1.0e8 ? 100000000 : (b < 0 ? 0 : (int) ceil(b) + 2);
         }
         info[warp] = r;
     }
@@ -94,30 +104,46 @@ __global__ void k_outer_info(const DevConsts *Cp, SoA X, long long so, long long
 // needed).  Stage 1b then aligns the first ceil4(n') moduli (it works on groups of four), stage 2 multiplies
 // n' of them and k_base_extend reconstructs the residues q >= n'.  One block.
 constexpr int kMaxReducedBase = 48;
+// sel[0] = number of small moduli (0: the small-modulus path is not used), sel[1] = reference moduli its input conversion reads.
+// When the small base is selected *nprime is 0 and the kernels of the reference-moduli path leave at once.
 __global__ void __launch_bounds__(256) k_choose_base(const DevConsts *Cp, const OuterInfo *ia, int m, const OuterInfo *ib, int n, int k,
-                                                     int enabled, int *nprime) {
-    __shared__ int sa[256], sb[256];
-    int wa = -1, wb = -1;
-    for (int i = threadIdx.x; i < m; i += 256) wa = max(wa, ia[i].win);
-    for (int j = threadIdx.x; j < n; j += 256) wb = max(wb, ib[j].win);
-    sa[threadIdx.x] = wa; sb[threadIdx.x] = wb;
+                                                     int enabled, int small_enabled, int *nprime, int *sel) {
+    __shared__ int sa[256], sb[256], sx[256];
+    int wa = -1, wb = -1, xb = 0;
+    for (int i = threadIdx.x; i < m; i += 256) { wa = max(wa, ia[i].win); xb = max(xb, ia[i].xb); }
+    for (int j = threadIdx.x; j < n; j += 256) { wb = max(wb, ib[j].win); xb = max(xb, ib[j].xb); }
+    sa[threadIdx.x] = wa; sb[threadIdx.x] = wb; sx[threadIdx.x] = xb;
     __syncthreads();
     for (int o = 128; o >= 1; o >>= 1) {
-        if (threadIdx.x < o) { sa[threadIdx.x] = max(sa[threadIdx.x], sa[threadIdx.x + o]); sb[threadIdx.x] = max(sb[threadIdx.x], sb[threadIdx.x + o]); }
+        if (threadIdx.x < o) {
+            sa[threadIdx.x] = max(sa[threadIdx.x], sa[threadIdx.x + o]); sb[threadIdx.x] = max(sb[threadIdx.x], sb[threadIdx.x + o]);
+            sx[threadIdx.x] = max(sx[threadIdx.x], sx[threadIdx.x + o]);
+        }
         __syncthreads();
     }
     if (threadIdx.x == 0) {
         const int N = Cp->N;
         int np = N;
+        int lgk = 0;
+        while ((1 << lgk) < k) ++lgk;
+        const long long need = (sa[0] < 0 || sb[0] < 0) ? 0 : (long long) sa[0] + sb[0] + lgk + 2;
         if (enabled && (N & 3) == 0) {
-            int lgk = 0;
-            while ((1 << lgk) < k) ++lgk;
-            const long long need = (sa[0] < 0 || sb[0] < 0) ? 0 : (long long) sa[0] + sb[0] + lgk + 2;
             for (int c = 1; c <= N; ++c)
                 if ((long long) Cp->prefix_log2[c] >= need) { np = c; break; }
             if (np > kMaxReducedBase) np = N;
         }
-        *nprime = np;
+        int P = 0, nin = 0;
+        const SmallDev *SD = Cp->small;
+        if (small_enabled && SD && SD->usable && sa[0] >= 0 && sb[0] >= 0 && sa[0] <= kSmallShiftMax && sb[0] <= kSmallShiftMax) {
+            for (int c = 1; c <= kSmallMax; ++c)
+                if ((long long) SD->prefix_log2[c] >= need) { P = c; break; }
+            const int cmax = min(kSmallNinMax, N - 1);
+            for (int c = 1; c <= cmax; ++c)
+                if (SD->in_log2_milli[c] >= sx[0]) { nin = c; break; }   // X < m_0 ... m_{c-1}
+            if (P == 0 || nin == 0) { P = 0; nin = 0; }
+        }
+        sel[0] = P; sel[1] = nin;
+        *nprime = P > 0 ? 0 : np;
     }
 }
 
@@ -191,6 +217,7 @@ __global__ void __launch_bounds__(256) k_align_planes4(const DevConsts *Cp, SoA 
     extern __shared__ uint8_t sm_stage[];   // [4][N][kRun + 4]
     const DevConsts &C = *Cp;
     const int N = C.N;
+    if (*nprime <= 0) return;                    // the small-modulus path was selected
     const int np = min(N, (*nprime + 3) & ~3);   // moduli q >= np are not needed (reduced base)
     const int Q4 = np >> 2;                 // active modulus groups
     const int EP = 256 / Q4;                // entries per pass
@@ -463,6 +490,7 @@ __global__ void __launch_bounds__(256, 1) k_limb_gemm(const DevConsts *Cp, const
 }  // namespace mpres
 
 #include "kernels_norm.cuh"
+#include "kernels_small.cuh"
 
 namespace mpres {
 
@@ -513,19 +541,27 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
     const int N = c->hc.N;
     const long long m_p = round_up(m, kBM), n_p = round_up(n, kBN), k_p = round_up(k, 128);
     if (k_p > 32000 * 128ll) return 0;
+    // the small-modulus stage 2 (kernels_small.cuh) is offered whenever its tables exist; k_choose_base decides per call
+    const bool small_on = c->stage2 == MPRES_STAGE2_SMALL && c->sc.usable;
+    const long long m_ps = round_up(m, kSN), n_ps = round_up(n, kSM);   // rows of the one-byte planes: 256 x 128 tiles of k_small_umma
     // workspace: planes A/B (u8), S (int), shifts, delta, infos, todo
     const size_t bytesPA = (size_t) N * 4 * m_p * k_p, bytesPB = (size_t) N * 4 * n_p * k_p;
     const size_t bytesS = (size_t) N * n_p * m_p * 4;
-    const size_t bytesSA = (size_t) m_p * k_p * 2, bytesSB = (size_t) n_p * k_p * 2, bytesD = (size_t) n_p * m_p * 2;
+    const size_t bytesSA = (size_t) m_ps * k_p * 2, bytesSB = (size_t) n_ps * k_p * 2, bytesD = (size_t) n_p * m_p * 2;
     const size_t bytesInfo = (size_t) (m_p + n_p) * sizeof(OuterInfo);
     const size_t bytesTab = (size_t) (3 * c->hc.log2M + 2) * N * sizeof(int);   // alpha * 2^j, beta * 2^j (stage 3)
     const size_t bytesTodo = (size_t) m * n * sizeof(long long);   // per list: reference-order todo, stage-3 slow list
-    void *pPA, *pPB, *pS, *pMisc;
+    void *pPA, *pPB, *pS, *pMisc, *pQA = nullptr, *pQB = nullptr, *pS8 = nullptr;
     int rc;
     if ((rc = ws_reserve(c, 3, bytesPA, &pPA))) return rc;
     if ((rc = ws_reserve(c, 4, bytesPB, &pPB))) return rc;
     if ((rc = ws_reserve(c, 5, bytesS, &pS))) return rc;
     if ((rc = ws_reserve(c, 6, bytesSA + bytesSB + bytesD + bytesInfo + 2 * bytesTodo + bytesTab + 1024, &pMisc))) return rc;
+    if (small_on) {
+        if ((rc = ws_reserve(c, 8, (size_t) kSmallMax * m_ps * k_p, &pQA))) return rc;
+        if ((rc = ws_reserve(c, 9, (size_t) kSmallMax * n_ps * k_p, &pQB))) return rc;
+        if ((rc = ws_reserve(c, 10, (size_t) kSmallMax * n_ps * m_ps, &pS8))) return rc;
+    }
     char *pm = (char *) pMisc;
     int16_t *SA = (int16_t *) pm; pm += bytesSA;
     int16_t *SB = (int16_t *) pm; pm += bytesSB;
@@ -535,15 +571,17 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
     long long *todo = (long long *) pm; pm += bytesTodo;
     long long *slow = (long long *) pm; pm += bytesTodo;
     int *scal_tab = (int *) pm;
+    int *nprime = c->d_counter + 2, *sel = c->d_counter + 4;
 
     // element (o, l) index strides: op(A)(i, l) and op(B)(l, j)
     const long long soA = ta ? lda : 1, slA = ta ? 1 : lda;
     const long long soB = tb ? 1 : ldb, slB = tb ? ldb : 1;
     auto mark = [&](int i) { if (c->profiling) { if (!c->ev[i]) cudaEventCreate(&c->ev[i]); cudaEventRecord(c->ev[i], st); } };
     mark(0);
+    int extra_launches = 0;
     k_outer_info<<<(unsigned) ((m * 32ll + 255) / 256), 256, 0, st>>>(c->dconsts, A, soA, slA, m, k, IA);
     k_outer_info<<<(unsigned) ((n * 32ll + 255) / 256), 256, 0, st>>>(c->dconsts, B, soB, slB, n, k, IB);
-    k_choose_base<<<1, 256, 0, st>>>(c->dconsts, IA, m, IB, n, k, c->reduced_base, c->d_counter + 2);
+    k_choose_base<<<1, 256, 0, st>>>(c->dconsts, IA, m, IB, n, k, c->reduced_base, small_on ? 1 : 0, nprime, sel);
     const size_t smem_align = (size_t) N * 4 * (kRun + 4);
     static bool attr_done = false;
     if (!attr_done) {
@@ -552,11 +590,18 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
         cudaFuncSetAttribute(k_base_extend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) base_extend_smem(128));
         cudaFuncSetAttribute(k_limb_gemm<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
         cudaFuncSetAttribute(k_limb_gemm<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
+        cudaFuncSetAttribute(k_ext_small<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ext_small_smem(512, 128));
+        cudaFuncSetAttribute(k_ext_small<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ext_small_smem(512, 128));
         attr_done = true;
     }
+    if (small_on) {
+        k_align_small<<<dim3((unsigned) (m_ps / kASo), (unsigned) (k_p / kASl)), 256, align_small_smem(), st>>>(c->dconsts, A, soA, slA, m, k, IA, (uint8_t *) pQA, SA, m_ps, k_p, sel);
+        k_align_small<<<dim3((unsigned) (n_ps / kASo), (unsigned) (k_p / kASl)), 256, align_small_smem(), st>>>(c->dconsts, B, soB, slB, n, k, IB, (uint8_t *) pQB, SB, n_ps, k_p, sel);
+        extra_launches += 2;
+    }
     if (N % 4 == 0 && N <= 128 && c->stage1 == 0) {
-        k_align_planes4<<<dim3((unsigned) m_p, (unsigned) (k_p / kRun)), 256, smem_align, st>>>(c->dconsts, A, soA, slA, m, k, IA, (uint8_t *) pPA, SA, m_p, k_p, c->d_counter + 2);
-        k_align_planes4<<<dim3((unsigned) n_p, (unsigned) (k_p / kRun)), 256, smem_align, st>>>(c->dconsts, B, soB, slB, n, k, IB, (uint8_t *) pPB, SB, n_p, k_p, c->d_counter + 2);
+        k_align_planes4<<<dim3((unsigned) m_p, (unsigned) (k_p / kRun)), 256, smem_align, st>>>(c->dconsts, A, soA, slA, m, k, IA, (uint8_t *) pPA, SA, m_p, k_p, nprime);
+        k_align_planes4<<<dim3((unsigned) n_p, (unsigned) (k_p / kRun)), 256, smem_align, st>>>(c->dconsts, B, soB, slB, n, k, IB, (uint8_t *) pPB, SB, n_p, k_p, nprime);
     } else {
         k_align_planes<<<dim3((unsigned) m_p, (unsigned) (k_p / kRun)), 256, smem_align, st>>>(c->dconsts, A, soA, slA, m, k, IA, (uint8_t *) pPA, SA, m_p, k_p);
         k_align_planes<<<dim3((unsigned) n_p, (unsigned) (k_p / kRun)), 256, smem_align, st>>>(c->dconsts, B, soB, slB, n, k, IB, (uint8_t *) pPB, SB, n_p, k_p);
@@ -565,14 +610,21 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
     dim3 grid((unsigned) (n_p / kBN), (unsigned) (m_p / kBM), (unsigned) N);
     mark(1);
     int gemm_launches = 0;
+    if (small_on) {
+        for (long long kb = 0; kb < k_p; kb += kSmallKChunk) {
+            const int kl = (int) std::min<long long>(kSmallKChunk, k_p - kb);
+            if ((rc = launch_small_umma(c, (const uint8_t *) pQA, (const uint8_t *) pQB, (uint8_t *) pS8, m_ps, n_ps, k_p, kb, kl, kb > 0, sel, st))) return rc;
+            gemm_launches += 1;
+        }
+    }
     for (long long kb = 0; kb < k_p; kb += 8064) {
         const int kl = (int) std::min<long long>(8064, k_p - kb);
         if (c->stage2 == MPRES_STAGE2_MMA_SYNC) {
-            k_limb_gemm<0><<<grid, 256, kGemmSmem, st>>>(c->dconsts, (const uint8_t *) pPA, (const uint8_t *) pPB, (int *) pS, m_p, n_p, k_p, kb, kl, kb > 0, c->d_counter + 2);
-            k_limb_gemm<1><<<grid, 256, kGemmSmem, st>>>(c->dconsts, (const uint8_t *) pPA, (const uint8_t *) pPB, (int *) pS, m_p, n_p, k_p, kb, kl, true, c->d_counter + 2);
+            k_limb_gemm<0><<<grid, 256, kGemmSmem, st>>>(c->dconsts, (const uint8_t *) pPA, (const uint8_t *) pPB, (int *) pS, m_p, n_p, k_p, kb, kl, kb > 0, nprime);
+            k_limb_gemm<1><<<grid, 256, kGemmSmem, st>>>(c->dconsts, (const uint8_t *) pPA, (const uint8_t *) pPB, (int *) pS, m_p, n_p, k_p, kb, kl, true, nprime);
             gemm_launches += 2;
         } else {
-            if ((rc = launch_limb_umma(c, c->stage2 == MPRES_STAGE2_UMMA, (const uint8_t *) pPA, (const uint8_t *) pPB, (int *) pS, m_p, n_p, k_p, kb, kl,
+            if ((rc = launch_limb_umma(c, c->stage2 != MPRES_STAGE2_UMMA_UNSTACKED, (const uint8_t *) pPA, (const uint8_t *) pPB, (int *) pS, m_p, n_p, k_p, kb, kl,
                                        kb > 0, st))) return rc;
             gemm_launches += 1;
         }
@@ -580,6 +632,17 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
     mark(2);
     const bool allow_fb = c->mode == MPRES_MODE_AUTO;
     int stage3_launches = 0;
+    bool have_fast = c->stage3 == 0;
+    switch (N) { case 8: case 16: case 24: case 32: case 40: case 48: case 56: case 64: break; default: have_fast = false; }
+    const bool f32 = c->sc.usable && c->sc.red_shift >= 24 && c->sc.red_shift <= 27 && c->norm32;
+    const bool fused = small_on && have_fast && c->fuse_ext;
+    if (small_on && !fused) {
+        const unsigned gx = (unsigned) ((m_p / kXT) * n);
+        const size_t sm = ext_small_smem(c->sc.ext_cols, N);
+        if (c->sc.red_shift) k_ext_small<true><<<gx, kXT, sm, st>>>(c->dconsts, m, n, (const uint8_t *) pS8, m_p, m_ps, n_ps, (int *) pS, n_p, sel);
+        else k_ext_small<false><<<gx, kXT, sm, st>>>(c->dconsts, m, n, (const uint8_t *) pS8, m_p, m_ps, n_ps, (int *) pS, n_p, sel);
+        ++extra_launches;
+    }
     if (c->reduced_base && N % 4 == 0) {
         const unsigned gx = (unsigned) ((long long) ((m + kExtThreads - 1) / kExtThreads) * n);
         k_base_extend<<<gx, kExtThreads, base_extend_smem(N), st>>>(c->dconsts, m, n, (int *) pS, m_p, n_p, c->d_counter + 2);
@@ -590,11 +653,35 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
         const unsigned g3 = (unsigned) ((long long) ((m + kNormFastThreads - 1) / kNormFastThreads) * n);
         const int rowsT = 3 * c->hc.log2M + 2;
         k_scalar_tables<<<(rowsT * NQ + 255) / 256, 256, 0, st>>>(c->dconsts, alpha, beta, scal_tab);
-        k_norm_fast<NQ><<<g3, kNormFastThreads, (size_t) kNormFastThreads * (NQ + 1) * sizeof(int), st>>>(c->dconsts, m, n, k, (const int *) pS, D, m_p, n_p, IA, IB, alpha, beta, Cm, ldc,
-                                                         scal_tab, todo, c->d_counter, slow, c->d_counter + 1, allow_fb);
+        const size_t sm_cds = (size_t) kNormFastThreads * (NQ + 1) * sizeof(int);
+        if (fused) {
+            // small-modulus path: base extension and normalisation in one kernel (leaves at once when the small base was not selected)
+            const unsigned gx = (unsigned) ((m_p / kXT) * n);
+            const size_t sm = ext_small_smem(c->sc.ext_cols, NQ) + (ext_norm_cds_aliased(NQ) ? 0 : sm_cds);
+            static bool attr_fused = false;
+            if (!attr_fused) {
+                cudaFuncSetAttribute(k_ext_norm_small<NQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm);
+                cudaFuncSetAttribute(k_ext_norm_small<NQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm);
+                attr_fused = true;
+            }
+            if (f32)
+                k_ext_norm_small<NQ, true><<<gx, kXT, sm, st>>>(c->dconsts, m, n, k, (const uint8_t *) pS8, m_p, m_ps, n_ps, (int *) pS, n_p, sel, D, IA, IB, alpha, beta, Cm, ldc,
+                                                               scal_tab, todo, c->d_counter, slow, c->d_counter + 1, allow_fb);
+            else
+                k_ext_norm_small<NQ, false><<<gx, kXT, sm, st>>>(c->dconsts, m, n, k, (const uint8_t *) pS8, m_p, m_ps, n_ps, (int *) pS, n_p, sel, D, IA, IB, alpha, beta, Cm, ldc,
+                                                                scal_tab, todo, c->d_counter, slow, c->d_counter + 1, allow_fb);
+            ++extra_launches;
+        }
+        // limb-plane path (or unfused small path); `gate`: leave at once when the fused kernel did the work
+        const int *gate = fused ? sel : nullptr;
+        if (f32)
+            k_norm_fast<NQ, true><<<g3, kNormFastThreads, sm_cds, st>>>(c->dconsts, m, n, k, (const int *) pS, D, m_p, n_p, IA, IB, alpha, beta, Cm, ldc,
+                                                                       scal_tab, todo, c->d_counter, slow, c->d_counter + 1, allow_fb, gate);
+        else
+            k_norm_fast<NQ, false><<<g3, kNormFastThreads, sm_cds, st>>>(c->dconsts, m, n, k, (const int *) pS, D, m_p, n_p, IA, IB, alpha, beta, Cm, ldc,
+                                                                        scal_tab, todo, c->d_counter, slow, c->d_counter + 1, allow_fb, gate);
         ++stage3_launches;
     };
-    bool have_fast = c->stage3 == 0;
     if (have_fast) {
         switch (N) {
             case 8: norm_fast(std::integral_constant<int, 8>{}); break;
@@ -628,7 +715,7 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
     mark(3);
     c->ev_valid = c->profiling;
     c->last_stage2_launches = gemm_launches;
-    for (int i = 0; i < 6 + stage3_launches + gemm_launches; ++i) LAUNCHED(c);
+    for (int i = 0; i < 6 + stage3_launches + gemm_launches + extra_launches; ++i) LAUNCHED(c);
     CUDA_TRY(cudaGetLastError());
     *done = true;
     return 0;

@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(kExtThreads, 6) k_base_extend(const DevConsts 
     const DevConsts &C = *Cp;
     const int N = C.N;
     const int np = *nprime;
-    if (np >= N) return;
+    if (np >= N || np <= 0) return;   // full base, or the small-modulus path was selected
     const int np4 = (np + 3) & ~3;
     unsigned long long *s_mu = (unsigned long long *) ext_smem;      // [N]
     double *s_rcp = (double *) (s_mu + N);                             // [N]   1 / m_i
@@ -313,7 +313,8 @@ __global__ void __launch_bounds__(256) k_norm_list(const DevConsts *Cp, int m, i
 
 // ---- entry-per-thread kernel ---------------------------------------------------------------------------
 struct QConst {          // per-modulus constants, broadcast from shared memory
-    int m, pad;
+    int m;
+    unsigned mu32;       // floor(2^(2 kb) / m) when every modulus has the same bit length kb (32-bit Barrett), else 0
     unsigned long long mu;
     double rrd, rru;
 };
@@ -340,34 +341,52 @@ __global__ void k_scalar_tables(const DevConsts *Cp, SoA alpha, SoA beta, int *t
 }
 struct ScalarEsi { int sign, exp; Er lo, up; };
 
+// a * b mod m for canonical a, b.  F32: every modulus has bit length kb (24 <= kb <= 27), so the product is below
+// 2^(2 kb) and a 32-bit Barrett step with mu32 = floor(2^(2 kb) / m) leaves a remainder below 3 m (HAC 14.42);
+// otherwise the generic 64-bit reduction.  Both return the canonical residue, hence identical results.
+template <bool F32>
+__device__ __forceinline__ int mulmod_q(int a, int b, const QConst &c, int kb) {
+    if (F32) {
+        const unsigned long long p = (unsigned long long) (unsigned) a * (unsigned) b;
+        const unsigned ph = (unsigned) (p >> (kb - 1));
+        const unsigned q = (unsigned) (((unsigned long long) ph * c.mu32) >> (kb + 1));
+        unsigned r = (unsigned) p - q * (unsigned) c.m;
+        r = r >= (unsigned) c.m ? r - (unsigned) c.m : r;
+        r = r >= (unsigned) c.m ? r - (unsigned) c.m : r;
+        return (int) r;
+    }
+    return mulmod(a, b, c.m, c.mu);
+}
+
 __host__ __device__ constexpr int pow2ceil_c(int n) { int p = 1; while (p < n) p <<= 1; return p; }
 __host__ __device__ constexpr int log2_c(int p) { int l = 0; while ((1 << l) < p) ++l; return l; }
 __host__ __device__ constexpr int trailing_ones_c(int q) { int t = 0; while (q & 1) { ++t; q >>= 1; } return t; }
 
 constexpr int kNormFastThreads = 128;
 
-template <int NQ>
-__global__ void __launch_bounds__(kNormFastThreads, 6) k_norm_fast(const DevConsts *Cp, int m, int n, int k, const int *S, const int16_t *delta,
-                                                                long long m_p, long long n_p, const OuterInfo *ia, const OuterInfo *ib,
-                                                                SoA alpha, SoA beta, SoA Cm, int ldc, const int *scal_tab, long long *todo, int *todo_count,
-                                                                long long *slow, int *slow_count, bool fallback_allowed) {
+// The body of the entry-per-thread kernel.  One block = kNormFastThreads consecutive rows (from row0) of column col.
+// Sp[q * plane] is residue q of the exact sum of this thread's entry: in the residue planes of stage 2 (global memory),
+// or -- SMEM_S -- in shared memory where the fused base-extension kernel (kernels_small.cuh) left it; then the residues of the
+// entries handed to the list kernel are copied to the global planes (Sg, stride gplane), which k_norm_list reads.
+template <int NQ, bool F32, bool SMEM_S>
+__device__ __forceinline__ void norm_fast_body(const DevConsts &C, int *cds, int m, int n, int k, int col, int row0, const int *Sp, long long plane,
+                                               int *Sg, long long gplane, const int16_t *delta, long long m_p, const OuterInfo *ia, const OuterInfo *ib,
+                                               SoA alpha, SoA beta, SoA Cm, int ldc, const int *scal_tab, long long *todo, int *todo_count,
+                                               long long *slow, int *slow_count, bool fallback_allowed) {
     constexpr int P = pow2ceil_c(NQ), LOGP = log2_c(P);
     constexpr int CP = NQ + 1;              // pitch of the staged C digits (conflict-free per-thread rows)
-    extern __shared__ int cds[];            // [kNormFastThreads][CP]: digits of C in, digits of the result out
+    // cds: [kNormFastThreads][CP]: digits of C in, digits of the result out
     __shared__ QConst qc[NQ];
     __shared__ ScalarEsi s_al, s_be;
     __shared__ unsigned char okf[kNormFastThreads];
-    const DevConsts &C = *Cp;
     for (int q = threadIdx.x; q < NQ; q += blockDim.x) {
         QConst c;
-        c.m = C.moduli[q]; c.pad = 0; c.mu = C.barrett[q]; c.rrd = C.recip_rd[q]; c.rru = C.recip_ru[q];
+        c.m = C.moduli[q]; c.mu32 = F32 ? C.small->red_mu[q] : 0u; c.mu = C.barrett[q]; c.rrd = C.recip_rd[q]; c.rru = C.recip_ru[q];
         qc[q] = c;
     }
+    const int kb = F32 ? C.small->red_shift : 0;
     if (threadIdx.x == 0) { s_al.sign = alpha.sign[0]; s_al.exp = alpha.exp[0]; s_al.lo = alpha.eval[0]; s_al.up = alpha.eval[alpha.len()]; }
     if (threadIdx.x == 32) { s_be.sign = beta.sign[0]; s_be.exp = beta.exp[0]; s_be.lo = beta.eval[0]; s_be.up = beta.eval[beta.len()]; }
-    const int tiles = (m + kNormFastThreads - 1) / kNormFastThreads;
-    const int col = blockIdx.x / tiles;
-    const int row0 = (blockIdx.x - col * tiles) * kNormFastThreads;
     const int row = row0 + threadIdx.x;
     const bool live = row < m;
     // the digits of this block's C entries are one contiguous run: stage them with coalesced 128-bit loads
@@ -392,43 +411,56 @@ __global__ void __launch_bounds__(kNormFastThreads, 6) k_norm_fast(const DevCons
         int K = log2M - (int) bound - 3;
         K = K < 0 ? 0 : K;
         // ---- pass 1 over the moduli: residues, magnified fractions, directed sums (balanced tree) ----
-        int nz = 0;
-        double stl[LOGP + 1], stu[LOGP + 1];
-        const int *Sp = S + (long long) col * m_p + row;
-        const long long plane = n_p * m_p;
-        {
-            const int *p2 = C.wpow2 + (long long) K * NQ;   // w_q 2^K mod m_q
-#pragma unroll
-            for (int q = 0; q < P; ++q) {
-                double vl = 0.0, vu = 0.0;
-                if (q < NQ) {
-                    const QConst c = qc[q];
-                    const int xq = __ldg(Sp + q * plane);
-                    nz |= xq;
-                    const int sq = mulmod(xq, __ldg(p2 + q), c.m, c.mu);
-                    vl = __dmul_rd((double) sq, c.rrd);
-                    vu = __dmul_ru((double) sq, c.rru);
-                }
-                const int t1s = trailing_ones_c(q);
-#pragma unroll
-                for (int b = 0; b < LOGP; ++b)
-                    if (b < t1s) { vl = __dadd_rd(stl[b], vl); vu = __dadd_ru(stu[b], vu); }
-                stl[t1s] = vl; stu[t1s] = vu;
-            }
-        }
-        if (nz == 0) { to_slow = true; break; }
-        const double suml = stl[LOGP], sumu = stu[LOGP];
-        const double wl = floor(suml), wu = floor(sumu);
-        if (wl != wu) { to_slow = true; break; }
-        const double dl = __dsub_rd(suml, wl), du = __dsub_ru(sumu, wu);
-        int sg;
+        // Up to four magnification rounds with exactly the decisions of sign_eval_window (further rounds are needed after
+        // cancellation, when the first magnified fraction is below the accuracy threshold); whatever is still open goes to the list.
+        int sg = 0;
         Er lo, up;
-        if (du < 0.25 && dl >= C.accuracy) { sg = 1; lo = er_from_double(dl); up = er_from_double(du); }
-        else {
-            const double ml = __dsub_rd(1.0, du), mh = __dsub_ru(1.0, dl);
-            if (dl > 0.75 && ml >= C.accuracy) { sg = -1; lo = er_from_double(ml); up = er_from_double(mh); }
-            else { to_slow = true; break; }                                   // needs further magnification rounds
+        bool open = true;
+        for (int round = 0; round < 4; ++round) {
+            int nz = 0;
+            double stl[LOGP + 1], stu[LOGP + 1];
+            {
+                const int *p2 = C.wpow2 + (long long) K * NQ;   // w_q 2^K mod m_q
+#pragma unroll
+                for (int q = 0; q < P; ++q) {
+                    double vl = 0.0, vu = 0.0;
+                    if (q < NQ) {
+                        const QConst c = qc[q];
+                        const int xq = SMEM_S ? Sp[q * plane] : __ldg(Sp + q * plane);
+                        nz |= xq;
+                        const int sq = mulmod_q<F32>(xq, __ldg(p2 + q), c, kb);
+                        vl = __dmul_rd((double) sq, c.rrd);
+                        vu = __dmul_ru((double) sq, c.rru);
+                    }
+                    const int t1s = trailing_ones_c(q);
+#pragma unroll
+                    for (int b = 0; b < LOGP; ++b)
+                        if (b < t1s) { vl = __dadd_rd(stl[b], vl); vu = __dadd_ru(stu[b], vu); }
+                    stl[t1s] = vl; stu[t1s] = vu;
+                }
+            }
+            if (nz == 0) break;                                                   // S == 0: the list kernel writes the zero
+            const double suml = stl[LOGP], sumu = stu[LOGP];
+            const double wl = floor(suml), wu = floor(sumu);
+            const double dl = __dsub_rd(suml, wl), du = __dsub_ru(sumu, wu);
+            double dist;
+            if (wl == wu) {
+                if (du < 0.25 && dl >= C.accuracy) { sg = 1; lo = er_from_double(dl); up = er_from_double(du); open = false; break; }
+                const double ml = __dsub_rd(1.0, du), mh = __dsub_ru(1.0, dl);
+                if (dl > 0.75 && ml >= C.accuracy) { sg = -1; lo = er_from_double(ml); up = er_from_double(mh); open = false; break; }
+                if (du >= 0.25 && dl <= 0.75) break;                              // outside both windows (MODE_FAST with a failed guard)
+                dist = du < 0.25 ? du : mh;
+            } else {
+                dist = __dadd_ru(du, __dsub_ru(1.0, dl));                         // straddles an integer
+            }
+            const int e = (int) (((unsigned long long) __double_as_longlong(dist) >> 52) & 0x7ff) - 1023;
+            int kk = -(e + 1) - 3;
+            kk = kk < 1 ? 1 : (kk > 60 ? 60 : kk);
+            if (K + kk > log2M) kk = log2M - K;
+            if (kk <= 0) break;
+            K += kk;
         }
+        if (open) { to_slow = true; break; }
         lo.exp -= K + d; up.exp -= K + d;
         if (up.exp >= mp_h) { to_slow = true; break; }                        // S itself needs a rounding
         const int s_sign = sg < 0 ? 1 : 0, s_exp = ra.emin + cb.emin + d;
@@ -456,10 +488,10 @@ __global__ void __launch_bounds__(kNormFastThreads, 6) k_norm_fast(const DevCons
 #pragma unroll 8
         for (int q = 0; q < NQ; ++q, sp2 += plane) {
             const QConst c = qc[q];
-            int v = __ldg(sp2);
+            int v = SMEM_S ? *sp2 : __ldg(sp2);
             if (sg < 0 && v) v = c.m - v;
-            const int ay = p.nzy ? mulmod(v, __ldg(ty + q), c.m, c.mu) : 0;
-            const int ax = p.nzx ? mulmod(mycd[q], __ldg(tx + q), c.m, c.mu) : 0;
+            const int ay = p.nzy ? mulmod_q<F32>(v, __ldg(ty + q), c, kb) : 0;
+            const int ax = p.nzx ? mulmod_q<F32>(mycd[q], __ldg(tx + q), c, kb) : 0;
             const int a = p.sx ? (ax ? c.m - ax : 0) : ax;
             const int b = p.sy ? (ay ? c.m - ay : 0) : ay;
             int r = a + b - c.m;
@@ -472,6 +504,10 @@ __global__ void __launch_bounds__(kNormFastThreads, 6) k_norm_fast(const DevCons
         Cm.eval[ic] = rlo;
         Cm.eval[ic + Cm.len()] = rup;
     } while (0);
+    if (SMEM_S && to_slow && live) {
+#pragma unroll 8
+        for (int q = 0; q < NQ; ++q) Sg[q * gplane] = Sp[q * plane];
+    }
     __syncthreads();
     for (int v = threadIdx.x; v < rows_live * (NQ / 4); v += kNormFastThreads) {
         const int ent = (4 * v) / NQ;
@@ -496,6 +532,20 @@ __global__ void __launch_bounds__(kNormFastThreads, 6) k_norm_fast(const DevCons
         base = __shfl_sync(0xffffffffu, base, 0);
         if (to_slow) slow[base + __popc(bal & ((1u << lane) - 1u))] = row + (long long) col * m;
     }
+}
+
+template <int NQ, bool F32>
+__global__ void __launch_bounds__(kNormFastThreads, 5) k_norm_fast(const DevConsts *Cp, int m, int n, int k, const int *S, const int16_t *delta,
+                                                                long long m_p, long long n_p, const OuterInfo *ia, const OuterInfo *ib,
+                                                                SoA alpha, SoA beta, SoA Cm, int ldc, const int *scal_tab, long long *todo, int *todo_count,
+                                                                long long *slow, int *slow_count, bool fallback_allowed, const int *gate) {
+    extern __shared__ int cds[];            // [kNormFastThreads][NQ + 1]
+    if (gate && *gate > 0) return;          // the fused small-modulus kernel handled this call
+    const int tiles = (m + kNormFastThreads - 1) / kNormFastThreads;
+    const int col = blockIdx.x / tiles;
+    const int row0 = (blockIdx.x - col * tiles) * kNormFastThreads;
+    norm_fast_body<NQ, F32, false>(*Cp, cds, m, n, k, col, row0, S + (long long) col * m_p + row0 + threadIdx.x, n_p * m_p, nullptr, 0, delta, m_p, ia, ib,
+                                   alpha, beta, Cm, ldc, scal_tab, todo, todo_count, slow, slow_count, fallback_allowed);
 }
 
 }  // namespace mpres

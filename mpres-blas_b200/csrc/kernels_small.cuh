@@ -1,0 +1,576 @@
+// kernels_small.cuh -- stage 2 of the fast mp_gemm path on a base of ONE-BYTE moduli.
+//
+// The exact sums S(i,j) = sum_l +-X_a X_b 2^(shift) of the fast path are plain integers with |S| < 2^need
+// (need from the per-row / per-column magnitude windows).  The reference's 26.6-bit moduli cost sixteen
+// limb x limb int8 GEMMs each on the tensor cores (kernels_umma.cuh): 1.7 bits of S per GEMM.  Any pairwise
+// coprime moduli determine S, so here the multiply-accumulate runs modulo 256, 251, 243, 241, ... (host_consts.hpp:
+// kSmallModuli): ONE u8 x u8 -> s32 GEMM per modulus, ~7.6 bits of S per GEMM, 4.5 times fewer tensor-core
+// cycles for the same exact result.  (The reference has no counterpart: its k-loop multiplies residues one
+// thread per entry, src/blas/gemm.cuh:39-58.)
+//
+//   k_align_small    stage 1: an entry's significand X is rebuilt in binary from its first n_in reference
+//                    residues (CRT with the nearest-integer rank: exact because X < M'/4 is known from the
+//                    interval evaluation), reduced modulo every small modulus with byte dot products (dp4a),
+//                    multiplied by +-2^shift and stored as one u8 plane per modulus, K-major.
+//   k_small_umma     stage 2: per modulus a 128 x 256 tile of A'_p B'_p^T on tcgen05.mma kind::i8, operands by
+//                    TMA through a 4-stage mbarrier ring, accumulator in TMEM, reduced mod p in the epilogue.
+//   k_ext_small      stage 3a: CRT base extension to the reference moduli.  xi_i = x_i (M'/p_i)^-1 mod p_i, rank
+//                    R = nearest integer of sum xi_i / p_i (|S| < M'/4), and
+//                        S mod m_q = sum_i xi_i (M'/p_i mod m_q) + R (m_q - M' mod m_q)      (mod m_q)
+//                    evaluated as an int8 MMA (mma.sync m16n8k32) of the byte vector (xi, R) with the four byte
+//                    limbs of the constants.  Output: the same residue planes S[q][j][i] the limb kernels produce,
+//                    so the normalisation kernels (kernels_norm.cuh) are shared and the results are identical.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ctx.hpp"
+#include "kernels_umma.cuh"
+
+namespace mpres {
+
+// v mod p for v < 2^30, mu = floor(2^32 / p)
+__device__ __forceinline__ unsigned small_mod(unsigned v, unsigned p, unsigned mu) {
+    const unsigned r = v - __umulhi(v, mu) * p;   // in [0, 2p)
+    return r >= p ? r - p : r;
+}
+
+// ---- stage 1: alignment into the small base ---------------------------------------------------------------
+// planes: [j][outer_p][inner_p] u8 (inner contiguous), shifts: [outer_p][inner_p] int16 as in k_align_planes.
+// A block handles kASo lines x kASl inner positions, one entry per thread.
+constexpr int kASo = 8, kASl = 32;
+
+// NW: words of the binary significand = reference residues read (>= n_in); CW = NW rounded up to a multiple of four
+// is the row pitch of the staged tables.
+template <int NW>
+__device__ __forceinline__ void align_small_entry(const int4 (&dg)[(NW + 3) / 4], int nin, int P, int srow, const unsigned *s_mi, const unsigned *s_negmp,
+                                                  const int *s_m, const unsigned long long *s_bmu, const int *s_w, const double *s_rcpm,
+                                                  const unsigned *s_cw, const int *s_p, const unsigned *s_pmu, const uint8_t *pws,
+                                                  uint8_t *out) {
+    constexpr int CW = (NW + 3) & ~3;
+    // CRT over the first nin residues: X = sum xi_i M'_i - R M' with R = floor(sum xi_i / m_i).  The double sum can miss R
+    // by one when X / M' is within 2^-48 of an integer; then the result is off by exactly M' and is put right below.
+    unsigned xi[NW];
+    double sum = 0.0;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+        const int4 d4 = dg[i >> 2];
+        const int d = (i & 3) == 0 ? d4.x : (i & 3) == 1 ? d4.y : (i & 3) == 2 ? d4.z : d4.w;
+        unsigned v = 0;
+        if (i < nin) {
+            v = (unsigned) mulmod(d, s_w[i], s_m[i], s_bmu[i]);
+            sum += (double) v * s_rcpm[i];
+        }
+        xi[i] = v;
+    }
+    const unsigned R = (unsigned) __double2int_rd(sum);
+    unsigned x[NW];
+    {
+        unsigned long long carry = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            unsigned long long col = carry + (unsigned long long) R * s_negmp[w];
+#pragma unroll
+            for (int i = 0; i < NW; ++i) col += (unsigned long long) xi[i] * s_mi[i * CW + w];
+            x[w] = w < nin ? (unsigned) col : 0u;
+            carry = col >> 32;
+        }
+        // t = x - M' (= x + negmp mod 2^(32 nin)); no borrow <=> x >= M'
+        unsigned t[NW];
+        unsigned long long c2 = 0;
+        unsigned top = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            if (w < nin) {
+                c2 += (unsigned long long) x[w] + s_negmp[w];
+                t[w] = (unsigned) c2;
+                c2 >>= 32;
+                top = x[w];
+            } else {
+                t[w] = 0;
+            }
+        }
+        if ((int) top < 0) {                        // x "negative" (M' < 2^(32 nin - 1)): the rank was one too large, x += M' (= x - negmp)
+            unsigned long long bw = 0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                if (w < nin) {
+                    const unsigned long long df = (unsigned long long) x[w] - s_negmp[w] - bw;
+                    x[w] = (unsigned) df;
+                    bw = (df >> 32) & 1ull;
+                }
+            }
+        } else if (c2) {                            // x >= M': the rank was one too small
+#pragma unroll
+            for (int w = 0; w < NW; ++w) x[w] = t[w];
+        }
+    }
+    // residues modulo the small moduli, times +-2^shift
+    const unsigned *mrow = (const unsigned *) (pws + (size_t) srow * 64);
+    for (int jg = 0; 4 * jg < P; ++jg) {
+        const unsigned mult4 = __ldg(mrow + jg);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int j = 4 * jg + e;
+            unsigned v = 0;
+#pragma unroll
+            for (int w4 = 0; w4 < CW / 4; ++w4) {
+                const uint4 c4 = *(const uint4 *) (s_cw + j * CW + 4 * w4);
+                v = __dp4a(x[4 * w4], c4.x, v);
+                if (4 * w4 + 1 < NW) v = __dp4a(x[4 * w4 + 1], c4.y, v);
+                if (4 * w4 + 2 < NW) v = __dp4a(x[4 * w4 + 2], c4.z, v);
+                if (4 * w4 + 3 < NW) v = __dp4a(x[4 * w4 + 3], c4.w, v);
+            }
+            const unsigned r = small_mod(v * ((mult4 >> (8 * e)) & 0xffu), (unsigned) s_p[j], s_pmu[j]);
+            if (j < P) out[j * (kASo * kASl)] = (uint8_t) r;
+        }
+    }
+}
+
+template <int NW>
+__device__ __forceinline__ void align_small_dispatch(const int *dig, int nin, int P, int srow, const unsigned *s_mi, const unsigned *s_negmp,
+                                                     const int *s_m, const unsigned long long *s_bmu, const int *s_w, const double *s_rcpm,
+                                                     const unsigned *s_cw, const int *s_p, const unsigned *s_pmu, const uint8_t *pws, uint8_t *out) {
+    int4 dg[(NW + 3) / 4];
+#pragma unroll
+    for (int g = 0; g < (NW + 3) / 4; ++g) dg[g] = (4 * g < nin) ? __ldg((const int4 *) dig + g) : make_int4(0, 0, 0, 0);
+    align_small_entry<NW>(dg, nin, P, srow, s_mi, s_negmp, s_m, s_bmu, s_w, s_rcpm, s_cw, s_p, s_pmu, pws, out);
+}
+
+__global__ void __launch_bounds__(256, 2) k_align_small(const DevConsts *Cp, SoA X, long long so, long long sl, int outer, int inner,
+                                                        const OuterInfo *info, uint8_t *planes, int16_t *shifts,
+                                                        long long outer_p, long long inner_p, const int *sel) {
+    extern __shared__ __align__(16) uint8_t as_smem[];
+    const int P = sel[0], nin = sel[1];
+    if (P <= 0) return;
+    const DevConsts &C = *Cp;
+    const SmallDev &SD = *C.small;
+    const int N = C.N;
+    const int NWr = nin <= 8 ? nin : (nin <= 12 ? 12 : 16);   // instantiated word counts
+    const int CW = (NWr + 3) & ~3;
+    // shared: out [64][256] u8 | shifts [8][32] i16 | cw [64][CW] | mi [CW][CW] | negmp [CW] | bmu [CW] u64 | rcpm [CW] f64 | m, w [CW] | p, pmu [64]
+    uint8_t *s_out = as_smem;
+    int16_t *s_sh = (int16_t *) (s_out + 64 * kASo * kASl);
+    unsigned *s_cw = (unsigned *) (s_sh + kASo * kASl);
+    unsigned *s_mi = s_cw + 64 * CW;
+    unsigned *s_negmp = s_mi + CW * CW;
+    unsigned long long *s_bmu = (unsigned long long *) (s_negmp + CW);
+    double *s_rcpm = (double *) (s_bmu + CW);
+    int *s_m = (int *) (s_rcpm + CW);
+    int *s_w = s_m + CW;
+    int *s_p = s_w + CW;
+    unsigned *s_pmu = (unsigned *) (s_p + 64);
+
+    // the entry of this thread: every global load is issued before the tables are staged
+    const int o0 = blockIdx.x * kASo, l0 = blockIdx.y * kASl;
+    int ol, ll;
+    if (so == 1) { ol = threadIdx.x & (kASo - 1); ll = threadIdx.x / kASo; }     // lines are the contiguous direction of the input
+    else { ll = threadIdx.x & (kASl - 1); ol = threadIdx.x / kASl; }
+    const int o = o0 + ol, l = l0 + ll;
+    const int slot = ol * kASl + ll;
+    const bool inside = o < outer && l < inner;
+    const long long idx = inside ? (long long) o * so + (long long) l * sl : 0;
+    const double upf = inside ? X.eval[idx + X.len()].frac : 0.0;
+    const int ex = inside ? X.exp[idx] : 0;
+    const int sg = inside ? X.sign[idx] : 0;
+    const int emin = inside ? info[o].emin : 0;
+
+    for (int t = threadIdx.x; t < ((P + 3) & ~3) * CW; t += 256) { const int j = t / CW, w = t - j * CW; s_cw[t] = SD.cw[j * 16 + w]; }
+    for (int t = threadIdx.x; t < CW * CW; t += 256) { const int i = t / CW, w = t - i * CW; s_mi[t] = (i < nin && w < nin) ? SD.in_mi[((size_t) nin * 16 + i) * 16 + w] : 0u; }
+    if (threadIdx.x < CW) {
+        const int i = threadIdx.x;
+        const bool on = i < nin;
+        s_negmp[i] = on ? SD.in_negmp[nin * 16 + i] : 0u;
+        s_m[i] = on ? C.moduli[i] : 1;
+        s_bmu[i] = on ? C.barrett[i] : 0ull;
+        s_rcpm[i] = on ? 1.0 / (double) C.moduli[i] : 0.0;
+        s_w[i] = on ? C.ext_w[nin * N + i] : 0;
+    }
+    if (threadIdx.x >= 64 && threadIdx.x < 128) { const int j = threadIdx.x - 64; s_p[j] = SD.p[j]; s_pmu[j] = SD.mu[j]; }
+    __syncthreads();
+
+    int sh16 = kShiftSentinel;
+    const bool live = inside && upf != 0;
+    int srow = 0;
+    if (live) {
+        const long long sh = (long long) ex - emin;
+        const int s = sh > kSmallShiftMax ? kSmallShiftMax : (sh < 0 ? 0 : (int) sh);   // the selection guarantees sh <= kSmallShiftMax
+        sh16 = s;
+        srow = 2 * s + (sg ? 1 : 0);
+    }
+    s_sh[slot] = (int16_t) sh16;
+    if (live) {
+        const int *dig = X.digits + idx * N;
+        uint8_t *outp = s_out + slot;
+#define MPRES_AS_CASE(NW_) case NW_: align_small_dispatch<NW_>(dig, nin, P, srow, s_mi, s_negmp, s_m, s_bmu, s_w, s_rcpm, s_cw, s_p, s_pmu, SD.pws, outp); break;
+        switch (NWr) {
+            MPRES_AS_CASE(1) MPRES_AS_CASE(2) MPRES_AS_CASE(3) MPRES_AS_CASE(4) MPRES_AS_CASE(5) MPRES_AS_CASE(6) MPRES_AS_CASE(7) MPRES_AS_CASE(8)
+            MPRES_AS_CASE(12)
+            default: align_small_dispatch<16>(dig, nin, P, srow, s_mi, s_negmp, s_m, s_bmu, s_w, s_rcpm, s_cw, s_p, s_pmu, SD.pws, outp); break;
+        }
+#undef MPRES_AS_CASE
+    } else {
+        for (int j = 0; j < P; ++j) s_out[j * (kASo * kASl) + slot] = 0;
+    }
+    __syncthreads();
+    // write out: (j, line) -> 32 contiguous bytes, two 16-byte halves
+    for (int v = threadIdx.x; v < P * kASo * 2; v += 256) {
+        const int j = v / (kASo * 2), rem = v - j * (kASo * 2);
+        const int oo = rem >> 1, h = rem & 1;
+        const uint4 val = *(const uint4 *) (s_out + j * (kASo * kASl) + oo * kASl + h * 16);
+        *(uint4 *) (planes + ((long long) j * outer_p + o0 + oo) * inner_p + l0 + h * 16) = val;
+    }
+    if (threadIdx.x < kASo * 4) {
+        const int oo = threadIdx.x >> 2, part = threadIdx.x & 3;
+        *(uint4 *) (shifts + (long long) (o0 + oo) * inner_p + l0 + part * 8) = *(const uint4 *) (s_sh + oo * kASl + part * 8);
+    }
+}
+inline size_t align_small_smem() {
+    const int CW = 16;
+    return 64 * kASo * kASl + kASo * kASl * 2 + 64 * CW * 4 + CW * CW * 4 + CW * 4 + CW * 8 + CW * 8 + CW * 4 * 2 + 64 * 4 * 2 + 64;
+}
+
+// ---- stage 2: one u8 GEMM per small modulus on tcgen05 -----------------------------------------------------
+constexpr int kSM = 128, kSN = 256, kSK = 64, kSStages = 4;
+constexpr int kSABytes = kSM * kSK, kSBBytes = kSN * kSK, kSStageBytes = kSABytes + kSBBytes;
+constexpr int kSSmem = kSStages * kSStageBytes + 1024 + 256;
+constexpr int kSThreads = 320;        // warps 0-7 epilogue, 8 TMA producer, 9 MMA issuer
+constexpr int kSTmemCols = 256;
+constexpr int kSmallKChunk = 32768;   // 250^2 * 32768 + 255 < 2^31
+
+// The A operand of the MMA (128 TMEM lanes) is the B' tile (rows j), the B operand (256 columns) the A' tile (rows i): the
+// accumulator holds S^T, so a thread of the epilogue owns one j and 128 consecutive i -- whole 16-byte runs of the output plane
+// S8[z][j][i] (i contiguous, pitch m_ps).
+__global__ void __launch_bounds__(kSThreads, 2)
+k_small_umma(const __grid_constant__ CUtensorMap tmJ, const __grid_constant__ CUtensorMap tmI, const DevConsts *Cp, uint8_t *S8,
+             long long m_ps, long long n_ps, int k_byte0, int nk, int add_to_S, const int *sel) {
+    extern __shared__ uint8_t smem_raw[];
+    const int z = blockIdx.z;
+    if (z >= sel[0]) return;   // modulus outside the selected base (whole CTA leaves before any setup)
+    uint8_t *smem = (uint8_t *) (((uintptr_t) smem_raw + 1023) & ~(uintptr_t) 1023);
+    uint64_t *full = (uint64_t *) (smem + kSStages * kSStageBytes);
+    uint64_t *empty = full + kSStages;
+    uint64_t *accum_bar = empty + kSStages;
+    uint32_t *tmem_slot = (uint32_t *) (accum_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i0 = blockIdx.x * kSN, j0 = blockIdx.y * kSM;
+
+    if (warp == 8 && lane == 0) {
+        ptx::prefetch_tmap(&tmJ);
+        ptx::prefetch_tmap(&tmI);
+        for (int s = 0; s < kSStages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+        ptx::mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 9) ptx::tmem_alloc(tmem_slot, kSTmemCols);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 8) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (int it = 0; it < nk; ++it) {
+                const int s = it % kSStages;
+                const uint32_t ph = (uint32_t) (it / kSStages) & 1u;
+                ptx::mbar_wait(&empty[s], ph ^ 1u);
+                ptx::mbar_expect_tx(&full[s], kSStageBytes);
+                uint8_t *dst = smem + s * kSStageBytes;
+                ptx::tma_load_3d(dst, &tmJ, &full[s], k_byte0 + it * kSK, j0, z);
+                ptx::tma_load_3d(dst + kSABytes, &tmI, &full[s], k_byte0 + it * kSK, i0, z);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 9) {
+        // ===== MMA issuer (one thread): D[128 x 256] += B'[128 x 32] A'[256 x 32]^T per 32-byte K step =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::idesc_u8(kSM, kSN);
+            for (int it = 0; it < nk; ++it) {
+                const int s = it % kSStages;
+                const uint32_t ph = (uint32_t) (it / kSStages) & 1u;
+                ptx::mbar_wait(&full[s], ph);
+                ptx::tc_fence_after();
+                const uint32_t a_addr = ptx::smem_u32(smem + s * kSStageBytes), b_addr = a_addr + kSABytes;
+#pragma unroll
+                for (int ks = 0; ks < kSK / 32; ++ks)
+                    ptx::umma_i8(tmem, ptx::smem_desc_sw64(a_addr + ks * 32), ptx::smem_desc_sw64(b_addr + ks * 32), idesc, (it | ks) ? 1u : 0u);
+                ptx::umma_commit(&empty[s]);   // frees the stage once these MMAs have read it
+            }
+            ptx::umma_commit(accum_bar);       // accumulator complete
+        }
+        __syncwarp();
+    } else {
+        // ===== epilogue: TMEM -> registers -> mod p -> 16-byte runs of the u8 plane =====
+        const SmallDev &SD = *Cp->small;
+        const unsigned p = (unsigned) SD.p[z], mu = SD.mu[z];
+        ptx::mbar_wait(accum_bar, 0);
+        ptx::tc_fence_after();
+        const int quad = warp & 3, half = warp >> 2;
+        const int j = j0 + quad * 32 + lane;
+        uint4 *dst = (uint4 *) (S8 + ((long long) z * n_ps + j) * m_ps + i0 + half * 128);
+        const uint32_t tbase = tmem + ((uint32_t) (quad * 32) << 16) + (uint32_t) (half * 128);
+#pragma unroll 1
+        for (int jc = 0; jc < 4; ++jc) {        // 32 columns = two 16-byte runs per pass
+            uint32_t d[4][8];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) ptx::tmem_ld8(tbase + (uint32_t) (jc * 32 + u * 8), d[u]);
+            uint4 prev[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+            if (add_to_S) { prev[0] = dst[2 * jc]; prev[1] = dst[2 * jc + 1]; }
+            ptx::tmem_ld_wait();
+            unsigned wd[8];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int hw = 0; hw < 2; ++hw) {
+                    const uint4 pv = prev[u >> 1];
+                    const unsigned pw = ((u & 1) * 2 + hw) == 0 ? pv.x : ((u & 1) * 2 + hw) == 1 ? pv.y : ((u & 1) * 2 + hw) == 2 ? pv.z : pv.w;
+                    unsigned o = 0;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const unsigned v = d[u][hw * 4 + e] + ((pw >> (8 * e)) & 0xffu);   // < 2^31 + 2^8
+                        unsigned r = v - __umulhi(v, mu) * p;
+                        r = r >= p ? r - p : r;
+                        o |= r << (8 * e);
+                    }
+                    wd[u * 2 + hw] = o;
+                }
+            dst[2 * jc] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+            dst[2 * jc + 1] = make_uint4(wd[4], wd[5], wd[6], wd[7]);
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 9) ptx::tmem_dealloc(tmem, kSTmemCols);
+}
+
+// ---- stage 3a: CRT base extension from the small base to the reference moduli ------------------------------
+constexpr int kXT = 128;        // entries per block (one per thread in the first phase)
+constexpr int kXPitch = 96;     // bytes per operand row in shared memory: 64-bit fragment loads are bank-conflict free
+constexpr int kXSPitch = 136;   // ints per residue row of the result tile: fragment-order writes and per-entry reads are conflict free
+
+__device__ __forceinline__ void mma_u8_frag(int (&c)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// shared memory of one extension block: operand rows of the entries | operand rows of the constants | staged one-byte
+// residues [56][128] | per-modulus constants | result tile [N][kXSPitch]
+struct ExtSmem {
+    uint8_t *At, *Bt, *X8;
+    int *s_p;
+    unsigned *s_mu, *s_inv;
+    float *s_rcp;
+    int *s_S;
+};
+__host__ __device__ inline size_t ext_small_smem(int ext_cols, int N) {
+    return (size_t) kXT * kXPitch + (size_t) ext_cols * kXPitch + 56 * kXT + 64 * 16 + (size_t) N * kXSPitch * 4;
+}
+__device__ __forceinline__ ExtSmem ext_carve(uint8_t *base, int ext_cols) {
+    ExtSmem e;
+    e.At = base;
+    e.X8 = e.At + kXT * kXPitch;              // At and X8 are dead once the block function returns: the fused kernel reuses them
+    e.Bt = e.X8 + 56 * kXT;
+    e.s_p = (int *) (e.Bt + (size_t) ext_cols * kXPitch);
+    e.s_mu = (unsigned *) (e.s_p + 64);
+    e.s_rcp = (float *) (e.s_mu + 64);
+    e.s_inv = (unsigned *) (e.s_rcp + 64);
+    e.s_S = (int *) (e.s_inv + 64);
+    return e;
+}
+
+__host__ __device__ constexpr bool ext_norm_cds_aliased(int NQ) { return (size_t) kXT * (NQ + 1) * 4 <= (size_t) kXT * kXPitch + 56 * kXT; }
+
+// One block: the kXT consecutive rows from row0 of column col.  Leaves S mod m_q of entry e at s_S[q * kXSPitch + e].
+// Ends with a __syncthreads().
+template <bool FASTRED>
+__device__ __forceinline__ void ext_small_block(const DevConsts &C, const SmallDev &SD, const ExtSmem &E, int P, const uint8_t *S8, long long m_ps,
+                                                long long n_ps, int col, int row0) {
+    const int N = C.N, cols = SD.ext_cols;
+    // the block's one-byte residues: P runs of 128 contiguous bytes, asynchronous 16-byte copies (all in flight at once)
+    {
+        const uint8_t *src = S8 + (long long) col * m_ps + row0;
+        const long long plane = n_ps * m_ps;
+        for (int v = threadIdx.x; v < P * (kXT / 16); v += kXT) {
+            const int j = v >> 3, part = v & 7;
+            cp_async16(E.X8 + j * kXT + part * 16, src + (long long) j * plane + part * 16);
+        }
+        cp_async_commit();
+        const uint4 *bsrc = (const uint4 *) (SD.ext_b + (size_t) P * cols * 64);
+        for (int v = threadIdx.x; v < cols * 4; v += kXT) *(uint4 *) (E.Bt + (v >> 2) * kXPitch + (v & 3) * 16) = __ldg(bsrc + v);
+        if (threadIdx.x < 64) {
+            const int j = threadIdx.x;
+            E.s_p[j] = SD.p[j]; E.s_mu[j] = SD.mu[j]; E.s_rcp[j] = SD.rcp[j]; E.s_inv[j] = SD.inv[P * 64 + j];
+        }
+        cp_async_wait<0>();
+    }
+    __syncthreads();
+    // ---- phase 1: xi_i and the rank, one entry per thread ----
+    {
+        const uint8_t *xsrc = E.X8 + threadIdx.x;
+        unsigned wds[16];
+        float sum = 0.f;
+#pragma unroll
+        for (int g = 0; g < 16; ++g) {
+            unsigned wd = 0;
+            if (4 * g < P) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int j = 4 * g + e;
+                    const unsigned xv = j < P ? (unsigned) xsrc[j * kXT] : 0u;
+                    const unsigned xi = small_mod(xv * E.s_inv[j], (unsigned) E.s_p[j], E.s_mu[j]);
+                    sum = fmaf((float) xi, E.s_rcp[j], sum);
+                    wd |= xi << (8 * e);
+                }
+            }
+            wds[g] = wd;
+        }
+        const unsigned R = (unsigned) __float2int_rn(sum);
+        wds[15] |= R << 24;
+        uint4 *dst = (uint4 *) (E.At + threadIdx.x * kXPitch);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) dst[g] = make_uint4(wds[4 * g], wds[4 * g + 1], wds[4 * g + 2], wds[4 * g + 3]);
+    }
+    __syncwarp();   // a warp only reads the 32 operand rows it wrote
+    // ---- phase 2: (xi, R) x limbs on the tensor cores, limbs recombined and reduced per reference modulus ----
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int kred = SD.red_shift;
+#pragma unroll 1
+    for (int hp = 0; hp * 64 < cols; ++hp) {     // 64 operand columns = 16 reference moduli per pass
+        int mq[4];
+        unsigned long long muq[4];
+        unsigned rmu[4];
+#pragma unroll
+        for (int pp = 0; pp < 4; ++pp) {
+            const int q = hp * 16 + pp * 4 + t;
+            const bool on = q < N;
+            mq[pp] = on ? C.moduli[q] : 1;
+            muq[pp] = (!FASTRED && on) ? C.barrett[q] : 0ull;
+            rmu[pp] = (FASTRED && on) ? SD.red_mu[q] : 0u;
+        }
+#pragma unroll 1
+        for (int mt = 0; mt < 2; ++mt) {
+            int acc[8][4];
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[nt][e] = 0;
+            const uint8_t *ar0 = E.At + (warp * 32 + mt * 16 + g) * kXPitch + 8 * t, *ar1 = ar0 + 8 * kXPitch;
+            const uint8_t *br = E.Bt + (size_t) (hp * 64 + g) * kXPitch + 8 * t;
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+                const uint2 a02 = *(const uint2 *) (ar0 + ks * 32), a13 = *(const uint2 *) (ar1 + ks * 32);
+                const unsigned a[4] = {a02.x, a13.x, a02.y, a13.y};
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) {
+                    const uint2 b = *(const uint2 *) (br + (size_t) nt * 8 * kXPitch + ks * 32);
+                    mma_u8_frag(acc[nt], a, b.x, b.y);
+                }
+            }
+#pragma unroll
+            for (int pp = 0; pp < 4; ++pp) {
+                const int q = hp * 16 + pp * 4 + t;
+#pragma unroll
+                for (int rh = 0; rh < 2; ++rh) {
+                    const unsigned long long v = (unsigned long long) (unsigned) acc[2 * pp][2 * rh] + ((unsigned long long) (unsigned) acc[2 * pp][2 * rh + 1] << 8) +
+                                                 ((unsigned long long) (unsigned) acc[2 * pp + 1][2 * rh] << 16) +
+                                                 ((unsigned long long) (unsigned) acc[2 * pp + 1][2 * rh + 1] << 24);   // < 2^47
+                    unsigned r;
+                    if (FASTRED) {
+                        const unsigned ph = (unsigned) (v >> (kred - 1));
+                        const unsigned qq = (unsigned) (((unsigned long long) ph * rmu[pp]) >> (kred + 1));
+                        r = (unsigned) v - qq * (unsigned) mq[pp];   // < 3 m
+                        r = r >= (unsigned) mq[pp] ? r - (unsigned) mq[pp] : r;
+                        r = r >= (unsigned) mq[pp] ? r - (unsigned) mq[pp] : r;
+                    } else {
+                        r = (unsigned) reduce64(v, mq[pp], muq[pp]);
+                    }
+                    if (q < N) E.s_S[q * kXSPitch + warp * 32 + mt * 16 + g + 8 * rh] = (int) r;
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// stand-alone extension: writes the residue planes S[q][col][row] (what the limb kernels produce)
+template <bool FASTRED>
+__global__ void __launch_bounds__(kXT, 4) k_ext_small(const DevConsts *Cp, int m, int n, const uint8_t *S8, long long m_p, long long m_ps, long long n_ps,
+                                                      int *S, long long n_p, const int *sel) {
+    extern __shared__ __align__(16) uint8_t xs_smem[];
+    const int P = sel[0];
+    if (P <= 0) return;
+    const DevConsts &C = *Cp;
+    const SmallDev &SD = *C.small;
+    const ExtSmem E = ext_carve(xs_smem, SD.ext_cols);
+    const int tiles = (int) (m_p / kXT);
+    const int col = blockIdx.x / tiles;
+    const int row0 = (blockIdx.x - col * tiles) * kXT;
+    ext_small_block<FASTRED>(C, SD, E, P, S8, m_ps, n_ps, col, row0);
+    const int N = C.N;
+    for (int v = threadIdx.x; v < N * (kXT / 4); v += kXT) {
+        const int q = v >> 5, part = v & 31;
+        *(int4 *) (S + ((long long) q * n_p + col) * m_p + row0 + part * 4) = *(const int4 *) (E.s_S + q * kXSPitch + part * 4);
+    }
+}
+
+// fused: base extension + entry-per-thread normalisation and alpha/beta epilogue (kernels_norm.cuh: norm_fast_body).  The residue
+// planes are only written for the entries handed to the list kernel.
+template <int NQ, bool F32>
+__global__ void __launch_bounds__(kXT, 4) k_ext_norm_small(const DevConsts *Cp, int m, int n, int k, const uint8_t *S8, long long m_p, long long m_ps, long long n_ps,
+                                                           int *S, long long n_p, const int *sel, const int16_t *delta, const OuterInfo *ia, const OuterInfo *ib,
+                                                           SoA alpha, SoA beta, SoA Cm, int ldc, const int *scal_tab, long long *todo, int *todo_count,
+                                                           long long *slow, int *slow_count, bool fallback_allowed) {
+    extern __shared__ __align__(16) uint8_t xs_smem[];
+    const int P = sel[0];
+    if (P <= 0) return;
+    const DevConsts &C = *Cp;
+    const SmallDev &SD = *C.small;
+    const ExtSmem E = ext_carve(xs_smem, SD.ext_cols);
+    // the staged digits of C: in the operand rows of the extension when they fit, else behind everything
+    int *cds = ext_norm_cds_aliased(NQ) ? (int *) E.At : (int *) (xs_smem + ext_small_smem(SD.ext_cols, NQ));
+    const int tiles = (int) (m_p / kXT);
+    const int col = blockIdx.x / tiles;
+    const int row0 = (blockIdx.x - col * tiles) * kXT;
+    ext_small_block<F32>(C, SD, E, P, S8, m_ps, n_ps, col, row0);
+    norm_fast_body<NQ, F32, true>(C, cds, m, n, k, col, row0, E.s_S + threadIdx.x, kXSPitch, S + (long long) col * m_p + row0 + threadIdx.x, n_p * m_p,
+                                  delta, m_p, ia, ib, alpha, beta, Cm, ldc, scal_tab, todo, todo_count, slow, slow_count, fallback_allowed);
+}
+
+}  // namespace mpres
+
+// 3-D map (k, row, plane) over u8 planes [planes][rows_p][k_p], box 64 B x box_rows x 1 plane, 64B swizzle
+inline int small_make_map(CUtensorMap *map, const void *planes, int nplanes, long long rows_p, long long k_p, int box_rows) {
+    mpres_encode_tiled_fn enc = umma_encode_fn();
+    if (!enc) return -30;
+    cuuint64_t dims[3] = {(cuuint64_t) k_p, (cuuint64_t) rows_p, (cuuint64_t) nplanes};
+    cuuint64_t strides[2] = {(cuuint64_t) k_p, (cuuint64_t) (rows_p * k_p)};
+    cuuint32_t box[3] = {(cuuint32_t) mpres::kSK, (cuuint32_t) box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(planes), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -31;
+}
+
+// One launch = every small modulus (CTAs beyond the selected base leave at once), all tiles, K range [k_begin, k_begin + k_len).
+// PA: planes of A' [.][m_ps][k_p] (m_ps % 256 == 0), PB: planes of B' [.][n_ps][k_p] (n_ps % 128 == 0), S8: [.][n_ps][m_ps].
+inline int launch_small_umma(mpres_ctx *c, const uint8_t *PA, const uint8_t *PB, uint8_t *S8, long long m_ps, long long n_ps, long long k_p,
+                             long long k_begin, int k_len, bool add_to_S, const int *sel, cudaStream_t st) {
+    CUtensorMap tmJ, tmI;
+    int rc;
+    if ((rc = small_make_map(&tmJ, PB, mpres::kSmallMax, n_ps, k_p, mpres::kSM))) return rc;
+    if ((rc = small_make_map(&tmI, PA, mpres::kSmallMax, m_ps, k_p, mpres::kSN))) return rc;
+    static bool attr_done = false;
+    if (!attr_done) {
+        CUDA_TRY(cudaFuncSetAttribute(mpres::k_small_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, mpres::kSSmem));
+        attr_done = true;
+    }
+    dim3 grid((unsigned) (m_ps / mpres::kSN), (unsigned) (n_ps / mpres::kSM), (unsigned) mpres::kSmallMax);
+    mpres::k_small_umma<<<grid, mpres::kSThreads, mpres::kSSmem, st>>>(tmJ, tmI, c->dconsts, S8, m_ps, n_ps, (int) k_begin, k_len / mpres::kSK, add_to_S ? 1 : 0, sel);
+    return 0;
+}

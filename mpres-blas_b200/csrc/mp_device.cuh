@@ -26,6 +26,8 @@ namespace mpres {
 constexpr int kMaxN = 128;
 constexpr int kThresh = 30;  // RNS_P2_SCALING_THRESHOLD
 
+struct SmallDev;
+
 struct Er {
     double frac;
     long long exp;
@@ -54,6 +56,7 @@ struct DevConsts {
     int ext_lazy, pad2;
     const int *wpow2;     // [log2M+1][N] w_i * 2^j mod m_i
     const int *spow2;     // [2 (log2M+1) + 1][N]  +2^s, -2^s interleaved; last row zeros
+    const struct SmallDev *small;   // tables of the small-modulus stage 2 (kernels_small.cuh); nullptr if unusable
 };
 
 // SoA view of mp_array_t / mp_collection_t (src/types.cuh:85-104).  `len` is the ALLOCATED length:

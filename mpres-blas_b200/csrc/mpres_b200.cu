@@ -76,11 +76,47 @@ int mpres_init_moduli(mpres_ctx **out, const int *moduli, int n, int device) {
         up(&c->d_ext_w, h.ext_w) != cudaSuccess || up(&c->d_ext_t, h.ext_t) != cudaSuccess || up(&c->d_wpow2, h.wpow2) != cudaSuccess || up(&c->d_spow2, h.spow2) != cudaSuccess) { delete d; delete c; return (int) e; }
     d->pow2 = c->d_pow2; d->inv_pow2 = c->d_inv_pow2; d->mrc_inv = c->d_mrc; d->prefix_mod = c->d_prefix; d->ext_w = c->d_ext_w; d->ext_t = c->d_ext_t; d->ext_lazy = h.ext_lazy; d->wpow2 = c->d_wpow2; d->spow2 = c->d_spow2;
     for (int i = 0; i <= h.N; ++i) d->prefix_log2[i] = h.prefix_log2[i];
+    // tables of the small-modulus stage 2
+    d->small = nullptr;
+    compute_small_consts(h, c->sc);
+    if (c->sc.usable) {
+        const SmallConsts &sc = c->sc;
+        SmallDev *sd = new SmallDev();
+        memset(sd, 0, sizeof(*sd));
+        sd->usable = 1; sd->ext_cols = sc.ext_cols; sd->red_shift = sc.red_shift; sd->log2M_up = sc.log2M_up;
+        for (int j = 0; j < 64; ++j) {
+            const int pj = j < kSmallMax ? kSmallModuli[j] : 1;
+            sd->p[j] = pj;
+            sd->mu[j] = j < kSmallMax ? (unsigned) ((1ull << 32) / (unsigned long long) pj) : 0u;
+            sd->rcp[j] = j < kSmallMax ? 1.0f / (float) pj : 0.f;
+        }
+        for (int j = 0; j <= kSmallMax; ++j) sd->prefix_log2[j] = sc.prefix_log2[j];
+        for (int j = 0; j <= kSmallNinMax; ++j) sd->in_log2_milli[j] = sc.in_log2_milli[j];
+        auto upb = [&](int slot, const void *src, size_t bytes) -> const void * {
+            if (cudaMalloc(&c->d_small[slot], bytes) != cudaSuccess) return nullptr;
+            if (cudaMemcpy(c->d_small[slot], src, bytes, cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+            return c->d_small[slot];
+        };
+        std::vector<uint32_t> cw64((size_t) 64 * 16, 0);
+        memcpy(cw64.data(), sc.cw.data(), sc.cw.size() * sizeof(uint32_t));
+        sd->inv = (const uint8_t *) upb(1, sc.inv.data(), sc.inv.size());
+        sd->ext_b = (const uint8_t *) upb(2, sc.ext_b.data(), sc.ext_b.size());
+        sd->cw = (const uint32_t *) upb(3, cw64.data(), cw64.size() * 4);
+        sd->pws = (const uint8_t *) upb(4, sc.pws.data(), sc.pws.size());
+        sd->in_mi = (const uint32_t *) upb(5, sc.in_mi.data(), sc.in_mi.size() * 4);
+        sd->in_negmp = (const uint32_t *) upb(6, sc.in_negmp.data(), sc.in_negmp.size() * 4);
+        sd->red_mu = (const uint32_t *) upb(7, sc.red_mu.data(), sc.red_mu.size() * 4);
+        const bool ok = sd->inv && sd->ext_b && sd->cw && sd->pws && sd->in_mi && sd->in_negmp && sd->red_mu;
+        const void *dev = ok ? upb(0, sd, sizeof(SmallDev)) : nullptr;
+        delete sd;
+        if (!dev) { delete d; delete c; return (int) cudaErrorMemoryAllocation; }
+        d->small = (const SmallDev *) dev;
+    }
     e = cudaMalloc(&c->dconsts, sizeof(DevConsts));
     if (e == cudaSuccess) e = cudaMemcpy(c->dconsts, d, sizeof(DevConsts), cudaMemcpyHostToDevice);
     delete d;
-    if (e == cudaSuccess) e = cudaMalloc(&c->d_counter, 4 * sizeof(int));
-    if (e == cudaSuccess) e = cudaMemset(c->d_counter, 0, 4 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_counter, 8 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(c->d_counter, 0, 8 * sizeof(int));
     if (e != cudaSuccess) { delete c; return (int) e; }
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
     *out = c;
@@ -98,7 +134,8 @@ int mpres_finalize(mpres_ctx *c) {
     if (c->device < 0) { delete c; return 0; }
     DeviceGuard g(c->device);
     cudaDeviceSynchronize();
-    for (int i = 0; i < 8; ++i) if (c->ws[i]) cudaFree(c->ws[i]);
+    for (int i = 0; i < 12; ++i) if (c->ws[i]) cudaFree(c->ws[i]);
+    for (int i = 0; i < 8; ++i) if (c->d_small[i]) cudaFree(c->d_small[i]);
     cudaFree(c->d_pow2); cudaFree(c->d_inv_pow2); cudaFree(c->d_mrc); cudaFree(c->d_prefix); cudaFree(c->d_ext_w); cudaFree(c->d_ext_t); cudaFree(c->d_wpow2); cudaFree(c->d_spow2); cudaFree(c->dconsts); cudaFree(c->d_counter);
     delete c;
     return 0;
@@ -113,8 +150,14 @@ int mpres_device(const mpres_ctx *c) { return c ? c->device : -1; }
 size_t mpres_sizeof_mp_float(const mpres_ctx *c) { return c ? 4 * (size_t) c->hc.N + 40 : 0; }
 int mpres_set_mode(mpres_ctx *c, int mode) { if (!c || mode < 0 || mode > 2) return -1; c->mode = mode; return 0; }
 int mpres_get_mode(const mpres_ctx *c) { return c ? c->mode : -1; }
-int mpres_set_stage2_kernel(mpres_ctx *c, int kind) { if (!c || kind < 0 || kind > 2) return -1; c->stage2 = kind; return 0; }
-int mpres_set_stage3_kernel(mpres_ctx *c, int kind) { if (!c || kind < 0 || kind > 1) return -1; c->stage3 = kind; return 0; }
+int mpres_set_stage2_kernel(mpres_ctx *c, int kind) { if (!c || kind < 0 || kind > 3) return -1; c->stage2 = kind; return 0; }
+int mpres_set_stage3_kernel(mpres_ctx *c, int kind) {
+    if (!c || kind < 0 || kind > 3) return -1;
+    c->stage3 = kind == 1 ? 1 : 0;
+    c->norm32 = kind == 2 ? 0 : 1;
+    c->fuse_ext = kind == 3 ? 0 : 1;
+    return 0;
+}
 int mpres_set_reduced_base(mpres_ctx *c, int on) { if (!c) return -1; c->reduced_base = on != 0; return 0; }
 long mpres_last_base_size(mpres_ctx *c) {
     if (!c || c->device < 0) return -1;
@@ -123,6 +166,28 @@ long mpres_last_base_size(mpres_ctx *c) {
     if (cudaStreamSynchronize(c->last_stream) != cudaSuccess) return -2;
     if (cudaMemcpy(&v, c->d_counter + 2, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
     return v;
+}
+int mpres_last_small_base(mpres_ctx *c, int *moduli, int *input_moduli) {
+    if (!c || c->device < 0) return -1;
+    DeviceGuard g(c->device);
+    int v[2] = {0, 0};
+    if (cudaStreamSynchronize(c->last_stream) != cudaSuccess) return -2;
+    if (cudaMemcpy(v, c->d_counter + 4, 2 * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+    if (moduli) *moduli = v[0];
+    if (input_moduli) *input_moduli = v[1];
+    return 0;
+}
+int mpres_small_modulus(const mpres_ctx *c, int index) {
+    if (!c || !c->sc.usable || index < 0 || index >= kSmallMax) return 0;
+    return kSmallModuli[index];
+}
+long mpres_debug_read_workspace(mpres_ctx *c, int slot, size_t offset, void *host, size_t bytes) {
+    if (!c || c->device < 0 || !host || slot < 0 || slot >= 12) return -1;
+    if (!c->ws[slot] || offset + bytes > c->ws_size[slot]) return -2;
+    DeviceGuard g(c->device);
+    if (cudaStreamSynchronize(c->last_stream) != cudaSuccess) return -3;
+    if (cudaMemcpy(host, (const char *) c->ws[slot] + offset, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return -3;
+    return (long) bytes;
 }
 int mpres_set_vec_config(mpres_ctx *c, int cfg) { if (!c || cfg < 0 || cfg > 2) return -1; c->vec_config = cfg; return 0; }
 int mpres_set_stage1_kernel(mpres_ctx *c, int kind) { if (!c || kind < 0 || kind > 1) return -1; c->stage1 = kind; return 0; }
@@ -392,7 +457,7 @@ static int gemm_impl(mpres_ctx *c, int transa, int transb, int m, int n, int k, 
     std::lock_guard<std::mutex> lk(c->mu);
     c->last_stream = st;
     const int N = c->hc.N;
-    CUDA_TRY(cudaMemsetAsync(c->d_counter, 0, 4 * sizeof(int), st));
+    CUDA_TRY(cudaMemsetAsync(c->d_counter, 0, 8 * sizeof(int), st));
 
     if (c->mode != MPRES_MODE_REFERENCE_ORDER) {
         bool done = false;
@@ -459,7 +524,7 @@ static int gemv_impl(mpres_ctx *c, int trans, int m, int n, SoA alpha, SoA A, in
     SoA ax;
     int rc = ws_soa(c, 1, (size_t) lenx, &ax);
     if (rc) return rc;
-    CUDA_TRY(cudaMemsetAsync(c->d_counter, 0, 4 * sizeof(int), st));
+    CUDA_TRY(cudaMemsetAsync(c->d_counter, 0, 8 * sizeof(int), st));
     c->ev_valid = false;
     mv_mark(c, 0, st);
     MPRES_DISPATCH(N, {
@@ -513,7 +578,7 @@ static int dot_to_record(mpres_ctx *c, int n, SoA x, int incx, SoA y, int incy, 
     const size_t rs = 4 * (size_t) N + 40;
     bool done = false, tried = false;
     int rc;
-    CUDA_TRY(cudaMemsetAsync(c->d_counter, 0, 4 * sizeof(int), st));
+    CUDA_TRY(cudaMemsetAsync(c->d_counter, 0, 8 * sizeof(int), st));
     c->ev_valid = false;
     if (c->mode != MPRES_MODE_REFERENCE_ORDER) {
         rc = dot_fast(c, n, x, incx, y, incy, rec_out, out, st, &done, &tried);

@@ -247,11 +247,12 @@ def test_gemm_stage3_kernels_identical(pkg, N, bits_div, shape):
     alpha = random_records(N, 1, bits, 74)
     beta = random_records(N, 1, bits, 75)
     out = []
-    for kind in (1, 0):
+    for kind in (1, 0, 2, 3):     # tile kernel, entry-per-thread (32-bit Barrett products), generic products, unfused base extension
         ctx.set_stage3_kernel(kind)
         out.append(_gemm(pkg, ctx, m, n, k, alpha, A, B, beta, C, pkg.MODE_FAST))
-    bad = diff_fields(out[0], out[1])
-    assert bad.size == 0, "%d/%d entries differ, first %d\n%s\n%s" % (bad.size, m * n, bad[0], out[0][bad[0]], out[1][bad[0]])
+    for other in out[1:]:
+        bad = diff_fields(out[0], other)
+        assert bad.size == 0, "%d/%d entries differ, first %d\n%s\n%s" % (bad.size, m * n, bad[0], out[0][bad[0]], other[bad[0]])
     if bits_div == 4:
         want = _gemm(pkg, ctx, m, n, k, alpha, A, B, beta, C, pkg.MODE_REFERENCE_ORDER)
         # Bit-identical except where an exact zero takes part (zero row / column / cancelling row): there the
@@ -265,10 +266,10 @@ def test_gemm_stage3_kernels_identical(pkg, N, bits_div, shape):
     zero = orc.set_ints([0], [0], [0])
     for al, be in ((alpha, zero), (zero, beta)):
         res = []
-        for kind in (1, 0):
+        for kind in (1, 0, 2, 3):
             ctx.set_stage3_kernel(kind)
             res.append(_gemm(pkg, ctx, m, n, k, al, A, B, be, C, pkg.MODE_FAST))
-        assert diff_fields(res[0], res[1]).size == 0
+        assert all(diff_fields(res[0], r).size == 0 for r in res[1:])
     ctx.close()
 
 
@@ -307,6 +308,7 @@ def test_gemm_reduced_base_identical(pkg, N, bits_div, shape):
     alpha = random_records(N, 1, bits, 94)
     beta = random_records(N, 1, bits, 95)
     out, base = [], []
+    ctx.set_stage2_kernel(pkg.STAGE2_UMMA)      # the limb planes on the format's own moduli (the default small-modulus path has its own test)
     for on in (False, True):
         ctx.set_reduced_base(on)
         out.append(_gemm(pkg, ctx, m, n, k, alpha, A, B, beta, C, pkg.MODE_AUTO))
