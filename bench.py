@@ -138,7 +138,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="gemm4096_424bit", choices=sorted(WORKLOADS))
     ap.add_argument("--mode", default="auto", choices=["auto", "reference_order", "fast"])
-    ap.add_argument("--stage2", default="small", choices=["small", "umma", "umma_unstacked", "mma_sync"], help="stage-2 kernel (A/B measurement)")
+    ap.add_argument("--stage2", default="small", choices=["small", "small_tiled", "umma", "umma_unstacked", "mma_sync"], help="stage-2 kernel (A/B measurement)")
     ap.add_argument("--stage3", type=int, default=0, choices=[0, 1, 2, 3], help="stage-3 kernel variant (mpres_set_stage3_kernel; A/B measurement)")
     ap.add_argument("--full-precision-inputs", action="store_true", help="p-bit significands instead of p/4")
     ap.add_argument("--no-e2e", action="store_true")
@@ -191,7 +191,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = pkg.Context(N, local_rank)
     ctx.set_mode({"auto": pkg.MODE_AUTO, "reference_order": pkg.MODE_REFERENCE_ORDER, "fast": pkg.MODE_FAST}[args.mode])
-    ctx.set_stage2_kernel({"small": pkg.STAGE2_SMALL, "umma": pkg.STAGE2_UMMA, "umma_unstacked": pkg.STAGE2_UMMA_UNSTACKED, "mma_sync": pkg.STAGE2_MMA_SYNC}[args.stage2])
+    ctx.set_stage2_kernel({"small": pkg.STAGE2_SMALL, "small_tiled": pkg.STAGE2_SMALL_TILED, "umma": pkg.STAGE2_UMMA, "umma_unstacked": pkg.STAGE2_UMMA_UNSTACKED, "mma_sync": pkg.STAGE2_MMA_SYNC}[args.stage2])
     config["stage2_kernel"] = args.stage2
     ctx.set_stage3_kernel(args.stage3)
     config["stage3_kernel"] = args.stage3
@@ -318,7 +318,8 @@ def main():
         ops = 2.0 * limb_macs
         achieved = ops / t2 / 1e12
         peak = 2.0 * bf16_peak                        # dense int8 = 2 x dense bf16 on the same tensor cores
-        kname = {"small": "k_small_umma (tcgen05.mma kind::i8 per one-byte modulus, TMA, TMEM)" if small_P > 0 else "k_limb_umma<stacked> (small base not selected)",
+        kname = {"small": "k_small_umma_p (persistent, tcgen05.mma kind::i8 per one-byte modulus, TMA ring, two TMEM accumulators)" if small_P > 0 else "k_limb_umma<stacked> (small base not selected)",
+                 "small_tiled": "k_small_umma (one tile per CTA)" if small_P > 0 else "k_limb_umma<stacked> (small base not selected)",
                  "umma": "k_limb_umma<stacked> (tcgen05.mma kind::i8, TMA, TMEM)", "umma_unstacked": "k_limb_umma<unstacked>",
                  "mma_sync": "k_limb_gemm<0>+<1> (legacy mma.sync IMMA)"}[args.stage2]
         roof = {"bound": "tensor", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "TOP/s (int8)",

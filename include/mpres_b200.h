@@ -60,7 +60,7 @@ enum { MPRES_NO_TRANS = 111, MPRES_TRANS = 112, MPRES_CONJ_TRANS = 113 };
  * kernels including the interval evaluations.  FAST = fast path only (elements whose guard fails
  * are reported through mpres_last_fallback_count). */
 enum { MPRES_MODE_AUTO = 0, MPRES_MODE_REFERENCE_ORDER = 1, MPRES_MODE_FAST = 2 };
-enum { MPRES_STAGE2_UMMA = 0, MPRES_STAGE2_UMMA_UNSTACKED = 1, MPRES_STAGE2_MMA_SYNC = 2, MPRES_STAGE2_SMALL = 3 };
+enum { MPRES_STAGE2_UMMA = 0, MPRES_STAGE2_UMMA_UNSTACKED = 1, MPRES_STAGE2_MMA_SYNC = 2, MPRES_STAGE2_SMALL = 3, MPRES_STAGE2_SMALL_TILED = 4 };
 
 typedef struct mpres_ctx mpres_ctx;
 typedef void *mpres_stream_t; /* cudaStream_t */
@@ -98,9 +98,10 @@ int mpres_get_mode(const mpres_ctx *ctx);
 /* Stage-2 kernel of the fast path.  SMALL (default) = the exact sums are accumulated modulo one-byte moduli
  * (256, 251, 243, ...): one tcgen05.mma kind::i8 GEMM per modulus, inputs converted through their binary
  * representation, results returned to the moduli of the number format by a CRT base extension; chosen per call
- * when the sums fit the small base (about 360 bits), otherwise the call runs as UMMA.  UMMA = tcgen05.mma
+ * when the sums fit the small base (about 360 bits), otherwise the call runs as UMMA; a persistent kernel (one
+ * CTA per SM, two TMEM accumulators), SMALL_TILED = the same with one tile per CTA.  UMMA = tcgen05.mma
  * kind::i8 over four byte limbs of the format's own moduli with TMA-fed limb tiles, UMMA_UNSTACKED = the same
- * kernel issuing one MMA per limb pair, MMA_SYNC = the legacy warp-level int8 MMA kernel.  All four produce
+ * kernel issuing one MMA per limb pair, MMA_SYNC = the legacy warp-level int8 MMA kernel.  All of them produce
  * identical residues; the switch exists for A/B measurement. */
 int mpres_set_stage2_kernel(mpres_ctx *ctx, int kind);
 /* Small-modulus base the last fast-path call used: *moduli = how many one-byte moduli (0: the call ran on the
@@ -116,8 +117,9 @@ long mpres_debug_read_workspace(mpres_ctx *ctx, int slot, size_t offset, void *h
  * kernel for the entries that need refinement / rounding / sign resolution (default), 1 = the
  * residue-parallel tile kernel for every entry, 2 = like 0 but with the generic 64-bit modular products
  * instead of the 32-bit Barrett step used when every modulus has the same bit length <= 27, 3 = like 0 but,
- * on the small-modulus path, with the base extension as a separate kernel that writes the residue planes
- * (default: fused into the normalisation kernel).  Identical results (including interval evaluations). */
+ * on the small-modulus path, with the base extension fused into the normalisation kernel (no residue planes
+ * in memory; measured slightly slower on B200 because of its register / shared-memory footprint).
+ * Identical results (including interval evaluations). */
 int mpres_set_stage3_kernel(mpres_ctx *ctx, int kind);
 /* Reduced-base fast path (default on): stages 1 and 2 run on the first n' moduli only, n' the smallest
  * multiple of four whose product exceeds four times the largest exact sum (from the per-row / per-column

@@ -363,6 +363,7 @@ __host__ __device__ constexpr int log2_c(int p) { int l = 0; while ((1 << l) < p
 __host__ __device__ constexpr int trailing_ones_c(int q) { int t = 0; while (q & 1) { ++t; q >>= 1; } return t; }
 
 constexpr int kNormFastThreads = 128;
+constexpr int kNormFastRounds = 1;
 
 // The body of the entry-per-thread kernel.  One block = kNormFastThreads consecutive rows (from row0) of column col.
 // Sp[q * plane] is residue q of the exact sum of this thread's entry: in the residue planes of stage 2 (global memory),
@@ -411,12 +412,15 @@ __device__ __forceinline__ void norm_fast_body(const DevConsts &C, int *cds, int
         int K = log2M - (int) bound - 3;
         K = K < 0 ? 0 : K;
         // ---- pass 1 over the moduli: residues, magnified fractions, directed sums (balanced tree) ----
-        // Up to four magnification rounds with exactly the decisions of sign_eval_window (further rounds are needed after
+        // kNormFastRounds magnification rounds with exactly the decisions of sign_eval_window (further rounds are needed after
         // cancellation, when the first magnified fraction is below the accuracy threshold); whatever is still open goes to the list.
+        // Measured on B200: more than one round here costs more (registers, divergence) than the list kernel does for the ~2 % of
+        // entries that need it.
         int sg = 0;
         Er lo, up;
         bool open = true;
-        for (int round = 0; round < 4; ++round) {
+#pragma unroll
+        for (int round = 0; round < kNormFastRounds; ++round) {
             int nz = 0;
             double stl[LOGP + 1], stu[LOGP + 1];
             {
@@ -535,7 +539,7 @@ __device__ __forceinline__ void norm_fast_body(const DevConsts &C, int *cds, int
 }
 
 template <int NQ, bool F32>
-__global__ void __launch_bounds__(kNormFastThreads, 5) k_norm_fast(const DevConsts *Cp, int m, int n, int k, const int *S, const int16_t *delta,
+__global__ void __launch_bounds__(kNormFastThreads, 6) k_norm_fast(const DevConsts *Cp, int m, int n, int k, const int *S, const int16_t *delta,
                                                                 long long m_p, long long n_p, const OuterInfo *ia, const OuterInfo *ib,
                                                                 SoA alpha, SoA beta, SoA Cm, int ldc, const int *scal_tab, long long *todo, int *todo_count,
                                                                 long long *slow, int *slow_count, bool fallback_allowed, const int *gate) {

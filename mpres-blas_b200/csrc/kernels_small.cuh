@@ -139,7 +139,7 @@ __device__ __forceinline__ void align_small_dispatch(const int *dig, int nin, in
     align_small_entry<NW>(dg, nin, P, srow, s_mi, s_negmp, s_m, s_bmu, s_w, s_rcpm, s_cw, s_p, s_pmu, pws, out);
 }
 
-__global__ void __launch_bounds__(256, 2) k_align_small(const DevConsts *Cp, SoA X, long long so, long long sl, int outer, int inner,
+__global__ void __launch_bounds__(256, 3) k_align_small(const DevConsts *Cp, SoA X, long long so, long long sl, int outer, int inner,
                                                         const OuterInfo *info, uint8_t *planes, int16_t *shifts,
                                                         long long outer_p, long long inner_p, const int *sel) {
     extern __shared__ __align__(16) uint8_t as_smem[];
@@ -346,6 +346,147 @@ k_small_umma(const __grid_constant__ CUtensorMap tmJ, const __grid_constant__ CU
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == 9) ptx::tmem_dealloc(tmem, kSTmemCols);
+}
+
+// Persistent variant: one CTA per SM walks the (modulus, tile) list; two TMEM accumulators, so the epilogue of a tile
+// (TMEM -> mod p -> global) runs while the MMAs of the next tile are issued, and the TMA ring (8 stages) keeps prefetching
+// across tile boundaries.  Tiles are ordered i-fastest within a modulus: the CTAs running at the same time share their
+// operand tiles in L2.  The number of moduli is read from `sel`, so no CTA is launched for work that does not exist.
+constexpr int kPStages = 8;
+constexpr int kPSmem = kPStages * kSStageBytes + 1024 + 256;
+constexpr int kPTmemCols = 512;
+
+namespace ptx {
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+}  // namespace ptx
+
+__global__ void __launch_bounds__(kSThreads, 1)
+k_small_umma_p(const __grid_constant__ CUtensorMap tmJ, const __grid_constant__ CUtensorMap tmI, const DevConsts *Cp, uint8_t *S8,
+               long long m_ps, long long n_ps, int k_byte0, int nk, int add_to_S, const int *sel) {
+    extern __shared__ uint8_t smem_raw[];
+    const int P = sel[0];
+    if (P <= 0) return;
+    const int tiles_i = (int) (m_ps / kSN), tiles_j = (int) (n_ps / kSM);
+    const int per_z = tiles_i * tiles_j;
+    const long long total = (long long) P * per_z;
+    if ((long long) blockIdx.x >= total) return;
+    uint8_t *smem = (uint8_t *) (((uintptr_t) smem_raw + 1023) & ~(uintptr_t) 1023);
+    uint64_t *full = (uint64_t *) (smem + kPStages * kSStageBytes);
+    uint64_t *empty = full + kPStages;
+    uint64_t *acc_full = empty + kPStages;      // [2]
+    uint64_t *acc_empty = acc_full + 2;         // [2]
+    uint32_t *tmem_slot = (uint32_t *) (acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 8 && lane == 0) {
+        ptx::prefetch_tmap(&tmJ);
+        ptx::prefetch_tmap(&tmI);
+        for (int s = 0; s < kPStages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { ptx::mbar_init(&acc_full[b], 1); ptx::mbar_init(&acc_empty[b], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 9) ptx::tmem_alloc(tmem_slot, kPTmemCols);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 8) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            long long g = 0;   // stage uses so far
+            for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
+                const int z = (int) (tile / per_z), r = (int) (tile - (long long) z * per_z);
+                const int j0 = (r / tiles_i) * kSM, i0 = (r % tiles_i) * kSN;
+                for (int it = 0; it < nk; ++it, ++g) {
+                    const int s = (int) (g % kPStages);
+                    const uint32_t ph = (uint32_t) (g / kPStages) & 1u;
+                    ptx::mbar_wait(&empty[s], ph ^ 1u);
+                    ptx::mbar_expect_tx(&full[s], kSStageBytes);
+                    uint8_t *dst = smem + s * kSStageBytes;
+                    ptx::tma_load_3d(dst, &tmJ, &full[s], k_byte0 + it * kSK, j0, z);
+                    ptx::tma_load_3d(dst + kSABytes, &tmI, &full[s], k_byte0 + it * kSK, i0, z);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 9) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::idesc_u8(kSM, kSN);
+            long long g = 0;
+            int lt = 0;
+            for (long long tile = blockIdx.x; tile < total; tile += gridDim.x, ++lt) {
+                const int b = lt & 1;
+                ptx::mbar_wait(&acc_empty[b], (uint32_t) (((lt >> 1) & 1) ^ 1));   // the epilogue has drained this accumulator
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem + (uint32_t) (b * kSN);
+                for (int it = 0; it < nk; ++it, ++g) {
+                    const int s = (int) (g % kPStages);
+                    const uint32_t ph = (uint32_t) (g / kPStages) & 1u;
+                    ptx::mbar_wait(&full[s], ph);
+                    ptx::tc_fence_after();
+                    const uint32_t a_addr = ptx::smem_u32(smem + s * kSStageBytes), b_addr = a_addr + kSABytes;
+#pragma unroll
+                    for (int ks = 0; ks < kSK / 32; ++ks)
+                        ptx::umma_i8(d_tmem, ptx::smem_desc_sw64(a_addr + ks * 32), ptx::smem_desc_sw64(b_addr + ks * 32), idesc, (it | ks) ? 1u : 0u);
+                    ptx::umma_commit(&empty[s]);
+                }
+                ptx::umma_commit(&acc_full[b]);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===== epilogue warps =====
+        const SmallDev &SD = *Cp->small;
+        const int quad = warp & 3, half = warp >> 2;
+        int lt = 0;
+        for (long long tile = blockIdx.x; tile < total; tile += gridDim.x, ++lt) {
+            const int z = (int) (tile / per_z), r = (int) (tile - (long long) z * per_z);
+            const int j0 = (r / tiles_i) * kSM, i0 = (r % tiles_i) * kSN;
+            const unsigned p = (unsigned) SD.p[z], mu = SD.mu[z];
+            const int b = lt & 1;
+            ptx::mbar_wait(&acc_full[b], (uint32_t) ((lt >> 1) & 1));
+            ptx::tc_fence_after();
+            const int j = j0 + quad * 32 + lane;
+            uint4 *dst = (uint4 *) (S8 + ((long long) z * n_ps + j) * m_ps + i0 + half * 128);
+            const uint32_t tbase = tmem + ((uint32_t) (quad * 32) << 16) + (uint32_t) (b * kSN + half * 128);
+            // all 128 columns of this thread into registers first, so the accumulator can be handed back early
+            uint32_t d[16][8];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) ptx::tmem_ld8(tbase + (uint32_t) (u * 8), d[u]);
+            ptx::tmem_ld_wait();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&acc_empty[b]);
+#pragma unroll
+            for (int c16 = 0; c16 < 8; ++c16) {     // 16 columns = one 16-byte run per pass
+                uint4 pv = make_uint4(0, 0, 0, 0);
+                if (add_to_S) pv = dst[c16];
+                unsigned wd[4];
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    const unsigned pw = w == 0 ? pv.x : w == 1 ? pv.y : w == 2 ? pv.z : pv.w;
+                    unsigned o = 0;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const unsigned v = d[c16 * 2 + (w >> 1)][(w & 1) * 4 + e] + ((pw >> (8 * e)) & 0xffu);
+                        unsigned rr = v - __umulhi(v, mu) * p;
+                        rr = rr >= p ? rr - p : rr;
+                        o |= rr << (8 * e);
+                    }
+                    wd[w] = o;
+                }
+                dst[c16] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 9) ptx::tmem_dealloc(tmem, kPTmemCols);
 }
 
 // ---- stage 3a: CRT base extension from the small base to the reference moduli ------------------------------
@@ -568,7 +709,14 @@ inline int launch_small_umma(mpres_ctx *c, const uint8_t *PA, const uint8_t *PB,
     static bool attr_done = false;
     if (!attr_done) {
         CUDA_TRY(cudaFuncSetAttribute(mpres::k_small_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, mpres::kSSmem));
+        CUDA_TRY(cudaFuncSetAttribute(mpres::k_small_umma_p, cudaFuncAttributeMaxDynamicSharedMemorySize, mpres::kPSmem));
         attr_done = true;
+    }
+    if (c->small_persistent) {
+        const long long max_tiles = (long long) mpres::kSmallMax * (m_ps / mpres::kSN) * (n_ps / mpres::kSM);
+        const unsigned gx = (unsigned) std::min<long long>(max_tiles, (long long) c->sm_count);
+        mpres::k_small_umma_p<<<gx, mpres::kSThreads, mpres::kPSmem, st>>>(tmJ, tmI, c->dconsts, S8, m_ps, n_ps, (int) k_begin, k_len / mpres::kSK, add_to_S ? 1 : 0, sel);
+        return 0;
     }
     dim3 grid((unsigned) (m_ps / mpres::kSN), (unsigned) (n_ps / mpres::kSM), (unsigned) mpres::kSmallMax);
     mpres::k_small_umma<<<grid, mpres::kSThreads, mpres::kSSmem, st>>>(tmJ, tmI, c->dconsts, S8, m_ps, n_ps, (int) k_begin, k_len / mpres::kSK, add_to_S ? 1 : 0, sel);

@@ -150,12 +150,17 @@ int mpres_device(const mpres_ctx *c) { return c ? c->device : -1; }
 size_t mpres_sizeof_mp_float(const mpres_ctx *c) { return c ? 4 * (size_t) c->hc.N + 40 : 0; }
 int mpres_set_mode(mpres_ctx *c, int mode) { if (!c || mode < 0 || mode > 2) return -1; c->mode = mode; return 0; }
 int mpres_get_mode(const mpres_ctx *c) { return c ? c->mode : -1; }
-int mpres_set_stage2_kernel(mpres_ctx *c, int kind) { if (!c || kind < 0 || kind > 3) return -1; c->stage2 = kind; return 0; }
+int mpres_set_stage2_kernel(mpres_ctx *c, int kind) {
+    if (!c || kind < 0 || kind > 4) return -1;
+    c->stage2 = kind == MPRES_STAGE2_SMALL_TILED ? MPRES_STAGE2_SMALL : kind;
+    c->small_persistent = kind == MPRES_STAGE2_SMALL_TILED ? 0 : 1;
+    return 0;
+}
 int mpres_set_stage3_kernel(mpres_ctx *c, int kind) {
     if (!c || kind < 0 || kind > 3) return -1;
     c->stage3 = kind == 1 ? 1 : 0;
     c->norm32 = kind == 2 ? 0 : 1;
-    c->fuse_ext = kind == 3 ? 0 : 1;
+    c->fuse_ext = kind == 3 ? 1 : 0;
     return 0;
 }
 int mpres_set_reduced_base(mpres_ctx *c, int on) { if (!c) return -1; c->reduced_base = on != 0; return 0; }

@@ -25,8 +25,9 @@ def _signed_ints(orc, recs):
     return out
 
 
-@pytest.mark.parametrize("N,shape,div", [(8, (40, 24, 70), 4), (32, (33, 20, 50), 4), (32, (20, 12, 40), 3), (16, (17, 9, 33), 5)])
-def test_small_path_stages_exact(pkg, N, shape, div):
+@pytest.mark.parametrize("N,shape,div,tiled", [(8, (40, 24, 70), 4, False), (32, (33, 20, 50), 4, False), (32, (20, 12, 40), 3, True), (16, (17, 9, 33), 5, False),
+                                               (8, (300, 260, 200), 4, False)])
+def test_small_path_stages_exact(pkg, N, shape, div, tiled):
     """one-byte planes of A' and B' (stage 1), per-modulus sums (stage 2) and the extended residue planes (stage 3a)
     against exact integers"""
     ctx = pkg.Context(N, 0)
@@ -36,8 +37,8 @@ def test_small_path_stages_exact(pkg, N, shape, div):
     A, B, C = _special_case_inputs(N, m, n, k, bits, 301)
     alpha = random_records(N, 1, bits, 304)
     beta = random_records(N, 1, bits, 305)
-    ctx.set_stage2_kernel(pkg.STAGE2_SMALL)
-    ctx.set_stage3_kernel(3)      # base extension as a separate kernel: the residue planes are written in full
+    ctx.set_stage2_kernel(pkg.STAGE2_SMALL_TILED if tiled else pkg.STAGE2_SMALL)
+    ctx.set_stage3_kernel(0)      # base extension as a separate kernel (the default): the residue planes are written in full
     _gemm(pkg, ctx, m, n, k, alpha, A, B, beta, C, pkg.MODE_AUTO)
     P, nin = ctx.last_small_base()
     assert P > 0 and nin > 0, "the small base must be selected for p/%d-bit inputs (got %d, %d)" % (div, P, nin)
@@ -101,12 +102,13 @@ def test_gemm_small_base_identical(pkg, N, bits_div, shape, ta, tb):
     alpha = random_records(N, 1, bits, 314)
     beta = random_records(N, 1, bits, 315)
     out, sel = [], []
-    for kind in (pkg.STAGE2_UMMA, pkg.STAGE2_SMALL):
+    for kind in (pkg.STAGE2_UMMA, pkg.STAGE2_SMALL, pkg.STAGE2_SMALL_TILED):
         ctx.set_stage2_kernel(kind)
         out.append(_gemm(pkg, ctx, m, n, k, alpha, A, B, beta, C, pkg.MODE_AUTO, ta, tb))
         sel.append(ctx.last_small_base())
-    bad = diff_fields(out[0], out[1])
-    assert bad.size == 0, "%d/%d entries differ, first %d\n%s\n%s" % (bad.size, m * n, bad[0], out[0][bad[0]], out[1][bad[0]])
+    for other in out[1:]:
+        bad = diff_fields(out[0], other)
+        assert bad.size == 0, "%d/%d entries differ, first %d\n%s\n%s" % (bad.size, m * n, bad[0], out[0][bad[0]], other[bad[0]])
     assert sel[0] == (0, 0)
     if 2 * bits + 100 < 362:      # the sums certainly fit the product of the one-byte moduli (~2^362)
         assert sel[1][0] > 0, "%d-bit inputs must select the small base" % bits
