@@ -38,6 +38,13 @@ WORKLOADS = {
     "gemm2048_742bit": (2048, 2048, 2048, 56),
     "gemm2048_848bit": (2048, 2048, 2048, 64),
 }
+# HBM-bound configurations (BASELINE config 4): name: (op, m, n, moduli); for dot m is the vector length
+VEC_WORKLOADS = {
+    "gemv16384_212bit": ("gemv", 16384, 16384, 16),
+    "gemvt16384_212bit": ("gemv_t", 16384, 16384, 16),
+    "dot16m_212bit": ("dot", 1 << 24, 0, 16),
+}
+FALLBACK_HBM_GBS = 6650.0        # /opt/skills/guides/B200_PROFILING.md fallback (MEASURED_PEAKS.json absent)
 # measured on this pool's B200 by tools/mma_bench.cu (profiles/r01_pipe_rates.json)
 R_MAC_IMAD_WIDE = 8.54e12        # residue-MAC/s through IMAD.WIDE.U32: the INT32 roofline of SURVEY 8(d)
 PEAK_INT8_LEGACY_MMA = 1.139e15  # int8 op/s (2 per MAC) through mma.sync m16n8k32 (IMMA.16832)
@@ -130,21 +137,210 @@ def cpu_reference_leg(N, m_s, n_s, k, bits, seed=7):
                       "reference" if kind == "reference" else "oracle-port")}
 
 
+def read_measured_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback"
+
+
+def run_vec(args):
+    """mp_gemv / mp_dot (HBM-bound).  One step = one call; GEMV (N) shards by row blocks of A and y (x replicated, no collective),
+    GEMV (T) and DOT shard by rows / segments and all-gather packed partials that every rank reduces in RNS."""
+    import ctypes
+    op, m, n, N = VEC_WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    import oracle
+    from oracle import constants
+    precision = constants.compute(oracle.moduli_sets()[N])["mp_precision"]
+    bits = precision // 4
+    rs = 4 * N + 40
+    config = {"workload": args.workload, "op": "mp_" + op, "m": m, "n": n, "moduli": N, "precision_bits": precision, "input_significand_bits": bits,
+              "sharding": "single GPU" if world == 1 else ("row blocks x%d" % world if op == "gemv" else "segments x%d, packed partials all-gathered (NCCL) and reduced in RNS on every rank" % world),
+              "l2": "operands exceed the 126 MB L2; no flush needed"}
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        orc = oracle.Oracle(N, oracle.HOST)
+        ns = 1 << 21                                  # bounded sample: a 2^21-element dot product on the host cores
+        vals = []
+        for i in range(args.warmup + args.steps):
+            x, y = orc.random_records(ns, bits, 11 + 2 * i), orc.random_records(ns, bits, 12 + 2 * i)
+            t0 = time.perf_counter()
+            if oracle.have_ref(N):
+                _, nt = oracle.RefLib(N).host_dot_omp(x, y); kind = "reference"
+            else:
+                orc.dot_omp(x, y); nt = os.cpu_count(); kind = "port"
+            dt = time.perf_counter() - t0
+            if i >= args.warmup:
+                vals.append(2.0 * ns / dt / 1e9)
+        v = statistics.mean(vals)
+        cb = {"value": v, "unit": "MP-GFLOP/s", "cores": int(nt), "kind": kind, "sample": "mp_dot of 2^21 elements (%d-bit inputs), %s host mp_mul+mp_add, OpenMP" % (bits, kind)}
+        print(json.dumps({"impl": "reference", "metric": "mp_%s MP-GFLOP/s" % op.split("_")[0], "value": v, "unit": "MP-GFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": 2.0 * ns / v / 1e6, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                          "dtype": "int32 residues (host mp_float_t arithmetic)", "data": "synthetic", "config": config, "cpu_baseline": cb,
+                          "e2e": {"value": v, "unit": "MP-GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+    import torch
+    import _pkg
+    pkg = _pkg.load()
+    from mpres_blas_b200 import parallel, torch_arrays as ta
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU path in this library")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = pkg.Context(N, local_rank)
+    stream = torch.cuda.current_stream().cuda_stream
+    lib = ctx.lib
+    assert m % world == 0
+    ml = m // world
+    part = torch.zeros(rs, dtype=torch.uint8, device="cuda")
+    gathered = torch.zeros(rs * world, dtype=torch.uint8, device="cuda")
+    if op == "dot":
+        x, y, r = ta.TorchMpArray(ctx, ml), ta.TorchMpArray(ctx, ml), ta.TorchMpArray(ctx, 1)
+        ta.random_fill(ctx, x, bits, 100 + rank); ta.random_fill(ctx, y, bits, 200 + rank)
+        flops, alg_bytes = 2.0 * m, 2.0 * m * rs
+
+        def step():
+            if world == 1:
+                pkg.mp_dot(ctx, ml, x, 1, y, 1, r, None, stream)
+            else:
+                pkg._check(lib.mpres_dot_partial(ctx.h, ml, ctypes.byref(x.s), 1, ctypes.byref(y.s), 1, ctypes.c_void_p(part.data_ptr()), ctypes.c_void_p(stream)), "mpres_dot_partial")
+                dist.all_gather_into_tensor(gathered, part)
+                pkg._check(lib.mpres_reduce_partials(ctx.h, ctypes.c_void_p(gathered.data_ptr()), world, ctypes.byref(r.s), ctypes.c_void_p(stream)), "mpres_reduce_partials")
+        host_arrays, out_arr = [(x, ml), (y, ml)], (r, 1)
+    else:
+        tr = op == "gemv_t"
+        A = ta.TorchMpArray(ctx, ml * n)
+        lenx, leny = (ml, n) if tr else (n, ml)
+        xv, yv, y0 = ta.TorchMpArray(ctx, lenx), ta.TorchMpArray(ctx, leny), ta.TorchMpArray(ctx, leny)
+        al, be = ta.TorchMpArray(ctx, 1), ta.TorchMpArray(ctx, 1)
+        ta.random_fill(ctx, A, bits, 300 + rank); ta.random_fill(ctx, xv, bits, 400 + (rank if tr else 0)); ta.random_fill(ctx, y0, bits, 500 + rank)
+        ta.random_fill(ctx, al, bits, 41); ta.random_fill(ctx, be, bits, 42)
+        flops, alg_bytes = 2.0 * m * n, float(m) * n * rs + (n + 2.0 * m) * rs
+        if tr and world > 1:
+            raise SystemExit("gemv_t on several GPUs: use the sharding helper in mpres-blas_b200/parallel.py (all-gather of partial y); not a bench line")
+
+        def step():
+            for dst, src in zip(yv.tensors(), y0.tensors()):
+                dst.copy_(src, non_blocking=True)
+            pkg.mp_gemv(ctx, pkg.mblas_trans if tr else pkg.mblas_no_trans, ml, n, al, A, ml, xv, 1, be, yv, 1, None, None, stream)
+        host_arrays, out_arr = [(A, ml * n), (xv, lenx), (y0, leny)], (yv, leny)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(); torch.cuda.synchronize()
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    ctx.set_profiling(True)
+    sampler = ClockSampler(local_rank); sampler.start()
+    launches0 = ctx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    launches = ctx.launch_count - launches0
+    fallback = ctx.last_fallback_count()
+    try:
+        stage_ms, _ = ctx.last_stage_ms()
+    except Exception:
+        stage_ms = None
+    ctx.set_profiling(False)
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = flops / (ms_step * 1e-3) / 1e9
+    e2e = None
+    host_bytes = sum(c for _, c in host_arrays) * rs
+    if not args.no_e2e and host_bytes <= 8e9:
+        bufs = [torch.empty(c * rs, dtype=torch.uint8).pin_memory() for _, c in host_arrays]
+        hout = torch.empty(out_arr[1] * rs, dtype=torch.uint8).pin_memory()
+        for (arr, c), b in zip(host_arrays, bufs):
+            arr.device2host_ptr(b.data_ptr(), c)
+
+        def e2e_step():
+            for (arr, c), b in zip(host_arrays, bufs):
+                arr.host2device_ptr(b.data_ptr(), c)
+            step()
+            out_arr[0].device2host_ptr(hout.data_ptr(), out_arr[1])
+        e2e_step(); barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        barrier()
+        dt = (time.perf_counter() - t0) / args.e2e_steps
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); dt = float(t.item())
+        e2e = {"value": flops / dt / 1e9, "unit": "MP-GFLOP/s", "h2d_bytes_per_step": int(host_bytes * world), "d2h_bytes_per_step": int(out_arr[1] * rs * world),
+               "ms_per_step": dt * 1e3, "steps": args.e2e_steps, "path": "mpres_array_host2device(operands) + the call + mpres_array_device2host(result), pinned host AoS mp_float_t[]"}
+    elif not args.no_e2e:
+        e2e = {"value": None, "unit": "MP-GFLOP/s", "skipped": "host copy of the operands is %.1f GB per step (PCIe-bound by construction); run with a smaller workload" % (host_bytes / 1e9)}
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    hbm, src = read_measured_hbm()
+    roof = None
+    if stage_ms:
+        tk = stage_ms[1] * 1e-3        # the single-pass accumulation kernel of this rank
+        ach = alg_bytes / world / tk / 1e9
+        roof = {"bound": "hbm", "kernel": "k_mv_acc_n" if op == "gemv" else "k_mv_acc_t", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+                "peak_source": "%s copy bandwidth" % src, "traffic": None, "avg_launch_ms": stage_ms[1], "algorithmic_bytes_per_launch": alg_bytes / world,
+                "stage_ms": {"scale_vectors": stage_ms[0], "accumulate": stage_ms[1], "finalize": stage_ms[2]},
+                "whole_call_frac": alg_bytes / world / (ms_step * 1e-3) / 1e9 / hbm}
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        orc = oracle.Oracle(N, oracle.HOST)
+        ns = 1 << 21
+        xh, yh = orc.random_records(ns, bits, 11), orc.random_records(ns, bits, 12)
+        t0 = time.perf_counter()
+        if oracle.have_ref(N):
+            _, nt = oracle.RefLib(N).host_dot_omp(xh, yh); kind = "reference"
+        else:
+            orc.dot_omp(xh, yh); nt = os.cpu_count(); kind = "port"
+        dt = time.perf_counter() - t0
+        cpu = {"value": 2.0 * ns / dt / 1e9, "unit": "MP-GFLOP/s", "cores": int(nt), "kind": kind, "seconds": dt,
+               "sample": "mp_dot of 2^21 elements (%d-bit inputs), %s host mp_mul+mp_add, OpenMP" % (bits, kind)}
+    print(json.dumps({"metric": "mp_%s MP-GFLOP/s" % op.split("_")[0], "value": value, "unit": "MP-GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                      "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                      "dtype": "int32 RNS residues, u64 lazy accumulation (f64 interval bounds)", "data": "synthetic", "config": config,
+                      "gpu_launches": int(launches), "fallback_elements_last_step": int(fallback), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e}))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="gemm4096_424bit", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="gemm4096_424bit", choices=sorted(WORKLOADS) + sorted(VEC_WORKLOADS))
     ap.add_argument("--mode", default="auto", choices=["auto", "reference_order", "fast"])
-    ap.add_argument("--stage2", default="small", choices=["small", "small_tiled", "umma", "umma_unstacked", "mma_sync"], help="stage-2 kernel (A/B measurement)")
+    ap.add_argument("--stage2", default="small", choices=["small", "small_k64", "small_tiled", "umma", "umma_unstacked", "mma_sync"], help="stage-2 kernel (A/B measurement)")
     ap.add_argument("--stage3", type=int, default=0, choices=[0, 1, 2, 3], help="stage-3 kernel variant (mpres_set_stage3_kernel; A/B measurement)")
     ap.add_argument("--full-precision-inputs", action="store_true", help="p-bit significands instead of p/4")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
     args = ap.parse_args()
+    if args.workload in VEC_WORKLOADS:
+        return run_vec(args)
 
     m, n, k, N = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -191,7 +387,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = pkg.Context(N, local_rank)
     ctx.set_mode({"auto": pkg.MODE_AUTO, "reference_order": pkg.MODE_REFERENCE_ORDER, "fast": pkg.MODE_FAST}[args.mode])
-    ctx.set_stage2_kernel({"small": pkg.STAGE2_SMALL, "small_tiled": pkg.STAGE2_SMALL_TILED, "umma": pkg.STAGE2_UMMA, "umma_unstacked": pkg.STAGE2_UMMA_UNSTACKED, "mma_sync": pkg.STAGE2_MMA_SYNC}[args.stage2])
+    ctx.set_stage2_kernel({"small": pkg.STAGE2_SMALL, "small_tiled": pkg.STAGE2_SMALL_TILED, "small_k64": pkg.STAGE2_SMALL_K64, "umma": pkg.STAGE2_UMMA, "umma_unstacked": pkg.STAGE2_UMMA_UNSTACKED, "mma_sync": pkg.STAGE2_MMA_SYNC}[args.stage2])
     config["stage2_kernel"] = args.stage2
     ctx.set_stage3_kernel(args.stage3)
     config["stage3_kernel"] = args.stage3
@@ -210,11 +406,26 @@ def main():
         ta.random_fill(ctx, B, bits, 33)
     stream = torch.cuda.current_stream().cuda_stream
 
+    # mp_gemm updates C in place, so every step gets its own pristine p/4-bit C: a ring of pre-filled copies (HBM has the room:
+    # 2.8 GB each at config 3); only when the run has more steps than buffers is a buffer restored (device copy) before reuse
+    free_b, _ = torch.cuda.mem_get_info()
+    c_bytes = C0.nbytes()
+    n_buf = int(max(1, min(args.steps + args.warmup, 24, (free_b - (16 << 30)) // max(1, c_bytes))))
+    ring = [C] + [ta.TorchMpArray(ctx, mr * n) for _ in range(n_buf - 1)]
+    for Cb in ring:
+        for dst, src in zip(Cb.tensors(), C0.tensors()):
+            dst.copy_(src)
+    state = {"i": 0}
+    config["step"] = "[B broadcast], C_i = alpha*A*B + beta*C_i on a pristine p/4-bit C_i (ring of %d pre-filled device buffers)" % n_buf
+
     def step():
-        for dst, src in zip(C.tensors(), C0.tensors()):   # fresh C every step (device-to-device, ~1 ms at 4096^2)
-            dst.copy_(src, non_blocking=True)
+        i = state["i"]; state["i"] = i + 1
+        Cb = ring[i % n_buf]
+        if i >= n_buf:                                    # buffer reuse: restore the pristine C first (device-to-device)
+            for dst, src in zip(Cb.tensors(), C0.tensors()):
+                dst.copy_(src, non_blocking=True)
         parallel.gemm_row_sharded(dist, B.tensors(), lambda: pkg.mp_gemm(
-            ctx, pkg.mblas_no_trans, pkg.mblas_no_trans, mr, n, k, alpha, A, mr, B, k, beta, C, mr, None, stream))
+            ctx, pkg.mblas_no_trans, pkg.mblas_no_trans, mr, n, k, alpha, A, mr, B, k, beta, Cb, mr, None, stream))
 
     def barrier():
         torch.cuda.synchronize()
@@ -320,6 +531,7 @@ def main():
         peak = 2.0 * bf16_peak                        # dense int8 = 2 x dense bf16 on the same tensor cores
         kname = {"small": "k_small_umma_p (persistent, tcgen05.mma kind::i8 per one-byte modulus, TMA ring, two TMEM accumulators)" if small_P > 0 else "k_limb_umma<stacked> (small base not selected)",
                  "small_tiled": "k_small_umma (one tile per CTA)" if small_P > 0 else "k_limb_umma<stacked> (small base not selected)",
+                 "small_k64": "k_small_umma_p<64> (persistent, 64-byte operand rows)" if small_P > 0 else "k_limb_umma<stacked> (small base not selected)",
                  "umma": "k_limb_umma<stacked> (tcgen05.mma kind::i8, TMA, TMEM)", "umma_unstacked": "k_limb_umma<unstacked>",
                  "mma_sync": "k_limb_gemm<0>+<1> (legacy mma.sync IMMA)"}[args.stage2]
         roof = {"bound": "tensor", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "TOP/s (int8)",

@@ -45,6 +45,7 @@ struct mpres_ctx {
     int reduced_base = 1;             // 1: run stages 1-2 on as many moduli as the exact sums need, then extend the base
     int stage1 = 0;                   // 0: vectorised alignment kernel, 1: round-1 kernel
     int stage3 = 0;                   // 0: entry-per-thread kernel + list, 1: residue-parallel tile kernel
+    int small_kb = 128;               // persistent small-modulus kernel: bytes of K per stage (128: SWIZZLE_128B rows, 64: SWIZZLE_64B)
     int small_persistent = 1;         // small-modulus stage 2: persistent kernel with two TMEM accumulators (0: one tile per CTA)
     int fuse_ext = 0;                 // small-modulus path: 1 = base extension fused into the entry-per-thread normalisation kernel (measured slower: occupancy)
     int norm32 = 1;                   // entry-per-thread kernel: 32-bit Barrett products where every modulus has the same bit length <= 27

@@ -273,7 +273,7 @@ struct SmallConsts {
     std::vector<uint32_t> in_mi;         // [kSmallNinMax + 1][16][16]  words of (m_0 ... m_{c-1}) / m_i
     std::vector<uint32_t> in_negmp;      // [kSmallNinMax + 1][16]      words of 2^(32 c) - m_0 ... m_{c-1}
     std::vector<int> in_log2_milli;      // [kSmallNinMax + 1]  floor(1024 log2(m_0 ... m_{c-1})) - 1
-    std::vector<uint32_t> red_mu;        // [N]  floor(2^(2 k) / m_q), k = red_shift (Barrett constant of the extension sums)
+    std::vector<uint32_t> red_mu;        // [N]  floor(2^(k + 30) / m_q), k = red_shift: one-correction 32-bit Barrett constant (barrett_k in mp_device.cuh)
     double log2M_up = 0;                 // log2(M), rounded up a little
 };
 
@@ -299,10 +299,10 @@ inline void compute_small_consts(const HostConsts &c, SmallConsts &s) {
     }
     s.usable = (N % 4 == 0) && mx < (1 << 27) && N >= 4;
     if (!s.usable) return;
-    s.red_shift = (kmin == kmax && kmin >= 24) ? kmin : 0;
+    s.red_shift = (kmin == kmax && kmin >= 24 && kmin <= 27) ? kmin : 0;
     s.red_mu.assign(N, 0);
     if (s.red_shift)
-        for (int i = 0; i < N; ++i) s.red_mu[i] = (uint32_t) ((1ull << (2 * s.red_shift)) / (uint64_t) c.moduli[i]);
+        for (int i = 0; i < N; ++i) s.red_mu[i] = (uint32_t) ((1ull << (s.red_shift + 30)) / (uint64_t) c.moduli[i]);
     s.ext_cols = ((N + 31) / 32) * 128;
     s.prefix_log2.assign(P + 1, 0);
     {

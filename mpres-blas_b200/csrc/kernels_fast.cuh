@@ -222,58 +222,66 @@ __global__ void __launch_bounds__(256) k_align_planes4(const DevConsts *Cp, SoA 
     const int Q4 = np >> 2;                 // active modulus groups
     const int EP = 256 / Q4;                // entries per pass
     const int o = blockIdx.x;
-    const int l0 = blockIdx.y * kRun;
     constexpr int pitch = kRun + 4;
     const long long len = X.len();
     const bool line_ok = o < outer;
     const OuterInfo oi = line_ok ? info[o] : OuterInfo{0, -1};
     const int q4 = threadIdx.x % Q4, slot = threadIdx.x / Q4;
+    int4 mq = make_int4(1, 1, 1, 1);
+    unsigned long long mu[4] = {0ull, 0ull, 0ull, 0ull};
     if (slot < EP) {
-        const int4 mq = *(const int4 *) (C.moduli + 4 * q4);
-        const int mv[4] = {mq.x, mq.y, mq.z, mq.w};
-        unsigned long long mu[4];
+        mq = *(const int4 *) (C.moduli + 4 * q4);
 #pragma unroll
         for (int e = 0; e < 4; ++e) mu[e] = C.barrett[4 * q4 + e];
-        const int log2M = C.log2M;
-        for (int ll = slot; ll < kRun; ll += EP) {
-            const int l = l0 + ll;
-            unsigned r[4] = {0u, 0u, 0u, 0u};
-            int sh16 = kShiftSentinel;
-            if (line_ok && l < inner) {
-                const long long idx = (long long) o * so + (long long) l * sl;
-                if (X.eval[idx + len].frac != 0) {
-                    long long sh = (long long) X.exp[idx] - oi.emin;
-                    const int s = sh > kShiftMax ? kShiftMax : (int) sh;
-                    sh16 = s;
-                    if (s <= log2M) {   // s > log2M: the line fails the window guard anyway
-                        const int4 dg = __ldg((const int4 *) (X.digits + idx * N) + q4);
-                        const int4 pw = __ldg((const int4 *) (C.pow2 + (long long) s * N) + q4);
-                        const int dv[4] = {dg.x, dg.y, dg.z, dg.w}, pv[4] = {pw.x, pw.y, pw.z, pw.w};
-                        const int neg = X.sign[idx];
+    }
+    const int mv[4] = {mq.x, mq.y, mq.z, mq.w};
+    const int log2M = C.log2M;
+    // a block walks the runs blockIdx.y, blockIdx.y + gridDim.y, ... of its line (few, long-lived blocks: cheap to skip when the
+    // small-modulus base was chosen)
+    for (int run = blockIdx.y; run * kRun < inner_p; run += gridDim.y) {
+        const int l0 = run * kRun;
+        if (slot < EP) {
+            for (int ll = slot; ll < kRun; ll += EP) {
+                const int l = l0 + ll;
+                unsigned r[4] = {0u, 0u, 0u, 0u};
+                int sh16 = kShiftSentinel;
+                if (line_ok && l < inner) {
+                    const long long idx = (long long) o * so + (long long) l * sl;
+                    if (X.eval[idx + len].frac != 0) {
+                        long long sh = (long long) X.exp[idx] - oi.emin;
+                        const int s = sh > kShiftMax ? kShiftMax : (int) sh;
+                        sh16 = s;
+                        if (s <= log2M) {   // s > log2M: the line fails the window guard anyway
+                            const int4 dg = __ldg((const int4 *) (X.digits + idx * N) + q4);
+                            const int4 pw = __ldg((const int4 *) (C.pow2 + (long long) s * N) + q4);
+                            const int dv[4] = {dg.x, dg.y, dg.z, dg.w}, pv[4] = {pw.x, pw.y, pw.z, pw.w};
+                            const int neg = X.sign[idx];
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            int v = mulmod(dv[e], pv[e], mv[e], mu[e]);
-                            if (neg && v) v = mv[e] - v;
-                            r[e] = (unsigned) v;
+                            for (int e = 0; e < 4; ++e) {
+                                int v = mulmod(dv[e], pv[e], mv[e], mu[e]);
+                                if (neg && v) v = mv[e] - v;
+                                r[e] = (unsigned) v;
+                            }
                         }
                     }
                 }
+                if (q4 == 0) shifts[(long long) o * inner_p + l] = (int16_t) sh16;
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) sm_stage[(b * N + 4 * q4 + e) * pitch + ll] = (uint8_t) (r[e] >> (8 * b));
             }
-            if (q4 == 0) shifts[(long long) o * inner_p + l] = (int16_t) sh16;
-#pragma unroll
-            for (int b = 0; b < 4; ++b)
-#pragma unroll
-                for (int e = 0; e < 4; ++e) sm_stage[(b * N + 4 * q4 + e) * pitch + ll] = (uint8_t) (r[e] >> (8 * b));
         }
-    }
-    __syncthreads();
-    // write out: shared row (b, q) -> plane row (q, b), kRun contiguous bytes, one warp per row
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int r = warp; r < 4 * np; r += 8) {
-        const int b = r / np, q = r - b * np;
-        const int row = b * N + q;
-        const uint32_t v = *(const uint32_t *) (sm_stage + row * pitch + lane * 4);
-        *(uint32_t *) (planes + ((long long) (q * 4 + b) * outer_p + o) * inner_p + l0 + lane * 4) = v;
+        __syncthreads();
+        // write out: shared row (b, q) -> plane row (q, b), kRun contiguous bytes, one warp per row
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        for (int r = warp; r < 4 * np; r += 8) {
+            const int b = r / np, q = r - b * np;
+            const int row = b * N + q;
+            const uint32_t v = *(const uint32_t *) (sm_stage + row * pitch + lane * 4);
+            *(uint32_t *) (planes + ((long long) (q * 4 + b) * outer_p + o) * inner_p + l0 + lane * 4) = v;
+        }
+        __syncthreads();
     }
 }
 
@@ -600,8 +608,8 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
         extra_launches += 2;
     }
     if (N % 4 == 0 && N <= 128 && c->stage1 == 0) {
-        k_align_planes4<<<dim3((unsigned) m_p, (unsigned) (k_p / kRun)), 256, smem_align, st>>>(c->dconsts, A, soA, slA, m, k, IA, (uint8_t *) pPA, SA, m_p, k_p, nprime);
-        k_align_planes4<<<dim3((unsigned) n_p, (unsigned) (k_p / kRun)), 256, smem_align, st>>>(c->dconsts, B, soB, slB, n, k, IB, (uint8_t *) pPB, SB, n_p, k_p, nprime);
+        k_align_planes4<<<dim3((unsigned) m_p, (unsigned) std::min<long long>(k_p / kRun, 4)), 256, smem_align, st>>>(c->dconsts, A, soA, slA, m, k, IA, (uint8_t *) pPA, SA, m_p, k_p, nprime);
+        k_align_planes4<<<dim3((unsigned) n_p, (unsigned) std::min<long long>(k_p / kRun, 4)), 256, smem_align, st>>>(c->dconsts, B, soB, slB, n, k, IB, (uint8_t *) pPB, SB, n_p, k_p, nprime);
     } else {
         k_align_planes<<<dim3((unsigned) m_p, (unsigned) (k_p / kRun)), 256, smem_align, st>>>(c->dconsts, A, soA, slA, m, k, IA, (uint8_t *) pPA, SA, m_p, k_p);
         k_align_planes<<<dim3((unsigned) n_p, (unsigned) (k_p / kRun)), 256, smem_align, st>>>(c->dconsts, B, soB, slB, n, k, IB, (uint8_t *) pPB, SB, n_p, k_p);
@@ -644,7 +652,7 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
         ++extra_launches;
     }
     if (c->reduced_base && N % 4 == 0) {
-        const unsigned gx = (unsigned) ((long long) ((m + kExtThreads - 1) / kExtThreads) * n);
+        const dim3 gx((unsigned) ((m + kExtThreads - 1) / kExtThreads), (unsigned) std::min(n, 256));
         k_base_extend<<<gx, kExtThreads, base_extend_smem(N), st>>>(c->dconsts, m, n, (int *) pS, m_p, n_p, c->d_counter + 2);
         ++stage3_launches;
     }

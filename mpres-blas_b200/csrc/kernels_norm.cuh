@@ -206,27 +206,28 @@ __global__ void __launch_bounds__(kExtThreads, 6) k_base_extend(const DevConsts 
         s_t[t] = i < np ? C.ext_t[((long long) np * N + q) * N + i] : 0;
     }
     __syncthreads();
-    const int tiles = (m + kExtThreads - 1) / kExtThreads;
-    const int col = blockIdx.x / tiles;
-    const int row = (blockIdx.x - col * tiles) * kExtThreads + threadIdx.x;
+    const int row = blockIdx.x * kExtThreads + threadIdx.x;
     if (row >= m) return;
-    int *Sp = S + (long long) col * m_p + row;
     const long long plane = n_p * m_p;
     const bool lazy = C.ext_lazy != 0;
-    switch (np4) {
-        case 4: base_extend_body<4>(np, N, lazy, Sp, plane, s_m, s_mu, s_w, s_rcp, s_negmp, s_t); break;
-        case 8: base_extend_body<8>(np, N, lazy, Sp, plane, s_m, s_mu, s_w, s_rcp, s_negmp, s_t); break;
-        case 12: base_extend_body<12>(np, N, lazy, Sp, plane, s_m, s_mu, s_w, s_rcp, s_negmp, s_t); break;
-        case 16: base_extend_body<16>(np, N, lazy, Sp, plane, s_m, s_mu, s_w, s_rcp, s_negmp, s_t); break;
-        case 20: base_extend_body<20>(np, N, lazy, Sp, plane, s_m, s_mu, s_w, s_rcp, s_negmp, s_t); break;
-        case 24: base_extend_body<24>(np, N, lazy, Sp, plane, s_m, s_mu, s_w, s_rcp, s_negmp, s_t); break;
-        case 28: base_extend_body<28>(np, N, lazy, Sp, plane, s_m, s_mu, s_w, s_rcp, s_negmp, s_t); break;
-        case 32: base_extend_body<32>(np, N, lazy, Sp, plane, s_m, s_mu, s_w, s_rcp, s_negmp, s_t); break;
-        case 36: base_extend_body<36>(np, N, lazy, Sp, plane, s_m, s_mu, s_w, s_rcp, s_negmp, s_t); break;
-        case 40: base_extend_body<40>(np, N, lazy, Sp, plane, s_m, s_mu, s_w, s_rcp, s_negmp, s_t); break;
-        case 44: base_extend_body<44>(np, N, lazy, Sp, plane, s_m, s_mu, s_w, s_rcp, s_negmp, s_t); break;
-        case 48: base_extend_body<48>(np, N, lazy, Sp, plane, s_m, s_mu, s_w, s_rcp, s_negmp, s_t); break;
-        default: break;   // k_choose_base never selects a reduced base above kMaxReducedBase
+    // a block walks the columns blockIdx.y, blockIdx.y + gridDim.y, ... (the tables are staged once)
+    for (int col = blockIdx.y; col < n; col += gridDim.y) {
+        int *Sp = S + (long long) col * m_p + row;
+        switch (np4) {
+            case 4: base_extend_body<4>(np, N, lazy, Sp, plane, s_m, s_mu, s_w, s_rcp, s_negmp, s_t); break;
+            case 8: base_extend_body<8>(np, N, lazy, Sp, plane, s_m, s_mu, s_w, s_rcp, s_negmp, s_t); break;
+            case 12: base_extend_body<12>(np, N, lazy, Sp, plane, s_m, s_mu, s_w, s_rcp, s_negmp, s_t); break;
+            case 16: base_extend_body<16>(np, N, lazy, Sp, plane, s_m, s_mu, s_w, s_rcp, s_negmp, s_t); break;
+            case 20: base_extend_body<20>(np, N, lazy, Sp, plane, s_m, s_mu, s_w, s_rcp, s_negmp, s_t); break;
+            case 24: base_extend_body<24>(np, N, lazy, Sp, plane, s_m, s_mu, s_w, s_rcp, s_negmp, s_t); break;
+            case 28: base_extend_body<28>(np, N, lazy, Sp, plane, s_m, s_mu, s_w, s_rcp, s_negmp, s_t); break;
+            case 32: base_extend_body<32>(np, N, lazy, Sp, plane, s_m, s_mu, s_w, s_rcp, s_negmp, s_t); break;
+            case 36: base_extend_body<36>(np, N, lazy, Sp, plane, s_m, s_mu, s_w, s_rcp, s_negmp, s_t); break;
+            case 40: base_extend_body<40>(np, N, lazy, Sp, plane, s_m, s_mu, s_w, s_rcp, s_negmp, s_t); break;
+            case 44: base_extend_body<44>(np, N, lazy, Sp, plane, s_m, s_mu, s_w, s_rcp, s_negmp, s_t); break;
+            case 48: base_extend_body<48>(np, N, lazy, Sp, plane, s_m, s_mu, s_w, s_rcp, s_negmp, s_t); break;
+            default: break;   // k_choose_base never selects a reduced base above kMaxReducedBase
+        }
     }
 }
 
@@ -314,7 +315,7 @@ __global__ void __launch_bounds__(256) k_norm_list(const DevConsts *Cp, int m, i
 // ---- entry-per-thread kernel ---------------------------------------------------------------------------
 struct QConst {          // per-modulus constants, broadcast from shared memory
     int m;
-    unsigned mu32;       // floor(2^(2 kb) / m) when every modulus has the same bit length kb (32-bit Barrett), else 0
+    unsigned mu32;       // floor(2^(kb + 30) / m) when every modulus has the same bit length kb <= 27 (barrett_k), else 0
     unsigned long long mu;
     double rrd, rru;
 };
@@ -342,22 +343,13 @@ __global__ void k_scalar_tables(const DevConsts *Cp, SoA alpha, SoA beta, int *t
 struct ScalarEsi { int sign, exp; Er lo, up; };
 
 // a * b mod m for canonical a, b.  F32: every modulus has bit length kb (24 <= kb <= 27), so the product is below
-// 2^(2 kb) and a 32-bit Barrett step with mu32 = floor(2^(2 kb) / m) leaves a remainder below 3 m (HAC 14.42);
-// otherwise the generic 64-bit reduction.  Both return the canonical residue, hence identical results.
+// 2^(2 kb) and the one-correction 32-bit Barrett step applies (mp_device.cuh: barrett_k); otherwise the generic 64-bit
+// reduction.  Both return the canonical residue, hence identical results.
 template <bool F32>
 __device__ __forceinline__ int mulmod_q(int a, int b, const QConst &c, int kb) {
-    if (F32) {
-        const unsigned long long p = (unsigned long long) (unsigned) a * (unsigned) b;
-        const unsigned ph = (unsigned) (p >> (kb - 1));
-        const unsigned q = (unsigned) (((unsigned long long) ph * c.mu32) >> (kb + 1));
-        unsigned r = (unsigned) p - q * (unsigned) c.m;
-        r = r >= (unsigned) c.m ? r - (unsigned) c.m : r;
-        r = r >= (unsigned) c.m ? r - (unsigned) c.m : r;
-        return (int) r;
-    }
+    if (F32) return (int) barrett_k((unsigned long long) (unsigned) a * (unsigned) b, (unsigned) c.m, c.mu32, kb);
     return mulmod(a, b, c.m, c.mu);
 }
-
 __host__ __device__ constexpr int pow2ceil_c(int n) { int p = 1; while (p < n) p <<= 1; return p; }
 __host__ __device__ constexpr int log2_c(int p) { int l = 0; while ((1 << l) < p) ++l; return l; }
 __host__ __device__ constexpr int trailing_ones_c(int q) { int t = 0; while (q & 1) { ++t; q >>= 1; } return t; }

@@ -47,7 +47,7 @@ constexpr int kASo = 8, kASl = 32;
 template <int NW>
 __device__ __forceinline__ void align_small_entry(const int4 (&dg)[(NW + 3) / 4], int nin, int P, int srow, const unsigned *s_mi, const unsigned *s_negmp,
                                                   const int *s_m, const unsigned long long *s_bmu, const int *s_w, const double *s_rcpm,
-                                                  const unsigned *s_cw, const int *s_p, const unsigned *s_pmu, const uint8_t *pws,
+                                                  const unsigned *s_cw, const unsigned *s_ppm, const uint8_t *pws,
                                                   uint8_t *out) {
     constexpr int CW = (NW + 3) & ~3;
     // CRT over the first nin residues: X = sum xi_i M'_i - R M' with R = floor(sum xi_i / m_i).  The double sum can miss R
@@ -123,8 +123,10 @@ __device__ __forceinline__ void align_small_entry(const int4 (&dg)[(NW + 3) / 4]
                 if (4 * w4 + 2 < NW) v = __dp4a(x[4 * w4 + 2], c4.z, v);
                 if (4 * w4 + 3 < NW) v = __dp4a(x[4 * w4 + 3], c4.w, v);
             }
-            const unsigned r = small_mod(v * ((mult4 >> (8 * e)) & 0xffu), (unsigned) s_p[j], s_pmu[j]);
-            if (j < P) out[j * (kASo * kASl)] = (uint8_t) r;
+            const uint2 pm = *(const uint2 *) (s_ppm + 2 * j);            // (p, floor(2^32 / p)); rows j >= P hold (1, 0) and are never written out
+            const unsigned t = v * ((mult4 >> (8 * e)) & 0xffu);
+            const unsigned r = t - __umulhi(t, pm.y) * pm.x;              // in [0, 2p)
+            out[j * (kASo * kASl)] = (uint8_t) min(r, r - pm.x);
         }
     }
 }
@@ -132,11 +134,11 @@ __device__ __forceinline__ void align_small_entry(const int4 (&dg)[(NW + 3) / 4]
 template <int NW>
 __device__ __forceinline__ void align_small_dispatch(const int *dig, int nin, int P, int srow, const unsigned *s_mi, const unsigned *s_negmp,
                                                      const int *s_m, const unsigned long long *s_bmu, const int *s_w, const double *s_rcpm,
-                                                     const unsigned *s_cw, const int *s_p, const unsigned *s_pmu, const uint8_t *pws, uint8_t *out) {
+                                                     const unsigned *s_cw, const unsigned *s_ppm, const uint8_t *pws, uint8_t *out) {
     int4 dg[(NW + 3) / 4];
 #pragma unroll
     for (int g = 0; g < (NW + 3) / 4; ++g) dg[g] = (4 * g < nin) ? __ldg((const int4 *) dig + g) : make_int4(0, 0, 0, 0);
-    align_small_entry<NW>(dg, nin, P, srow, s_mi, s_negmp, s_m, s_bmu, s_w, s_rcpm, s_cw, s_p, s_pmu, pws, out);
+    align_small_entry<NW>(dg, nin, P, srow, s_mi, s_negmp, s_m, s_bmu, s_w, s_rcpm, s_cw, s_ppm, pws, out);
 }
 
 __global__ void __launch_bounds__(256, 3) k_align_small(const DevConsts *Cp, SoA X, long long so, long long sl, int outer, int inner,
@@ -160,8 +162,7 @@ __global__ void __launch_bounds__(256, 3) k_align_small(const DevConsts *Cp, SoA
     double *s_rcpm = (double *) (s_bmu + CW);
     int *s_m = (int *) (s_rcpm + CW);
     int *s_w = s_m + CW;
-    int *s_p = s_w + CW;
-    unsigned *s_pmu = (unsigned *) (s_p + 64);
+    unsigned *s_ppm = (unsigned *) (s_w + CW);      // [64] x (p, floor(2^32 / p))
 
     // the entry of this thread: every global load is issued before the tables are staged
     const int o0 = blockIdx.x * kASo, l0 = blockIdx.y * kASl;
@@ -188,7 +189,7 @@ __global__ void __launch_bounds__(256, 3) k_align_small(const DevConsts *Cp, SoA
         s_rcpm[i] = on ? 1.0 / (double) C.moduli[i] : 0.0;
         s_w[i] = on ? C.ext_w[nin * N + i] : 0;
     }
-    if (threadIdx.x >= 64 && threadIdx.x < 128) { const int j = threadIdx.x - 64; s_p[j] = SD.p[j]; s_pmu[j] = SD.mu[j]; }
+    if (threadIdx.x >= 64 && threadIdx.x < 128) { const int j = threadIdx.x - 64; s_ppm[2 * j] = (unsigned) SD.p[j]; s_ppm[2 * j + 1] = SD.mu[j]; }
     __syncthreads();
 
     int sh16 = kShiftSentinel;
@@ -204,11 +205,11 @@ __global__ void __launch_bounds__(256, 3) k_align_small(const DevConsts *Cp, SoA
     if (live) {
         const int *dig = X.digits + idx * N;
         uint8_t *outp = s_out + slot;
-#define MPRES_AS_CASE(NW_) case NW_: align_small_dispatch<NW_>(dig, nin, P, srow, s_mi, s_negmp, s_m, s_bmu, s_w, s_rcpm, s_cw, s_p, s_pmu, SD.pws, outp); break;
+#define MPRES_AS_CASE(NW_) case NW_: align_small_dispatch<NW_>(dig, nin, P, srow, s_mi, s_negmp, s_m, s_bmu, s_w, s_rcpm, s_cw, s_ppm, SD.pws, outp); break;
         switch (NWr) {
             MPRES_AS_CASE(1) MPRES_AS_CASE(2) MPRES_AS_CASE(3) MPRES_AS_CASE(4) MPRES_AS_CASE(5) MPRES_AS_CASE(6) MPRES_AS_CASE(7) MPRES_AS_CASE(8)
             MPRES_AS_CASE(12)
-            default: align_small_dispatch<16>(dig, nin, P, srow, s_mi, s_negmp, s_m, s_bmu, s_w, s_rcpm, s_cw, s_p, s_pmu, SD.pws, outp); break;
+            default: align_small_dispatch<16>(dig, nin, P, srow, s_mi, s_negmp, s_m, s_bmu, s_w, s_rcpm, s_cw, s_ppm, SD.pws, outp); break;
         }
 #undef MPRES_AS_CASE
     } else {
@@ -352,8 +353,11 @@ k_small_umma(const __grid_constant__ CUtensorMap tmJ, const __grid_constant__ CU
 // (TMEM -> mod p -> global) runs while the MMAs of the next tile are issued, and the TMA ring (8 stages) keeps prefetching
 // across tile boundaries.  Tiles are ordered i-fastest within a modulus: the CTAs running at the same time share their
 // operand tiles in L2.  The number of moduli is read from `sel`, so no CTA is launched for work that does not exist.
-constexpr int kPStages = 8;
-constexpr int kPSmem = kPStages * kSStageBytes + 1024 + 256;
+// KB = bytes of K per pipeline stage = width of the TMA box and of the shared-memory swizzle: 128 (SWIZZLE_128B, 4 stages) moves
+// the operands in full 128-byte rows -- ncu showed the 64-byte rows of the first version saturating L1TEX (93 %) at 57 % tensor
+// activity; 64 (SWIZZLE_64B, 8 stages) is kept for comparison.
+constexpr int kPRingBytes = 8 * kSStageBytes;     // 192 KB of operand stages either way
+constexpr int kPSmem = kPRingBytes + 1024 + 256;
 constexpr int kPTmemCols = 512;
 
 namespace ptx {
@@ -362,6 +366,20 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 }
 }  // namespace ptx
 
+namespace ptx {
+// K-major operand in the 128B-swizzle canonical layout (rows of 128 bytes, 8-row atoms of 1024 bytes): SBO = 1024 B
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t) ((saddr & 0x3ffffu) >> 4);
+    d |= (uint64_t) 1 << 16;
+    d |= (uint64_t) (1024 >> 4) << 32;
+    d |= (uint64_t) 1 << 46;
+    d |= (uint64_t) 2 << 61;                           // layout type SWIZZLE_128B
+    return d;
+}
+}  // namespace ptx
+
+template <int KB>
 __global__ void __launch_bounds__(kSThreads, 1)
 k_small_umma_p(const __grid_constant__ CUtensorMap tmJ, const __grid_constant__ CUtensorMap tmI, const DevConsts *Cp, uint8_t *S8,
                long long m_ps, long long n_ps, int k_byte0, int nk, int add_to_S, const int *sel) {
@@ -373,7 +391,9 @@ k_small_umma_p(const __grid_constant__ CUtensorMap tmJ, const __grid_constant__ 
     const long long total = (long long) P * per_z;
     if ((long long) blockIdx.x >= total) return;
     uint8_t *smem = (uint8_t *) (((uintptr_t) smem_raw + 1023) & ~(uintptr_t) 1023);
-    uint64_t *full = (uint64_t *) (smem + kPStages * kSStageBytes);
+    constexpr int kStageA = kSM * KB, kStageB = kSN * KB, kStage = kStageA + kStageB, kPStages = kPRingBytes / kStage;
+    nk = nk * kSK / KB;                           // the caller counts 64-byte steps
+    uint64_t *full = (uint64_t *) (smem + kPRingBytes);
     uint64_t *empty = full + kPStages;
     uint64_t *acc_full = empty + kPStages;      // [2]
     uint64_t *acc_empty = acc_full + 2;         // [2]
@@ -405,10 +425,10 @@ k_small_umma_p(const __grid_constant__ CUtensorMap tmJ, const __grid_constant__ 
                     const int s = (int) (g % kPStages);
                     const uint32_t ph = (uint32_t) (g / kPStages) & 1u;
                     ptx::mbar_wait(&empty[s], ph ^ 1u);
-                    ptx::mbar_expect_tx(&full[s], kSStageBytes);
-                    uint8_t *dst = smem + s * kSStageBytes;
-                    ptx::tma_load_3d(dst, &tmJ, &full[s], k_byte0 + it * kSK, j0, z);
-                    ptx::tma_load_3d(dst + kSABytes, &tmI, &full[s], k_byte0 + it * kSK, i0, z);
+                    ptx::mbar_expect_tx(&full[s], kStage);
+                    uint8_t *dst = smem + s * kStage;
+                    ptx::tma_load_3d(dst, &tmJ, &full[s], k_byte0 + it * KB, j0, z);
+                    ptx::tma_load_3d(dst + kStageA, &tmI, &full[s], k_byte0 + it * KB, i0, z);
                 }
             }
         }
@@ -429,10 +449,13 @@ k_small_umma_p(const __grid_constant__ CUtensorMap tmJ, const __grid_constant__ 
                     const uint32_t ph = (uint32_t) (g / kPStages) & 1u;
                     ptx::mbar_wait(&full[s], ph);
                     ptx::tc_fence_after();
-                    const uint32_t a_addr = ptx::smem_u32(smem + s * kSStageBytes), b_addr = a_addr + kSABytes;
+                    const uint32_t a_addr = ptx::smem_u32(smem + s * kStage), b_addr = a_addr + kStageA;
 #pragma unroll
-                    for (int ks = 0; ks < kSK / 32; ++ks)
-                        ptx::umma_i8(d_tmem, ptx::smem_desc_sw64(a_addr + ks * 32), ptx::smem_desc_sw64(b_addr + ks * 32), idesc, (it | ks) ? 1u : 0u);
+                    for (int ks = 0; ks < KB / 32; ++ks) {
+                        const uint64_t ad = KB == 128 ? ptx::smem_desc_sw128(a_addr + ks * 32) : ptx::smem_desc_sw64(a_addr + ks * 32);
+                        const uint64_t bd = KB == 128 ? ptx::smem_desc_sw128(b_addr + ks * 32) : ptx::smem_desc_sw64(b_addr + ks * 32);
+                        ptx::umma_i8(d_tmem, ad, bd, idesc, (it | ks) ? 1u : 0u);
+                    }
                     ptx::umma_commit(&empty[s]);
                 }
                 ptx::umma_commit(&acc_full[b]);
@@ -623,11 +646,7 @@ __device__ __forceinline__ void ext_small_block(const DevConsts &C, const SmallD
                                                  ((unsigned long long) (unsigned) acc[2 * pp + 1][2 * rh + 1] << 24);   // < 2^47
                     unsigned r;
                     if (FASTRED) {
-                        const unsigned ph = (unsigned) (v >> (kred - 1));
-                        const unsigned qq = (unsigned) (((unsigned long long) ph * rmu[pp]) >> (kred + 1));
-                        r = (unsigned) v - qq * (unsigned) mq[pp];   // < 3 m
-                        r = r >= (unsigned) mq[pp] ? r - (unsigned) mq[pp] : r;
-                        r = r >= (unsigned) mq[pp] ? r - (unsigned) mq[pp] : r;
+                        r = barrett_k(v, (unsigned) mq[pp], rmu[pp], kred);
                     } else {
                         r = (unsigned) reduce64(v, mq[pp], muq[pp]);
                     }
@@ -686,15 +705,15 @@ __global__ void __launch_bounds__(kXT, 4) k_ext_norm_small(const DevConsts *Cp, 
 }  // namespace mpres
 
 // 3-D map (k, row, plane) over u8 planes [planes][rows_p][k_p], box 64 B x box_rows x 1 plane, 64B swizzle
-inline int small_make_map(CUtensorMap *map, const void *planes, int nplanes, long long rows_p, long long k_p, int box_rows) {
+inline int small_make_map(CUtensorMap *map, const void *planes, int nplanes, long long rows_p, long long k_p, int box_rows, int box_k = mpres::kSK) {
     mpres_encode_tiled_fn enc = umma_encode_fn();
     if (!enc) return -30;
     cuuint64_t dims[3] = {(cuuint64_t) k_p, (cuuint64_t) rows_p, (cuuint64_t) nplanes};
     cuuint64_t strides[2] = {(cuuint64_t) k_p, (cuuint64_t) (rows_p * k_p)};
-    cuuint32_t box[3] = {(cuuint32_t) mpres::kSK, (cuuint32_t) box_rows, 1};
+    cuuint32_t box[3] = {(cuuint32_t) box_k, (cuuint32_t) box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(planes), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     box_k == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : -31;
 }
 
@@ -704,18 +723,23 @@ inline int launch_small_umma(mpres_ctx *c, const uint8_t *PA, const uint8_t *PB,
                              long long k_begin, int k_len, bool add_to_S, const int *sel, cudaStream_t st) {
     CUtensorMap tmJ, tmI;
     int rc;
-    if ((rc = small_make_map(&tmJ, PB, mpres::kSmallMax, n_ps, k_p, mpres::kSM))) return rc;
-    if ((rc = small_make_map(&tmI, PA, mpres::kSmallMax, m_ps, k_p, mpres::kSN))) return rc;
+    const int box_k = (c->small_persistent && c->small_kb == 128 && k_len % 128 == 0 && k_begin % 128 == 0) ? 128 : mpres::kSK;
+    if ((rc = small_make_map(&tmJ, PB, mpres::kSmallMax, n_ps, k_p, mpres::kSM, box_k))) return rc;
+    if ((rc = small_make_map(&tmI, PA, mpres::kSmallMax, m_ps, k_p, mpres::kSN, box_k))) return rc;
     static bool attr_done = false;
     if (!attr_done) {
         CUDA_TRY(cudaFuncSetAttribute(mpres::k_small_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, mpres::kSSmem));
-        CUDA_TRY(cudaFuncSetAttribute(mpres::k_small_umma_p, cudaFuncAttributeMaxDynamicSharedMemorySize, mpres::kPSmem));
+        CUDA_TRY(cudaFuncSetAttribute(mpres::k_small_umma_p<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, mpres::kPSmem));
+        CUDA_TRY(cudaFuncSetAttribute(mpres::k_small_umma_p<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, mpres::kPSmem));
         attr_done = true;
     }
     if (c->small_persistent) {
         const long long max_tiles = (long long) mpres::kSmallMax * (m_ps / mpres::kSN) * (n_ps / mpres::kSM);
         const unsigned gx = (unsigned) std::min<long long>(max_tiles, (long long) c->sm_count);
-        mpres::k_small_umma_p<<<gx, mpres::kSThreads, mpres::kPSmem, st>>>(tmJ, tmI, c->dconsts, S8, m_ps, n_ps, (int) k_begin, k_len / mpres::kSK, add_to_S ? 1 : 0, sel);
+        if (box_k == 128)
+            mpres::k_small_umma_p<128><<<gx, mpres::kSThreads, mpres::kPSmem, st>>>(tmJ, tmI, c->dconsts, S8, m_ps, n_ps, (int) k_begin, k_len / mpres::kSK, add_to_S ? 1 : 0, sel);
+        else
+            mpres::k_small_umma_p<64><<<gx, mpres::kSThreads, mpres::kPSmem, st>>>(tmJ, tmI, c->dconsts, S8, m_ps, n_ps, (int) k_begin, k_len / mpres::kSK, add_to_S ? 1 : 0, sel);
         return 0;
     }
     dim3 grid((unsigned) (m_ps / mpres::kSN), (unsigned) (n_ps / mpres::kSM), (unsigned) mpres::kSmallMax);

@@ -37,6 +37,7 @@ constexpr int kUStageBytes = kUABytes + kUBBytes;
 constexpr int kUSmem = kUStages * kUStageBytes + 1024 /* alignment slack */ + 256 /* barriers */;
 constexpr int kUThreads = 320;                 // warps 0-7 epilogue, 8 TMA producer, 9 MMA issuer
 constexpr int kUTmemCols = 512;
+constexpr int kUTilesPerCta = 8;
 
 namespace ptx {
 
@@ -142,7 +143,11 @@ k_limb_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = blockIdx.z;
-    const int i0 = blockIdx.y * kUM, j0 = blockIdx.x * kUN;
+    const int i0 = blockIdx.y * kUM;
+    // A CTA walks kUTilesPerCta consecutive column tiles (one after the other, no overlap between them): eight times fewer CTAs,
+    // which is what the launch costs when every CTA leaves at once because the small-modulus base was chosen.
+    const int jt0 = blockIdx.x * kUTilesPerCta;
+    const int ntile = min(kUTilesPerCta, (int) (n_p / kUN) - jt0);
 
     if (warp == 8 && lane == 0) {
         ptx::prefetch_tmap(&tmA);
@@ -158,6 +163,9 @@ k_limb_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     ptx::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
+  for (int tt = 0; tt < ntile; ++tt) {
+    const int j0 = (jt0 + tt) * kUN;
+    const int itb = tt * nk;                        // pipeline steps issued before this tile (stage index and phase continue)
     // zero the seven accumulators: warp w < 8 owns lanes 32 (w & 3) .. +31, columns 224 (w >> 2) .. +223
     if (warp < 8) {
         const uint32_t base = tmem + ((uint32_t) ((warp & 3) * 32) << 16) + (uint32_t) ((warp >> 2) * 224);
@@ -173,8 +181,8 @@ k_limb_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // ===== TMA producer =====
         if (lane == 0) {
             for (int it = 0; it < nk; ++it) {
-                const int s = it % kUStages;
-                const uint32_t ph = (uint32_t) (it / kUStages) & 1u;
+                const int s = (itb + it) % kUStages;
+                const uint32_t ph = (uint32_t) ((itb + it) / kUStages) & 1u;
                 ptx::mbar_wait(&empty[s], ph ^ 1u);
                 ptx::mbar_expect_tx(&full[s], kUStageBytes);
                 uint8_t *dst = smem + s * kUStageBytes;
@@ -188,8 +196,8 @@ k_limb_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (lane == 0) {
             constexpr uint32_t idesc = STACKED ? ptx::idesc_u8(kUM, 256) : ptx::idesc_u8(kUM, kUN);
             for (int it = 0; it < nk; ++it) {
-                const int s = it % kUStages;
-                const uint32_t ph = (uint32_t) (it / kUStages) & 1u;
+                const int s = (itb + it) % kUStages;
+                const uint32_t ph = (uint32_t) ((itb + it) / kUStages) & 1u;
                 ptx::mbar_wait(&full[s], ph);
                 ptx::tc_fence_after();
                 const uint32_t a_addr = ptx::smem_u32(smem + s * kUStageBytes), b_addr = a_addr + kUABytes;
@@ -219,7 +227,7 @@ k_limb_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         unsigned long long cu[7];
 #pragma unroll
         for (int u = 0; u < 7; ++u) cu[u] = (unsigned long long) (unsigned) Cp->pow2[(long long) (8 * u) * Cp->N + q];
-        ptx::mbar_wait(accum_bar, 0);
+        ptx::mbar_wait(accum_bar, (uint32_t) (tt & 1));
         ptx::tc_fence_after();
         const int quad = warp & 3, half = warp >> 2;
         const int i = i0 + quad * 32 + lane;
@@ -243,7 +251,9 @@ k_limb_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
     }
     ptx::tc_fence_before();
-    __syncthreads();
+    __syncthreads();          // the epilogue has read the accumulators: the next tile may zero them
+    ptx::tc_fence_after();
+  }
     if (warp == 9) ptx::tmem_dealloc(tmem, kUTmemCols);
 }
 
@@ -295,7 +305,7 @@ inline int launch_limb_umma(mpres_ctx *c, bool stacked, const uint8_t *PA, const
         CUDA_TRY(cudaFuncSetAttribute(mpres::k_limb_umma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mpres::kUSmem));
         attr_done = true;
     }
-    dim3 grid((unsigned) (n_p / mpres::kUN), (unsigned) (m_p / mpres::kUM), (unsigned) N);
+    dim3 grid((unsigned) ((n_p / mpres::kUN + mpres::kUTilesPerCta - 1) / mpres::kUTilesPerCta), (unsigned) (m_p / mpres::kUM), (unsigned) N);
     if (stacked)
         mpres::k_limb_umma<true><<<grid, mpres::kUThreads, mpres::kUSmem, st>>>(tmA, tmB, c->dconsts, S, m_p, n_p, (int) k_begin, k_len / mpres::kUK, add_to_S ? 1 : 0, c->d_counter + 2);
     else

@@ -102,7 +102,7 @@ def test_gemm_small_base_identical(pkg, N, bits_div, shape, ta, tb):
     alpha = random_records(N, 1, bits, 314)
     beta = random_records(N, 1, bits, 315)
     out, sel = [], []
-    for kind in (pkg.STAGE2_UMMA, pkg.STAGE2_SMALL, pkg.STAGE2_SMALL_TILED):
+    for kind in (pkg.STAGE2_UMMA, pkg.STAGE2_SMALL, pkg.STAGE2_SMALL_K64, pkg.STAGE2_SMALL_TILED):
         ctx.set_stage2_kernel(kind)
         out.append(_gemm(pkg, ctx, m, n, k, alpha, A, B, beta, C, pkg.MODE_AUTO, ta, tb))
         sel.append(ctx.last_small_base())
