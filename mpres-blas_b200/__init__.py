@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmpres_b200.so")
+LIB_PATH = os.environ.get("MPRES_B200_LIB") or os.path.join(_HERE, "libmpres_b200.so")   # the override serves A/B builds of the same library
 
 mblas_no_trans, mblas_trans, mblas_conj_trans = 111, 112, 113  # src/blas/mblas_enum.cuh:25-29
 MODE_AUTO, MODE_REFERENCE_ORDER, MODE_FAST = 0, 1, 2

@@ -355,7 +355,10 @@ __host__ __device__ constexpr int log2_c(int p) { int l = 0; while ((1 << l) < p
 __host__ __device__ constexpr int trailing_ones_c(int q) { int t = 0; while (q & 1) { ++t; q >>= 1; } return t; }
 
 constexpr int kNormFastThreads = 128;
-constexpr int kNormFastRounds = 1;
+#ifndef MPRES_NORM_ROUNDS
+#define MPRES_NORM_ROUNDS 1
+#endif
+constexpr int kNormFastRounds = MPRES_NORM_ROUNDS;
 
 // The body of the entry-per-thread kernel.  One block = kNormFastThreads consecutive rows (from row0) of column col.
 // Sp[q * plane] is residue q of the exact sum of this thread's entry: in the residue planes of stage 2 (global memory),
