@@ -334,11 +334,17 @@ def main():
     ap.add_argument("--mode", default="auto", choices=["auto", "reference_order", "fast"])
     ap.add_argument("--stage2", default="small", choices=["small", "small_k64", "small_tiled", "umma", "umma_unstacked", "mma_sync"], help="stage-2 kernel (A/B measurement)")
     ap.add_argument("--stage3", type=int, default=0, choices=[0, 1, 2, 3], help="stage-3 kernel variant (mpres_set_stage3_kernel; A/B measurement)")
+    ap.add_argument("--bcast", default="lean", choices=["lean", "full"], help="N > 1: what the per-step broadcast of B moves (lean: the fields the small-base path reads, verified on the device; full: all four SoA arrays)")
     ap.add_argument("--full-precision-inputs", action="store_true", help="p-bit significands instead of p/4")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
     args = ap.parse_args()
+    if args.impl == "reference":
+        # torchrun pins OMP_NUM_THREADS to 1; the CPU arm is meant to use every host core (set before any OpenMP runtime loads)
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"     # keep NCCL's version banner off stdout: the bench prints ONE JSON line
     if args.workload in VEC_WORKLOADS:
         return run_vec(args)
 
@@ -389,6 +395,8 @@ def main():
     ctx.set_mode({"auto": pkg.MODE_AUTO, "reference_order": pkg.MODE_REFERENCE_ORDER, "fast": pkg.MODE_FAST}[args.mode])
     ctx.set_stage2_kernel({"small": pkg.STAGE2_SMALL, "small_tiled": pkg.STAGE2_SMALL_TILED, "small_k64": pkg.STAGE2_SMALL_K64, "umma": pkg.STAGE2_UMMA, "umma_unstacked": pkg.STAGE2_UMMA_UNSTACKED, "mma_sync": pkg.STAGE2_MMA_SYNC}[args.stage2])
     config["stage2_kernel"] = args.stage2
+    if world > 1:
+        config["broadcast"] = args.bcast
     ctx.set_stage3_kernel(args.stage3)
     config["stage3_kernel"] = args.stage3
     assert m % world == 0
@@ -418,14 +426,29 @@ def main():
     state = {"i": 0}
     config["step"] = "[B broadcast], C_i = alpha*A*B + beta*C_i on a pristine p/4-bit C_i (ring of %d pre-filled device buffers)" % n_buf
 
+    lean = parallel.LeanBroadcast(dist, N) if (world > 1 and args.bcast == "lean") else None
+    lean_state = {"on": False, "repeats": 0}
+
     def step():
         i = state["i"]; state["i"] = i + 1
         Cb = ring[i % n_buf]
         if i >= n_buf:                                    # buffer reuse: restore the pristine C first (device-to-device)
             for dst, src in zip(Cb.tensors(), C0.tensors()):
                 dst.copy_(src, non_blocking=True)
-        parallel.gemm_row_sharded(dist, B.tensors(), lambda: pkg.mp_gemm(
-            ctx, pkg.mblas_no_trans, pkg.mblas_no_trans, mr, n, k, alpha, A, mr, B, k, beta, Cb, mr, None, stream))
+        gemm = lambda: pkg.mp_gemm(ctx, pkg.mblas_no_trans, pkg.mblas_no_trans, mr, n, k, alpha, A, mr, B, k, beta, Cb, mr, None, stream)
+        if lean is not None and lean_state["on"]:
+            # only the fields of B the small-base fast path reads travel; a device-side check guards it (parallel.LeanBroadcast)
+            lean.broadcast(B.digits, B.sign, B.exp, B.eval)
+            gemm()
+            P_used, nin_used = ctx.last_small_base()
+            ok = torch.tensor([1 if lean.verify(P_used, nin_used, ctx.last_fallback_count()) else 0], dtype=torch.int32, device="cuda")
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 1:
+                return
+            lean_state["repeats"] += 1                   # the lean copy was not enough somewhere: repeat with the complete B
+            for dst, src in zip(Cb.tensors(), C0.tensors()):
+                dst.copy_(src, non_blocking=True)
+        parallel.gemm_row_sharded(dist, B.tensors(), gemm)
 
     def barrier():
         torch.cuda.synchronize()
@@ -433,8 +456,13 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
+    for w in range(args.warmup):
         step()
+        if lean is not None and w == 0:
+            # the first (fully replicated) call tells how many residues per entry the input conversion reads on this rank
+            P_used, nin_used = ctx.last_small_base()
+            nin_all = lean.agree(nin_used if P_used > 0 else 0, "cuda")
+            lean_state["on"] = nin_all > 0
     barrier()
     ctx.set_profiling(True)
     sampler = ClockSampler(local_rank)
@@ -553,6 +581,8 @@ def main():
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u8 limbs of int32 RNS residues, s32 accumulate (f64 interval bounds)", "data": "synthetic", "config": config,
             "gpu_launches": int(launches), "fallback_elements_last_step": int(fallback), "stage3_listed_elements_last_step": int(slow_listed), "reduced_base_moduli": int(base_size), "small_base_moduli": int(small_P), "clocks": clocks,
+            "broadcast_bytes_per_step": (int(lean.nbytes(k * n)) if (lean is not None and lean_state["on"]) else (B.nbytes() if world > 1 else 0)),
+            "lean_broadcast_repeats": lean_state["repeats"],
             "roofline": roof, "int32_roofline": int32_roof, "cpu_baseline": cpu, "e2e": e2e}
     print(json.dumps(line))
     if dist is not None:

@@ -128,8 +128,12 @@ int mpres_set_stage3_kernel(mpres_ctx *ctx, int kind);
  * to the full-base path.  mpres_last_base_size returns n' of the last call (synchronises). */
 int mpres_set_reduced_base(mpres_ctx *ctx, int on);
 long mpres_last_base_size(mpres_ctx *ctx);
-/* Stage-1 alignment kernel: 0 = vectorised (four residues per work item, default), 1 = one residue per thread. */
+/* Stage-1 kernels: 0 = vectorised alignment (four residues per work item) and the (min,+) exponent product from
+ * candidate lists (default), 1 = one-residue-per-thread alignment kernel and the dense (min,+) kernel, 2 = vectorised
+ * alignment and the dense (min,+) kernel.  Identical results. */
 int mpres_set_stage1_kernel(mpres_ctx *ctx, int kind);
+/* entries of the last fast-path call whose (min,+) value the candidate lists did not cover (recomputed densely; synchronises) */
+long mpres_last_minplus_dense_count(mpres_ctx *ctx);
 /* Tile configuration of the single-pass mp_gemv / mp_dot kernels: 0 = 8 columns (4 row tiles) per stage, 2-deep
  * ring (default); 1 = 4 columns (2 row tiles), 3-deep; 2 = 8 columns (4 row tiles), 3-deep.  Identical results. */
 int mpres_set_vec_config(mpres_ctx *ctx, int cfg);

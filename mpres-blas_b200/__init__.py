@@ -39,7 +39,7 @@ EXPORTS = [
     "mpres_init", "mpres_init_moduli", "mpres_finalize", "mpres_moduli_size", "mpres_moduli_product_log2",
     "mpres_precision", "mpres_mp_h", "mpres_mp_j", "mpres_device", "mpres_sizeof_mp_float", "mpres_get_constant",
     "mpres_set_mode", "mpres_get_mode", "mpres_set_stage2_kernel", "mpres_set_stage3_kernel", "mpres_set_stage1_kernel", "mpres_set_reduced_base", "mpres_last_base_size", "mpres_last_slow_count", "mpres_last_fallback_count", "mpres_launch_count",
-    "mpres_set_profiling", "mpres_last_stage_ms", "mpres_set_vec_config", "mpres_last_small_base", "mpres_small_modulus", "mpres_debug_read_workspace",
+    "mpres_set_profiling", "mpres_last_stage_ms", "mpres_set_vec_config", "mpres_last_small_base", "mpres_small_modulus", "mpres_debug_read_workspace", "mpres_last_minplus_dense_count",
     "mpres_array_init", "mpres_array_clear", "mpres_array_host2device", "mpres_array_device2host",
     "mpres_collection_init", "mpres_collection_clear", "mpres_collection_host2device", "mpres_collection_device2host",
     "mpres_array_set_binary", "mpres_gemm", "mpres_gemv", "mpres_dot", "mpres_gemm_coll", "mpres_gemv_coll",
@@ -58,7 +58,7 @@ def load_library():
     lib = ctypes.CDLL(LIB_PATH)
     lib.mpres_version.restype = ctypes.c_char_p
     lib.mpres_sizeof_mp_float.restype = ctypes.c_size_t
-    for f in ("mpres_get_constant", "mpres_last_fallback_count", "mpres_launch_count", "mpres_last_slow_count", "mpres_last_base_size", "mpres_debug_read_workspace"):
+    for f in ("mpres_get_constant", "mpres_last_fallback_count", "mpres_launch_count", "mpres_last_slow_count", "mpres_last_base_size", "mpres_debug_read_workspace", "mpres_last_minplus_dense_count"):
         getattr(lib, f).restype = ctypes.c_long
     _lib = lib
     return lib
@@ -143,6 +143,9 @@ class Context:
 
     def set_stage1_kernel(self, kind):
         _check(self.lib.mpres_set_stage1_kernel(self.h, kind), "mpres_set_stage1_kernel")
+
+    def last_minplus_dense_count(self):
+        return self.lib.mpres_last_minplus_dense_count(self.h)
 
     def last_slow_count(self):
         return self.lib.mpres_last_slow_count(self.h)

@@ -499,6 +499,7 @@ __global__ void __launch_bounds__(256, 1) k_limb_gemm(const DevConsts *Cp, const
 
 #include "kernels_norm.cuh"
 #include "kernels_small.cuh"
+#include "kernels_minplus.cuh"
 
 namespace mpres {
 
@@ -614,7 +615,36 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
         k_align_planes<<<dim3((unsigned) m_p, (unsigned) (k_p / kRun)), 256, smem_align, st>>>(c->dconsts, A, soA, slA, m, k, IA, (uint8_t *) pPA, SA, m_p, k_p);
         k_align_planes<<<dim3((unsigned) n_p, (unsigned) (k_p / kRun)), 256, smem_align, st>>>(c->dconsts, B, soB, slB, n, k, IB, (uint8_t *) pPB, SB, n_p, k_p);
     }
-    k_minplus<<<dim3((unsigned) (m_p / kMpTI), (unsigned) (n_p / kMpTJ)), 256, 0, st>>>(SA, SB, D, k_p, m_p, n_p);
+    if (c->minplus_sparse && k_p >= 512) {
+        // (min,+) from candidate lists (kernels_minplus.cuh); SA / SB have m_ps / n_ps allocated rows
+        const size_t bT = (size_t) k_p * (m_ps + n_ps) * 2, bD = (size_t) m_p * n_p * 2 * 2, bC = (size_t) (m_p + n_p) * kMcT * 8 + (size_t) (m_p + n_p) * 4;
+        void *pMp;
+        if ((rc = ws_reserve(c, 11, bT + bD + bC + (size_t) m * n * 8 + 256, &pMp))) return rc;
+        char *q = (char *) pMp;
+        int16_t *SAT = (int16_t *) q; q += (size_t) k_p * m_ps * 2;
+        int16_t *SBT = (int16_t *) q; q += (size_t) k_p * n_ps * 2;
+        int16_t *D1 = (int16_t *) q; q += (size_t) m_p * n_p * 2;
+        int16_t *D2 = (int16_t *) q; q += (size_t) m_p * n_p * 2;
+        int *cposA = (int *) q; q += (size_t) m_p * kMcT * 4;
+        int *cvalA = (int *) q; q += (size_t) m_p * kMcT * 4;
+        int *cposB = (int *) q; q += (size_t) n_p * kMcT * 4;
+        int *cvalB = (int *) q; q += (size_t) n_p * kMcT * 4;
+        int *thrA = (int *) q; q += (size_t) m_p * 4;
+        int *thrB = (int *) q; q += (size_t) n_p * 4;
+        q = (char *) (((uintptr_t) q + 15) & ~(uintptr_t) 15);
+        long long *mplist = (long long *) q;
+        k_mp_select<<<(unsigned) m, 256, 0, st>>>(SA, k_p, (int) k_p, m, cposA, cvalA, thrA);
+        k_mp_select<<<(unsigned) n, 256, 0, st>>>(SB, k_p, (int) k_p, n, cposB, cvalB, thrB);
+        k_mp_transpose<<<dim3((unsigned) (m_ps / 64), (unsigned) (k_p / 64)), 256, 0, st>>>(SA, k_p, SAT, m_ps);
+        k_mp_transpose<<<dim3((unsigned) (n_ps / 64), (unsigned) (k_p / 64)), 256, 0, st>>>(SB, k_p, SBT, n_ps);
+        k_mp_gather<<<(unsigned) m, 256, 0, st>>>(cposA, cvalA, SBT, n_ps, m, (int) n_p, D1, n_p);
+        k_mp_gather<<<(unsigned) n, 256, 0, st>>>(cposB, cvalB, SAT, m_ps, n, (int) m_p, D2, m_p);
+        k_mp_combine<<<dim3((unsigned) (m_p / 64), (unsigned) (n_p / 64)), 256, 0, st>>>(D1, n_p, D2, m_p, thrA, thrB, m, n, D, m_p, mplist, c->d_counter + 6);
+        k_mp_fix<<<c->sm_count * 4, 256, 0, st>>>(SA, SB, k_p, D, m_p, mplist, c->d_counter + 6);
+        extra_launches += 7;
+    } else {
+        k_minplus<<<dim3((unsigned) (m_p / kMpTI), (unsigned) (n_p / kMpTJ)), 256, 0, st>>>(SA, SB, D, k_p, m_p, n_p);
+    }
     dim3 grid((unsigned) (n_p / kBN), (unsigned) (m_p / kBM), (unsigned) N);
     mark(1);
     int gemm_launches = 0;

@@ -356,7 +356,7 @@ __host__ __device__ constexpr int trailing_ones_c(int q) { int t = 0; while (q &
 
 constexpr int kNormFastThreads = 128;
 #ifndef MPRES_NORM_ROUNDS
-#define MPRES_NORM_ROUNDS 1
+#define MPRES_NORM_ROUNDS 2
 #endif
 constexpr int kNormFastRounds = MPRES_NORM_ROUNDS;
 
@@ -409,8 +409,8 @@ __device__ __forceinline__ void norm_fast_body(const DevConsts &C, int *cds, int
         // ---- pass 1 over the moduli: residues, magnified fractions, directed sums (balanced tree) ----
         // kNormFastRounds magnification rounds with exactly the decisions of sign_eval_window (further rounds are needed after
         // cancellation, when the first magnified fraction is below the accuracy threshold); whatever is still open goes to the list.
-        // Measured on B200: more than one round here costs more (registers, divergence) than the list kernel does for the ~2 % of
-        // entries that need it.
+        // Measured on B200 at config 3: two unrolled rounds take the list from 2.2 % of the entries to none and the step from 13.07 to
+        // 12.58 ms; a four-round loop spills and costs more than the list kernel did.
         int sg = 0;
         Er lo, up;
         bool open = true;

@@ -196,7 +196,20 @@ long mpres_debug_read_workspace(mpres_ctx *c, int slot, size_t offset, void *hos
     return (long) bytes;
 }
 int mpres_set_vec_config(mpres_ctx *c, int cfg) { if (!c || cfg < 0 || cfg > 2) return -1; c->vec_config = cfg; return 0; }
-int mpres_set_stage1_kernel(mpres_ctx *c, int kind) { if (!c || kind < 0 || kind > 1) return -1; c->stage1 = kind; return 0; }
+int mpres_set_stage1_kernel(mpres_ctx *c, int kind) {
+    if (!c || kind < 0 || kind > 2) return -1;
+    c->stage1 = kind == 1 ? 1 : 0;
+    c->minplus_sparse = kind == 0 ? 1 : 0;
+    return 0;
+}
+long mpres_last_minplus_dense_count(mpres_ctx *c) {
+    if (!c || c->device < 0) return -1;
+    DeviceGuard g(c->device);
+    int v = 0;
+    if (cudaStreamSynchronize(c->last_stream) != cudaSuccess) return -2;
+    if (cudaMemcpy(&v, c->d_counter + 6, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+    return v;
+}
 long mpres_launch_count(const mpres_ctx *c) { return c ? c->launches.load() : -1; }
 
 long mpres_last_fallback_count(mpres_ctx *c) {

@@ -36,6 +36,51 @@ def gemm_row_sharded(dist, b_tensors, local_gemm, src=0):
     return local_gemm()
 
 
+class LeanBroadcast:
+    """Replication of B for the row-sharded mp_gemm that moves only what the chosen path reads.
+
+    The exact-window fast path with the small-modulus base reads, per entry of B, its first n_in residues, its sign,
+    its exponent and the UPPER interval bound: 4 n_in + 24 of the 4 N + 40 bytes (40 of 168 at the 424-bit set).  The
+    receiving ranks therefore never hold a complete copy of B -- which is only sound while (a) the small base is the
+    one chosen, (b) no entry falls back to the reference-order recomputation (that reads whole records) and (c) no
+    rank's input conversion reads more than n_in residues.  `verify` checks exactly that on the device after the call
+    (mpres_last_small_base, mpres_last_fallback_count); when it fails the caller repeats the step with the full
+    broadcast (`broadcast_arrays`).  n_in is agreed once: the maximum over ranks of what a first, fully replicated
+    call used.
+    """
+
+    def __init__(self, dist, N, src=0):
+        self.dist, self.N, self.src, self.nin, self.buf = dist, N, src, 0, None
+
+    def agree(self, nin_local, device):
+        t = torch.tensor([int(nin_local)], dtype=torch.int32, device=device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        self.nin = int(t.item())
+        return self.nin
+
+    def nbytes(self, count):
+        return count * (4 * self.nin + 4 + 4 + 16)
+
+    def broadcast(self, digits, sign, exp, ev):
+        """digits [len * N] int32, sign / exp [len] int32, ev [2 * len * 2] int64 (lower bounds, then upper bounds)"""
+        n = sign.numel()
+        d2 = digits.view(n, self.N)
+        if self.buf is None or self.buf.shape != (n, self.nin):
+            self.buf = torch.empty((n, self.nin), dtype=digits.dtype, device=digits.device)
+        rank = self.dist.get_rank()
+        if rank == self.src:
+            self.buf.copy_(d2[:, : self.nin])
+        self.dist.broadcast(self.buf, src=self.src)
+        if rank != self.src:
+            d2[:, : self.nin].copy_(self.buf)
+        self.dist.broadcast(sign, src=self.src)
+        self.dist.broadcast(exp, src=self.src)
+        self.dist.broadcast(ev[2 * n:], src=self.src)
+
+    def verify(self, small_moduli, nin_used, fallback_count):
+        return small_moduli > 0 and 0 < nin_used <= self.nin and fallback_count == 0
+
+
 def dot_segment_sharded(dist, local_partial, reduce_partials):
     """local_partial() -> uint8 tensor holding one packed mp_float_t; reduce_partials(bytes, count) sums
     `count` packed records in index order and returns whatever the caller's result type is"""

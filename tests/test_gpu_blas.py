@@ -288,10 +288,10 @@ def test_gemm_stage1_kernels_identical(pkg, N, shape, ta, tb):
     alpha = random_records(N, 1, bits, 84)
     beta = random_records(N, 1, bits, 85)
     out = []
-    for kind in (1, 0):
+    for kind in (1, 0, 2):      # round-1 alignment + dense (min,+); vectorised + candidate-list (min,+); vectorised + dense
         ctx.set_stage1_kernel(kind)
         out.append(_gemm(pkg, ctx, m, n, k, alpha, A, B, beta, C, pkg.MODE_AUTO, ta, tb))
-    assert diff_fields(out[0], out[1]).size == 0
+    assert diff_fields(out[0], out[1]).size == 0 and diff_fields(out[0], out[2]).size == 0
     ctx.close()
 
 

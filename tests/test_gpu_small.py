@@ -136,3 +136,38 @@ def test_gemm_small_base_long_k(pkg):
     bad = diff_fields(got, want, ("digits", "sign", "exp"))
     assert bad.size == 0, "%d/%d differ" % (bad.size, m * n)
     ctx.close()
+
+
+@pytest.mark.parametrize("N,shape,spread", [(8, (70, 50, 600), 0), (16, (130, 64, 1100), 40), (32, (33, 20, 520), 3)])
+def test_minplus_candidate_lists(pkg, N, shape, spread):
+    """(min,+) exponent product from candidate lists == dense kernel (records identical), on inputs whose exponents are spread so
+    that few / many pairs fall outside the candidates (the dense recomputation list is exercised when spread is large)"""
+    ctx = pkg.Context(N, 0)
+    orc = get_oracle(N, oracle.DEVICE)
+    bits = orc.precision // 4
+    m, n, k = shape
+    A = random_records(N, m * k, bits, 331)
+    B = random_records(N, k * n, bits, 332)
+    C = random_records(N, m * n, bits, 333)
+    if spread:
+        rng = np.random.RandomState(7)
+        # every entry gets a large random exponent offset except a few per line: the small shifts (candidates) are rare and scattered
+        A["exp"] += rng.randint(0, spread, size=A.shape).astype(np.int32)
+        B["exp"] += rng.randint(0, spread, size=B.shape).astype(np.int32)
+    alpha = random_records(N, 1, bits, 334)
+    beta = random_records(N, 1, bits, 335)
+    out, dense = [], []
+    for kind in (2, 0):
+        ctx.set_stage1_kernel(kind)
+        out.append(_gemm(pkg, ctx, m, n, k, alpha, A, B, beta, C, pkg.MODE_AUTO))
+        dense.append(ctx.last_minplus_dense_count())
+    bad = diff_fields(out[0], out[1])
+    assert bad.size == 0, "%d/%d entries differ, first %d" % (bad.size, m * n, bad[0])
+    assert dense[0] == 0
+    if spread == 0:
+        assert dense[1] < m * n // 10
+    want = _gemm(pkg, ctx, m, n, k, alpha, A, B, beta, C, pkg.MODE_REFERENCE_ORDER)
+    assert ctx.last_fallback_count() == 0
+    bad = diff_fields(out[1], want, ("digits", "sign", "exp"))
+    assert bad.size == 0
+    ctx.close()

@@ -85,6 +85,25 @@ def _worker(rank, world, port, tmp):
     yt = parallel.gemv_t_sharded(dist, local_partial_y, reduce_columns)
     want_y = orc.gemv(112, m, k, al, Ak, xv, be, yv, block=1)
     assert diff_fields(yt, want_y, ("digits", "sign", "exp")).size == 0
+    # --- lean broadcast of B: only the first n_in residues, sign, exponent and the upper bounds travel
+    lb = parallel.LeanBroadcast(dist, N)
+    assert lb.agree(2 if rank == 0 else 3, "cpu") == 3
+    cnt = k * n
+    src_d = torch.from_numpy(np.ascontiguousarray(B["digits"]).reshape(-1).copy())
+    src_s, src_e = torch.from_numpy(B["sign"].copy()), torch.from_numpy(B["exp"].copy())
+    ev_np = np.concatenate([B["eval"][:, 0].copy().view(np.int64).reshape(-1), B["eval"][:, 1].copy().view(np.int64).reshape(-1)])
+    src_ev = torch.from_numpy(ev_np.copy())
+    if rank == 0:
+        d, sg, ex, ev = src_d.clone(), src_s.clone(), src_e.clone(), src_ev.clone()
+    else:
+        d, sg, ex, ev = torch.full_like(src_d, -7), torch.zeros_like(src_s), torch.zeros_like(src_e), torch.full_like(src_ev, -7)
+    lb.broadcast(d, sg, ex, ev)
+    assert torch.equal(d.view(cnt, N)[:, :3], src_d.view(cnt, N)[:, :3]) and torch.equal(sg, src_s) and torch.equal(ex, src_e)
+    assert torch.equal(ev[2 * cnt:], src_ev[2 * cnt:])
+    if rank != 0:      # nothing else was moved
+        assert bool((d.view(cnt, N)[:, 3:] == -7).all()) and bool((ev[: 2 * cnt] == -7).all())
+    assert lb.nbytes(cnt) == cnt * (4 * 3 + 24)
+    assert lb.verify(40, 3, 0) and not lb.verify(0, 0, 0) and not lb.verify(40, 4, 0) and not lb.verify(40, 3, 2)
     dist.barrier()
     dist.destroy_process_group()
     open(os.path.join(tmp, "ok%d" % rank), "w").write("ok")
