@@ -579,6 +579,7 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
     OuterInfo *IB = (OuterInfo *) pm; pm += (size_t) n_p * sizeof(OuterInfo);
     long long *todo = (long long *) pm; pm += bytesTodo;
     long long *slow = (long long *) pm; pm += bytesTodo;
+    pm = (char *) (((uintptr_t) pm + 15) & ~(uintptr_t) 15);   // the table rows are read as 128-bit loads
     int *scal_tab = (int *) pm;
     int *nprime = c->d_counter + 2, *sel = c->d_counter + 4;
 
@@ -604,8 +605,8 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
         attr_done = true;
     }
     if (small_on) {
-        k_align_small<<<dim3((unsigned) (m_ps / kASo), (unsigned) (k_p / kASl)), 256, align_small_smem(), st>>>(c->dconsts, A, soA, slA, m, k, IA, (uint8_t *) pQA, SA, m_ps, k_p, sel);
-        k_align_small<<<dim3((unsigned) (n_ps / kASo), (unsigned) (k_p / kASl)), 256, align_small_smem(), st>>>(c->dconsts, B, soB, slB, n, k, IB, (uint8_t *) pQB, SB, n_ps, k_p, sel);
+        k_align_small<<<(unsigned) std::min<long long>((m_ps / kASo) * (k_p / kASl), (long long) c->sm_count * 3), 256, align_small_smem(), st>>>(c->dconsts, A, soA, slA, m, k, IA, (uint8_t *) pQA, SA, m_ps, k_p, sel);
+        k_align_small<<<(unsigned) std::min<long long>((n_ps / kASo) * (k_p / kASl), (long long) c->sm_count * 3), 256, align_small_smem(), st>>>(c->dconsts, B, soB, slB, n, k, IB, (uint8_t *) pQB, SB, n_ps, k_p, sel);
         extra_launches += 2;
     }
     if (N % 4 == 0 && N <= 128 && c->stage1 == 0) {

@@ -385,24 +385,34 @@ __device__ __forceinline__ void norm_fast_body(const DevConsts &C, int *cds, int
     if (threadIdx.x == 32) { s_be.sign = beta.sign[0]; s_be.exp = beta.exp[0]; s_be.lo = beta.eval[0]; s_be.up = beta.eval[beta.len()]; }
     const int row = row0 + threadIdx.x;
     const bool live = row < m;
-    // the digits of this block's C entries are one contiguous run: stage them with coalesced 128-bit loads
+    // the digits of this block's C entries are one contiguous run: asynchronous 4-byte copies into the padded rows (coalesced: a
+    // warp copies 128 consecutive bytes per instruction); they are only waited for before the digit pass, so the DRAM latency hides
+    // behind the sign / interval work
     const int rows_live = min(kNormFastThreads, m - row0);
     int4 *cd4 = (int4 *) (Cm.digits + (row0 + (long long) col * ldc) * NQ);
-    for (int v = threadIdx.x; v < rows_live * (NQ / 4); v += kNormFastThreads) {
-        const int4 t = cd4[v];
-        int *dst = cds + ((4 * v) / NQ) * CP + (4 * v) % NQ;
-        dst[0] = t.x; dst[1] = t.y; dst[2] = t.z; dst[3] = t.w;
+    {
+        const int *csrc = (const int *) cd4;
+        for (int v = threadIdx.x; v < rows_live * NQ; v += kNormFastThreads) {
+            const unsigned sa = (unsigned) __cvta_generic_to_shared(cds + (v / NQ) * CP + v % NQ);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(csrc + v));
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
     }
     okf[threadIdx.x] = 0;
     __syncthreads();
-    bool to_slow = false, to_todo = false;
+    bool to_slow = false, to_todo = false, go = false;
+    int sg = 0, d = 0, sign = 0;
+    long long ic = 0;
+    AddEsi p;
+    Er rlo, rup;
+    const int log2M = C.log2M;
     if (live) do {
-        const int log2M = C.log2M, mp_h = C.mp_h;
+        const int mp_h = C.mp_h;
         const OuterInfo ra = ia[row], cb = ib[col];
         if (ra.win < 0 || cb.win < 0) { to_slow = true; break; }             // a line of exact zeros: S == 0
         const long long bound = (long long) ra.win + cb.win + ceil_log2(k);
         if (bound > (long long) log2M - 2) { to_todo = true; to_slow = !fallback_allowed; break; }   // window guard failed
-        const int d = delta[(long long) col * m_p + row];
+        d = delta[(long long) col * m_p + row];
         if (d >= kShiftSentinel) { to_slow = true; break; }                   // every term is an exact zero
         int K = log2M - (int) bound - 3;
         K = K < 0 ? 0 : K;
@@ -411,7 +421,6 @@ __device__ __forceinline__ void norm_fast_body(const DevConsts &C, int *cds, int
         // cancellation, when the first magnified fraction is below the accuracy threshold); whatever is still open goes to the list.
         // Measured on B200 at config 3: two unrolled rounds take the list from 2.2 % of the entries to none and the step from 13.07 to
         // 12.58 ms; a four-round loop spills and costs more than the list kernel did.
-        int sg = 0;
         Er lo, up;
         bool open = true;
 #pragma unroll
@@ -419,15 +428,17 @@ __device__ __forceinline__ void norm_fast_body(const DevConsts &C, int *cds, int
             int nz = 0;
             double stl[LOGP + 1], stu[LOGP + 1];
             {
-                const int *p2 = C.wpow2 + (long long) K * NQ;   // w_q 2^K mod m_q
+                const int4 *p2 = (const int4 *) (C.wpow2 + (long long) K * NQ);   // w_q 2^K mod m_q, four moduli per load
+                int4 t4 = make_int4(0, 0, 0, 0);
 #pragma unroll
                 for (int q = 0; q < P; ++q) {
                     double vl = 0.0, vu = 0.0;
                     if (q < NQ) {
+                        if ((q & 3) == 0) t4 = __ldg(p2 + (q >> 2));
                         const QConst c = qc[q];
                         const int xq = SMEM_S ? Sp[q * plane] : __ldg(Sp + q * plane);
                         nz |= xq;
-                        const int sq = mulmod_q<F32>(xq, __ldg(p2 + q), c, kb);
+                        const int sq = mulmod_q<F32>(xq, (q & 3) == 0 ? t4.x : (q & 3) == 1 ? t4.y : (q & 3) == 2 ? t4.z : t4.w, c, kb);
                         vl = __dmul_rd((double) sq, c.rrd);
                         vu = __dmul_ru((double) sq, c.rru);
                     }
@@ -467,30 +478,39 @@ __device__ __forceinline__ void norm_fast_body(const DevConsts &C, int *cds, int
         const ScalarEsi al = s_al, be = s_be;
         const Er t1lo = er_md_dir<false>(lo, al.lo, C.unit_upp), t1up = er_md_dir<true>(up, al.up, C.unit_low);
         if (t1up.frac != 0 && t1up.exp >= mp_h) { to_slow = true; break; }
-        const long long ic = row + (long long) col * ldc;
+        ic = row + (long long) col * ldc;
         const Er clo = Cm.eval[ic], cup = Cm.eval[ic + Cm.len()];
         const Er t2lo = er_md_dir<false>(clo, be.lo, C.unit_upp), t2up = er_md_dir<true>(cup, be.up, C.unit_low);
         if (t2up.frac != 0 && t2up.exp >= mp_h) { to_slow = true; break; }
         // ---- C = t2 + t1 (mp_add, src/arith/add.cuh:126-184) ----
-        const AddEsi p = add_esi(C, t2lo, t2up, t1lo, t1up, Cm.exp[ic] + be.exp, s_exp + al.exp, Cm.sign[ic] ^ be.sign, s_sign ^ al.sign);
+        p = add_esi(C, t2lo, t2up, t1lo, t1up, Cm.exp[ic] + be.exp, s_exp + al.exp, Cm.sign[ic] ^ be.sign, s_sign ^ al.sign);
         if (p.gamma > log2M || p.theta > log2M) { to_slow = true; break; }   // shift outside the power table
-        const int sign = p.lo.frac < 0;
+        sign = p.lo.frac < 0;
         if (sign != (p.up.frac < 0)) { to_slow = true; break; }              // sign needs the mixed-radix comparison
-        Er rlo = p.lo, rup = p.up;
+        rlo = p.lo; rup = p.up;
         if (sign) { rlo.frac = -p.up.frac; rlo.exp = p.up.exp; rup.frac = -p.lo.frac; rup.exp = p.lo.exp; }
         if (rup.frac != 0 && rup.exp >= mp_h) { to_slow = true; break; }    // result needs a rounding
+        go = true;
+    } while (0);
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
+    __syncthreads();                                                            // the staged digits of C are in place
+    if (go) {
         // ---- pass 2 over the moduli: digits ----
-        const int *ty = scal_tab + (long long) (p.theta - d + log2M) * NQ;          // alpha 2^(theta - d)
-        const int *tx = scal_tab + (long long) (2 * log2M + 1 + p.gamma) * NQ;      // beta 2^gamma
+        const int4 *ty = (const int4 *) (scal_tab + (long long) (p.theta - d + log2M) * NQ);          // alpha 2^(theta - d)
+        const int4 *tx = (const int4 *) (scal_tab + (long long) (2 * log2M + 1 + p.gamma) * NQ);      // beta 2^gamma
         int *mycd = cds + threadIdx.x * CP;
         const int *sp2 = Sp;
+        int4 y4 = make_int4(0, 0, 0, 0), x4 = make_int4(0, 0, 0, 0);
 #pragma unroll 8
         for (int q = 0; q < NQ; ++q, sp2 += plane) {
+            if ((q & 3) == 0) { y4 = __ldg(ty + (q >> 2)); x4 = __ldg(tx + (q >> 2)); }
+            const int tyq = (q & 3) == 0 ? y4.x : (q & 3) == 1 ? y4.y : (q & 3) == 2 ? y4.z : y4.w;
+            const int txq = (q & 3) == 0 ? x4.x : (q & 3) == 1 ? x4.y : (q & 3) == 2 ? x4.z : x4.w;
             const QConst c = qc[q];
             int v = SMEM_S ? *sp2 : __ldg(sp2);
             if (sg < 0 && v) v = c.m - v;
-            const int ay = p.nzy ? mulmod_q<F32>(v, __ldg(ty + q), c, kb) : 0;
-            const int ax = p.nzx ? mulmod_q<F32>(mycd[q], __ldg(tx + q), c, kb) : 0;
+            const int ay = p.nzy ? mulmod_q<F32>(v, tyq, c, kb) : 0;
+            const int ax = p.nzx ? mulmod_q<F32>(mycd[q], txq, c, kb) : 0;
             const int a = p.sx ? (ax ? c.m - ax : 0) : ax;
             const int b = p.sy ? (ay ? c.m - ay : 0) : ay;
             int r = a + b - c.m;
@@ -502,7 +522,7 @@ __device__ __forceinline__ void norm_fast_body(const DevConsts &C, int *cds, int
         Cm.exp[ic] = (p.ex == 0) ? p.ey : p.ex;
         Cm.eval[ic] = rlo;
         Cm.eval[ic + Cm.len()] = rup;
-    } while (0);
+    }
     if (SMEM_S && to_slow && live) {
 #pragma unroll 8
         for (int q = 0; q < NQ; ++q) Sg[q * gplane] = Sp[q * plane];
@@ -533,8 +553,11 @@ __device__ __forceinline__ void norm_fast_body(const DevConsts &C, int *cds, int
     }
 }
 
+#ifndef MPRES_NORM_BLOCKS
+#define MPRES_NORM_BLOCKS 6
+#endif
 template <int NQ, bool F32>
-__global__ void __launch_bounds__(kNormFastThreads, 6) k_norm_fast(const DevConsts *Cp, int m, int n, int k, const int *S, const int16_t *delta,
+__global__ void __launch_bounds__(kNormFastThreads, MPRES_NORM_BLOCKS) k_norm_fast(const DevConsts *Cp, int m, int n, int k, const int *S, const int16_t *delta,
                                                                 long long m_p, long long n_p, const OuterInfo *ia, const OuterInfo *ib,
                                                                 SoA alpha, SoA beta, SoA Cm, int ldc, const int *scal_tab, long long *todo, int *todo_count,
                                                                 long long *slow, int *slow_count, bool fallback_allowed, const int *gate) {

@@ -132,12 +132,13 @@ __device__ __forceinline__ void align_small_entry(const int4 (&dg)[(NW + 3) / 4]
 }
 
 template <int NW>
-__device__ __forceinline__ void align_small_dispatch(const int *dig, int nin, int P, int srow, const unsigned *s_mi, const unsigned *s_negmp,
+__device__ __forceinline__ void align_small_dispatch(const int *dig, const int4 &d0, int nin, int P, int srow, const unsigned *s_mi, const unsigned *s_negmp,
                                                      const int *s_m, const unsigned long long *s_bmu, const int *s_w, const double *s_rcpm,
                                                      const unsigned *s_cw, const unsigned *s_ppm, const uint8_t *pws, uint8_t *out) {
     int4 dg[(NW + 3) / 4];
+    dg[0] = d0;                                   // prefetched with the entry's other fields
 #pragma unroll
-    for (int g = 0; g < (NW + 3) / 4; ++g) dg[g] = (4 * g < nin) ? __ldg((const int4 *) dig + g) : make_int4(0, 0, 0, 0);
+    for (int g = 1; g < (NW + 3) / 4; ++g) dg[g] = (4 * g < nin) ? __ldg((const int4 *) dig + g) : make_int4(0, 0, 0, 0);
     align_small_entry<NW>(dg, nin, P, srow, s_mi, s_negmp, s_m, s_bmu, s_w, s_rcpm, s_cw, s_ppm, pws, out);
 }
 
@@ -164,19 +165,30 @@ __global__ void __launch_bounds__(256, 3) k_align_small(const DevConsts *Cp, SoA
     int *s_w = s_m + CW;
     unsigned *s_ppm = (unsigned *) (s_w + CW);      // [64] x (p, floor(2^32 / p))
 
-    // the entry of this thread: every global load is issued before the tables are staged
-    const int o0 = blockIdx.x * kASo, l0 = blockIdx.y * kASl;
+    // Persistent: a block walks the tiles blockIdx.x, blockIdx.x + gridDim.x, ... (line-block fastest); the tables are staged once and
+    // the entry fields of the NEXT tile (interval bound, exponent, sign, line base, first four residues) are loaded while the current
+    // tile is converted, so their DRAM latency is off the critical path.
+    struct Fields { double upf; int ex, sg, emin; long long idx; bool inside; int4 d0; };
+    const int tiles_o = (int) (outer_p / kASo);
+    const long long ntiles = (long long) tiles_o * (inner_p / kASl);
     int ol, ll;
     if (so == 1) { ol = threadIdx.x & (kASo - 1); ll = threadIdx.x / kASo; }     // lines are the contiguous direction of the input
     else { ll = threadIdx.x & (kASl - 1); ol = threadIdx.x / kASl; }
-    const int o = o0 + ol, l = l0 + ll;
     const int slot = ol * kASl + ll;
-    const bool inside = o < outer && l < inner;
-    const long long idx = inside ? (long long) o * so + (long long) l * sl : 0;
-    const double upf = inside ? X.eval[idx + X.len()].frac : 0.0;
-    const int ex = inside ? X.exp[idx] : 0;
-    const int sg = inside ? X.sign[idx] : 0;
-    const int emin = inside ? info[o].emin : 0;
+    const long long xlen = X.len();
+    auto load_fields = [&](long long tile) {
+        Fields f;
+        const int o = (int) (tile % tiles_o) * kASo + ol, l = (int) (tile / tiles_o) * kASl + ll;
+        f.inside = tile < ntiles && o < outer && l < inner;
+        f.idx = f.inside ? (long long) o * so + (long long) l * sl : 0;
+        f.upf = f.inside ? X.eval[f.idx + xlen].frac : 0.0;
+        f.ex = f.inside ? X.exp[f.idx] : 0;
+        f.sg = f.inside ? X.sign[f.idx] : 0;
+        f.emin = f.inside ? info[o].emin : 0;
+        f.d0 = f.inside ? __ldg((const int4 *) (X.digits + f.idx * N)) : make_int4(0, 0, 0, 0);
+        return f;
+    };
+    Fields cur = load_fields(blockIdx.x);
 
     for (int t = threadIdx.x; t < ((P + 3) & ~3) * CW; t += 256) { const int j = t / CW, w = t - j * CW; s_cw[t] = SD.cw[j * 16 + w]; }
     for (int t = threadIdx.x; t < CW * CW; t += 256) { const int i = t / CW, w = t - i * CW; s_mi[t] = (i < nin && w < nin) ? SD.in_mi[((size_t) nin * 16 + i) * 16 + w] : 0u; }
@@ -192,40 +204,46 @@ __global__ void __launch_bounds__(256, 3) k_align_small(const DevConsts *Cp, SoA
     if (threadIdx.x >= 64 && threadIdx.x < 128) { const int j = threadIdx.x - 64; s_ppm[2 * j] = (unsigned) SD.p[j]; s_ppm[2 * j + 1] = SD.mu[j]; }
     __syncthreads();
 
-    int sh16 = kShiftSentinel;
-    const bool live = inside && upf != 0;
-    int srow = 0;
-    if (live) {
-        const long long sh = (long long) ex - emin;
-        const int s = sh > kSmallShiftMax ? kSmallShiftMax : (sh < 0 ? 0 : (int) sh);   // the selection guarantees sh <= kSmallShiftMax
-        sh16 = s;
-        srow = 2 * s + (sg ? 1 : 0);
-    }
-    s_sh[slot] = (int16_t) sh16;
-    if (live) {
-        const int *dig = X.digits + idx * N;
-        uint8_t *outp = s_out + slot;
-#define MPRES_AS_CASE(NW_) case NW_: align_small_dispatch<NW_>(dig, nin, P, srow, s_mi, s_negmp, s_m, s_bmu, s_w, s_rcpm, s_cw, s_ppm, SD.pws, outp); break;
-        switch (NWr) {
-            MPRES_AS_CASE(1) MPRES_AS_CASE(2) MPRES_AS_CASE(3) MPRES_AS_CASE(4) MPRES_AS_CASE(5) MPRES_AS_CASE(6) MPRES_AS_CASE(7) MPRES_AS_CASE(8)
-            MPRES_AS_CASE(12)
-            default: align_small_dispatch<16>(dig, nin, P, srow, s_mi, s_negmp, s_m, s_bmu, s_w, s_rcpm, s_cw, s_ppm, SD.pws, outp); break;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int o0 = (int) (tile % tiles_o) * kASo, l0 = (int) (tile / tiles_o) * kASl;
+        const Fields nxt = load_fields(tile + gridDim.x);
+        int sh16 = kShiftSentinel;
+        const bool live = cur.inside && cur.upf != 0;
+        int srow = 0;
+        if (live) {
+            const long long sh = (long long) cur.ex - cur.emin;
+            const int s = sh > kSmallShiftMax ? kSmallShiftMax : (sh < 0 ? 0 : (int) sh);   // the selection guarantees sh <= kSmallShiftMax
+            sh16 = s;
+            srow = 2 * s + (cur.sg ? 1 : 0);
         }
+        s_sh[slot] = (int16_t) sh16;
+        if (live) {
+            const int *dig = X.digits + cur.idx * N;
+            uint8_t *outp = s_out + slot;
+#define MPRES_AS_CASE(NW_) case NW_: align_small_dispatch<NW_>(dig, cur.d0, nin, P, srow, s_mi, s_negmp, s_m, s_bmu, s_w, s_rcpm, s_cw, s_ppm, SD.pws, outp); break;
+            switch (NWr) {
+                MPRES_AS_CASE(1) MPRES_AS_CASE(2) MPRES_AS_CASE(3) MPRES_AS_CASE(4) MPRES_AS_CASE(5) MPRES_AS_CASE(6) MPRES_AS_CASE(7) MPRES_AS_CASE(8)
+                MPRES_AS_CASE(12)
+                default: align_small_dispatch<16>(dig, cur.d0, nin, P, srow, s_mi, s_negmp, s_m, s_bmu, s_w, s_rcpm, s_cw, s_ppm, SD.pws, outp); break;
+            }
 #undef MPRES_AS_CASE
-    } else {
-        for (int j = 0; j < P; ++j) s_out[j * (kASo * kASl) + slot] = 0;
-    }
-    __syncthreads();
-    // write out: (j, line) -> 32 contiguous bytes, two 16-byte halves
-    for (int v = threadIdx.x; v < P * kASo * 2; v += 256) {
-        const int j = v / (kASo * 2), rem = v - j * (kASo * 2);
-        const int oo = rem >> 1, h = rem & 1;
-        const uint4 val = *(const uint4 *) (s_out + j * (kASo * kASl) + oo * kASl + h * 16);
-        *(uint4 *) (planes + ((long long) j * outer_p + o0 + oo) * inner_p + l0 + h * 16) = val;
-    }
-    if (threadIdx.x < kASo * 4) {
-        const int oo = threadIdx.x >> 2, part = threadIdx.x & 3;
-        *(uint4 *) (shifts + (long long) (o0 + oo) * inner_p + l0 + part * 8) = *(const uint4 *) (s_sh + oo * kASl + part * 8);
+        } else {
+            for (int j = 0; j < P; ++j) s_out[j * (kASo * kASl) + slot] = 0;
+        }
+        __syncthreads();
+        // write out: (j, line) -> 32 contiguous bytes, two 16-byte halves
+        for (int v = threadIdx.x; v < P * kASo * 2; v += 256) {
+            const int j = v / (kASo * 2), rem = v - j * (kASo * 2);
+            const int oo = rem >> 1, h = rem & 1;
+            const uint4 val = *(const uint4 *) (s_out + j * (kASo * kASl) + oo * kASl + h * 16);
+            *(uint4 *) (planes + ((long long) j * outer_p + o0 + oo) * inner_p + l0 + h * 16) = val;
+        }
+        if (threadIdx.x < kASo * 4) {
+            const int oo = threadIdx.x >> 2, part = threadIdx.x & 3;
+            *(uint4 *) (shifts + (long long) (o0 + oo) * inner_p + l0 + part * 8) = *(const uint4 *) (s_sh + oo * kASl + part * 8);
+        }
+        __syncthreads();
+        cur = nxt;
     }
 }
 inline size_t align_small_smem() {
