@@ -605,8 +605,17 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
         attr_done = true;
     }
     if (small_on) {
-        k_align_small<<<(unsigned) std::min<long long>((m_ps / kASo) * (k_p / kASl), (long long) c->sm_count * 3), 256, align_small_smem(), st>>>(c->dconsts, A, soA, slA, m, k, IA, (uint8_t *) pQA, SA, m_ps, k_p, sel);
-        k_align_small<<<(unsigned) std::min<long long>((n_ps / kASo) * (k_p / kASl), (long long) c->sm_count * 3), 256, align_small_smem(), st>>>(c->dconsts, B, soB, slB, n, k, IB, (uint8_t *) pQB, SB, n_ps, k_p, sel);
+        const unsigned gA = (unsigned) std::min<long long>((m_ps / kASo) * (k_p / kASl), (long long) c->sm_count * 3);
+        const unsigned gB = (unsigned) std::min<long long>((n_ps / kASo) * (k_p / kASl), (long long) c->sm_count * 3);
+        if (c->align_mma) {
+            static bool attr_am = false;
+            if (!attr_am) { cudaFuncSetAttribute(k_align_small<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) align_small_smem(true)); attr_am = true; }
+            k_align_small<true><<<gA, 256, align_small_smem(true), st>>>(c->dconsts, A, soA, slA, m, k, IA, (uint8_t *) pQA, SA, m_ps, k_p, sel);
+            k_align_small<true><<<gB, 256, align_small_smem(true), st>>>(c->dconsts, B, soB, slB, n, k, IB, (uint8_t *) pQB, SB, n_ps, k_p, sel);
+        } else {
+            k_align_small<false><<<gA, 256, align_small_smem(false), st>>>(c->dconsts, A, soA, slA, m, k, IA, (uint8_t *) pQA, SA, m_ps, k_p, sel);
+            k_align_small<false><<<gB, 256, align_small_smem(false), st>>>(c->dconsts, B, soB, slB, n, k, IB, (uint8_t *) pQB, SB, n_ps, k_p, sel);
+        }
         extra_launches += 2;
     }
     if (N % 4 == 0 && N <= 128 && c->stage1 == 0) {

@@ -37,6 +37,12 @@ __device__ __forceinline__ unsigned small_mod(unsigned v, unsigned p, unsigned m
     return r >= p ? r - p : r;
 }
 
+__device__ __forceinline__ void mma_u8_frag(int (&c)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
 // ---- stage 1: alignment into the small base ---------------------------------------------------------------
 // planes: [j][outer_p][inner_p] u8 (inner contiguous), shifts: [outer_p][inner_p] int16 as in k_align_planes.
 // A block handles kASo lines x kASl inner positions, one entry per thread.
@@ -44,11 +50,11 @@ constexpr int kASo = 8, kASl = 32;
 
 // NW: words of the binary significand = reference residues read (>= n_in); CW = NW rounded up to a multiple of four
 // is the row pitch of the staged tables.
-template <int NW>
+template <int NW, bool MMA>
 __device__ __forceinline__ void align_small_entry(const int4 (&dg)[(NW + 3) / 4], int nin, int P, int srow, const unsigned *s_mi, const unsigned *s_negmp,
                                                   const int *s_m, const unsigned long long *s_bmu, const int *s_w, const double *s_rcpm,
                                                   const unsigned *s_cw, const unsigned *s_ppm, const uint8_t *pws,
-                                                  uint8_t *out) {
+                                                  uint8_t *out, uint8_t *xrow) {
     constexpr int CW = (NW + 3) & ~3;
     // CRT over the first nin residues: X = sum xi_i M'_i - R M' with R = floor(sum xi_i / m_i).  The double sum can miss R
     // by one when X / M' is within 2^-48 of an integer; then the result is off by exactly M' and is put right below.
@@ -107,6 +113,14 @@ __device__ __forceinline__ void align_small_entry(const int4 (&dg)[(NW + 3) / 4]
             for (int w = 0; w < NW; ++w) x[w] = t[w];
         }
     }
+    if (MMA) {
+        // the binary significand goes to this entry's operand row; the residues follow on the tensor cores (k_align_small<true>)
+#pragma unroll
+        for (int w4 = 0; w4 < (NW + 7) / 8 * 2; ++w4)
+            *(uint4 *) (xrow + 16 * w4) = make_uint4(4 * w4 < NW ? x[4 * w4] : 0u, 4 * w4 + 1 < NW ? x[4 * w4 + 1] : 0u,
+                                                     4 * w4 + 2 < NW ? x[4 * w4 + 2] : 0u, 4 * w4 + 3 < NW ? x[4 * w4 + 3] : 0u);
+        return;
+    }
     // residues modulo the small moduli, times +-2^shift
     const unsigned *mrow = (const unsigned *) (pws + (size_t) srow * 64);
     for (int jg = 0; 4 * jg < P; ++jg) {
@@ -131,17 +145,26 @@ __device__ __forceinline__ void align_small_entry(const int4 (&dg)[(NW + 3) / 4]
     }
 }
 
-template <int NW>
+template <int NW, bool MMA>
 __device__ __forceinline__ void align_small_dispatch(const int *dig, const int4 &d0, int nin, int P, int srow, const unsigned *s_mi, const unsigned *s_negmp,
                                                      const int *s_m, const unsigned long long *s_bmu, const int *s_w, const double *s_rcpm,
-                                                     const unsigned *s_cw, const unsigned *s_ppm, const uint8_t *pws, uint8_t *out) {
+                                                     const unsigned *s_cw, const unsigned *s_ppm, const uint8_t *pws, uint8_t *out, uint8_t *xrow) {
     int4 dg[(NW + 3) / 4];
     dg[0] = d0;                                   // prefetched with the entry's other fields
 #pragma unroll
     for (int g = 1; g < (NW + 3) / 4; ++g) dg[g] = (4 * g < nin) ? __ldg((const int4 *) dig + g) : make_int4(0, 0, 0, 0);
-    align_small_entry<NW>(dg, nin, P, srow, s_mi, s_negmp, s_m, s_bmu, s_w, s_rcpm, s_cw, s_ppm, pws, out);
+    align_small_entry<NW, MMA>(dg, nin, P, srow, s_mi, s_negmp, s_m, s_bmu, s_w, s_rcpm, s_cw, s_ppm, pws, out, xrow);
 }
 
+// MMA = true: the residues modulo the one-byte moduli are computed on the tensor cores -- per warp, the 32 binary significands
+// (operand rows of 32 or 64 bytes) times the byte table 256^b mod p_j (mma.sync m16n8k32, u8 x u8 -> s32), each thread then finishing
+// the (entry, modulus) pairs of its accumulator fragment: times +-2^shift, one Barrett step, one byte store.  MMA = false: byte dot
+// products (dp4a) per entry and modulus.  Same planes either way.
+__host__ __device__ constexpr size_t align_small_smem_base() {   // output tile, shifts and the tables at their largest (16 words)
+    return 64 * kASo * kASl + kASo * kASl * 2 + 64 * 16 * 4 + 16 * 16 * 4 + 16 * 4 + 16 * 8 + 16 * 8 + 16 * 4 * 2 + 64 * 4 * 2 + 64;
+}
+constexpr int kAXPitch = 96;      // bytes per operand row (conflict-free 64-bit fragment loads)
+template <bool MMA>
 __global__ void __launch_bounds__(256, 3) k_align_small(const DevConsts *Cp, SoA X, long long so, long long sl, int outer, int inner,
                                                         const OuterInfo *info, uint8_t *planes, int16_t *shifts,
                                                         long long outer_p, long long inner_p, const int *sel) {
@@ -164,6 +187,10 @@ __global__ void __launch_bounds__(256, 3) k_align_small(const DevConsts *Cp, SoA
     int *s_m = (int *) (s_rcpm + CW);
     int *s_w = s_m + CW;
     unsigned *s_ppm = (unsigned *) (s_w + CW);      // [64] x (p, floor(2^32 / p))
+    // MMA only (behind the tables of the largest configuration): operand rows of the entries, their table rows, the byte table
+    uint8_t *s_x = as_smem + align_small_smem_base();          // [256][kAXPitch]
+    int *s_srow = (int *) (s_x + 256 * kAXPitch);                // [256]
+    uint8_t *s_cwB = (uint8_t *) (s_srow + 256);                 // [56][kAXPitch]
 
     // Persistent: a block walks the tiles blockIdx.x, blockIdx.x + gridDim.x, ... (line-block fastest); the tables are staged once and
     // the entry fields of the NEXT tile (interval bound, exponent, sign, line base, first four residues) are loaded while the current
@@ -202,7 +229,11 @@ __global__ void __launch_bounds__(256, 3) k_align_small(const DevConsts *Cp, SoA
         s_w[i] = on ? C.ext_w[nin * N + i] : 0;
     }
     if (threadIdx.x >= 64 && threadIdx.x < 128) { const int j = threadIdx.x - 64; s_ppm[2 * j] = (unsigned) SD.p[j]; s_ppm[2 * j + 1] = SD.mu[j]; }
+    if (MMA) {
+        for (int t = threadIdx.x; t < 56 * 16; t += 256) { const int j = t >> 4, w = t & 15; *(unsigned *) (s_cwB + j * kAXPitch + 4 * w) = SD.cw[j * 16 + w]; }
+    }
     __syncthreads();
+    const int KS = (NWr + 7) / 8, NT = (P + 7) / 8;     // 32-byte K steps, 8-modulus column tiles
 
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int o0 = (int) (tile % tiles_o) * kASo, l0 = (int) (tile / tiles_o) * kASl;
@@ -217,18 +248,75 @@ __global__ void __launch_bounds__(256, 3) k_align_small(const DevConsts *Cp, SoA
             srow = 2 * s + (cur.sg ? 1 : 0);
         }
         s_sh[slot] = (int16_t) sh16;
+        uint8_t *xrow = s_x + threadIdx.x * kAXPitch;
         if (live) {
             const int *dig = X.digits + cur.idx * N;
             uint8_t *outp = s_out + slot;
-#define MPRES_AS_CASE(NW_) case NW_: align_small_dispatch<NW_>(dig, cur.d0, nin, P, srow, s_mi, s_negmp, s_m, s_bmu, s_w, s_rcpm, s_cw, s_ppm, SD.pws, outp); break;
+#define MPRES_AS_CASE(NW_) case NW_: align_small_dispatch<NW_, MMA>(dig, cur.d0, nin, P, srow, s_mi, s_negmp, s_m, s_bmu, s_w, s_rcpm, s_cw, s_ppm, SD.pws, outp, xrow); break;
             switch (NWr) {
                 MPRES_AS_CASE(1) MPRES_AS_CASE(2) MPRES_AS_CASE(3) MPRES_AS_CASE(4) MPRES_AS_CASE(5) MPRES_AS_CASE(6) MPRES_AS_CASE(7) MPRES_AS_CASE(8)
                 MPRES_AS_CASE(12)
-                default: align_small_dispatch<16>(dig, cur.d0, nin, P, srow, s_mi, s_negmp, s_m, s_bmu, s_w, s_rcpm, s_cw, s_ppm, SD.pws, outp); break;
+                default: align_small_dispatch<16, MMA>(dig, cur.d0, nin, P, srow, s_mi, s_negmp, s_m, s_bmu, s_w, s_rcpm, s_cw, s_ppm, SD.pws, outp, xrow); break;
             }
 #undef MPRES_AS_CASE
+        } else if (MMA) {
+#pragma unroll
+            for (int w4 = 0; w4 < 4; ++w4) *(uint4 *) (xrow + 16 * w4) = make_uint4(0u, 0u, 0u, 0u);   // a zero significand gives zero residues
         } else {
             for (int j = 0; j < P; ++j) s_out[j * (kASo * kASl) + slot] = 0;
+        }
+        if (MMA) {
+            s_srow[threadIdx.x] = srow;
+            __syncwarp();                                   // a warp consumes the 32 operand rows it wrote
+            const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+            int acc[2][7][4];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 7; ++nt)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0;
+            for (int ks = 0; ks < KS; ++ks) {
+                unsigned a[2][4];
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    const uint8_t *r0 = s_x + (warp * 32 + mt * 16 + g) * kAXPitch + ks * 32 + 8 * t;
+                    const uint2 a02 = *(const uint2 *) r0, a13 = *(const uint2 *) (r0 + 8 * kAXPitch);
+                    a[mt][0] = a02.x; a[mt][1] = a13.x; a[mt][2] = a02.y; a[mt][3] = a13.y;
+                }
+#pragma unroll
+                for (int nt = 0; nt < 7; ++nt) {
+                    if (nt < NT) {
+                        const uint2 b = *(const uint2 *) (s_cwB + (nt * 8 + g) * kAXPitch + ks * 32 + 8 * t);
+                        mma_u8_frag(acc[0][nt], a[0], b.x, b.y);
+                        mma_u8_frag(acc[1][nt], a[1], b.x, b.y);
+                    }
+                }
+            }
+            // the four entries of this thread's fragment rows: table row and position in the output tile
+            int e_srow[4], e_slot[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int te = warp * 32 + (q >> 1) * 16 + g + 8 * (q & 1);
+                e_srow[q] = s_srow[te];
+                e_slot[q] = so == 1 ? ((te & (kASo - 1)) * kASl + te / kASo) : te;
+            }
+#pragma unroll
+            for (int nt = 0; nt < 7; ++nt) {
+                if (nt < NT) {
+                    const int j = nt * 8 + 2 * t;
+                    const uint4 pm = *(const uint4 *) (s_ppm + 2 * j);            // (p_j, mu_j, p_j+1, mu_j+1)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const unsigned mult2 = __ldg((const unsigned short *) (SD.pws + (size_t) e_srow[q] * 64 + j));
+                        const unsigned t0 = (unsigned) acc[q >> 1][nt][2 * (q & 1)] * (mult2 & 0xffu);
+                        const unsigned t1 = (unsigned) acc[q >> 1][nt][2 * (q & 1) + 1] * (mult2 >> 8);
+                        const unsigned r0 = t0 - __umulhi(t0, pm.y) * pm.x, r1 = t1 - __umulhi(t1, pm.w) * pm.z;
+                        s_out[j * (kASo * kASl) + e_slot[q]] = (uint8_t) min(r0, r0 - pm.x);
+                        s_out[(j + 1) * (kASo * kASl) + e_slot[q]] = (uint8_t) min(r1, r1 - pm.z);
+                    }
+                }
+            }
         }
         __syncthreads();
         // write out: (j, line) -> 32 contiguous bytes, two 16-byte halves
@@ -246,10 +334,7 @@ __global__ void __launch_bounds__(256, 3) k_align_small(const DevConsts *Cp, SoA
         cur = nxt;
     }
 }
-inline size_t align_small_smem() {
-    const int CW = 16;
-    return 64 * kASo * kASl + kASo * kASl * 2 + 64 * CW * 4 + CW * CW * 4 + CW * 4 + CW * 8 + CW * 8 + CW * 4 * 2 + 64 * 4 * 2 + 64;
-}
+inline size_t align_small_smem(bool mma) { return align_small_smem_base() + (mma ? 256 * kAXPitch + 256 * 4 + 56 * kAXPitch : 0); }
 
 // ---- stage 2: one u8 GEMM per small modulus on tcgen05 -----------------------------------------------------
 constexpr int kSM = 128, kSN = 256, kSK = 64, kSStages = 4;
@@ -535,11 +620,6 @@ constexpr int kXT = 128;        // entries per block (one per thread in the firs
 constexpr int kXPitch = 96;     // bytes per operand row in shared memory: 64-bit fragment loads are bank-conflict free
 constexpr int kXSPitch = 136;   // ints per residue row of the result tile: fragment-order writes and per-entry reads are conflict free
 
-__device__ __forceinline__ void mma_u8_frag(int (&c)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
-    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
-                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
 
 // shared memory of one extension block: operand rows of the entries | operand rows of the constants | staged one-byte
 // residues [56][128] | per-modulus constants | result tile [N][kXSPitch]

@@ -197,9 +197,10 @@ long mpres_debug_read_workspace(mpres_ctx *c, int slot, size_t offset, void *hos
 }
 int mpres_set_vec_config(mpres_ctx *c, int cfg) { if (!c || cfg < 0 || cfg > 2) return -1; c->vec_config = cfg; return 0; }
 int mpres_set_stage1_kernel(mpres_ctx *c, int kind) {
-    if (!c || kind < 0 || kind > 2) return -1;
+    if (!c || kind < 0 || kind > 3) return -1;
     c->stage1 = kind == 1 ? 1 : 0;
-    c->minplus_sparse = kind == 0 ? 1 : 0;
+    c->minplus_sparse = (kind == 0 || kind == 3) ? 1 : 0;
+    c->align_mma = kind == 3 ? 0 : 1;
     return 0;
 }
 long mpres_last_minplus_dense_count(mpres_ctx *c) {
