@@ -130,8 +130,8 @@ int mpres_set_reduced_base(mpres_ctx *ctx, int on);
 long mpres_last_base_size(mpres_ctx *ctx);
 /* Stage-1 kernels: 0 = vectorised alignment (four residues per work item) and the (min,+) exponent product from
  * candidate lists (default), 1 = one-residue-per-thread alignment kernel and the dense (min,+) kernel, 2 = vectorised
- * alignment and the dense (min,+) kernel, 3 = like 0 but the small-modulus alignment computes its residues with byte dot
- * products (dp4a) instead of the tensor cores.  Identical results. */
+ * alignment and the dense (min,+) kernel, 3 = like 0 but the small-modulus alignment computes its residues on the tensor
+ * cores (mma.sync) instead of with byte dot products (dp4a); measured slower on B200.  Identical results. */
 int mpres_set_stage1_kernel(mpres_ctx *ctx, int kind);
 /* entries of the last fast-path call whose (min,+) value the candidate lists did not cover (recomputed densely; synchronises) */
 long mpres_last_minplus_dense_count(mpres_ctx *ctx);

@@ -200,7 +200,7 @@ int mpres_set_stage1_kernel(mpres_ctx *c, int kind) {
     if (!c || kind < 0 || kind > 3) return -1;
     c->stage1 = kind == 1 ? 1 : 0;
     c->minplus_sparse = (kind == 0 || kind == 3) ? 1 : 0;
-    c->align_mma = kind == 3 ? 0 : 1;
+    c->align_mma = kind == 3 ? 1 : 0;
     return 0;
 }
 long mpres_last_minplus_dense_count(mpres_ctx *c) {

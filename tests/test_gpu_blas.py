@@ -288,7 +288,7 @@ def test_gemm_stage1_kernels_identical(pkg, N, shape, ta, tb):
     alpha = random_records(N, 1, bits, 84)
     beta = random_records(N, 1, bits, 85)
     out = []
-    for kind in (1, 0, 2, 3):   # round-1 alignment + dense (min,+); default; vectorised + dense (min,+); dp4a residues in the small-modulus alignment
+    for kind in (1, 0, 2, 3):   # round-1 alignment + dense (min,+); default; vectorised + dense (min,+); tensor-core residues in the small-modulus alignment
         ctx.set_stage1_kernel(kind)
         out.append(_gemm(pkg, ctx, m, n, k, alpha, A, B, beta, C, pkg.MODE_AUTO, ta, tb))
     assert all(diff_fields(out[0], o).size == 0 for o in out[1:])
