@@ -501,21 +501,23 @@ __device__ __forceinline__ void norm_fast_body(const DevConsts &C, int *cds, int
         int *mycd = cds + threadIdx.x * CP;
         const int *sp2 = Sp;
         int4 y4 = make_int4(0, 0, 0, 0), x4 = make_int4(0, 0, 0, 0);
+        const bool negx = (p.sx != 0) != (sign != 0), negy = ((p.sy != 0) != (sign != 0)) != (sg < 0);
 #pragma unroll 8
         for (int q = 0; q < NQ; ++q, sp2 += plane) {
             if ((q & 3) == 0) { y4 = __ldg(ty + (q >> 2)); x4 = __ldg(tx + (q >> 2)); }
             const int tyq = (q & 3) == 0 ? y4.x : (q & 3) == 1 ? y4.y : (q & 3) == 2 ? y4.z : y4.w;
             const int txq = (q & 3) == 0 ? x4.x : (q & 3) == 1 ? x4.y : (q & 3) == 2 ? x4.z : x4.w;
             const QConst c = qc[q];
-            int v = SMEM_S ? *sp2 : __ldg(sp2);
-            if (sg < 0 && v) v = c.m - v;
-            const int ay = p.nzy ? mulmod_q<F32>(v, tyq, c, kb) : 0;
-            const int ax = p.nzx ? mulmod_q<F32>(mycd[q], txq, c, kb) : 0;
-            const int a = p.sx ? (ax ? c.m - ax : 0) : ax;
-            const int b = p.sy ? (ay ? c.m - ay : 0) : ay;
-            int r = a + b - c.m;
-            r = r < 0 ? r + c.m : r;
-            mycd[q] = sign ? (r ? c.m - r : 0) : r;
+            const int v = SMEM_S ? *sp2 : __ldg(sp2);
+            // +-(beta 2^gamma C) +- (alpha 2^(theta-d) S) with every sign (of S, of the two products, of the result) folded into two flags:
+            // negation commutes with the modular products, so the digits are those of the reference's sequence of operations
+            const unsigned ay = p.nzy ? (unsigned) mulmod_q<F32>(v, tyq, c, kb) : 0u;
+            const unsigned ax = p.nzx ? (unsigned) mulmod_q<F32>(mycd[q], txq, c, kb) : 0u;
+            const unsigned um = (unsigned) c.m;
+            unsigned r = (negx ? um - ax : ax) + (negy ? um - ay : ay);     // in [0, 2 m]
+            r = min(r, r - um);
+            r = min(r, r - um);                                              // r == m -> 0
+            mycd[q] = (int) r;
         }
         okf[threadIdx.x] = 1;
         Cm.sign[ic] = sign;

@@ -626,9 +626,7 @@ constexpr int kXSPitch = 136;   // ints per residue row of the result tile: frag
 // residues [56][128] | per-modulus constants | result tile [N][kXSPitch]
 struct ExtSmem {
     uint8_t *At, *Bt, *X8;
-    int *s_p;
-    unsigned *s_mu, *s_inv;
-    float *s_rcp;
+    uint4 *s_c4;       // [64] per small modulus: (p, floor(2^32 / p), (M'/p)^-1 mod p, bits of 1 / p)
     int *s_S;
 };
 __host__ __device__ inline size_t ext_small_smem(int ext_cols, int N) {
@@ -639,11 +637,8 @@ __device__ __forceinline__ ExtSmem ext_carve(uint8_t *base, int ext_cols) {
     e.At = base;
     e.X8 = e.At + kXT * kXPitch;              // At and X8 are dead once the block function returns: the fused kernel reuses them
     e.Bt = e.X8 + 56 * kXT;
-    e.s_p = (int *) (e.Bt + (size_t) ext_cols * kXPitch);
-    e.s_mu = (unsigned *) (e.s_p + 64);
-    e.s_rcp = (float *) (e.s_mu + 64);
-    e.s_inv = (unsigned *) (e.s_rcp + 64);
-    e.s_S = (int *) (e.s_inv + 64);
+    e.s_c4 = (uint4 *) (e.Bt + (size_t) ext_cols * kXPitch);
+    e.s_S = (int *) (e.s_c4 + 64);
     return e;
 }
 
@@ -668,7 +663,7 @@ __device__ __forceinline__ void ext_small_block(const DevConsts &C, const SmallD
         for (int v = threadIdx.x; v < cols * 4; v += kXT) *(uint4 *) (E.Bt + (v >> 2) * kXPitch + (v & 3) * 16) = __ldg(bsrc + v);
         if (threadIdx.x < 64) {
             const int j = threadIdx.x;
-            E.s_p[j] = SD.p[j]; E.s_mu[j] = SD.mu[j]; E.s_rcp[j] = SD.rcp[j]; E.s_inv[j] = SD.inv[P * 64 + j];
+            E.s_c4[j] = make_uint4((unsigned) SD.p[j], SD.mu[j], (unsigned) SD.inv[P * 64 + j], __float_as_uint(SD.rcp[j]));
         }
         cp_async_wait<0>();
     }
@@ -686,8 +681,11 @@ __device__ __forceinline__ void ext_small_block(const DevConsts &C, const SmallD
                 for (int e = 0; e < 4; ++e) {
                     const int j = 4 * g + e;
                     const unsigned xv = j < P ? (unsigned) xsrc[j * kXT] : 0u;
-                    const unsigned xi = small_mod(xv * E.s_inv[j], (unsigned) E.s_p[j], E.s_mu[j]);
-                    sum = fmaf((float) xi, E.s_rcp[j], sum);
+                    const uint4 cj = E.s_c4[j];                                   // (p, floor(2^32 / p), (M'/p)^-1 mod p, 1 / p)
+                    const unsigned tj = xv * cj.z;
+                    const unsigned rj = tj - __umulhi(tj, cj.y) * cj.x;
+                    const unsigned xi = min(rj, rj - cj.x);
+                    sum = fmaf((float) xi, __uint_as_float(cj.w), sum);
                     wd |= xi << (8 * e);
                 }
             }
