@@ -49,6 +49,9 @@ FALLBACK_HBM_GBS = 6650.0        # /opt/skills/guides/B200_PROFILING.md fallback
 R_MAC_IMAD_WIDE = 8.54e12        # residue-MAC/s through IMAD.WIDE.U32: the INT32 roofline of SURVEY 8(d)
 PEAK_INT8_LEGACY_MMA = 1.139e15  # int8 op/s (2 per MAC) through mma.sync m16n8k32 (IMMA.16832)
 CPU_SAMPLE = (64, 256)             # block of C timed on the host cores (full k)
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_small_umma_p<128> launch of the default workload (ncu --set full,
+# profiles/r01_ncu_full_gemm4096_424bit_final.txt): 1.344 GB + 0.651 GB; algorithmic: 40 x (2 x 16.8 MB operand planes + 16.8 MB result plane) = 2.01 GB
+NCU_DRAM_BYTES_SMALL_UMMA = 1.995e9
 FALLBACK_BF16_TFLOPS = 1590.0    # /opt/skills/guides/B200_PROFILING.md fallback (MEASURED_PEAKS.json absent)
 
 
@@ -332,7 +335,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="gemm4096_424bit", choices=sorted(WORKLOADS) + sorted(VEC_WORKLOADS))
     ap.add_argument("--mode", default="auto", choices=["auto", "reference_order", "fast"])
-    ap.add_argument("--stage2", default="small", choices=["small", "small_k64", "small_tiled", "umma", "umma_unstacked", "mma_sync"], help="stage-2 kernel (A/B measurement)")
+    ap.add_argument("--stage2", default="small", choices=["small", "small_t128", "small_k64", "small_tiled", "umma", "umma_unstacked", "mma_sync"], help="stage-2 kernel (A/B measurement)")
     ap.add_argument("--stage3", type=int, default=0, choices=[0, 1, 2, 3], help="stage-3 kernel variant (mpres_set_stage3_kernel; A/B measurement)")
     ap.add_argument("--bcast", default="lean", choices=["lean", "full"], help="N > 1: what the per-step broadcast of B moves (lean: the fields the small-base path reads, verified on the device; full: all four SoA arrays)")
     ap.add_argument("--full-precision-inputs", action="store_true", help="p-bit significands instead of p/4")
@@ -393,7 +396,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = pkg.Context(N, local_rank)
     ctx.set_mode({"auto": pkg.MODE_AUTO, "reference_order": pkg.MODE_REFERENCE_ORDER, "fast": pkg.MODE_FAST}[args.mode])
-    ctx.set_stage2_kernel({"small": pkg.STAGE2_SMALL, "small_tiled": pkg.STAGE2_SMALL_TILED, "small_k64": pkg.STAGE2_SMALL_K64, "umma": pkg.STAGE2_UMMA, "umma_unstacked": pkg.STAGE2_UMMA_UNSTACKED, "mma_sync": pkg.STAGE2_MMA_SYNC}[args.stage2])
+    ctx.set_stage2_kernel({"small": pkg.STAGE2_SMALL, "small_tiled": pkg.STAGE2_SMALL_TILED, "small_k64": pkg.STAGE2_SMALL_K64, "small_t128": pkg.STAGE2_SMALL_T128, "umma": pkg.STAGE2_UMMA, "umma_unstacked": pkg.STAGE2_UMMA_UNSTACKED, "mma_sync": pkg.STAGE2_MMA_SYNC}[args.stage2])
     config["stage2_kernel"] = args.stage2
     if world > 1:
         config["broadcast"] = args.bcast
@@ -559,12 +562,14 @@ def main():
         peak = 2.0 * bf16_peak                        # dense int8 = 2 x dense bf16 on the same tensor cores
         kname = {"small": "k_small_umma_p (persistent, tcgen05.mma kind::i8 per one-byte modulus, TMA ring, two TMEM accumulators)" if small_P > 0 else "k_limb_umma<stacked> (small base not selected)",
                  "small_tiled": "k_small_umma (one tile per CTA)" if small_P > 0 else "k_limb_umma<stacked> (small base not selected)",
+                 "small_t128": "k_small_umma_p<128,128> (persistent, 128 x 256 tiles, double-buffered accumulator)" if small_P > 0 else "k_limb_umma<stacked> (small base not selected)",
                  "small_k64": "k_small_umma_p<64> (persistent, 64-byte operand rows)" if small_P > 0 else "k_limb_umma<stacked> (small base not selected)",
                  "umma": "k_limb_umma<stacked> (tcgen05.mma kind::i8, TMA, TMEM)", "umma_unstacked": "k_limb_umma<unstacked>",
                  "mma_sync": "k_limb_gemm<0>+<1> (legacy mma.sync IMMA)"}[args.stage2]
         roof = {"bound": "tensor", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "TOP/s (int8)",
                 "frac": achieved / peak, "peak_source": "2 x bf16 %s peak of %s TFLOP/s (int8 dense = 2 x bf16 dense)" % (peak_src, bf16_peak),
-                "traffic": None, "launches_per_step": s2_launches, "avg_launch_ms": stage_ms[1] / s2_launches,
+                "traffic": (NCU_DRAM_BYTES_SMALL_UMMA if (small_P == 40 and args.workload == "gemm4096_424bit" and world == 1 and args.stage2 == "small") else None),
+                "launches_per_step": s2_launches, "avg_launch_ms": stage_ms[1] / s2_launches,
                 "algorithmic_ops_per_launch": ops / s2_launches, "moduli_in_stage2": small_P if small_P > 0 else nb, "moduli_total": N,
                 "small_base": {"one_byte_moduli": small_P, "input_residues_read": small_nin},
                 "frac_of_nominal_int8_peak_4500": achieved / 4500.0,

@@ -60,7 +60,7 @@ enum { MPRES_NO_TRANS = 111, MPRES_TRANS = 112, MPRES_CONJ_TRANS = 113 };
  * kernels including the interval evaluations.  FAST = fast path only (elements whose guard fails
  * are reported through mpres_last_fallback_count). */
 enum { MPRES_MODE_AUTO = 0, MPRES_MODE_REFERENCE_ORDER = 1, MPRES_MODE_FAST = 2 };
-enum { MPRES_STAGE2_UMMA = 0, MPRES_STAGE2_UMMA_UNSTACKED = 1, MPRES_STAGE2_MMA_SYNC = 2, MPRES_STAGE2_SMALL = 3, MPRES_STAGE2_SMALL_TILED = 4, MPRES_STAGE2_SMALL_K64 = 5 };
+enum { MPRES_STAGE2_UMMA = 0, MPRES_STAGE2_UMMA_UNSTACKED = 1, MPRES_STAGE2_MMA_SYNC = 2, MPRES_STAGE2_SMALL = 3, MPRES_STAGE2_SMALL_TILED = 4, MPRES_STAGE2_SMALL_K64 = 5, MPRES_STAGE2_SMALL_T128 = 6 };
 
 typedef struct mpres_ctx mpres_ctx;
 typedef void *mpres_stream_t; /* cudaStream_t */
@@ -99,7 +99,8 @@ int mpres_get_mode(const mpres_ctx *ctx);
  * (256, 251, 243, ...): one tcgen05.mma kind::i8 GEMM per modulus, inputs converted through their binary
  * representation, results returned to the moduli of the number format by a CRT base extension; chosen per call
  * when the sums fit the small base (about 360 bits), otherwise the call runs as UMMA; a persistent kernel (one
- * CTA per SM, two TMEM accumulators, 128-byte operand rows), SMALL_K64 = the same with 64-byte operand rows,
+ * CTA per SM, 256 x 256 tiles, 128-byte operand rows), SMALL_T128 = 128 x 256 tiles with a double-buffered
+ * accumulator, SMALL_K64 = the latter with 64-byte operand rows,
  * SMALL_TILED = one tile per CTA.  UMMA = tcgen05.mma
  * kind::i8 over four byte limbs of the format's own moduli with TMA-fed limb tiles, UMMA_UNSTACKED = the same
  * kernel issuing one MMA per limb pair, MMA_SYNC = the legacy warp-level int8 MMA kernel.  All of them produce

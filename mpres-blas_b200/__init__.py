@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("MPRES_B200_LIB") or os.path.join(_HERE, "libmpres_b20
 
 mblas_no_trans, mblas_trans, mblas_conj_trans = 111, 112, 113  # src/blas/mblas_enum.cuh:25-29
 MODE_AUTO, MODE_REFERENCE_ORDER, MODE_FAST = 0, 1, 2
-STAGE2_UMMA, STAGE2_UMMA_UNSTACKED, STAGE2_MMA_SYNC, STAGE2_SMALL, STAGE2_SMALL_TILED, STAGE2_SMALL_K64 = 0, 1, 2, 3, 4, 5
+STAGE2_UMMA, STAGE2_UMMA_UNSTACKED, STAGE2_MMA_SYNC, STAGE2_SMALL, STAGE2_SMALL_TILED, STAGE2_SMALL_K64, STAGE2_SMALL_T128 = 0, 1, 2, 3, 4, 5, 6
 
 _lib = None
 

@@ -47,6 +47,7 @@ struct mpres_ctx {
     int align_mma = 0;                // small-modulus alignment: 1 = residues on the tensor cores (measured slower: 2.8 vs 2.3 ms), 0 = dp4a per entry and modulus
     int minplus_sparse = 1;           // (min,+) of the shift planes from candidate lists (0: dense DPX kernel)
     int stage3 = 0;                   // 0: entry-per-thread kernel + list, 1: residue-parallel tile kernel
+    int small_tj = 256;               // persistent small-modulus kernel: rows of B' per tile (256: two MMAs share the A' operand; 128: one MMA, double-buffered accumulator)
     int small_kb = 128;               // persistent small-modulus kernel: bytes of K per stage (128: SWIZZLE_128B rows, 64: SWIZZLE_64B)
     int small_persistent = 1;         // small-modulus stage 2: persistent kernel with two TMEM accumulators (0: one tile per CTA)
     int fuse_ext = 0;                 // small-modulus path: 1 = base extension fused into the entry-per-thread normalisation kernel (measured slower: occupancy)

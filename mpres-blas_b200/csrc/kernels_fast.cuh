@@ -552,7 +552,7 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
     if (k_p > 32000 * 128ll) return 0;
     // the small-modulus stage 2 (kernels_small.cuh) is offered whenever its tables exist; k_choose_base decides per call
     const bool small_on = c->stage2 == MPRES_STAGE2_SMALL && c->sc.usable;
-    const long long m_ps = round_up(m, kSN), n_ps = round_up(n, kSM);   // rows of the one-byte planes: 256 x 128 tiles of k_small_umma
+    const long long m_ps = round_up(m, kSN), n_ps = round_up(n, 256);   // rows of the one-byte planes: 256 x (128 | 256) tiles of k_small_umma
     // workspace: planes A/B (u8), S (int), shifts, delta, infos, todo
     const size_t bytesPA = (size_t) N * 4 * m_p * k_p, bytesPB = (size_t) N * 4 * n_p * k_p;
     const size_t bytesS = (size_t) N * n_p * m_p * 4;

@@ -483,19 +483,23 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
 }
 }  // namespace ptx
 
-template <int KB>
+// TJ = rows of B' per tile: 128 (one MMA per K step, two accumulators: the epilogue of a tile overlaps the next tile's MMAs) or 256
+// (two MMAs per K step share the 256-row A' operand: a third less operand traffic and twice the work per pipeline stage; both
+// accumulators belong to one tile, so its epilogue runs while the TMA ring prefetches the next tile).
+template <int KB, int TJ>
 __global__ void __launch_bounds__(kSThreads, 1)
 k_small_umma_p(const __grid_constant__ CUtensorMap tmJ, const __grid_constant__ CUtensorMap tmI, const DevConsts *Cp, uint8_t *S8,
                long long m_ps, long long n_ps, int k_byte0, int nk, int add_to_S, const int *sel) {
     extern __shared__ uint8_t smem_raw[];
     const int P = sel[0];
     if (P <= 0) return;
-    const int tiles_i = (int) (m_ps / kSN), tiles_j = (int) (n_ps / kSM);
+    const int tiles_i = (int) (m_ps / kSN), tiles_j = (int) (n_ps / TJ);
     const int per_z = tiles_i * tiles_j;
     const long long total = (long long) P * per_z;
     if ((long long) blockIdx.x >= total) return;
     uint8_t *smem = (uint8_t *) (((uintptr_t) smem_raw + 1023) & ~(uintptr_t) 1023);
-    constexpr int kStageA = kSM * KB, kStageB = kSN * KB, kStage = kStageA + kStageB, kPStages = kPRingBytes / kStage;
+    constexpr int kStageA = TJ * KB, kStageB = kSN * KB, kStage = kStageA + kStageB, kPStages = kPRingBytes / kStage;
+    constexpr int NH = TJ / kSM;                  // MMAs (128-row halves of the B' tile) per K step
     nk = nk * kSK / KB;                           // the caller counts 64-byte steps
     uint64_t *full = (uint64_t *) (smem + kPRingBytes);
     uint64_t *empty = full + kPStages;
@@ -524,7 +528,7 @@ k_small_umma_p(const __grid_constant__ CUtensorMap tmJ, const __grid_constant__ 
             long long g = 0;   // stage uses so far
             for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
                 const int z = (int) (tile / per_z), r = (int) (tile - (long long) z * per_z);
-                const int j0 = (r / tiles_i) * kSM, i0 = (r % tiles_i) * kSN;
+                const int j0 = (r / tiles_i) * TJ, i0 = (r % tiles_i) * kSN;
                 for (int it = 0; it < nk; ++it, ++g) {
                     const int s = (int) (g % kPStages);
                     const uint32_t ph = (uint32_t) (g / kPStages) & 1u;
@@ -544,8 +548,8 @@ k_small_umma_p(const __grid_constant__ CUtensorMap tmJ, const __grid_constant__ 
             long long g = 0;
             int lt = 0;
             for (long long tile = blockIdx.x; tile < total; tile += gridDim.x, ++lt) {
-                const int b = lt & 1;
-                ptx::mbar_wait(&acc_empty[b], (uint32_t) (((lt >> 1) & 1) ^ 1));   // the epilogue has drained this accumulator
+                const int b = NH == 1 ? (lt & 1) : 0, use = NH == 1 ? (lt >> 1) : lt;
+                ptx::mbar_wait(&acc_empty[b], (uint32_t) ((use & 1) ^ 1));   // the epilogue has drained this accumulator
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem + (uint32_t) (b * kSN);
                 for (int it = 0; it < nk; ++it, ++g) {
@@ -556,9 +560,13 @@ k_small_umma_p(const __grid_constant__ CUtensorMap tmJ, const __grid_constant__ 
                     const uint32_t a_addr = ptx::smem_u32(smem + s * kStage), b_addr = a_addr + kStageA;
 #pragma unroll
                     for (int ks = 0; ks < KB / 32; ++ks) {
-                        const uint64_t ad = KB == 128 ? ptx::smem_desc_sw128(a_addr + ks * 32) : ptx::smem_desc_sw64(a_addr + ks * 32);
                         const uint64_t bd = KB == 128 ? ptx::smem_desc_sw128(b_addr + ks * 32) : ptx::smem_desc_sw64(b_addr + ks * 32);
-                        ptx::umma_i8(d_tmem, ad, bd, idesc, (it | ks) ? 1u : 0u);
+#pragma unroll
+                        for (int h = 0; h < NH; ++h) {
+                            const uint32_t ah = a_addr + h * (kSM * KB) + ks * 32;
+                            const uint64_t ad = KB == 128 ? ptx::smem_desc_sw128(ah) : ptx::smem_desc_sw64(ah);
+                            ptx::umma_i8(d_tmem + (uint32_t) (h * kSN), ad, bd, idesc, (it | ks) ? 1u : 0u);
+                        }
                     }
                     ptx::umma_commit(&empty[s]);
                 }
@@ -573,41 +581,46 @@ k_small_umma_p(const __grid_constant__ CUtensorMap tmJ, const __grid_constant__ 
         int lt = 0;
         for (long long tile = blockIdx.x; tile < total; tile += gridDim.x, ++lt) {
             const int z = (int) (tile / per_z), r = (int) (tile - (long long) z * per_z);
-            const int j0 = (r / tiles_i) * kSM, i0 = (r % tiles_i) * kSN;
+            const int j0 = (r / tiles_i) * TJ, i0 = (r % tiles_i) * kSN;
             const unsigned p = (unsigned) SD.p[z], mu = SD.mu[z];
-            const int b = lt & 1;
-            ptx::mbar_wait(&acc_full[b], (uint32_t) ((lt >> 1) & 1));
+            const int b = NH == 1 ? (lt & 1) : 0, use = NH == 1 ? (lt >> 1) : lt;
+            ptx::mbar_wait(&acc_full[b], (uint32_t) (use & 1));
             ptx::tc_fence_after();
-            const int j = j0 + quad * 32 + lane;
-            uint4 *dst = (uint4 *) (S8 + ((long long) z * n_ps + j) * m_ps + i0 + half * 128);
-            const uint32_t tbase = tmem + ((uint32_t) (quad * 32) << 16) + (uint32_t) (b * kSN + half * 128);
-            // all 128 columns of this thread into registers first, so the accumulator can be handed back early
-            uint32_t d[16][8];
+#pragma unroll 1
+            for (int h = 0; h < NH; ++h) {
+                const int j = j0 + h * kSM + quad * 32 + lane;
+                uint4 *dst = (uint4 *) (S8 + ((long long) z * n_ps + j) * m_ps + i0 + half * 128);
+                const uint32_t tbase = tmem + ((uint32_t) (quad * 32) << 16) + (uint32_t) ((NH == 1 ? b : h) * kSN + half * 128);
+                // all 128 columns of this thread into registers first, so the accumulator can be handed back early
+                uint32_t d[16][8];
 #pragma unroll
-            for (int u = 0; u < 16; ++u) ptx::tmem_ld8(tbase + (uint32_t) (u * 8), d[u]);
-            ptx::tmem_ld_wait();
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&acc_empty[b]);
-#pragma unroll
-            for (int c16 = 0; c16 < 8; ++c16) {     // 16 columns = one 16-byte run per pass
-                uint4 pv = make_uint4(0, 0, 0, 0);
-                if (add_to_S) pv = dst[c16];
-                unsigned wd[4];
-#pragma unroll
-                for (int w = 0; w < 4; ++w) {
-                    const unsigned pw = w == 0 ? pv.x : w == 1 ? pv.y : w == 2 ? pv.z : pv.w;
-                    unsigned o = 0;
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const unsigned v = d[c16 * 2 + (w >> 1)][(w & 1) * 4 + e] + ((pw >> (8 * e)) & 0xffu);
-                        unsigned rr = v - __umulhi(v, mu) * p;
-                        rr = rr >= p ? rr - p : rr;
-                        o |= rr << (8 * e);
-                    }
-                    wd[w] = o;
+                for (int u = 0; u < 16; ++u) ptx::tmem_ld8(tbase + (uint32_t) (u * 8), d[u]);
+                ptx::tmem_ld_wait();
+                if (h == NH - 1) {
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&acc_empty[b]);
                 }
-                dst[c16] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+#pragma unroll
+                for (int c16 = 0; c16 < 8; ++c16) {     // 16 columns = one 16-byte run per pass
+                    uint4 pv = make_uint4(0, 0, 0, 0);
+                    if (add_to_S) pv = dst[c16];
+                    unsigned wd[4];
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) {
+                        const unsigned pw = w == 0 ? pv.x : w == 1 ? pv.y : w == 2 ? pv.z : pv.w;
+                        unsigned o = 0;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const unsigned v = d[c16 * 2 + (w >> 1)][(w & 1) * 4 + e] + ((pw >> (8 * e)) & 0xffu);
+                            unsigned rr = v - __umulhi(v, mu) * p;
+                            rr = rr >= p ? rr - p : rr;
+                            o |= rr << (8 * e);
+                        }
+                        wd[w] = o;
+                    }
+                    dst[c16] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+                }
             }
         }
     }
@@ -821,22 +834,26 @@ inline int launch_small_umma(mpres_ctx *c, const uint8_t *PA, const uint8_t *PB,
     CUtensorMap tmJ, tmI;
     int rc;
     const int box_k = (c->small_persistent && c->small_kb == 128 && k_len % 128 == 0 && k_begin % 128 == 0) ? 128 : mpres::kSK;
-    if ((rc = small_make_map(&tmJ, PB, mpres::kSmallMax, n_ps, k_p, mpres::kSM, box_k))) return rc;
+    const int tj = (c->small_persistent && box_k == 128 && c->small_tj == 256 && n_ps % 256 == 0) ? 256 : mpres::kSM;
+    if ((rc = small_make_map(&tmJ, PB, mpres::kSmallMax, n_ps, k_p, tj, box_k))) return rc;
     if ((rc = small_make_map(&tmI, PA, mpres::kSmallMax, m_ps, k_p, mpres::kSN, box_k))) return rc;
     static bool attr_done = false;
     if (!attr_done) {
         CUDA_TRY(cudaFuncSetAttribute(mpres::k_small_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, mpres::kSSmem));
-        CUDA_TRY(cudaFuncSetAttribute(mpres::k_small_umma_p<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, mpres::kPSmem));
-        CUDA_TRY(cudaFuncSetAttribute(mpres::k_small_umma_p<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, mpres::kPSmem));
+        CUDA_TRY(cudaFuncSetAttribute(mpres::k_small_umma_p<64, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, mpres::kPSmem));
+        CUDA_TRY(cudaFuncSetAttribute(mpres::k_small_umma_p<128, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, mpres::kPSmem));
+        CUDA_TRY(cudaFuncSetAttribute(mpres::k_small_umma_p<128, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, mpres::kPSmem));
         attr_done = true;
     }
     if (c->small_persistent) {
-        const long long max_tiles = (long long) mpres::kSmallMax * (m_ps / mpres::kSN) * (n_ps / mpres::kSM);
+        const long long max_tiles = (long long) mpres::kSmallMax * (m_ps / mpres::kSN) * (n_ps / tj);
         const unsigned gx = (unsigned) std::min<long long>(max_tiles, (long long) c->sm_count);
-        if (box_k == 128)
-            mpres::k_small_umma_p<128><<<gx, mpres::kSThreads, mpres::kPSmem, st>>>(tmJ, tmI, c->dconsts, S8, m_ps, n_ps, (int) k_begin, k_len / mpres::kSK, add_to_S ? 1 : 0, sel);
+        if (tj == 256)
+            mpres::k_small_umma_p<128, 256><<<gx, mpres::kSThreads, mpres::kPSmem, st>>>(tmJ, tmI, c->dconsts, S8, m_ps, n_ps, (int) k_begin, k_len / mpres::kSK, add_to_S ? 1 : 0, sel);
+        else if (box_k == 128)
+            mpres::k_small_umma_p<128, 128><<<gx, mpres::kSThreads, mpres::kPSmem, st>>>(tmJ, tmI, c->dconsts, S8, m_ps, n_ps, (int) k_begin, k_len / mpres::kSK, add_to_S ? 1 : 0, sel);
         else
-            mpres::k_small_umma_p<64><<<gx, mpres::kSThreads, mpres::kPSmem, st>>>(tmJ, tmI, c->dconsts, S8, m_ps, n_ps, (int) k_begin, k_len / mpres::kSK, add_to_S ? 1 : 0, sel);
+            mpres::k_small_umma_p<64, 128><<<gx, mpres::kSThreads, mpres::kPSmem, st>>>(tmJ, tmI, c->dconsts, S8, m_ps, n_ps, (int) k_begin, k_len / mpres::kSK, add_to_S ? 1 : 0, sel);
         return 0;
     }
     dim3 grid((unsigned) (m_ps / mpres::kSN), (unsigned) (n_ps / mpres::kSM), (unsigned) mpres::kSmallMax);

@@ -151,10 +151,11 @@ size_t mpres_sizeof_mp_float(const mpres_ctx *c) { return c ? 4 * (size_t) c->hc
 int mpres_set_mode(mpres_ctx *c, int mode) { if (!c || mode < 0 || mode > 2) return -1; c->mode = mode; return 0; }
 int mpres_get_mode(const mpres_ctx *c) { return c ? c->mode : -1; }
 int mpres_set_stage2_kernel(mpres_ctx *c, int kind) {
-    if (!c || kind < 0 || kind > 5) return -1;
-    c->stage2 = (kind == MPRES_STAGE2_SMALL_TILED || kind == MPRES_STAGE2_SMALL_K64) ? MPRES_STAGE2_SMALL : kind;
+    if (!c || kind < 0 || kind > 6) return -1;
+    c->stage2 = (kind == MPRES_STAGE2_SMALL_TILED || kind == MPRES_STAGE2_SMALL_K64 || kind == MPRES_STAGE2_SMALL_T128) ? MPRES_STAGE2_SMALL : kind;
     c->small_persistent = kind == MPRES_STAGE2_SMALL_TILED ? 0 : 1;
     c->small_kb = kind == MPRES_STAGE2_SMALL_K64 ? 64 : 128;
+    c->small_tj = kind == MPRES_STAGE2_SMALL ? 256 : 128;
     return 0;
 }
 int mpres_set_stage3_kernel(mpres_ctx *c, int kind) {

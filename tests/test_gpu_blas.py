@@ -197,7 +197,7 @@ def test_gemm_stage2_kernels_agree(pkg, N, shape):
     alpha = random_records(N, 1, bits, 64)
     beta = random_records(N, 1, bits, 65)
     want = _gemm(pkg, ctx, m, n, k, alpha, A, B, beta, C, pkg.MODE_REFERENCE_ORDER)
-    for kind in (pkg.STAGE2_SMALL, pkg.STAGE2_SMALL_K64, pkg.STAGE2_SMALL_TILED, pkg.STAGE2_UMMA, pkg.STAGE2_UMMA_UNSTACKED, pkg.STAGE2_MMA_SYNC):
+    for kind in (pkg.STAGE2_SMALL, pkg.STAGE2_SMALL_T128, pkg.STAGE2_SMALL_K64, pkg.STAGE2_SMALL_TILED, pkg.STAGE2_UMMA, pkg.STAGE2_UMMA_UNSTACKED, pkg.STAGE2_MMA_SYNC):
         ctx.set_stage2_kernel(kind)
         got = _gemm(pkg, ctx, m, n, k, alpha, A, B, beta, C, pkg.MODE_AUTO)
         assert ctx.last_fallback_count() == 0

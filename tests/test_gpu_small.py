@@ -45,7 +45,7 @@ def test_small_path_stages_exact(pkg, N, shape, div, tiled):
     assert ctx.last_base_size() == 0
     ps = ctx.small_moduli(P)
     assert ps[0] == 256 and all(p > 1 for p in ps)
-    m_p, m_ps, k_p, n_ps, n_p = _round_up(m, 128), _round_up(m, 256), _round_up(k, 128), _round_up(n, 128), _round_up(n, 64)
+    m_p, m_ps, k_p, n_ps, n_p = _round_up(m, 128), _round_up(m, 256), _round_up(k, 128), _round_up(n, 256), _round_up(n, 64)
     a = _signed_ints(orc, A)     # column-major m x k: entry (i, l) at i + l m
     b = _signed_ints(orc, B)     # column-major k x n: entry (l, j) at l + j k
 
@@ -102,7 +102,7 @@ def test_gemm_small_base_identical(pkg, N, bits_div, shape, ta, tb):
     alpha = random_records(N, 1, bits, 314)
     beta = random_records(N, 1, bits, 315)
     out, sel = [], []
-    for kind in (pkg.STAGE2_UMMA, pkg.STAGE2_SMALL, pkg.STAGE2_SMALL_K64, pkg.STAGE2_SMALL_TILED):
+    for kind in (pkg.STAGE2_UMMA, pkg.STAGE2_SMALL, pkg.STAGE2_SMALL_T128, pkg.STAGE2_SMALL_K64, pkg.STAGE2_SMALL_TILED):
         ctx.set_stage2_kernel(kind)
         out.append(_gemm(pkg, ctx, m, n, k, alpha, A, B, beta, C, pkg.MODE_AUTO, ta, tb))
         sel.append(ctx.last_small_base())
