@@ -61,7 +61,10 @@ __global__ void k_outer_info(const DevConsts *Cp, SoA X, long long so, long long
     const long long len = X.len();
     int emin = INT_MAX;
     long long top = LLONG_MIN;
-    double lx = -1.0e300;   // max of log2(upper bound of X / M)
+    // largest upper bound of X / M over the line, compared without floating point: (binary exponent of the bound, fraction bits) is
+    // monotone in the value for positive doubles; its log2 is taken once per line
+    long long be = LLONG_MIN;
+    unsigned long long bm = 0;
     for (int l = lane; l < inner; l += 32) {
         const long long idx = warp * so + l * sl;
         const Er up = X.eval[idx + len];
@@ -71,8 +74,10 @@ __global__ void k_outer_info(const DevConsts *Cp, SoA X, long long so, long long
             // X/M < 2^(up.exp+1) and M < 2^(log2M+1)  =>  X < 2^(log2M + up.exp + 2)
             long long t = (long long) e + up.exp;
             top = t > top ? t : top;
-            const long long ue = up.exp > 100000 ? 100000 : (up.exp < -100000 ? -100000 : up.exp);
-            lx = fmax(lx, (double) ue + log2(fabs(up.frac)));
+            const unsigned long long fb = (unsigned long long) __double_as_longlong(fabs(up.frac));
+            const long long ue = (up.exp > 100000 ? 100000 : (up.exp < -100000 ? -100000 : up.exp)) + (long long) (fb >> 52);   // + biased exponent of frac
+            const unsigned long long fm = fb & 0xfffffffffffffull;
+            if (ue > be || (ue == be && fm > bm)) { be = ue; bm = fm; }
         }
     }
 #pragma unroll
@@ -80,8 +85,12 @@ __global__ void k_outer_info(const DevConsts *Cp, SoA X, long long so, long long
         emin = min(emin, __shfl_xor_sync(0xffffffffu, emin, o));
         long long t = __shfl_xor_sync(0xffffffffu, top, o);
         top = t > top ? t : top;
-        lx = fmax(lx, __shfl_xor_sync(0xffffffffu, lx, o));
+        const long long oe = __shfl_xor_sync(0xffffffffu, be, o);
+        const unsigned long long om = __shfl_xor_sync(0xffffffffu, bm, o);
+        if (oe > be || (oe == be && om > bm)) { be = oe; bm = om; }
     }
+    // log2 of the largest bound: (be - 1023) + log2(1.fraction)
+    const double lx = (double) (be - 1023) + log2(__longlong_as_double((long long) (bm | 0x3ff0000000000000ull)));
     if (lane == 0) {
         OuterInfo r;
         r.pad = 0;

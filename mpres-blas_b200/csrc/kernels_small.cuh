@@ -138,9 +138,10 @@ __device__ __forceinline__ void align_small_entry(const int4 (&dg)[(NW + 3) / 4]
                 if (4 * w4 + 3 < NW) v = __dp4a(x[4 * w4 + 3], c4.w, v);
             }
             const uint2 pm = *(const uint2 *) (s_ppm + 2 * j);            // (p, floor(2^32 / p)); rows j >= P hold (1, 0) and are never written out
-            const unsigned t = v * ((mult4 >> (8 * e)) & 0xffu);
-            const unsigned r = t - __umulhi(t, pm.y) * pm.x;              // in [0, 2p)
-            out[j * (kASo * kASl)] = (uint8_t) min(r, r - pm.x);
+            const unsigned np_ = 0u - pm.x;
+            const unsigned t = v * __byte_perm(mult4, 0u, 0x4440u + e);   // times byte e of the +-2^shift row
+            const unsigned r = t + __umulhi(t, pm.y) * np_;               // t - floor(t mu / 2^32) p, in [0, 2p)
+            out[j * (kASo * kASl)] = (uint8_t) min(r, r + np_);
         }
     }
 }
