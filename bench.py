@@ -49,9 +49,9 @@ FALLBACK_HBM_GBS = 6650.0        # /opt/skills/guides/B200_PROFILING.md fallback
 R_MAC_IMAD_WIDE = 8.54e12        # residue-MAC/s through IMAD.WIDE.U32: the INT32 roofline of SURVEY 8(d)
 PEAK_INT8_LEGACY_MMA = 1.139e15  # int8 op/s (2 per MAC) through mma.sync m16n8k32 (IMMA.16832)
 CPU_SAMPLE = (64, 256)             # block of C timed on the host cores (full k)
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_small_umma_p<128> launch of the default workload (ncu --set full,
-# profiles/r01_ncu_full_gemm4096_424bit_final.txt): 1.344 GB + 0.651 GB; algorithmic: 40 x (2 x 16.8 MB operand planes + 16.8 MB result plane) = 2.01 GB
-NCU_DRAM_BYTES_SMALL_UMMA = 1.995e9
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_small_umma_p<128,256> launch of the default workload (ncu --set full,
+# profiles/r01_ncu_full_gemm4096_424bit_final.txt): 1.385 GB + 0.650 GB; algorithmic: 40 x (2 x 16.8 MB operand planes + 16.8 MB result plane) = 2.01 GB
+NCU_DRAM_BYTES_SMALL_UMMA = 2.035e9
 FALLBACK_BF16_TFLOPS = 1590.0    # /opt/skills/guides/B200_PROFILING.md fallback (MEASURED_PEAKS.json absent)
 
 
