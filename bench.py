@@ -305,7 +305,10 @@ def run_vec(args):
         roof = {"bound": "hbm", "kernel": "k_mv_acc_n" if op == "gemv" else "k_mv_acc_t", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
                 "peak_source": "%s copy bandwidth" % src, "traffic": None, "avg_launch_ms": stage_ms[1], "algorithmic_bytes_per_launch": alg_bytes / world,
                 "stage_ms": {"scale_vectors": stage_ms[0], "accumulate": stage_ms[1], "finalize": stage_ms[2]},
-                "whole_call_frac": alg_bytes / world / (ms_step * 1e-3) / 1e9 / hbm}
+                "whole_call_frac": alg_bytes / world / (ms_step * 1e-3) / 1e9 / hbm,
+                # the kernel never reads the lower interval bounds (16 of the 4N+40 bytes per element): the same time against the bytes it must touch
+                "frac_of_touched_bytes": ach / hbm * (rs - 16) / rs,
+                "note": "achieved counts the algorithmic bytes of SURVEY 8(d), (4N+40) per element; the kernel touches (4N+24), so frac can exceed 1"}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         orc = oracle.Oracle(N, oracle.HOST)

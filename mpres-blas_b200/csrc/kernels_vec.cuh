@@ -534,17 +534,19 @@ __global__ void __launch_bounds__(256) k_mv_acc_t(const DevConsts *Cp, SoA M, lo
 struct MvParts { int *pd, *lab, *mn, *top; };
 
 // ---- many splits, few outputs (DOT): fold the partial sums of one output with a whole block ---------------------
-// `out` holds ONE partial per output (layout of nsplit = 1).
-__global__ void __launch_bounds__(256) k_mv_combine(const DevConsts *Cp, int nout, int nsplit, MvParts in, MvParts out) {
+// Block (o, g) folds the splits [g gs, (g + 1) gs) of output o into partial g of `out` (layout [g][o]); with gs >= nsplit `out` holds
+// ONE partial per output.  DOT with ~1200 splits folds in two levels (37 blocks, then one) instead of one block walking all of them.
+__global__ void __launch_bounds__(256) k_mv_combine(const DevConsts *Cp, int nout, int nsplit, int gs, MvParts in, MvParts out) {
     __shared__ int s_lab, s_min, s_top;
     __shared__ unsigned long long s_sum[kMaxN];
     const DevConsts &C = *Cp;
     const int N = C.N, t = threadIdx.x, o = blockIdx.x;
+    const int p0 = blockIdx.y * gs, p1 = min(nsplit, p0 + gs);
     if (t == 0) { s_lab = kVecNone; s_min = kVecNone; s_top = INT_MIN; }
     for (int i = t; i < N; i += 256) s_sum[i] = 0ull;
     __syncthreads();
     int lb = kVecNone, mn = kVecNone, mx = INT_MIN;
-    for (int p = t; p < nsplit; p += 256) {
+    for (int p = p0 + t; p < p1; p += 256) {
         const long long e = (long long) p * nout + o;
         const int b = in.lab[e];
         if (b != kVecNone) { lb = min(lb, b); mn = min(mn, in.mn[e]); mx = max(mx, in.top[e]); }
@@ -552,8 +554,8 @@ __global__ void __launch_bounds__(256) k_mv_combine(const DevConsts *Cp, int nou
     if (lb != kVecNone) { atomicMin(&s_lab, lb); atomicMin(&s_min, mn); atomicMax(&s_top, mx); }
     __syncthreads();
     const int nb = s_lab;
-    for (long long it = t; it < (long long) nsplit * N; it += 256) {
-        const int p = (int) (it / N), q = (int) (it - (long long) p * N);
+    for (long long it = t; it < (long long) (p1 - p0) * N; it += 256) {
+        const int p = p0 + (int) (it / N), q = (int) (it % N);
         const long long e = (long long) p * nout + o;
         const int b = in.lab[e];
         if (b == kVecNone) continue;
@@ -563,8 +565,9 @@ __global__ void __launch_bounds__(256) k_mv_combine(const DevConsts *Cp, int nou
         if (v) atomicAdd(&s_sum[q], (unsigned long long) v);
     }
     __syncthreads();
-    for (int i = t; i < N; i += 256) out.pd[(long long) o * N + i] = reduce64(s_sum[i], C.moduli[i], C.barrett[i]);
-    if (t == 0) { out.lab[o] = nb; out.mn[o] = s_min; out.top[o] = s_top; }
+    const long long eo = (long long) blockIdx.y * nout + o;
+    for (int i = t; i < N; i += 256) out.pd[eo * N + i] = reduce64(s_sum[i], C.moduli[i], C.barrett[i]);
+    if (t == 0) { out.lab[eo] = nb; out.mn[eo] = s_min; out.top[eo] = s_top; }
 }
 
 // ---- combine the splits, normalise, apply --------------------------------------------------------------------
@@ -676,16 +679,22 @@ static inline int mv_small_moduli_bits(const mpres_ctx *c) {
 }
 
 // partial-sum workspace: [nsplit][nout] partials, one folded partial per output, todo list [nout]
-struct MvWork { MvParts parts, folded; int *todo; };
+constexpr int kMvMidMax = 64;   // partials of the first folding level (DOT)
+struct MvWork { MvParts parts, folded, mid; int *todo; };
 static inline int mv_workspace(mpres_ctx *c, long long nout, int nsplit, MvWork *w) {
     const size_t cnt = (size_t) nout * nsplit;
-    const size_t bytes = (cnt + nout) * c->hc.N * 4 + 32 + (cnt + nout) * 12 + (size_t) nout * 4 + 64;
+    const size_t nmid = nout == 1 ? kMvMidMax : 0;
+    const size_t bytes = (cnt + nout + nmid) * c->hc.N * 4 + 48 + (cnt + nout + nmid) * 12 + (size_t) nout * 4 + 64;
     void *p;
     int rc = ws_reserve(c, 2, bytes, &p);
     if (rc) return rc;
     char *b = (char *) p;
     w->parts.pd = (int *) b; b += (cnt * c->hc.N * 4 + 15) / 16 * 16;
     w->folded.pd = (int *) b; b += ((size_t) nout * c->hc.N * 4 + 15) / 16 * 16;
+    w->mid.pd = (int *) b; b += (nmid * c->hc.N * 4 + 15) / 16 * 16;
+    w->mid.lab = (int *) b; b += nmid * 4;
+    w->mid.mn = (int *) b; b += nmid * 4;
+    w->mid.top = (int *) b; b += nmid * 4;
     w->parts.lab = (int *) b; b += cnt * 4;
     w->parts.mn = (int *) b; b += cnt * 4;
     w->parts.top = (int *) b; b += cnt * 4;
@@ -827,7 +836,17 @@ inline int dot_fast(mpres_ctx *c, int n, SoA x, int incx, SoA y, int incy, char 
     CUDA_TRY(cudaGetLastError());
     mv_mark(c, 2, st);
     const bool fold = nsplit > 4;
-    if (fold) { k_mv_combine<<<1, 256, 0, st>>>(c->dconsts, 1, nsplit, w.parts, w.folded); LAUNCHED(c); }
+    if (fold) {
+        const int gs = 32, groups = (nsplit + gs - 1) / gs;
+        if (groups > 1 && groups <= kMvMidMax) {      // two levels: `groups` blocks fold 32 splits each, one block folds their partials
+            k_mv_combine<<<dim3(1, (unsigned) groups), 256, 0, st>>>(c->dconsts, 1, nsplit, gs, w.parts, w.mid);
+            k_mv_combine<<<1, 256, 0, st>>>(c->dconsts, 1, groups, groups, w.mid, w.folded);
+            LAUNCHED(c);
+        } else {
+            k_mv_combine<<<1, 256, 0, st>>>(c->dconsts, 1, nsplit, nsplit, w.parts, w.folded);
+        }
+        LAUNCHED(c);
+    }
     MPRES_DISPATCH(N, {
         k_mv_finalize<G, R><<<1, 256, 0, st>>>(c->dconsts, 1, fold ? 1 : nsplit, fold ? w.folded : w.parts, (long long) n, false, out, 1, rec_out, w.todo,
                                                c->d_counter, allow_fb);
