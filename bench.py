@@ -341,6 +341,8 @@ def main():
     ap.add_argument("--stage2", default="small", choices=["small", "small_t128", "small_k64", "small_tiled", "umma", "umma_unstacked", "mma_sync"], help="stage-2 kernel (A/B measurement)")
     ap.add_argument("--stage3", type=int, default=0, choices=[0, 1, 2, 3], help="stage-3 kernel variant (mpres_set_stage3_kernel; A/B measurement)")
     ap.add_argument("--bcast", default="lean", choices=["lean", "full"], help="N > 1: what the per-step broadcast of B moves (lean: the fields the small-base path reads, verified on the device; full: all four SoA arrays)")
+    ap.add_argument("--prefetch", action="store_true", help="N > 1, lean broadcast: issue the next step's broadcast of B on a second stream behind the current multiply "
+                    "(measured: no gain on B200 -- NCCL's blocks find no room beside the multiply kernels, which fill every SM; kept for experiments)")
     ap.add_argument("--full-precision-inputs", action="store_true", help="p-bit significands instead of p/4")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -434,6 +436,29 @@ def main():
 
     lean = parallel.LeanBroadcast(dist, N) if (world > 1 and args.bcast == "lean") else None
     lean_state = {"on": False, "repeats": 0}
+    # Prefetch (--prefetch): two B buffers; the broadcast of step i+1 runs on a second stream while step i multiplies,
+    # so a step costs max(broadcast, multiply) instead of their sum.  Every timed step still broadcasts B inside the timed region; the first
+    # timed step is not prefetched from the warm-up.
+    overlap = lean is not None and args.prefetch
+    Bbuf = [B]
+    if overlap:
+        B1 = ta.TorchMpArray(ctx, k * n)
+        for dst, src in zip(B1.tensors(), B.tensors()):
+            dst.copy_(src)                                   # on rank 0 both buffers hold B (the source of every broadcast)
+        Bbuf.append(B1)
+    side = torch.cuda.Stream(priority=-1) if overlap else None      # high priority: its blocks are placed as soon as an SM has room
+    ev_b, ev_g = {}, {}
+    total_steps = args.warmup + args.steps
+    config["broadcast_prefetch"] = bool(overlap)
+
+    def issue_bcast(i):
+        Bi = Bbuf[i % len(Bbuf)]
+        with torch.cuda.stream(side):
+            if (i - 2) in ev_g:
+                side.wait_event(ev_g.pop(i - 2))             # the multiply that read this buffer two steps ago has finished
+            lean.broadcast(Bi.digits, Bi.sign, Bi.exp, Bi.eval)
+            e = torch.cuda.Event(); e.record(side)
+            ev_b[i] = e
 
     def step():
         i = state["i"]; state["i"] = i + 1
@@ -441,11 +466,22 @@ def main():
         if i >= n_buf:                                    # buffer reuse: restore the pristine C first (device-to-device)
             for dst, src in zip(Cb.tensors(), C0.tensors()):
                 dst.copy_(src, non_blocking=True)
-        gemm = lambda: pkg.mp_gemm(ctx, pkg.mblas_no_trans, pkg.mblas_no_trans, mr, n, k, alpha, A, mr, B, k, beta, Cb, mr, None, stream)
+        Bi = Bbuf[i % len(Bbuf)] if (overlap and lean_state["on"]) else B
+        gemm = lambda: pkg.mp_gemm(ctx, pkg.mblas_no_trans, pkg.mblas_no_trans, mr, n, k, alpha, A, mr, Bi, k, beta, Cb, mr, None, stream)
         if lean is not None and lean_state["on"]:
             # only the fields of B the small-base fast path reads travel; a device-side check guards it (parallel.LeanBroadcast)
-            lean.broadcast(B.digits, B.sign, B.exp, B.eval)
-            gemm()
+            if overlap:
+                main = torch.cuda.current_stream()
+                if i not in ev_b:
+                    issue_bcast(i)
+                if i + 1 < total_steps and i + 1 != args.warmup:
+                    issue_bcast(i + 1)
+                main.wait_event(ev_b.pop(i))
+                gemm()
+                e = torch.cuda.Event(); e.record(main); ev_g[i] = e
+            else:
+                lean.broadcast(B.digits, B.sign, B.exp, B.eval)
+                gemm()
             P_used, nin_used = ctx.last_small_base()
             ok = torch.tensor([1 if lean.verify(P_used, nin_used, ctx.last_fallback_count()) else 0], dtype=torch.int32, device="cuda")
             dist.all_reduce(ok, op=dist.ReduceOp.MIN)
@@ -454,6 +490,7 @@ def main():
             lean_state["repeats"] += 1                   # the lean copy was not enough somewhere: repeat with the complete B
             for dst, src in zip(Cb.tensors(), C0.tensors()):
                 dst.copy_(src, non_blocking=True)
+            gemm = lambda: pkg.mp_gemm(ctx, pkg.mblas_no_trans, pkg.mblas_no_trans, mr, n, k, alpha, A, mr, B, k, beta, Cb, mr, None, stream)
         parallel.gemm_row_sharded(dist, B.tensors(), gemm)
 
     def barrier():
