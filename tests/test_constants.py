@@ -63,3 +63,20 @@ def test_bad_moduli_rejected(pkg):
         pkg.Context(moduli=[15, 21, 1000003], device=-1)    # not coprime
     with pytest.raises(pkg.MpresError):
         pkg.Context(7, -1)                                  # no such predefined set
+
+
+def test_small_modulus_base(pkg):
+    """the one-byte moduli of the tensor-core stage 2: pairwise coprime, one byte each, product about 2^362, and coprime to nothing they
+    have to be (the extension to the format's moduli only needs the small moduli coprime among themselves)"""
+    import math
+    ctx = pkg.Context(32, -1)          # constants-only context: no device needed
+    ps = ctx.small_moduli(54)
+    assert ps[0] == 256 and len(set(ps)) == 54 and all(2 <= p <= 256 for p in ps)
+    for i in range(54):
+        for j in range(i):
+            assert math.gcd(ps[i], ps[j]) == 1, (ps[i], ps[j])
+    assert ctx.lib.mpres_small_modulus(ctx.h, 54) == 0 and ctx.lib.mpres_small_modulus(ctx.h, -1) == 0
+    bits = sum(math.log2(p) for p in ps)
+    assert 362 < bits < 363.5
+    assert sorted(ps, reverse=True) == ps
+    ctx.close()
