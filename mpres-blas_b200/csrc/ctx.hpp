@@ -70,6 +70,9 @@ struct mpres_ctx {
     cudaEvent_t ev[6] = {nullptr};
     bool ev_valid = false;
     int last_stage2_launches = 0;
+    // opt-in shared-memory sizes (cudaFuncSetAttribute) are per device: remembered per context, not per process
+    bool attr_fast = false, attr_align_mma = false, attr_small = false, attr_umma = false;
+    unsigned long long attr_fused = 0;   // bit NQ / 8: k_ext_norm_small<NQ, *>
     std::mutex mu;
 };
 

@@ -602,8 +602,7 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
     k_outer_info<<<(unsigned) ((n * 32ll + 255) / 256), 256, 0, st>>>(c->dconsts, B, soB, slB, n, k, IB);
     k_choose_base<<<1, 256, 0, st>>>(c->dconsts, IA, m, IB, n, k, c->reduced_base, small_on ? 1 : 0, nprime, sel);
     const size_t smem_align = (size_t) N * 4 * (kRun + 4);
-    static bool attr_done = false;
-    if (!attr_done) {
+    if (!c->attr_fast) {
         cudaFuncSetAttribute(k_align_planes, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 4 * (kRun + 4));
         cudaFuncSetAttribute(k_align_planes4, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 4 * (kRun + 4));
         cudaFuncSetAttribute(k_base_extend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) base_extend_smem(128));
@@ -611,14 +610,13 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
         cudaFuncSetAttribute(k_limb_gemm<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
         cudaFuncSetAttribute(k_ext_small<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ext_small_smem(512, 128));
         cudaFuncSetAttribute(k_ext_small<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ext_small_smem(512, 128));
-        attr_done = true;
+        c->attr_fast = true;
     }
     if (small_on) {
         const unsigned gA = (unsigned) std::min<long long>((m_ps / kASo) * (k_p / kASl), (long long) c->sm_count * 3);
         const unsigned gB = (unsigned) std::min<long long>((n_ps / kASo) * (k_p / kASl), (long long) c->sm_count * 3);
         if (c->align_mma) {
-            static bool attr_am = false;
-            if (!attr_am) { cudaFuncSetAttribute(k_align_small<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) align_small_smem(true)); attr_am = true; }
+            if (!c->attr_align_mma) { cudaFuncSetAttribute(k_align_small<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) align_small_smem(true)); c->attr_align_mma = true; }
             k_align_small<true><<<gA, 256, align_small_smem(true), st>>>(c->dconsts, A, soA, slA, m, k, IA, (uint8_t *) pQA, SA, m_ps, k_p, sel);
             k_align_small<true><<<gB, 256, align_small_smem(true), st>>>(c->dconsts, B, soB, slB, n, k, IB, (uint8_t *) pQB, SB, n_ps, k_p, sel);
         } else {
@@ -715,11 +713,10 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
             // small-modulus path: base extension and normalisation in one kernel (leaves at once when the small base was not selected)
             const unsigned gx = (unsigned) ((m_p / kXT) * n);
             const size_t sm = ext_small_smem(c->sc.ext_cols, NQ) + (ext_norm_cds_aliased(NQ) ? 0 : sm_cds);
-            static bool attr_fused = false;
-            if (!attr_fused) {
+            if (!(c->attr_fused >> (NQ / 8) & 1ull)) {
                 cudaFuncSetAttribute(k_ext_norm_small<NQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm);
                 cudaFuncSetAttribute(k_ext_norm_small<NQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm);
-                attr_fused = true;
+                c->attr_fused |= 1ull << (NQ / 8);
             }
             if (f32)
                 k_ext_norm_small<NQ, true><<<gx, kXT, sm, st>>>(c->dconsts, m, n, k, (const uint8_t *) pS8, m_p, m_ps, n_ps, (int *) pS, n_p, sel, D, IA, IB, alpha, beta, Cm, ldc,

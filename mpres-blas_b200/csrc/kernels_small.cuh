@@ -838,13 +838,12 @@ inline int launch_small_umma(mpres_ctx *c, const uint8_t *PA, const uint8_t *PB,
     const int tj = (c->small_persistent && box_k == 128 && c->small_tj == 256 && n_ps % 256 == 0) ? 256 : mpres::kSM;
     if ((rc = small_make_map(&tmJ, PB, mpres::kSmallMax, n_ps, k_p, tj, box_k))) return rc;
     if ((rc = small_make_map(&tmI, PA, mpres::kSmallMax, m_ps, k_p, mpres::kSN, box_k))) return rc;
-    static bool attr_done = false;
-    if (!attr_done) {
+    if (!c->attr_small) {
         CUDA_TRY(cudaFuncSetAttribute(mpres::k_small_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, mpres::kSSmem));
         CUDA_TRY(cudaFuncSetAttribute(mpres::k_small_umma_p<64, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, mpres::kPSmem));
         CUDA_TRY(cudaFuncSetAttribute(mpres::k_small_umma_p<128, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, mpres::kPSmem));
         CUDA_TRY(cudaFuncSetAttribute(mpres::k_small_umma_p<128, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, mpres::kPSmem));
-        attr_done = true;
+        c->attr_small = true;
     }
     if (c->small_persistent) {
         const long long max_tiles = (long long) mpres::kSmallMax * (m_ps / mpres::kSN) * (n_ps / tj);

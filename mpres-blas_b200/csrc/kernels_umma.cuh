@@ -299,11 +299,10 @@ inline int launch_limb_umma(mpres_ctx *c, bool stacked, const uint8_t *PA, const
     int rc;
     if ((rc = umma_make_map(&tmA, PA, N, m_p, k_p, mpres::kUM))) return rc;
     if ((rc = umma_make_map(&tmB, PB, N, n_p, k_p, mpres::kUN))) return rc;
-    static bool attr_done = false;
-    if (!attr_done) {
+    if (!c->attr_umma) {
         CUDA_TRY(cudaFuncSetAttribute(mpres::k_limb_umma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mpres::kUSmem));
         CUDA_TRY(cudaFuncSetAttribute(mpres::k_limb_umma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mpres::kUSmem));
-        attr_done = true;
+        c->attr_umma = true;
     }
     dim3 grid((unsigned) ((n_p / mpres::kUN + mpres::kUTilesPerCta - 1) / mpres::kUTilesPerCta), (unsigned) (m_p / mpres::kUM), (unsigned) N);
     if (stacked)
