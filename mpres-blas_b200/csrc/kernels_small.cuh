@@ -9,11 +9,14 @@
 // thread per entry, src/blas/gemm.cuh:39-58.)
 //
 //   k_align_small    stage 1: an entry's significand X is rebuilt in binary from its first n_in reference
-//                    residues (CRT with the nearest-integer rank: exact because X < M'/4 is known from the
-//                    interval evaluation), reduced modulo every small modulus with byte dot products (dp4a),
-//                    multiplied by +-2^shift and stored as one u8 plane per modulus, K-major.
-//   k_small_umma     stage 2: per modulus a 128 x 256 tile of A'_p B'_p^T on tcgen05.mma kind::i8, operands by
-//                    TMA through a 4-stage mbarrier ring, accumulator in TMEM, reduced mod p in the epilogue.
+//                    residues (CRT with a floating-point rank that is put right when it is off by one; n_in is
+//                    the smallest count whose moduli product exceeds every significand, known from the interval
+//                    evaluations), reduced modulo every small modulus with byte dot products (dp4a),
+//                    multiplied by +-2^shift and stored as one u8 plane per modulus, K-major.  Persistent.
+//   k_small_umma_p   stage 2 (default): persistent, per modulus 256 x 256 tiles of B'_p A'_p^T on tcgen05.mma
+//                    kind::i8 (two M128 N256 MMAs per 32-byte K step), operands by TMA in 128-byte swizzled
+//                    rows through an mbarrier ring, accumulators in TMEM, reduced mod p in the epilogue.
+//   k_small_umma     the first version: one 128 x 256 tile per CTA, 64-byte rows (kept for A/B).
 //   k_ext_small      stage 3a: CRT base extension to the reference moduli.  xi_i = x_i (M'/p_i)^-1 mod p_i, rank
 //                    R = nearest integer of sum xi_i / p_i (|S| < M'/4), and
 //                        S mod m_q = sum_i xi_i (M'/p_i mod m_q) + R (m_q - M' mod m_q)      (mod m_q)
