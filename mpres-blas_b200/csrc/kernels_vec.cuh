@@ -132,11 +132,9 @@ constexpr int kVecExpLimit = 1 << 28;   // exponents beyond this magnitude make 
 // v = round(alpha x) (compact, inc 1).  RB = 2^lgRB rows, blockDim = RB * N/4.  Outputs per (split, row):
 // pd[(split m + row) N + q] digits, plab label, pmin smallest term exponent, ptop window top.
 // SMALL: every modulus has bit length kb <= 27.
-#ifndef MPRES_MV_BLOCKS
-#define MPRES_MV_BLOCKS 1
-#endif
+// (forcing three blocks per SM through __launch_bounds__ was measured: 6.0 ms against 5.4 ms at config 4 -- the default allocation stays)
 template <bool SMALL, int CB, int STAGES>
-__global__ void __launch_bounds__(256, MPRES_MV_BLOCKS) k_mv_acc_n(const DevConsts *Cp, SoA A, int lda, int m, int n, SoA v, int lgRB, int cols_per_split,
+__global__ void __launch_bounds__(256) k_mv_acc_n(const DevConsts *Cp, SoA A, int lda, int m, int n, SoA v, int lgRB, int cols_per_split,
                                                   int *pd, int *plab, int *pmin, int *ptop) {
     extern __shared__ __align__(16) unsigned char vsm[];
     typedef typename VecAcc<SMALL>::type acc_t;
