@@ -227,13 +227,33 @@ def run_vec(args):
         ta.random_fill(ctx, A, bits, 300 + rank); ta.random_fill(ctx, xv, bits, 400 + (rank if tr else 0)); ta.random_fill(ctx, y0, bits, 500 + rank)
         ta.random_fill(ctx, al, bits, 41); ta.random_fill(ctx, be, bits, 42)
         flops, alg_bytes = 2.0 * m * n, float(m) * n * rs + (n + 2.0 * m) * rs
-        if tr and world > 1:
-            raise SystemExit("gemv_t on several GPUs: use the sharding helper in mpres-blas_b200/parallel.py (all-gather of partial y); not a bench line")
+        sharded_t = tr and world > 1
+        if sharded_t:
+            # y = alpha A^T x + beta y with A and x split by rows: every rank forms t_r = alpha A_r^T x_r (a full-length vector), the t_r are
+            # all-gathered (the four SoA arrays) and added to round(beta y) in rank order with mp_axpy on every rank (GEMV (T))
+            one = ta.TorchMpArray(ctx, 1)
+            pkg._check(lib.mpres_array_set_binary(ctx.h, ctypes.byref(one.s), ctypes.c_size_t(0), ctypes.c_void_p(torch.zeros(1, dtype=torch.int32, device="cuda").data_ptr()),
+                                                  ctypes.c_void_p(torch.zeros(1, dtype=torch.int32, device="cuda").data_ptr()),
+                                                  ctypes.c_void_p(torch.ones(1, dtype=torch.int32, device="cuda").data_ptr()), 1, ctypes.c_size_t(1), None), "mpres_array_set_binary")
+            torch.cuda.synchronize()
+            tpart, tzero = ta.TorchMpArray(ctx, n), ta.TorchMpArray(ctx, n)
+            tall = [ta.TorchMpArray(ctx, n) for _ in range(world)]
+            config["sharding"] = "row blocks x%d of A and x, partial y all-gathered (NCCL) and summed with mp_axpy in rank order on every rank" % world
 
         def step():
             for dst, src in zip(yv.tensors(), y0.tensors()):
                 dst.copy_(src, non_blocking=True)
-            pkg.mp_gemv(ctx, pkg.mblas_trans if tr else pkg.mblas_no_trans, ml, n, al, A, ml, xv, 1, be, yv, 1, None, None, stream)
+            if not sharded_t:
+                pkg.mp_gemv(ctx, pkg.mblas_trans if tr else pkg.mblas_no_trans, ml, n, al, A, ml, xv, 1, be, yv, 1, None, None, stream)
+                return
+            for dst, src in zip(tpart.tensors(), tzero.tensors()):
+                dst.copy_(src, non_blocking=True)
+            pkg.mp_gemv(ctx, pkg.mblas_trans, ml, n, al, A, ml, xv, 1, be, tpart, 1, None, None, stream)     # beta * 0 = 0
+            for f in range(4):
+                dist.all_gather([t.tensors()[f] for t in tall], tpart.tensors()[f])
+            pkg.mp_scal(ctx, n, be, yv, 1, stream)
+            for t in tall:
+                pkg.mp_axpy(ctx, n, one, t, 1, yv, 1, None, stream)
         host_arrays, out_arr = [(A, ml * n), (xv, lenx), (y0, leny)], (yv, leny)
 
     def barrier():

@@ -194,6 +194,14 @@ int mpres_gemv(mpres_ctx *ctx, int trans, int m, int n, const mpres_array_t *alp
 int mpres_dot(mpres_ctx *ctx, int n, const mpres_array_t *x, int incx, const mpres_array_t *y, int incy,
               mpres_array_t *r, mpres_array_t *buffer, mpres_stream_t stream);
 
+/* cuda::mp_scal<gridDim1, blockDim1, gridDim2> (src/blas/scal.cuh:45-62): x = round(alpha * x); n <= 0 or incx <= 0 return silently. */
+int mpres_scal(mpres_ctx *ctx, int n, const mpres_array_t *alpha, mpres_array_t *x, int incx, mpres_stream_t stream);
+
+/* cuda::mp_axpy<gridDim1, blockDim1, gridDim2> (src/blas/axpy.cuh:46-76): y = round(round(alpha * x) + y), one fused pass.
+ * `buffer` (n scratch elements in the reference) may be NULL. */
+int mpres_axpy(mpres_ctx *ctx, int n, const mpres_array_t *alpha, const mpres_array_t *x, int incx, mpres_array_t *y, int incy,
+               mpres_array_t *buffer, mpres_stream_t stream);
+
 /* The same three operations over mp_collection_t operands with explicit allocated lengths (the
  * reference only uses mp_collection_t in its sparse kernels, src/sparse/mpmtx/*.cuh; north_star asks
  * for the dense path over both containers). */

@@ -105,6 +105,16 @@ void mp_dot(const int n, mp_array_t &x, const int incx, mp_array_t &y, const int
     mpres_compat::status() = mpres_dot(mpres_compat::ctx(), n, &x, incx, &y, incy, &r, &buffer, nullptr);
 }
 
+/* src/blas/scal.cuh:45-46, src/blas/axpy.cuh:46 */
+template <int gridDim1, int blockDim1, int gridDim2>
+void mp_scal(const int n, mp_array_t &alpha, mp_array_t &x, const int incx) {
+    mpres_compat::status() = mpres_scal(mpres_compat::ctx(), n, &alpha, &x, incx, nullptr);
+}
+template <int gridDim1, int blockDim1, int gridDim2>
+void mp_axpy(const int n, mp_array_t &alpha, mp_array_t &x, const int incx, mp_array_t &y, const int incy, mp_array_t &buffer) {
+    mpres_compat::status() = mpres_axpy(mpres_compat::ctx(), n, &alpha, &x, incx, &y, incy, &buffer, nullptr);
+}
+
 }  // namespace cuda
 
 #endif /* MPRES_COMPAT_CUH */

@@ -42,7 +42,7 @@ EXPORTS = [
     "mpres_set_profiling", "mpres_last_stage_ms", "mpres_set_vec_config", "mpres_last_small_base", "mpres_small_modulus", "mpres_debug_read_workspace", "mpres_last_minplus_dense_count",
     "mpres_array_init", "mpres_array_clear", "mpres_array_host2device", "mpres_array_device2host",
     "mpres_collection_init", "mpres_collection_clear", "mpres_collection_host2device", "mpres_collection_device2host",
-    "mpres_array_set_binary", "mpres_gemm", "mpres_gemv", "mpres_dot", "mpres_gemm_coll", "mpres_gemv_coll",
+    "mpres_array_set_binary", "mpres_gemm", "mpres_gemv", "mpres_dot", "mpres_scal", "mpres_axpy", "mpres_gemm_coll", "mpres_gemv_coll",
     "mpres_dot_coll", "mpres_dot_partial", "mpres_reduce_partials", "mpres_probe", "mpres_version",
 ]
 
@@ -289,6 +289,16 @@ def mp_dot(ctx, n, x, incx, y, incy, r, buffer=None, stream=0):
                                       _ref(r), _vp(stream)), "mpres_dot_coll")
         return
     _check(ctx.lib.mpres_dot(ctx.h, n, _ref(x), incx, _ref(y), incy, _ref(r), _ref(buffer), _vp(stream)), "mpres_dot")
+
+
+def mp_scal(ctx, n, alpha, x, incx, stream=0):
+    """cuda::mp_scal (src/blas/scal.cuh:45-46): x = alpha*x."""
+    _check(ctx.lib.mpres_scal(ctx.h, n, _ref(alpha), _ref(x), incx, _vp(stream)), "mpres_scal")
+
+
+def mp_axpy(ctx, n, alpha, x, incx, y, incy, buffer=None, stream=0):
+    """cuda::mp_axpy (src/blas/axpy.cuh:46): y = alpha*x + y."""
+    _check(ctx.lib.mpres_axpy(ctx.h, n, _ref(alpha), _ref(x), incx, _ref(y), incy, _ref(buffer), _vp(stream)), "mpres_axpy")
 
 
 def synchronize(ctx):

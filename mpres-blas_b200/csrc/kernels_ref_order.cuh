@@ -104,6 +104,28 @@ __global__ void k_vec_scale(const DevConsts *Cp, long long n, SoA r, int incr, S
     }
 }
 
+// y = round(round(alpha * x) + y): cuda::mp_axpy (src/blas/axpy.cuh:46-76: product into a buffer, rounding, sum, rounding), fused:
+// no buffer, one pass over x and y.  The sum uses scalar mp_add semantics.
+template <int G, int R>
+__global__ void k_vec_axpy(const DevConsts *Cp, long long n, SoA s, SoA x, int incx, SoA y, int incy) {
+    const DevConsts &C = *Cp;
+    Lane<R> L;
+    lane_init<G, R>(C, L);
+    long long grp = ((long long) blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const long long ngrp = (long long) gridDim.x * blockDim.x / G;
+    Num<R> sc;
+    load_num<G, R>(C, L, s, 0, sc);
+    for (; grp < n; grp += ngrp) {
+        Num<R> a, b, t, r;
+        load_num<G, R>(C, L, x, inc_index(grp, n, incx), a);
+        const long long iy = inc_index(grp, n, incy);
+        load_num<G, R>(C, L, y, iy, b);
+        mp_mul<G, R, true>(C, L, t, a, sc);
+        mp_add<G, R, true>(C, L, r, t, b);
+        store_num<G, R>(C, L, y, iy, r);
+    }
+}
+
 // ---- GEMV, reference order: y[o] = y[o] + sum_q op(A)(o, q) * ax[q]  (src/blas/gemv.cuh:199-218) ----
 // y already holds round(beta * y) and ax = round(alpha * x).  One group per output element.
 template <int G, int R>

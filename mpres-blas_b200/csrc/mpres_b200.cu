@@ -592,6 +592,43 @@ int mpres_gemv_coll(mpres_ctx *c, int trans, int m, int n, const mpres_collectio
                      (cudaStream_t) stream);
 }
 
+/* ---- SCAL, AXPY (the first of the other v1 operations) ------------------------------ */
+
+int mpres_scal(mpres_ctx *c, int n, const mpres_array_t *alpha, mpres_array_t *x, int incx, mpres_stream_t stream) {
+    NEED_DEVICE(c);
+    if (!c || !alpha || !x) return -1;
+    if (n <= 0 || incx <= 0) return 0;      // src/blas/scal.cuh:47-49 (silent return)
+    DeviceGuard g(c->device);
+    cudaStream_t st = (cudaStream_t) stream;
+    MPRES_DISPATCH(c->hc.N, {
+        const int block = 128;
+        const unsigned nb = (unsigned) std::min<long long>(((long long) n * G + block - 1) / block, (long long) c->sm_count * 32);
+        k_vec_scale<G, R><<<nb, block, 0, st>>>(c->dconsts, n, view(x), incx, view(x), incx, view(alpha));
+    });
+    LAUNCHED(c);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int mpres_axpy(mpres_ctx *c, int n, const mpres_array_t *alpha, const mpres_array_t *x, int incx, mpres_array_t *y, int incy,
+               mpres_array_t *buffer, mpres_stream_t stream) {
+    NEED_DEVICE(c);
+    (void) buffer;
+    if (!c || !alpha || !x || !y) return -1;
+    if (n <= 0) return 0;                   // src/blas/axpy.cuh:49-51
+    if (incx == 0 || incy == 0) return -3;
+    DeviceGuard g(c->device);
+    cudaStream_t st = (cudaStream_t) stream;
+    MPRES_DISPATCH(c->hc.N, {
+        const int block = 128;
+        const unsigned nb = (unsigned) std::min<long long>(((long long) n * G + block - 1) / block, (long long) c->sm_count * 32);
+        k_vec_axpy<G, R><<<nb, block, 0, st>>>(c->dconsts, n, view(alpha), view(x), incx, view(y), incy);
+    });
+    LAUNCHED(c);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 /* ---- DOT ------------------------------------------------------------------------------------------- */
 
 // partial (device AoS record) := sum x_i * y_i

@@ -39,6 +39,9 @@ int main(int argc, char **argv) {
     fwrite(C.data(), sizeof(mp_float_t), C.size(), f);
     fwrite(r.data(), sizeof(mp_float_t), 1, f);
     fclose(f);
+    cuda::mp_scal<128, 64, 128>(k, dal, dx, 1);                        /* the level-1 entry points build through the shim too */
+    cuda::mp_axpy<128, 64, 128>(k, dal, dx, 1, dy, 1, dbuf2);
+    if (mpres_compat_last_status() != 0) return 9;
     cuda::mp_array_clear(dA); cuda::mp_array_clear(dB); cuda::mp_array_clear(dC);
     printf("MP_PRECISION %d MP_H %d\n", MP_PRECISION, MP_H);
     return 0;
