@@ -202,6 +202,21 @@ int mpres_scal(mpres_ctx *ctx, int n, const mpres_array_t *alpha, mpres_array_t 
 int mpres_axpy(mpres_ctx *ctx, int n, const mpres_array_t *alpha, const mpres_array_t *x, int incx, mpres_array_t *y, int incy,
                mpres_array_t *buffer, mpres_stream_t stream);
 
+/* cuda::mp_waxpby<gridDim1, blockDim1, gridDim2> (src/blas/waxpby.cuh:50-93): w = round(round(beta * y) + round(alpha * x)). */
+int mpres_waxpby(mpres_ctx *ctx, int n, const mpres_array_t *alpha, const mpres_array_t *x, int incx, const mpres_array_t *beta,
+                 const mpres_array_t *y, int incy, mpres_array_t *w, int incw, mpres_array_t *buffer, mpres_stream_t stream);
+
+/* cuda::mp_ge_add<...> (src/blas/geadd.cuh:58-105): C = alpha * A + beta * B, and cuda::mp_ge_acc<...> (src/blas/geacc.cuh:57-97):
+ * B = alpha * A + beta * B; m x n, column-major, non-transposed; products and sum rounded as in the reference. */
+int mpres_ge_add(mpres_ctx *ctx, int m, int n, const mpres_array_t *alpha, const mpres_array_t *A, int lda, const mpres_array_t *beta,
+                 const mpres_array_t *B, int ldb, mpres_array_t *C, int ldc, mpres_array_t *buffer, mpres_stream_t stream);
+int mpres_ge_acc(mpres_ctx *ctx, int m, int n, const mpres_array_t *alpha, const mpres_array_t *A, int lda, const mpres_array_t *beta,
+                 mpres_array_t *B, int ldb, mpres_array_t *buffer, mpres_stream_t stream);
+
+/* cuda::mp_ger<...> (src/blas/ger.cuh:157-206): A = alpha * x * y^T + A (rank-1 update; alpha * y is rounded first, as in the reference). */
+int mpres_ger(mpres_ctx *ctx, int m, int n, const mpres_array_t *alpha, const mpres_array_t *x, int incx, const mpres_array_t *y, int incy,
+              mpres_array_t *A, int lda, mpres_array_t *buffer1, mpres_array_t *buffer2, mpres_stream_t stream);
+
 /* The same three operations over mp_collection_t operands with explicit allocated lengths (the
  * reference only uses mp_collection_t in its sparse kernels, src/sparse/mpmtx/*.cuh; north_star asks
  * for the dense path over both containers). */

@@ -115,6 +115,27 @@ void mp_axpy(const int n, mp_array_t &alpha, mp_array_t &x, const int incx, mp_a
     mpres_compat::status() = mpres_axpy(mpres_compat::ctx(), n, &alpha, &x, incx, &y, incy, &buffer, nullptr);
 }
 
+/* src/blas/waxpby.cuh:50, geadd.cuh:58, geacc.cuh:57, ger.cuh:157 */
+template <int gridDim1, int blockDim1, int gridDim2>
+void mp_waxpby(const int n, mp_array_t &alpha, mp_array_t &x, const int incx, mp_array_t &beta, mp_array_t &y, const int incy, mp_array_t &w,
+               const int incw, mp_array_t &buffer) {
+    mpres_compat::status() = mpres_waxpby(mpres_compat::ctx(), n, &alpha, &x, incx, &beta, &y, incy, &w, incw, &buffer, nullptr);
+}
+template <int blockDim1x, int blockDim1y, int gridDim2x, int gridDim2y>
+void mp_ge_add(const int m, const int n, mp_array_t &alpha, mp_array_t &A, const int lda, mp_array_t &beta, mp_array_t &B, const int ldb, mp_array_t &C,
+               const int ldc, mp_array_t &buffer) {
+    mpres_compat::status() = mpres_ge_add(mpres_compat::ctx(), m, n, &alpha, &A, lda, &beta, &B, ldb, &C, ldc, &buffer, nullptr);
+}
+template <int blockDim1x, int blockDim1y, int gridDim2x, int gridDim2y>
+void mp_ge_acc(const int m, const int n, mp_array_t &alpha, mp_array_t &A, const int lda, mp_array_t &beta, mp_array_t &B, const int ldb, mp_array_t &buffer) {
+    mpres_compat::status() = mpres_ge_acc(mpres_compat::ctx(), m, n, &alpha, &A, lda, &beta, &B, ldb, &buffer, nullptr);
+}
+template <int blockDim1x, int blockDim1y, int gridDim2x, int gridDim2y>
+void mp_ger(const int m, const int n, mp_array_t &alpha, mp_array_t &x, const int incx, mp_array_t &y, const int incy, mp_array_t &A, const int lda,
+            mp_array_t &buffer1, mp_array_t &buffer2) {
+    mpres_compat::status() = mpres_ger(mpres_compat::ctx(), m, n, &alpha, &x, incx, &y, incy, &A, lda, &buffer1, &buffer2, nullptr);
+}
+
 }  // namespace cuda
 
 #endif /* MPRES_COMPAT_CUH */

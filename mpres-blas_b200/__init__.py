@@ -42,7 +42,7 @@ EXPORTS = [
     "mpres_set_profiling", "mpres_last_stage_ms", "mpres_set_vec_config", "mpres_last_small_base", "mpres_small_modulus", "mpres_debug_read_workspace", "mpres_last_minplus_dense_count",
     "mpres_array_init", "mpres_array_clear", "mpres_array_host2device", "mpres_array_device2host",
     "mpres_collection_init", "mpres_collection_clear", "mpres_collection_host2device", "mpres_collection_device2host",
-    "mpres_array_set_binary", "mpres_gemm", "mpres_gemv", "mpres_dot", "mpres_scal", "mpres_axpy", "mpres_gemm_coll", "mpres_gemv_coll",
+    "mpres_array_set_binary", "mpres_gemm", "mpres_gemv", "mpres_dot", "mpres_scal", "mpres_axpy", "mpres_waxpby", "mpres_ge_add", "mpres_ge_acc", "mpres_ger", "mpres_gemm_coll", "mpres_gemv_coll",
     "mpres_dot_coll", "mpres_dot_partial", "mpres_reduce_partials", "mpres_probe", "mpres_version",
 ]
 
@@ -299,6 +299,26 @@ def mp_scal(ctx, n, alpha, x, incx, stream=0):
 def mp_axpy(ctx, n, alpha, x, incx, y, incy, buffer=None, stream=0):
     """cuda::mp_axpy (src/blas/axpy.cuh:46): y = alpha*x + y."""
     _check(ctx.lib.mpres_axpy(ctx.h, n, _ref(alpha), _ref(x), incx, _ref(y), incy, _ref(buffer), _vp(stream)), "mpres_axpy")
+
+
+def mp_waxpby(ctx, n, alpha, x, incx, beta, y, incy, w, incw, buffer=None, stream=0):
+    """cuda::mp_waxpby (src/blas/waxpby.cuh:50): w = alpha*x + beta*y."""
+    _check(ctx.lib.mpres_waxpby(ctx.h, n, _ref(alpha), _ref(x), incx, _ref(beta), _ref(y), incy, _ref(w), incw, _ref(buffer), _vp(stream)), "mpres_waxpby")
+
+
+def mp_ge_add(ctx, m, n, alpha, A, lda, beta, B, ldb, C, ldc, buffer=None, stream=0):
+    """cuda::mp_ge_add (src/blas/geadd.cuh:58): C = alpha*A + beta*B."""
+    _check(ctx.lib.mpres_ge_add(ctx.h, m, n, _ref(alpha), _ref(A), lda, _ref(beta), _ref(B), ldb, _ref(C), ldc, _ref(buffer), _vp(stream)), "mpres_ge_add")
+
+
+def mp_ge_acc(ctx, m, n, alpha, A, lda, beta, B, ldb, buffer=None, stream=0):
+    """cuda::mp_ge_acc (src/blas/geacc.cuh:57): B = alpha*A + beta*B."""
+    _check(ctx.lib.mpres_ge_acc(ctx.h, m, n, _ref(alpha), _ref(A), lda, _ref(beta), _ref(B), ldb, _ref(buffer), _vp(stream)), "mpres_ge_acc")
+
+
+def mp_ger(ctx, m, n, alpha, x, incx, y, incy, A, lda, buffer1=None, buffer2=None, stream=0):
+    """cuda::mp_ger (src/blas/ger.cuh:157): A = alpha*x*y^T + A."""
+    _check(ctx.lib.mpres_ger(ctx.h, m, n, _ref(alpha), _ref(x), incx, _ref(y), incy, _ref(A), lda, _ref(buffer1), _ref(buffer2), _vp(stream)), "mpres_ger")
 
 
 def synchronize(ctx):

@@ -126,6 +126,76 @@ __global__ void k_vec_axpy(const DevConsts *Cp, long long n, SoA s, SoA x, int i
     }
 }
 
+// w = round(round(beta * y) + round(alpha * x)): cuda::mp_waxpby (src/blas/waxpby.cuh:50-93), one pass
+template <int G, int R>
+__global__ void k_vec_waxpby(const DevConsts *Cp, long long n, SoA al, SoA x, int incx, SoA be, SoA y, int incy, SoA w, int incw) {
+    const DevConsts &C = *Cp;
+    Lane<R> L;
+    lane_init<G, R>(C, L);
+    long long grp = ((long long) blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const long long ngrp = (long long) gridDim.x * blockDim.x / G;
+    Num<R> sa, sb;
+    load_num<G, R>(C, L, al, 0, sa);
+    load_num<G, R>(C, L, be, 0, sb);
+    for (; grp < n; grp += ngrp) {
+        Num<R> a, b, ta, tb, r;
+        load_num<G, R>(C, L, x, inc_index(grp, n, incx), a);
+        load_num<G, R>(C, L, y, inc_index(grp, n, incy), b);
+        mp_mul<G, R, true>(C, L, ta, a, sa);
+        mp_mul<G, R, true>(C, L, tb, b, sb);
+        mp_add<G, R, true>(C, L, r, tb, ta);
+        store_num<G, R>(C, L, w, inc_index(grp, n, incw), r);
+    }
+}
+
+// C = round(round(beta * B) + round(alpha * A)), m x n column-major: cuda::mp_ge_add (src/blas/geadd.cuh:58-105) and, with C = B,
+// cuda::mp_ge_acc (src/blas/geacc.cuh:57-97); one pass
+template <int G, int R>
+__global__ void k_ge_add(const DevConsts *Cp, int m, int n, SoA al, SoA A, int lda, SoA be, SoA B, int ldb, SoA Cm, int ldc) {
+    const DevConsts &C = *Cp;
+    Lane<R> L;
+    lane_init<G, R>(C, L);
+    long long grp = ((long long) blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const long long ngrp = (long long) gridDim.x * blockDim.x / G, total = (long long) m * n;
+    Num<R> sa, sb;
+    load_num<G, R>(C, L, al, 0, sa);
+    load_num<G, R>(C, L, be, 0, sb);
+    for (; grp < total; grp += ngrp) {
+        const long long i = grp % m, j = grp / m;
+        Num<R> a, b, ta, tb, r;
+        load_num<G, R>(C, L, A, i + j * lda, a);
+        load_num<G, R>(C, L, B, i + j * ldb, b);
+        mp_mul<G, R, true>(C, L, ta, a, sa);
+        mp_mul<G, R, true>(C, L, tb, b, sb);
+        mp_add<G, R, true>(C, L, r, tb, ta);
+        store_num<G, R>(C, L, Cm, i + j * ldc, r);
+    }
+}
+
+// A = round(A + round(x_i * round(alpha * y_j))): cuda::mp_ger (src/blas/ger.cuh:157-206), one pass (alpha * y_j is recomputed per
+// entry: a handful of instructions against the 2 (4N+40) bytes of A moved)
+template <int G, int R>
+__global__ void k_ger(const DevConsts *Cp, int m, int n, SoA al, SoA x, int incx, SoA y, int incy, SoA A, int lda) {
+    const DevConsts &C = *Cp;
+    Lane<R> L;
+    lane_init<G, R>(C, L);
+    long long grp = ((long long) blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const long long ngrp = (long long) gridDim.x * blockDim.x / G, total = (long long) m * n;
+    Num<R> sa;
+    load_num<G, R>(C, L, al, 0, sa);
+    for (; grp < total; grp += ngrp) {
+        const long long i = grp % m, j = grp / m;
+        Num<R> xv, yv, ay, pr, a, r;
+        load_num<G, R>(C, L, x, inc_index(i, m, incx), xv);
+        load_num<G, R>(C, L, y, inc_index(j, n, incy), yv);
+        load_num<G, R>(C, L, A, i + j * lda, a);
+        mp_mul<G, R, true>(C, L, ay, yv, sa);
+        mp_mul<G, R, true>(C, L, pr, xv, ay);
+        mp_add<G, R, true>(C, L, r, a, pr);
+        store_num<G, R>(C, L, A, i + j * lda, r);
+    }
+}
+
 // ---- GEMV, reference order: y[o] = y[o] + sum_q op(A)(o, q) * ax[q]  (src/blas/gemv.cuh:199-218) ----
 // y already holds round(beta * y) and ax = round(alpha * x).  One group per output element.
 template <int G, int R>

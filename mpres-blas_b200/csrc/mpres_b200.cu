@@ -629,6 +629,69 @@ int mpres_axpy(mpres_ctx *c, int n, const mpres_array_t *alpha, const mpres_arra
     return 0;
 }
 
+int mpres_waxpby(mpres_ctx *c, int n, const mpres_array_t *alpha, const mpres_array_t *x, int incx, const mpres_array_t *beta,
+                 const mpres_array_t *y, int incy, mpres_array_t *w, int incw, mpres_array_t *buffer, mpres_stream_t stream) {
+    NEED_DEVICE(c);
+    (void) buffer;
+    if (!c || !alpha || !x || !beta || !y || !w) return -1;
+    if (n <= 0) return 0;                   // src/blas/waxpby.cuh:53-55
+    if (incx == 0 || incy == 0 || incw == 0) return -3;
+    DeviceGuard g(c->device);
+    cudaStream_t st = (cudaStream_t) stream;
+    MPRES_DISPATCH(c->hc.N, {
+        const int block = 128;
+        const unsigned nb = (unsigned) std::min<long long>(((long long) n * G + block - 1) / block, (long long) c->sm_count * 32);
+        k_vec_waxpby<G, R><<<nb, block, 0, st>>>(c->dconsts, n, view(alpha), view(x), incx, view(beta), view(y), incy, view(w), incw);
+    });
+    LAUNCHED(c);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int mpres_ge_add(mpres_ctx *c, int m, int n, const mpres_array_t *alpha, const mpres_array_t *A, int lda, const mpres_array_t *beta,
+                 const mpres_array_t *B, int ldb, mpres_array_t *Cm, int ldc, mpres_array_t *buffer, mpres_stream_t stream) {
+    NEED_DEVICE(c);
+    (void) buffer;
+    if (!c || !alpha || !A || !beta || !B || !Cm) return -1;
+    if (m <= 0 || n <= 0) return 0;         // src/blas/geadd.cuh:60-63
+    if (lda < std::max(1, m) || ldb < std::max(1, m) || ldc < std::max(1, m)) return -3;
+    DeviceGuard g(c->device);
+    cudaStream_t st = (cudaStream_t) stream;
+    MPRES_DISPATCH(c->hc.N, {
+        const int block = 128;
+        const unsigned nb = (unsigned) std::min<long long>(((long long) m * n * G + block - 1) / block, (long long) c->sm_count * 32);
+        k_ge_add<G, R><<<nb, block, 0, st>>>(c->dconsts, m, n, view(alpha), view(A), lda, view(beta), view(B), ldb, view(Cm), ldc);
+    });
+    LAUNCHED(c);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int mpres_ge_acc(mpres_ctx *c, int m, int n, const mpres_array_t *alpha, const mpres_array_t *A, int lda, const mpres_array_t *beta,
+                 mpres_array_t *B, int ldb, mpres_array_t *buffer, mpres_stream_t stream) {
+    return mpres_ge_add(c, m, n, alpha, A, lda, beta, B, ldb, B, ldb, buffer, stream);   // src/blas/geacc.cuh:57: B = alpha A + beta B
+}
+
+int mpres_ger(mpres_ctx *c, int m, int n, const mpres_array_t *alpha, const mpres_array_t *x, int incx, const mpres_array_t *y, int incy,
+              mpres_array_t *A, int lda, mpres_array_t *buffer1, mpres_array_t *buffer2, mpres_stream_t stream) {
+    NEED_DEVICE(c);
+    (void) buffer1; (void) buffer2;
+    if (!c || !alpha || !x || !y || !A) return -1;
+    if (m < 0 || n < 0 || lda < std::max(1, m)) return -3;   // src/blas/ger.cuh:160-168
+    if (incx == 0 || incy == 0) return -3;
+    if (m == 0 || n == 0) return 0;
+    DeviceGuard g(c->device);
+    cudaStream_t st = (cudaStream_t) stream;
+    MPRES_DISPATCH(c->hc.N, {
+        const int block = 128;
+        const unsigned nb = (unsigned) std::min<long long>(((long long) m * n * G + block - 1) / block, (long long) c->sm_count * 32);
+        k_ger<G, R><<<nb, block, 0, st>>>(c->dconsts, m, n, view(alpha), view(x), incx, view(y), incy, view(A), lda);
+    });
+    LAUNCHED(c);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 /* ---- DOT ------------------------------------------------------------------------------------------- */
 
 // partial (device AoS record) := sum x_i * y_i

@@ -98,3 +98,58 @@ def test_gemv_t_row_sharded_composition(pkg):
     bad = diff_fields(got, want, ("digits", "sign", "exp"))
     assert bad.size == 0, "%d/%d differ, first %d\n%s\n%s" % (bad.size, n, bad[0], got[bad[0]], want[bad[0]])
     ctx.close()
+
+
+@pytest.mark.parametrize("N,full,incs", [(8, False, (1, 1, 1)), (16, True, (2, -1, 1)), (32, True, (1, 1, 2))])
+def test_waxpby(pkg, N, full, incs):
+    ctx = pkg.Context(N, 0)
+    orc = get_oracle(N, oracle.DEVICE)
+    bits = orc.precision if full else orc.precision // 4
+    n = 211
+    incx, incy, incw = incs
+    x, y, w = random_records(N, n * abs(incx), bits, 41), random_records(N, n * abs(incy), bits, 42), random_records(N, n * abs(incw), bits, 43)
+    al, be = random_records(N, 1, bits, 44), random_records(N, 1, bits, 45)
+    ix, iy, iw = _blas_view(n, incx), _blas_view(n, incy), _blas_view(n, incw)
+    dx, dy, dw = ctx.mp_array_from_host(x), ctx.mp_array_from_host(y), ctx.mp_array_from_host(w)
+    pkg.mp_waxpby(ctx, n, ctx.mp_array_from_host(al), dx, incx, ctx.mp_array_from_host(be), dy, incy, dw, incw)
+    got = dw.device2host()
+    want = w.copy()
+    want[iw] = orc.add(orc.mul(y[iy], np.repeat(be, n)), orc.mul(x[ix], np.repeat(al, n)))
+    assert diff_fields(got, want, ("digits", "sign", "exp")).size == 0
+    ctx.close()
+
+
+@pytest.mark.parametrize("N,full", [(8, False), (24, True)])
+def test_ge_add_ge_acc_ger(pkg, N, full):
+    ctx = pkg.Context(N, 0)
+    orc = get_oracle(N, oracle.DEVICE)
+    bits = orc.precision if full else orc.precision // 4
+    m, n, lda, ldb, ldc = 19, 13, 23, 19, 21
+    A, B, C = random_records(N, lda * n, bits, 51), random_records(N, ldb * n, bits, 52), random_records(N, ldc * n, bits, 53)
+    al, be = random_records(N, 1, bits, 54), random_records(N, 1, bits, 55)
+    dal, dbe = ctx.mp_array_from_host(al), ctx.mp_array_from_host(be)
+
+    def sub(X, ld):      # the m x n part of a column-major array with leading dimension ld, flattened column by column
+        return X.reshape(n, ld)[:, :m].reshape(-1)
+    want_sum = orc.add(orc.mul(sub(B, ldb), np.repeat(be, m * n)), orc.mul(sub(A, lda), np.repeat(al, m * n)))
+    # C = alpha A + beta B
+    dA, dB, dC = ctx.mp_array_from_host(A), ctx.mp_array_from_host(B), ctx.mp_array_from_host(C)
+    pkg.mp_ge_add(ctx, m, n, dal, dA, lda, dbe, dB, ldb, dC, ldc)
+    got = dC.device2host()
+    assert diff_fields(sub(got, ldc), want_sum, ("digits", "sign", "exp")).size == 0
+    pad = got.reshape(n, ldc)[:, m:]
+    assert diff_fields(pad.reshape(-1), C.reshape(n, ldc)[:, m:].reshape(-1)).size == 0      # outside the m x n part nothing is written
+    # B = alpha A + beta B
+    pkg.mp_ge_acc(ctx, m, n, dal, dA, lda, dbe, dB, ldb)
+    assert diff_fields(sub(dB.device2host(), ldb), want_sum, ("digits", "sign", "exp")).size == 0
+    # A = alpha x y^T + A
+    x, y = random_records(N, m, bits, 56), random_records(N, 2 * n, bits, 57)
+    incy = -2
+    iy = _blas_view(n, incy)
+    ay = orc.mul(y[iy], np.repeat(al, n))
+    prod = orc.mul(np.tile(x, n), np.repeat(ay, m))          # entry (i, j) at i + j m: x_i * (alpha y_j)
+    want_A = orc.add(sub(A, lda), prod)
+    dA2 = ctx.mp_array_from_host(A)
+    pkg.mp_ger(ctx, m, n, dal, ctx.mp_array_from_host(x), 1, ctx.mp_array_from_host(y), incy, dA2, lda)
+    assert diff_fields(sub(dA2.device2host(), lda), want_A, ("digits", "sign", "exp")).size == 0
+    ctx.close()
