@@ -53,6 +53,7 @@ typedef struct {
 
 /* src/blas/mblas_enum.cuh:25-29 */
 enum { MPRES_NO_TRANS = 111, MPRES_TRANS = 112, MPRES_CONJ_TRANS = 113 };
+enum { MPRES_LEFT_SIDE = 141, MPRES_RIGHT_SIDE = 142 };   /* mblas_side_type, src/blas/mblas_enum.cuh:37-40 */
 
 /* Stage-2 strategy.  AUTO = exact-window fast path wherever its guard holds, reference-order
  * fallback per element otherwise.  REFERENCE_ORDER = the k-loop of src/blas/gemm.cuh:46-49 step by
@@ -216,6 +217,26 @@ int mpres_ge_acc(mpres_ctx *ctx, int m, int n, const mpres_array_t *alpha, const
 /* cuda::mp_ger<...> (src/blas/ger.cuh:157-206): A = alpha * x * y^T + A (rank-1 update; alpha * y is rounded first, as in the reference). */
 int mpres_ger(mpres_ctx *ctx, int m, int n, const mpres_array_t *alpha, const mpres_array_t *x, int incx, const mpres_array_t *y, int incy,
               mpres_array_t *A, int lda, mpres_array_t *buffer1, mpres_array_t *buffer2, mpres_stream_t stream);
+
+/* cuda::mp_ge_diag_scale<...> (src/blas/gediagscale.cuh:54-99): A = round(A D) (MPRES_RIGHT_SIDE, D of n elements) or round(D A)
+ * (MPRES_LEFT_SIDE, D of m elements), D a diagonal matrix stored as a vector with increment incd (negative increments in the BLAS
+ * convention). Where the reference returns silently on incd == 0 or lda < max(1, m), this returns -3 and writes nothing. */
+int mpres_ge_diag_scale(mpres_ctx *ctx, int side, int m, int n, const mpres_array_t *D, int incd, mpres_array_t *A, int lda, mpres_stream_t stream);
+
+/* cuda::mp_ge_lr_scale<...> (src/blas/gelrscale.cuh:56-93): A = round(round(DL A) DR). */
+int mpres_ge_lr_scale(mpres_ctx *ctx, int m, int n, const mpres_array_t *DL, int incdl, const mpres_array_t *DR, int incdr, mpres_array_t *A, int lda,
+                      mpres_stream_t stream);
+
+/* cuda::mp_rot<gridDim1, blockDim1, gridDim2> (src/blas/rot.cuh:49-100): x = round(round(c x) + round(s y)), y = round(round(c y) - round(s x)).
+ * Unit increments: one fused pass, the buffers (n elements each in the reference) are not touched and may be NULL.  Other increments
+ * follow the reference's kernel sequence step for step (its mp_scal(n, c, x, 1) calls included) and need both buffers. */
+int mpres_rot(mpres_ctx *ctx, int n, mpres_array_t *x, int incx, mpres_array_t *y, int incy, const mpres_array_t *c, const mpres_array_t *s,
+              mpres_array_t *buffer1, mpres_array_t *buffer2, mpres_stream_t stream);
+
+/* cuda::mp_axpy_dot<gridDim1, blockDim1, gridDim2, gridDim3, blockDim3> (src/blas/axpydot.cuh:33-68): w = round(w - round(alpha v)) in one
+ * fused pass, then r[0] = u^T w through mpres_dot (same result contract as mpres_dot). `buffer` may be NULL. */
+int mpres_axpy_dot(mpres_ctx *ctx, int n, const mpres_array_t *alpha, mpres_array_t *w, int incw, const mpres_array_t *v, int incv,
+                   const mpres_array_t *u, int incu, mpres_array_t *r, mpres_array_t *buffer, mpres_stream_t stream);
 
 /* The same three operations over mp_collection_t operands with explicit allocated lengths (the
  * reference only uses mp_collection_t in its sparse kernels, src/sparse/mpmtx/*.cuh; north_star asks

@@ -43,6 +43,7 @@ typedef mpres_array_t mp_array_t;
 typedef mpres_collection_t mp_collection_t;
 
 enum mblas_trans_type { mblas_no_trans = 111, mblas_trans = 112, mblas_conj_trans = 113 }; /* src/blas/mblas_enum.cuh:25-29 */
+enum mblas_side_type { mblas_left_side = 141, mblas_right_side = 142 };                    /* src/blas/mblas_enum.cuh:37-40 */
 
 namespace mpres_compat {
 inline mpres_ctx *&ctx() { static mpres_ctx *c = nullptr; return c; }
@@ -134,6 +135,29 @@ template <int blockDim1x, int blockDim1y, int gridDim2x, int gridDim2y>
 void mp_ger(const int m, const int n, mp_array_t &alpha, mp_array_t &x, const int incx, mp_array_t &y, const int incy, mp_array_t &A, const int lda,
             mp_array_t &buffer1, mp_array_t &buffer2) {
     mpres_compat::status() = mpres_ger(mpres_compat::ctx(), m, n, &alpha, &x, incx, &y, incy, &A, lda, &buffer1, &buffer2, nullptr);
+}
+
+/* src/blas/gediagscale.cuh:53-54, gelrscale.cuh:55-56, rot.cuh:48-49 */
+template <int gridDim1, int blockDim1, int gridDim2>
+void mp_ge_diag_scale(enum mblas_side_type side, const int m, const int n, mp_array_t &D, const int incd, mp_array_t &A, const int lda) {
+    mpres_compat::status() = mpres_ge_diag_scale(mpres_compat::ctx(), side, m, n, &D, incd, &A, lda, nullptr);
+}
+template <int gridDim1, int blockDim1, int gridDim2>
+void mp_ge_lr_scale(const int m, const int n, mp_array_t &DL, const int incdl, mp_array_t &DR, const int incdr, mp_array_t &A, const int lda) {
+    mpres_compat::status() = mpres_ge_lr_scale(mpres_compat::ctx(), m, n, &DL, incdl, &DR, incdr, &A, lda, nullptr);
+}
+template <int gridDim1, int blockDim1, int gridDim2>
+void mp_rot(const int n, mp_array_t &x, const int incx, mp_array_t &y, const int incy, mp_array_t &c, mp_array_t &s, mp_array_t &buffer1,
+            mp_array_t &buffer2) {
+    mpres_compat::status() = mpres_rot(mpres_compat::ctx(), n, &x, incx, &y, incy, &c, &s, &buffer1, &buffer2, nullptr);
+}
+
+
+/* src/blas/axpydot.cuh:32-33 */
+template <int gridDim1, int blockDim1, int gridDim2, int gridDim3, int blockDim3>
+void mp_axpy_dot(const int n, mp_array_t &alpha, mp_array_t &w, const int incw, mp_array_t &v, const int incv, mp_array_t &u, const int incu,
+                 mp_array_t &r, mp_array_t &buffer) {
+    mpres_compat::status() = mpres_axpy_dot(mpres_compat::ctx(), n, &alpha, &w, incw, &v, incv, &u, incu, &r, &buffer, nullptr);
 }
 
 }  // namespace cuda

@@ -42,7 +42,7 @@ EXPORTS = [
     "mpres_set_profiling", "mpres_last_stage_ms", "mpres_set_vec_config", "mpres_last_small_base", "mpres_small_modulus", "mpres_debug_read_workspace", "mpres_last_minplus_dense_count",
     "mpres_array_init", "mpres_array_clear", "mpres_array_host2device", "mpres_array_device2host",
     "mpres_collection_init", "mpres_collection_clear", "mpres_collection_host2device", "mpres_collection_device2host",
-    "mpres_array_set_binary", "mpres_gemm", "mpres_gemv", "mpres_dot", "mpres_scal", "mpres_axpy", "mpres_waxpby", "mpres_ge_add", "mpres_ge_acc", "mpres_ger", "mpres_gemm_coll", "mpres_gemv_coll",
+    "mpres_array_set_binary", "mpres_gemm", "mpres_gemv", "mpres_dot", "mpres_scal", "mpres_axpy", "mpres_waxpby", "mpres_ge_add", "mpres_ge_acc", "mpres_ger", "mpres_ge_diag_scale", "mpres_ge_lr_scale", "mpres_rot", "mpres_axpy_dot", "mpres_gemm_coll", "mpres_gemv_coll",
     "mpres_dot_coll", "mpres_dot_partial", "mpres_reduce_partials", "mpres_probe", "mpres_version",
 ]
 
@@ -319,6 +319,29 @@ def mp_ge_acc(ctx, m, n, alpha, A, lda, beta, B, ldb, buffer=None, stream=0):
 def mp_ger(ctx, m, n, alpha, x, incx, y, incy, A, lda, buffer1=None, buffer2=None, stream=0):
     """cuda::mp_ger (src/blas/ger.cuh:157): A = alpha*x*y^T + A."""
     _check(ctx.lib.mpres_ger(ctx.h, m, n, _ref(alpha), _ref(x), incx, _ref(y), incy, _ref(A), lda, _ref(buffer1), _ref(buffer2), _vp(stream)), "mpres_ger")
+
+
+LEFT_SIDE, RIGHT_SIDE = 141, 142     # mblas_side_type, src/blas/mblas_enum.cuh:37-40
+
+
+def mp_ge_diag_scale(ctx, side, m, n, D, incd, A, lda, stream=0):
+    """cuda::mp_ge_diag_scale (src/blas/gediagscale.cuh:54): A = A*D (RIGHT_SIDE) or D*A (LEFT_SIDE), D diagonal, stored as a vector."""
+    _check(ctx.lib.mpres_ge_diag_scale(ctx.h, side, m, n, _ref(D), incd, _ref(A), lda, _vp(stream)), "mpres_ge_diag_scale")
+
+
+def mp_ge_lr_scale(ctx, m, n, DL, incdl, DR, incdr, A, lda, stream=0):
+    """cuda::mp_ge_lr_scale (src/blas/gelrscale.cuh:56): A = DL*A*DR."""
+    _check(ctx.lib.mpres_ge_lr_scale(ctx.h, m, n, _ref(DL), incdl, _ref(DR), incdr, _ref(A), lda, _vp(stream)), "mpres_ge_lr_scale")
+
+
+def mp_rot(ctx, n, x, incx, y, incy, c, s, buffer1=None, buffer2=None, stream=0):
+    """cuda::mp_rot (src/blas/rot.cuh:49): x = c*x + s*y, y = c*y - s*x."""
+    _check(ctx.lib.mpres_rot(ctx.h, n, _ref(x), incx, _ref(y), incy, _ref(c), _ref(s), _ref(buffer1), _ref(buffer2), _vp(stream)), "mpres_rot")
+
+
+def mp_axpy_dot(ctx, n, alpha, w, incw, v, incv, u, incu, r, buffer=None, stream=0):
+    """cuda::mp_axpy_dot (src/blas/axpydot.cuh:33): w = w - alpha*v, r[0] = u^T w."""
+    _check(ctx.lib.mpres_axpy_dot(ctx.h, n, _ref(alpha), _ref(w), incw, _ref(v), incv, _ref(u), incu, _ref(r), _ref(buffer), _vp(stream)), "mpres_axpy_dot")
 
 
 def synchronize(ctx):

@@ -196,6 +196,105 @@ __global__ void k_ger(const DevConsts *Cp, int m, int n, SoA al, SoA x, int incx
     }
 }
 
+// w = round(w - round(alpha * v)): the first half of cuda::mp_axpy_dot (src/blas/axpydot.cuh:47-64; the difference is a sum with the
+// sign of the product inverted, src/mpvector.cuh:512), one pass
+template <int G, int R>
+__global__ void k_vec_wsub(const DevConsts *Cp, long long n, SoA s, SoA v, int incv, SoA w, int incw) {
+    const DevConsts &C = *Cp;
+    Lane<R> L;
+    lane_init<G, R>(C, L);
+    long long grp = ((long long) blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const long long ngrp = (long long) gridDim.x * blockDim.x / G;
+    Num<R> sc;
+    load_num<G, R>(C, L, s, 0, sc);
+    for (; grp < n; grp += ngrp) {
+        Num<R> a, b, t, r;
+        load_num<G, R>(C, L, v, inc_index(grp, n, incv), a);
+        const long long iw = inc_index(grp, n, incw);
+        load_num<G, R>(C, L, w, iw, b);
+        mp_mul<G, R, true>(C, L, t, a, sc);
+        t.sign ^= 1;
+        mp_add<G, R, true>(C, L, r, b, t);
+        store_num<G, R>(C, L, w, iw, r);
+    }
+}
+
+// A = round(A D) (right side: column j times d_j) or round(D A) (left side: row i times d_i): cuda::mp_ge_diag_scale
+// (src/blas/gediagscale.cuh:54-99), and, with both diagonals, A = round(round(DL A) DR): cuda::mp_ge_lr_scale
+// (src/blas/gelrscale.cuh:56-93: left product, rounding, right product, rounding); one pass over A
+template <int G, int R>
+__global__ void k_ge_diag_scale(const DevConsts *Cp, int m, int n, SoA DL, int incdl, SoA DR, int incdr, bool left, bool right, SoA A, int lda) {
+    const DevConsts &C = *Cp;
+    Lane<R> L;
+    lane_init<G, R>(C, L);
+    long long grp = ((long long) blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const long long ngrp = (long long) gridDim.x * blockDim.x / G, total = (long long) m * n;
+    for (; grp < total; grp += ngrp) {
+        const long long i = grp % m, j = grp / m;
+        Num<R> a, d, t;
+        load_num<G, R>(C, L, A, i + j * lda, a);
+        if (left) {
+            load_num<G, R>(C, L, DL, inc_index(i, m, incdl), d);
+            mp_mul<G, R, true>(C, L, t, a, d);
+            a = t;
+        }
+        if (right) {
+            load_num<G, R>(C, L, DR, inc_index(j, n, incdr), d);
+            mp_mul<G, R, true>(C, L, t, a, d);
+            a = t;
+        }
+        store_num<G, R>(C, L, A, i + j * lda, a);
+    }
+}
+
+// Givens rotation, x = round(round(c x) + round(s y)), y = round(round(c y) - round(s x)): cuda::mp_rot (src/blas/rot.cuh:49-100:
+// s x and s y into the buffers, mp_scal by c, sum / difference (the difference is a sum with the sign of s x inverted,
+// src/mpvector.cuh:512), final rounding); unit increments, one pass, no buffers
+template <int G, int R>
+__global__ void k_vec_rot(const DevConsts *Cp, long long n, SoA x, SoA y, SoA c, SoA s) {
+    const DevConsts &C = *Cp;
+    Lane<R> L;
+    lane_init<G, R>(C, L);
+    long long grp = ((long long) blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const long long ngrp = (long long) gridDim.x * blockDim.x / G;
+    Num<R> cc, ss;
+    load_num<G, R>(C, L, c, 0, cc);
+    load_num<G, R>(C, L, s, 0, ss);
+    for (; grp < n; grp += ngrp) {
+        Num<R> a, b, sx, sy, cx, cy, r;
+        load_num<G, R>(C, L, x, grp, a);
+        load_num<G, R>(C, L, y, grp, b);
+        mp_mul<G, R, true>(C, L, sx, a, ss);
+        mp_mul<G, R, true>(C, L, sy, b, ss);
+        mp_mul<G, R, true>(C, L, cx, a, cc);
+        mp_mul<G, R, true>(C, L, cy, b, cc);
+        mp_add<G, R, true>(C, L, r, cx, sy);
+        store_num<G, R>(C, L, x, grp, r);
+        sx.sign ^= 1;
+        mp_add<G, R, true>(C, L, r, cy, sx);
+        store_num<G, R>(C, L, y, grp, r);
+    }
+}
+
+// r = round(x + y) or round(x - y), strided: the last two steps of cuda::mp_rot with general increments
+template <int G, int R>
+__global__ void k_vec_addsub(const DevConsts *Cp, long long n, SoA x, int incx, SoA y, int incy, bool sub) {
+    const DevConsts &C = *Cp;
+    Lane<R> L;
+    lane_init<G, R>(C, L);
+    long long grp = ((long long) blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const long long ngrp = (long long) gridDim.x * blockDim.x / G;
+    for (; grp < n; grp += ngrp) {
+        Num<R> a, b, r;
+        const long long ix = inc_index(grp, n, incx);
+        load_num<G, R>(C, L, x, ix, a);
+        load_num<G, R>(C, L, y, inc_index(grp, n, incy), b);
+        if (sub) b.sign ^= 1;
+        mp_add<G, R, true>(C, L, r, a, b);
+        store_num<G, R>(C, L, x, ix, r);
+    }
+}
+
 // ---- GEMV, reference order: y[o] = y[o] + sum_q op(A)(o, q) * ax[q]  (src/blas/gemv.cuh:199-218) ----
 // y already holds round(beta * y) and ax = round(alpha * x).  One group per output element.
 template <int G, int R>

@@ -692,6 +692,71 @@ int mpres_ger(mpres_ctx *c, int m, int n, const mpres_array_t *alpha, const mpre
     return 0;
 }
 
+static int ge_scale_impl(mpres_ctx *c, int m, int n, const mpres_array_t *DL, int incdl, const mpres_array_t *DR, int incdr, mpres_array_t *A, int lda,
+                         cudaStream_t st) {
+    DeviceGuard g(c->device);
+    const bool left = DL != nullptr, right = DR != nullptr;
+    MPRES_DISPATCH(c->hc.N, {
+        const int block = 128;
+        const unsigned nb = (unsigned) std::min<long long>(((long long) m * n * G + block - 1) / block, (long long) c->sm_count * 32);
+        k_ge_diag_scale<G, R><<<nb, block, 0, st>>>(c->dconsts, m, n, left ? view(DL) : view(A), incdl, right ? view(DR) : view(A), incdr, left, right,
+                                                    view(A), lda);
+    });
+    LAUNCHED(c);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int mpres_ge_diag_scale(mpres_ctx *c, int side, int m, int n, const mpres_array_t *D, int incd, mpres_array_t *A, int lda, mpres_stream_t stream) {
+    NEED_DEVICE(c);
+    if (!c || !D || !A) return -1;
+    if (side != MPRES_LEFT_SIDE && side != MPRES_RIGHT_SIDE) return -3;
+    if (m <= 0 || n <= 0) return 0;                         // src/blas/gediagscale.cuh:57-59
+    if (incd == 0 || lda < std::max(1, m)) return -3;       // :61-63 (the reference returns silently)
+    const bool left = side == MPRES_LEFT_SIDE;
+    return ge_scale_impl(c, m, n, left ? D : nullptr, incd, left ? nullptr : D, incd, A, lda, (cudaStream_t) stream);
+}
+
+int mpres_ge_lr_scale(mpres_ctx *c, int m, int n, const mpres_array_t *DL, int incdl, const mpres_array_t *DR, int incdr, mpres_array_t *A, int lda,
+                      mpres_stream_t stream) {
+    NEED_DEVICE(c);
+    if (!c || !DL || !DR || !A) return -1;
+    if (m <= 0 || n <= 0) return 0;                         // src/blas/gelrscale.cuh:59-61
+    if (incdl == 0 || incdr == 0 || lda < std::max(1, m)) return -3;
+    return ge_scale_impl(c, m, n, DL, incdl, DR, incdr, A, lda, (cudaStream_t) stream);
+}
+
+int mpres_rot(mpres_ctx *c, int n, mpres_array_t *x, int incx, mpres_array_t *y, int incy, const mpres_array_t *cs, const mpres_array_t *sn,
+              mpres_array_t *buffer1, mpres_array_t *buffer2, mpres_stream_t stream) {
+    NEED_DEVICE(c);
+    if (!c || !x || !y || !cs || !sn) return -1;
+    if (n <= 0) return 0;                                   // src/blas/rot.cuh:52-54
+    if (incx == 0 || incy == 0) return -3;
+    const bool unit = incx == 1 && incy == 1;
+    if (!unit && (!buffer1 || !buffer2)) return -1;
+    DeviceGuard g(c->device);
+    cudaStream_t st = (cudaStream_t) stream;
+    MPRES_DISPATCH(c->hc.N, {
+        const int block = 128;
+        const unsigned nb = (unsigned) std::min<long long>(((long long) n * G + block - 1) / block, (long long) c->sm_count * 32);
+        if (unit) {
+            k_vec_rot<G, R><<<nb, block, 0, st>>>(c->dconsts, n, view(x), view(y), view(cs), view(sn));
+        } else {
+            // the reference's sequence, step for step -- including its mp_scal(n, c, x, 1) calls, which scale the first n
+            // CONTIGUOUS elements whatever incx is (src/blas/rot.cuh:79-82)
+            k_vec_scale<G, R><<<nb, block, 0, st>>>(c->dconsts, n, view(buffer1), 1, view(x), incx, view(sn));
+            k_vec_scale<G, R><<<nb, block, 0, st>>>(c->dconsts, n, view(buffer2), 1, view(y), incy, view(sn));
+            k_vec_scale<G, R><<<nb, block, 0, st>>>(c->dconsts, n, view(x), 1, view(x), 1, view(cs));
+            k_vec_scale<G, R><<<nb, block, 0, st>>>(c->dconsts, n, view(y), 1, view(y), 1, view(cs));
+            k_vec_addsub<G, R><<<nb, block, 0, st>>>(c->dconsts, n, view(x), incx, view(buffer2), 1, false);
+            k_vec_addsub<G, R><<<nb, block, 0, st>>>(c->dconsts, n, view(y), incy, view(buffer1), 1, true);
+        }
+    });
+    if (unit) { LAUNCHED(c); } else { for (int i = 0; i < 6; ++i) LAUNCHED(c); }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 /* ---- DOT ------------------------------------------------------------------------------------------- */
 
 // partial (device AoS record) := sum x_i * y_i
@@ -747,6 +812,25 @@ int mpres_dot_coll(mpres_ctx *c, int n, const mpres_collection_t *x, int incx, s
     std::lock_guard<std::mutex> lk(c->mu);
     c->last_stream = (cudaStream_t) stream;
     return dot_to_record(c, n, view(x, lenx), incx, view(y, leny), incy, nullptr, view(r, 1), (cudaStream_t) stream);
+}
+int mpres_axpy_dot(mpres_ctx *c, int n, const mpres_array_t *alpha, mpres_array_t *w, int incw, const mpres_array_t *v, int incv,
+                   const mpres_array_t *u, int incu, mpres_array_t *r, mpres_array_t *buffer, mpres_stream_t stream) {
+    NEED_DEVICE(c);
+    if (!c || !alpha || !w || !v || !u || !r) return -1;
+    if (n <= 0) return 0;                   // src/blas/axpydot.cuh:36-38
+    if (incw == 0 || incv == 0 || incu == 0) return -3;
+    {
+        DeviceGuard g(c->device);
+        cudaStream_t st = (cudaStream_t) stream;
+        MPRES_DISPATCH(c->hc.N, {
+            const int block = 128;
+            const unsigned nb = (unsigned) std::min<long long>(((long long) n * G + block - 1) / block, (long long) c->sm_count * 32);
+            k_vec_wsub<G, R><<<nb, block, 0, st>>>(c->dconsts, n, view(alpha), view(v), incv, view(w), incw);
+        });
+        LAUNCHED(c);
+        CUDA_TRY(cudaGetLastError());
+    }
+    return mpres_dot(c, n, u, incu, w, incw, r, buffer, stream);      // src/blas/axpydot.cuh:67
 }
 int mpres_dot_partial(mpres_ctx *c, int n, const mpres_array_t *x, int incx, const mpres_array_t *y, int incy, void *partial,
                       mpres_stream_t stream) {

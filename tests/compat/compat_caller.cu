@@ -41,6 +41,9 @@ int main(int argc, char **argv) {
     fclose(f);
     cuda::mp_scal<128, 64, 128>(k, dal, dx, 1);                        /* the level-1 entry points build through the shim too */
     cuda::mp_axpy<128, 64, 128>(k, dal, dx, 1, dy, 1, dbuf2);
+    cuda::mp_rot<128, 64, 128>(k, dx, 1, dy, 1, dal, dbe, dbuf2, dbuf2);
+    cuda::mp_ge_diag_scale<128, 64, 128>(mblas_right_side, m, n, dy, 1, dC, m);     /* n <= k elements of y as the diagonal */
+    cuda::mp_ge_lr_scale<128, 64, 128>(m, n, dx, 1, dy, 1, dC, m);
     if (mpres_compat_last_status() != 0) return 9;
     cuda::mp_array_clear(dA); cuda::mp_array_clear(dB); cuda::mp_array_clear(dC);
     printf("MP_PRECISION %d MP_H %d\n", MP_PRECISION, MP_H);

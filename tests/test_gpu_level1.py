@@ -1,4 +1,5 @@
-"""mp_scal and mp_axpy through the C-ABI against the C oracle's mp_mul / mp_add (the DEVICE flavour, itself pinned
+"""The level-1 / elementwise operations (mp_scal, mp_axpy, mp_waxpby, mp_axpy_dot, mp_rot, mp_ge_add, mp_ge_acc, mp_ger,
+mp_ge_diag_scale, mp_ge_lr_scale) through the C-ABI against the C oracle's mp_mul / mp_add (the DEVICE flavour, itself pinned
 against the reference's cuda:: functions): digits, sign and exponent bit for bit, with roundings (p-bit inputs), BLAS strides and the
 silent-return cases of src/blas/scal.cuh:47-49 and src/blas/axpy.cuh:49-51."""
 import numpy as np
@@ -152,4 +153,126 @@ def test_ge_add_ge_acc_ger(pkg, N, full):
     dA2 = ctx.mp_array_from_host(A)
     pkg.mp_ger(ctx, m, n, dal, ctx.mp_array_from_host(x), 1, ctx.mp_array_from_host(y), incy, dA2, lda)
     assert diff_fields(sub(dA2.device2host(), lda), want_A, ("digits", "sign", "exp")).size == 0
+    ctx.close()
+
+
+@pytest.mark.parametrize("N,full,incd", [(8, False, 1), (8, True, -1), (32, True, 2), (16, True, 1)])
+def test_ge_diag_scale_lr_scale(pkg, N, full, incd):
+    """cuda::mp_ge_diag_scale (both sides) and cuda::mp_ge_lr_scale against the oracle's mp_mul, entry by entry (row i times d_i / column j
+    times d_j, rounded after every product: src/blas/gediagscale.cuh:75-98, gelrscale.cuh:75-92)"""
+    ctx = pkg.Context(N, 0)
+    orc = get_oracle(N, oracle.DEVICE)
+    bits = orc.precision if full else orc.precision // 4
+    m, n, lda = 37, 21, 40
+    A = random_records(N, lda * n, bits, 61)
+    DL = random_records(N, m * abs(incd), bits, 62)
+    DR = random_records(N, n * abs(incd), bits, 63)
+    il, ir = _blas_view(m, incd), _blas_view(n, incd)
+    zero = orc.set_ints([0], [0], [0])[0]
+    DL[il[3]] = zero
+    A[5 + 2 * lda] = zero
+    rows = np.array([i + j * lda for j in range(n) for i in range(m)])
+    dl_e = DL[[il[i] for j in range(n) for i in range(m)]]
+    dr_e = DR[[ir[j] for j in range(n) for i in range(m)]]
+    dDL, dDR = ctx.mp_array_from_host(DL), ctx.mp_array_from_host(DR)
+    # left
+    dA = ctx.mp_array_from_host(A)
+    pkg.mp_ge_diag_scale(ctx, pkg.LEFT_SIDE, m, n, dDL, incd, dA, lda)
+    want = A.copy(); want[rows] = orc.mul(A[rows], dl_e)
+    got_l = dA.device2host()
+    assert diff_fields(got_l, want, ("digits", "sign", "exp")).size == 0
+    # right
+    dA = ctx.mp_array_from_host(A)
+    pkg.mp_ge_diag_scale(ctx, pkg.RIGHT_SIDE, m, n, dDR, incd, dA, lda)
+    want = A.copy(); want[rows] = orc.mul(A[rows], dr_e)
+    assert diff_fields(dA.device2host(), want, ("digits", "sign", "exp")).size == 0
+    # both
+    dA = ctx.mp_array_from_host(A)
+    pkg.mp_ge_lr_scale(ctx, m, n, dDL, incd, dDR, incd, dA, lda)
+    want = A.copy(); want[rows] = orc.mul(orc.mul(A[rows], dl_e), dr_e)
+    got = dA.device2host()
+    bad = diff_fields(got, want, ("digits", "sign", "exp"))
+    assert bad.size == 0, "%d differ, first %d" % (bad.size, bad[0])
+    # the padding rows of A (m <= i < lda) are never touched
+    pad = np.array([i + j * lda for j in range(n) for i in range(m, lda)])
+    assert diff_fields(got[pad], A[pad]).size == 0
+    # silent returns of the reference: nothing is written
+    pkg.mp_ge_lr_scale(ctx, 0, n, dDL, incd, dDR, incd, dA, lda)
+    pkg.mp_ge_diag_scale(ctx, pkg.LEFT_SIDE, m, 0, dDL, incd, dA, lda)
+    with pytest.raises(Exception):
+        pkg.mp_ge_diag_scale(ctx, pkg.LEFT_SIDE, m, n, dDL, 0, dA, lda)
+    with pytest.raises(Exception):
+        pkg.mp_ge_lr_scale(ctx, m, n, dDL, incd, dDR, incd, dA, m - 1)
+    assert diff_fields(dA.device2host(), got).size == 0
+    ctx.close()
+
+
+@pytest.mark.parametrize("N,full,incx,incy", [(8, False, 1, 1), (8, True, 1, 1), (32, True, 1, 1), (16, True, 2, -1), (24, True, -1, 3)])
+def test_rot(pkg, N, full, incx, incy):
+    """cuda::mp_rot against the oracle: x = round(round(c x) + round(s y)), y = round(round(c y) - round(s x)) (src/blas/rot.cuh:60-99).  With
+    non-unit increments the reference scales the first n contiguous elements by c (its mp_scal(n, c, x, 1) calls) -- reproduced as is."""
+    ctx = pkg.Context(N, 0)
+    orc = get_oracle(N, oracle.DEVICE)
+    bits = orc.precision if full else orc.precision // 4
+    n = 211
+    x = random_records(N, n * abs(incx), bits, 71)
+    y = random_records(N, n * abs(incy), bits, 72)
+    c, s = random_records(N, 1, bits, 73), random_records(N, 1, bits, 74)
+    ix, iy = _blas_view(n, incx), _blas_view(n, incy)
+    zero = orc.set_ints([0], [0], [0])[0]
+    x[ix[4]] = zero
+    y[iy[6]] = zero
+    x[ix[8]] = zero; y[iy[8]] = zero
+    cn, sn = np.repeat(c, n), np.repeat(s, n)
+    b1, b2 = orc.mul(x[ix], sn), orc.mul(y[iy], sn)
+    wx, wy = x.copy(), y.copy()
+    wx[:n] = orc.mul(x[:n], cn)
+    wy[:n] = orc.mul(y[:n], cn)
+    nb1 = b1.copy(); nb1["sign"] ^= 1
+    wx[ix] = orc.add(wx[ix], b2)
+    wy[iy] = orc.add(wy[iy], nb1)
+    dx, dy, dc, ds = ctx.mp_array_from_host(x), ctx.mp_array_from_host(y), ctx.mp_array_from_host(c), ctx.mp_array_from_host(s)
+    buf1 = buf2 = None
+    if incx != 1 or incy != 1:
+        buf1, buf2 = ctx.mp_array_from_host(random_records(N, n, bits, 75)), ctx.mp_array_from_host(random_records(N, n, bits, 76))
+    pkg.mp_rot(ctx, n, dx, incx, dy, incy, dc, ds, buf1, buf2)
+    gx, gy = dx.device2host(), dy.device2host()
+    bad = diff_fields(gx, wx, ("digits", "sign", "exp"))
+    assert bad.size == 0, "x: %d differ, first %d\n%s\n%s" % (bad.size, bad[0], gx[bad[0]], wx[bad[0]])
+    bad = diff_fields(gy, wy, ("digits", "sign", "exp"))
+    assert bad.size == 0, "y: %d differ, first %d\n%s\n%s" % (bad.size, bad[0], gy[bad[0]], wy[bad[0]])
+    pkg.mp_rot(ctx, 0, dx, incx, dy, incy, dc, ds, buf1, buf2)
+    assert diff_fields(dx.device2host(), gx).size == 0
+    ctx.close()
+
+
+@pytest.mark.parametrize("N,incw,incv,incu", [(8, 1, 1, 1), (32, 1, 1, 1), (16, 2, -1, 3)])
+def test_axpy_dot(pkg, N, incw, incv, incu):
+    """cuda::mp_axpy_dot: w = round(w - round(alpha v)) record for record against the oracle, then r = u^T w (p/8-bit w, v, alpha and
+    p/4-bit u: neither the products nor the sums round, so every summation order gives the oracle's sequential dot product)"""
+    ctx = pkg.Context(N, 0)
+    orc = get_oracle(N, oracle.DEVICE)
+    bits = orc.precision // 8
+    n = 1500
+    w = random_records(N, n * abs(incw), bits, 81)
+    v = random_records(N, n * abs(incv), bits, 82)
+    u = random_records(N, n * abs(incu), 2 * bits, 83)
+    al = random_records(N, 1, bits, 84)
+    iw, iv, iu = _blas_view(n, incw), _blas_view(n, incv), _blas_view(n, incu)
+    prod = orc.mul(v[iv], np.repeat(al, n))
+    w[iw[3]] = prod[3]                       # exact cancellation
+    prod["sign"] ^= 1
+    want_w = w.copy()
+    want_w[iw] = orc.add(w[iw], prod)
+    assert orc.to_fraction(want_w[iw[3]]) == 0
+    want_r = orc.dot_seq(u[iu], want_w[iw])
+    dw, dv, du, dal, dr = (ctx.mp_array_from_host(w), ctx.mp_array_from_host(v), ctx.mp_array_from_host(u), ctx.mp_array_from_host(al),
+                           ctx.mp_array_init(1))
+    pkg.mp_axpy_dot(ctx, n, dal, dw, incw, dv, incv, du, incu, dr)
+    got_w, got_r = dw.device2host(), dr.device2host()
+    bad = diff_fields(got_w, want_w, ("digits", "sign", "exp"))
+    assert bad.size == 0, "w: %d differ, first %d" % (bad.size, bad[0])
+    assert diff_fields(got_r, np.array([want_r]), ("digits", "sign", "exp")).size == 0
+    pkg.mp_axpy_dot(ctx, 0, dal, dw, incw, dv, incv, du, incu, dr)
+    assert diff_fields(dw.device2host(), got_w).size == 0
     ctx.close()
