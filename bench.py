@@ -367,6 +367,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-path", choices=["pipelined", "sequential"], default="pipelined",
+                    help="GEMM end-to-end leg: mpres_gemm_host (one call, transfers overlapped) or the reference caller's call-by-call sequence")
+    ap.add_argument("--e2e-panels", type=int, default=0, help="column panels of mpres_gemm_host (0 = the library's choice)")
     args = ap.parse_args()
     if args.impl == "reference":
         # torchrun pins OMP_NUM_THREADS to 1; the CPU arm is meant to use every host core (set before any OpenMP runtime loads)
@@ -579,6 +582,11 @@ def main():
         alpha.device2host_ptr(hal.data_ptr(), 1); beta.device2host_ptr(hbe.data_ptr(), 1)
 
         def e2e_step():
+            if args.e2e_path == "pipelined":
+                # one call over the host buffers: uploads, compute and download overlapped by column panels (mpres_gemm_host)
+                pkg.mp_gemm_host(ctx, pkg.mblas_no_trans, pkg.mblas_no_trans, mr, n, k, hal, hA, mr, hB, k, hbe, hC, mr, out=hOut, panels=args.e2e_panels)
+                return
+            # the reference caller's sequence, call by call (tests/blas/test_gemm.cu)
             A.host2device_ptr(hA.data_ptr(), mr * k)
             B.host2device_ptr(hB.data_ptr(), k * n)
             C.host2device_ptr(hC.data_ptr(), mr * n)
@@ -600,7 +608,9 @@ def main():
         d2h = mr * n * rs
         e2e = {"value": 2.0 * m * n * k / dt / 1e9, "unit": "MP-GFLOP/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                "ms_per_step": dt * 1e3, "steps": args.e2e_steps,
-               "path": "mpres_array_host2device(A,B,C,alpha,beta) + mpres_gemm + mpres_array_device2host(C), pinned host AoS mp_float_t[]"}
+               "path": ("mpres_gemm_host(alpha, A, B, beta, C -> out): pinned host AoS mp_float_t[], PCIe transfers pipelined with the compute by column panels"
+                        if args.e2e_path == "pipelined" else
+                        "mpres_array_host2device(A,B,C,alpha,beta) + mpres_gemm + mpres_array_device2host(C), pinned host AoS mp_float_t[]")}
 
     if rank != 0:
         if dist is not None:

@@ -238,6 +238,16 @@ int mpres_rot(mpres_ctx *ctx, int n, mpres_array_t *x, int incx, mpres_array_t *
 int mpres_axpy_dot(mpres_ctx *ctx, int n, const mpres_array_t *alpha, mpres_array_t *w, int incw, const mpres_array_t *v, int incv,
                    const mpres_array_t *u, int incu, mpres_array_t *r, mpres_array_t *buffer, mpres_stream_t stream);
 
+/* mp_gemm over HOST operands: the reference caller's mp_array_host2device x 3 + cuda::mp_gemm + mp_array_device2host sequence
+ * (tests/blas/test_gemm.cu) as ONE call that pipelines the PCIe transfers with the compute by column panels of B and C (both bus
+ * directions busy at once; the device arrays live in the context's workspace).  alpha, beta: one mp_float_t record each; A, B, Cin,
+ * Cout: column-major AoS mp_float_t[] with the leading dimensions of mpres_gemm (Cout may alias Cin; rows m..ldc-1 of Cout receive
+ * Cin's records).  Pinned host memory (cudaHostAlloc / cudaHostRegister) is needed for the overlap, pageable memory works unpipelined.
+ * panels = 0 picks the panel count (<= 8, whole multiples of 256 columns); transposed B runs as one panel.  Synchronous: the result
+ * is in Cout on return.  The fallback / base counters afterwards describe the last panel. */
+int mpres_gemm_host(mpres_ctx *ctx, int transa, int transb, int m, int n, int k, const void *alpha, const void *A, int lda, const void *B, int ldb,
+                    const void *beta, const void *Cin, void *Cout, int ldc, int panels);
+
 /* The same three operations over mp_collection_t operands with explicit allocated lengths (the
  * reference only uses mp_collection_t in its sparse kernels, src/sparse/mpmtx/*.cuh; north_star asks
  * for the dense path over both containers). */

@@ -60,8 +60,12 @@ struct mpres_ctx {
     int *d_pow2 = nullptr, *d_inv_pow2 = nullptr, *d_mrc = nullptr, *d_prefix = nullptr, *d_ext_w = nullptr, *d_ext_t = nullptr, *d_wpow2 = nullptr, *d_spow2 = nullptr;
     std::atomic<long> launches{0};
     // workspace pool (grown on demand, never freed per call)
-    void *ws[12] = {nullptr};
-    size_t ws_size[12] = {0};
+    void *ws[18] = {nullptr};            // 12..17: device operands and staging rings of mpres_gemm_host
+    size_t ws_size[18] = {0};
+    cudaStream_t hs[4] = {nullptr};      // mpres_gemm_host: upload, unpack, compute, download
+    cudaEvent_t hev[16] = {nullptr};
+    bool host_ready = false;
+    std::mutex host_mu;
     int *d_counter = nullptr;      // fallback element counter of the last call
     cudaStream_t last_stream = nullptr;
     int sm_count = 148;

@@ -135,7 +135,9 @@ int mpres_finalize(mpres_ctx *c) {
     if (c->device < 0) { delete c; return 0; }
     DeviceGuard g(c->device);
     cudaDeviceSynchronize();
-    for (int i = 0; i < 12; ++i) if (c->ws[i]) cudaFree(c->ws[i]);
+    for (int i = 0; i < 18; ++i) if (c->ws[i]) cudaFree(c->ws[i]);
+    for (int i = 0; i < 4; ++i) if (c->hs[i]) cudaStreamDestroy(c->hs[i]);
+    for (int i = 0; i < 16; ++i) if (c->hev[i]) cudaEventDestroy(c->hev[i]);
     for (int i = 0; i < 8; ++i) if (c->d_small[i]) cudaFree(c->d_small[i]);
     cudaFree(c->d_pow2); cudaFree(c->d_inv_pow2); cudaFree(c->d_mrc); cudaFree(c->d_prefix); cudaFree(c->d_ext_w); cudaFree(c->d_ext_t); cudaFree(c->d_wpow2); cudaFree(c->d_spow2); cudaFree(c->dconsts); cudaFree(c->d_counter);
     delete c;
@@ -520,6 +522,132 @@ int mpres_gemm(mpres_ctx *c, int transa, int transb, int m, int n, int k, const 
     return gemm_impl(c, transa, transb, m, n, k, view(alpha), view(A), lda, view(B), ldb, view(beta), view(Cm), ldc,
                      (buffer && buffer->digits) ? &buf : nullptr, (cudaStream_t) stream);
 }
+/* ---- GEMM over HOST operands: upload, compute and download pipelined by column panels ------------------------------
+ * The reference's caller does mp_array_host2device x 3, mp_gemm, mp_array_device2host (tests/blas/test_gemm.cu); over PCIe the
+ * copies are 20 x the compute, so the end-to-end rate is the bus rate.  Here C is cut into column panels: while panel j is
+ * computed and its result travels back, panels j+1.. of B and C travel up -- the two PCIe directions run at the same time
+ * and the device never waits for more than one panel. */
+
+namespace {
+
+constexpr int kHostRing = 3;
+struct HostPipe {
+    mpres_ctx *c;
+    size_t rs, chunk;           // record size, records per staging chunk
+    char *up_stage;             // kHostRing chunks
+    int seq = 0;
+    cudaStream_t s_up, s_unp, s_comp, s_down;
+};
+
+// records [off, off + cnt) of a host AoS array into the same positions of a device SoA (asynchronous: s_up copies, s_unp unpacks)
+int host_upload(HostPipe &hp, const void *host, size_t off, size_t cnt, const SoA &dst) {
+    mpres_ctx *c = hp.c;
+    const int N = c->hc.N;
+    while (cnt) {
+        const size_t now = std::min(cnt, hp.chunk);
+        const int slot = hp.seq % kHostRing;
+        cudaEvent_t done = c->hev[slot], freed = c->hev[kHostRing + slot];
+        char *stage = hp.up_stage + (size_t) slot * hp.chunk * hp.rs;
+        CUDA_TRY(cudaStreamWaitEvent(hp.s_up, freed, 0));
+        CUDA_TRY(cudaMemcpyAsync(stage, (const char *) host + off * hp.rs, now * hp.rs, cudaMemcpyHostToDevice, hp.s_up));
+        CUDA_TRY(cudaEventRecord(done, hp.s_up));
+        CUDA_TRY(cudaStreamWaitEvent(hp.s_unp, done, 0));
+        k_aos_to_soa<<<c->sm_count * 4, 256, 0, hp.s_unp>>>(N, stage, (long long) now, dst.digits + off * N, dst.sign + off, dst.exp + off, dst.eval + off,
+                                                            dst.len_val);
+        LAUNCHED(c);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaEventRecord(freed, hp.s_unp));
+        ++hp.seq;
+        off += now; cnt -= now;
+    }
+    return 0;
+}
+
+SoA soa_offset(const SoA &a, size_t off, int N) {
+    SoA v = a;
+    v.digits += off * N; v.sign += off; v.exp += off; v.eval += off;      // len_val (the offset of the upper bounds) is unchanged
+    return v;
+}
+
+}  // namespace
+
+int mpres_gemm_host(mpres_ctx *c, int transa, int transb, int m, int n, int k, const void *alpha, const void *A, int lda, const void *B, int ldb,
+                    const void *beta, const void *Cin, void *Cout, int ldc, int panels) {
+    NEED_DEVICE(c);
+    if (!c || !alpha || !A || !B || !beta || !Cin || !Cout) return -1;
+    if (m <= 0 || n <= 0 || k <= 0) return 0;                       // src/blas/gemm.cuh:75-78
+    const bool ta = transa != MPRES_NO_TRANS, tb = transb != MPRES_NO_TRANS;
+    if (transa != MPRES_NO_TRANS && transa != MPRES_TRANS && transa != MPRES_CONJ_TRANS) return -2;
+    if (transb != MPRES_NO_TRANS && transb != MPRES_TRANS && transb != MPRES_CONJ_TRANS) return -2;
+    if (lda < std::max(1, ta ? k : m)) return -3;
+    if (ldb < std::max(1, tb ? n : k)) return -4;
+    if (ldc < std::max(1, m)) return -5;
+    DeviceGuard g(c->device);
+    std::lock_guard<std::mutex> hl(c->host_mu);
+    const int N = c->hc.N;
+    if (!c->host_ready) {
+        for (int i = 0; i < 4; ++i) CUDA_TRY(cudaStreamCreateWithFlags(&c->hs[i], cudaStreamNonBlocking));
+        for (int i = 0; i < 16; ++i) CUDA_TRY(cudaEventCreateWithFlags(&c->hev[i], cudaEventDisableTiming));
+        c->host_ready = true;
+    }
+    // panels: whole columns of B and C are contiguous only when B is not transposed
+    int np = panels;
+    if (np <= 0) { const int w = ((n + 7) / 8 + 255) / 256 * 256; np = (n + w - 1) / w; }
+    if (tb) np = 1;
+    np = std::max(1, std::min(np, n));
+    const int wcols = (n + np - 1) / np;
+    np = (n + wcols - 1) / wcols;
+
+    const size_t extA = (size_t) lda * ((ta ? m : k) - 1) + (ta ? k : m), lenA = (size_t) lda * (ta ? m : k);
+    const size_t extB = (size_t) ldb * ((tb ? k : n) - 1) + (tb ? n : k), lenB = (size_t) ldb * (tb ? k : n);
+    const size_t lenC = (size_t) ldc * n;
+    HostPipe hp;
+    hp.c = c; hp.rs = 4 * (size_t) N + 40;
+    hp.chunk = std::max<size_t>(1, ((size_t) 64 << 20) / hp.rs);
+    hp.s_up = c->hs[0]; hp.s_unp = c->hs[1]; hp.s_comp = c->hs[2]; hp.s_down = c->hs[3];
+    SoA dA, dB, dC, dS;
+    int rc;
+    void *p;
+    // (a growing workspace frees and reallocates: cudaFree synchronises, no transfer of an earlier call is in flight here anyway)
+    if ((rc = ws_soa(c, 12, lenA, &dA)) || (rc = ws_soa(c, 13, lenB, &dB)) || (rc = ws_soa(c, 14, lenC, &dC)) || (rc = ws_soa(c, 17, 2, &dS))) return rc;
+    if ((rc = ws_reserve(c, 15, (size_t) kHostRing * hp.chunk * hp.rs, &p))) return rc;
+    hp.up_stage = (char *) p;
+    const size_t panel_recs = (size_t) ldc * wcols;
+    if ((rc = ws_reserve(c, 16, 2 * panel_recs * hp.rs, &p))) return rc;
+    char *down_stage = (char *) p;
+    cudaEvent_t ev_ready = c->hev[6], ev_packed = c->hev[7], ev_dfree[2] = {c->hev[8], c->hev[9]};
+
+    if ((rc = host_upload(hp, alpha, 0, 1, dS))) return rc;
+    { SoA b1 = soa_offset(dS, 1, N); if ((rc = host_upload(hp, beta, 0, 1, b1))) return rc; }
+    if ((rc = host_upload(hp, A, 0, extA, dA))) return rc;
+    if (tb && (rc = host_upload(hp, B, 0, extB, dB))) return rc;
+    for (int j = 0; j < np; ++j) {
+        const int j0 = j * wcols, nj = std::min(wcols, n - j0);
+        if (!tb && (rc = host_upload(hp, B, (size_t) ldb * j0, (size_t) ldb * (nj - 1) + k, dB))) return rc;
+        const size_t coff = (size_t) ldc * j0, ccnt = (size_t) ldc * (nj - 1) + m;
+        if ((rc = host_upload(hp, Cin, coff, ccnt, dC))) return rc;
+        CUDA_TRY(cudaEventRecord(ev_ready, hp.s_unp));
+        CUDA_TRY(cudaStreamWaitEvent(hp.s_comp, ev_ready, 0));
+        rc = gemm_impl(c, transa, transb, m, nj, k, dS, dA, lda, tb ? dB : soa_offset(dB, (size_t) ldb * j0, N), ldb, soa_offset(dS, 1, N),
+                       soa_offset(dC, coff, N), ldc, nullptr, hp.s_comp);
+        if (rc) { cudaDeviceSynchronize(); return rc; }
+        char *stage = down_stage + (size_t) (j & 1) * panel_recs * hp.rs;
+        CUDA_TRY(cudaStreamWaitEvent(hp.s_comp, ev_dfree[j & 1], 0));
+        k_soa_to_aos<<<c->sm_count * 4, 256, 0, hp.s_comp>>>(N, stage, (long long) ccnt, dC.digits + coff * N, dC.sign + coff, dC.exp + coff, dC.eval + coff,
+                                                             dC.len_val);
+        LAUNCHED(c);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaEventRecord(ev_packed, hp.s_comp));
+        CUDA_TRY(cudaStreamWaitEvent(hp.s_down, ev_packed, 0));
+        CUDA_TRY(cudaMemcpyAsync((char *) Cout + coff * hp.rs, stage, ccnt * hp.rs, cudaMemcpyDeviceToHost, hp.s_down));
+        CUDA_TRY(cudaEventRecord(ev_dfree[j & 1], hp.s_down));
+    }
+    CUDA_TRY(cudaStreamSynchronize(hp.s_down));
+    CUDA_TRY(cudaStreamSynchronize(hp.s_comp));
+    CUDA_TRY(cudaStreamSynchronize(hp.s_unp));
+    return 0;
+}
+
 int mpres_gemm_coll(mpres_ctx *c, int transa, int transb, int m, int n, int k, const mpres_collection_t *alpha,
                     const mpres_collection_t *A, int lda, size_t lenA, const mpres_collection_t *B, int ldb, size_t lenB,
                     const mpres_collection_t *beta, mpres_collection_t *Cm, int ldc, size_t lenC, mpres_stream_t stream) {
