@@ -359,7 +359,7 @@ def main():
     ap.add_argument("--workload", default="gemm4096_424bit", choices=sorted(WORKLOADS) + sorted(VEC_WORKLOADS))
     ap.add_argument("--mode", default="auto", choices=["auto", "reference_order", "fast"])
     ap.add_argument("--stage2", default="small", choices=["small", "small_t128", "small_k64", "small_tiled", "umma", "umma_unstacked", "mma_sync"], help="stage-2 kernel (A/B measurement)")
-    ap.add_argument("--stage3", type=int, default=0, choices=[0, 1, 2, 3], help="stage-3 kernel variant (mpres_set_stage3_kernel; A/B measurement)")
+    ap.add_argument("--stage3", type=int, default=0, choices=[0, 1, 2, 3, 4], help="stage-3 kernel variant (mpres_set_stage3_kernel; A/B measurement)")
     ap.add_argument("--bcast", default="lean", choices=["lean", "full"], help="N > 1: what the per-step broadcast of B moves (lean: the fields the small-base path reads, verified on the device; full: all four SoA arrays)")
     ap.add_argument("--prefetch", action="store_true", help="N > 1, lean broadcast: issue the next step's broadcast of B on a second stream behind the current multiply "
                     "(measured: no gain on B200 -- NCCL's blocks find no room beside the multiply kernels, which fill every SM; kept for experiments)")

@@ -121,7 +121,8 @@ long mpres_debug_read_workspace(mpres_ctx *ctx, int slot, size_t offset, void *h
  * residue-parallel tile kernel for every entry, 2 = like 0 but with the generic 64-bit modular products
  * instead of the 32-bit Barrett step used when every modulus has the same bit length <= 27, 3 = like 0 but,
  * on the small-modulus path, with the base extension fused into the normalisation kernel (no residue planes
- * in memory; measured slightly slower on B200 because of its register / shared-memory footprint).
+ * in memory; measured slightly slower on B200 because of its register / shared-memory footprint), 4 = like 0 but
+ * reading the residues of the sums straight from global memory instead of staging them in shared memory (cp.async).
  * Identical results (including interval evaluations). */
 int mpres_set_stage3_kernel(mpres_ctx *ctx, int kind);
 /* Reduced-base fast path (default on): stages 1 and 2 run on the first n' moduli only, n' the smallest

@@ -728,12 +728,21 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
         }
         // limb-plane path (or unfused small path); `gate`: leave at once when the fused kernel did the work
         const int *gate = fused ? sel : nullptr;
-        if (f32)
-            k_norm_fast<NQ, true><<<g3, kNormFastThreads, sm_cds, st>>>(c->dconsts, m, n, k, (const int *) pS, D, m_p, n_p, IA, IB, alpha, beta, Cm, ldc,
-                                                                       scal_tab, todo, c->d_counter, slow, c->d_counter + 1, allow_fb, gate);
-        else
-            k_norm_fast<NQ, false><<<g3, kNormFastThreads, sm_cds, st>>>(c->dconsts, m, n, k, (const int *) pS, D, m_p, n_p, IA, IB, alpha, beta, Cm, ldc,
-                                                                        scal_tab, todo, c->d_counter, slow, c->d_counter + 1, allow_fb, gate);
+        auto launch_norm = [&](auto kern, size_t smem) {
+            kern<<<g3, kNormFastThreads, smem, st>>>(c->dconsts, m, n, k, (const int *) pS, D, m_p, n_p, IA, IB, alpha, beta, Cm, ldc,
+                                                     scal_tab, todo, c->d_counter, slow, c->d_counter + 1, allow_fb, gate);
+        };
+        if (c->norm_staged) {
+            const size_t sm_st = sm_cds + (size_t) NQ * kNormFastThreads * sizeof(int);
+            if (sm_st > 48 * 1024 && !(c->attr_norm >> (NQ / 8) & 1ull)) {
+                cudaFuncSetAttribute(k_norm_fast<NQ, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm_st);
+                cudaFuncSetAttribute(k_norm_fast<NQ, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm_st);
+                c->attr_norm |= 1ull << (NQ / 8);
+            }
+            if (f32) launch_norm(k_norm_fast<NQ, true, true>, sm_st); else launch_norm(k_norm_fast<NQ, false, true>, sm_st);
+        } else {
+            if (f32) launch_norm(k_norm_fast<NQ, true, false>, sm_cds); else launch_norm(k_norm_fast<NQ, false, false>, sm_cds);
+        }
         ++stage3_launches;
     };
     if (have_fast) {

@@ -399,6 +399,7 @@ __device__ __forceinline__ void norm_fast_body(const DevConsts &C, int *cds, int
         asm volatile("cp.async.commit_group;\n" ::);
     }
     okf[threadIdx.x] = 0;
+    if (SMEM_S) asm volatile("cp.async.wait_group 1;\n" ::: "memory");        // the staged residues of S (an older group than the digits of C)
     __syncthreads();
     bool to_slow = false, to_todo = false, go = false;
     int sg = 0, d = 0, sign = 0;
@@ -525,7 +526,7 @@ __device__ __forceinline__ void norm_fast_body(const DevConsts &C, int *cds, int
         Cm.eval[ic] = rlo;
         Cm.eval[ic + Cm.len()] = rup;
     }
-    if (SMEM_S && to_slow && live) {
+    if (SMEM_S && Sg && to_slow && live) {
 #pragma unroll 8
         for (int q = 0; q < NQ; ++q) Sg[q * gplane] = Sp[q * plane];
     }
@@ -558,16 +559,34 @@ __device__ __forceinline__ void norm_fast_body(const DevConsts &C, int *cds, int
 #ifndef MPRES_NORM_BLOCKS
 #define MPRES_NORM_BLOCKS 6
 #endif
-template <int NQ, bool F32>
+// STAGED: the block's residues of S (NQ runs of kNormFastThreads consecutive ints) are brought into shared memory with 16-byte
+// cp.async copies up front -- one exposed DRAM latency per block (hidden by the other resident blocks) instead of one per batch of
+// loads in each of the two passes, and the second pass reads them from shared memory.
+template <int NQ, bool F32, bool STAGED>
 __global__ void __launch_bounds__(kNormFastThreads, MPRES_NORM_BLOCKS) k_norm_fast(const DevConsts *Cp, int m, int n, int k, const int *S, const int16_t *delta,
                                                                 long long m_p, long long n_p, const OuterInfo *ia, const OuterInfo *ib,
                                                                 SoA alpha, SoA beta, SoA Cm, int ldc, const int *scal_tab, long long *todo, int *todo_count,
                                                                 long long *slow, int *slow_count, bool fallback_allowed, const int *gate) {
-    extern __shared__ int cds[];            // [kNormFastThreads][NQ + 1]
+    extern __shared__ __align__(16) int cds[];   // [kNormFastThreads][NQ + 1], then (STAGED) [NQ][kNormFastThreads]
     if (gate && *gate > 0) return;          // the fused small-modulus kernel handled this call
     const int tiles = (m + kNormFastThreads - 1) / kNormFastThreads;
     const int col = blockIdx.x / tiles;
     const int row0 = (blockIdx.x - col * tiles) * kNormFastThreads;
+    if (STAGED) {
+        int *sst = cds + kNormFastThreads * (NQ + 1);
+        const int *src = S + (long long) col * m_p + row0;             // 512-byte aligned: m_p and row0 are multiples of kNormFastThreads
+        const long long plane = n_p * m_p;
+        constexpr int CH = kNormFastThreads / 4;                         // 16-byte chunks per modulus
+        for (int v = threadIdx.x; v < NQ * CH; v += kNormFastThreads) {
+            const int q = v / CH, ch = v - q * CH;
+            const unsigned sa = (unsigned) __cvta_generic_to_shared(sst + q * kNormFastThreads + 4 * ch);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(src + q * plane + 4 * ch));
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
+        norm_fast_body<NQ, F32, true>(*Cp, cds, m, n, k, col, row0, sst + threadIdx.x, kNormFastThreads, nullptr, 0, delta, m_p, ia, ib,
+                                      alpha, beta, Cm, ldc, scal_tab, todo, todo_count, slow, slow_count, fallback_allowed);
+        return;
+    }
     norm_fast_body<NQ, F32, false>(*Cp, cds, m, n, k, col, row0, S + (long long) col * m_p + row0 + threadIdx.x, n_p * m_p, nullptr, 0, delta, m_p, ia, ib,
                                    alpha, beta, Cm, ldc, scal_tab, todo, todo_count, slow, slow_count, fallback_allowed);
 }

@@ -162,7 +162,8 @@ int mpres_set_stage2_kernel(mpres_ctx *c, int kind) {
     return 0;
 }
 int mpres_set_stage3_kernel(mpres_ctx *c, int kind) {
-    if (!c || kind < 0 || kind > 3) return -1;
+    if (!c || kind < 0 || kind > 4) return -1;
+    c->norm_staged = kind == 4 ? 0 : 1;
     c->stage3 = kind == 1 ? 1 : 0;
     c->norm32 = kind == 2 ? 0 : 1;
     c->fuse_ext = kind == 3 ? 1 : 0;

@@ -247,7 +247,7 @@ def test_gemm_stage3_kernels_identical(pkg, N, bits_div, shape):
     alpha = random_records(N, 1, bits, 74)
     beta = random_records(N, 1, bits, 75)
     out = []
-    for kind in (1, 0, 2, 3):     # tile kernel, entry-per-thread (32-bit Barrett products), generic products, fused base extension
+    for kind in (1, 0, 2, 3, 4):  # tile kernel, entry-per-thread (32-bit Barrett products, staged sums), generic products, fused base extension, unstaged sums
         ctx.set_stage3_kernel(kind)
         out.append(_gemm(pkg, ctx, m, n, k, alpha, A, B, beta, C, pkg.MODE_FAST))
     for other in out[1:]:
@@ -266,7 +266,7 @@ def test_gemm_stage3_kernels_identical(pkg, N, bits_div, shape):
     zero = orc.set_ints([0], [0], [0])
     for al, be in ((alpha, zero), (zero, beta)):
         res = []
-        for kind in (1, 0, 2, 3):
+        for kind in (1, 0, 2, 3, 4):
             ctx.set_stage3_kernel(kind)
             res.append(_gemm(pkg, ctx, m, n, k, al, A, B, be, C, pkg.MODE_FAST))
         assert all(diff_fields(res[0], r).size == 0 for r in res[1:])
