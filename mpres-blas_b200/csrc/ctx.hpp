@@ -75,7 +75,7 @@ struct mpres_ctx {
     bool ev_valid = false;
     int last_stage2_launches = 0;
     // opt-in shared-memory sizes (cudaFuncSetAttribute) are per device: remembered per context, not per process
-    bool attr_fast = false, attr_align_mma = false, attr_small = false, attr_umma = false;
+    bool attr_fast = false, attr_align_mma = false, attr_align = false, attr_small = false, attr_umma = false;
     unsigned long long attr_norm = 0;    // bit NQ / 8: k_norm_fast<NQ, *, true> (staged residues of S)
     int norm_staged = 1;                 // k_norm_fast stages the residues of S in shared memory (mpres_set_stage3_kernel(4) = off)
     unsigned long long attr_fused = 0;   // bit NQ / 8: k_ext_norm_small<NQ, *>

@@ -620,6 +620,7 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
             k_align_small<true><<<gA, 256, align_small_smem(true), st>>>(c->dconsts, A, soA, slA, m, k, IA, (uint8_t *) pQA, SA, m_ps, k_p, sel);
             k_align_small<true><<<gB, 256, align_small_smem(true), st>>>(c->dconsts, B, soB, slB, n, k, IB, (uint8_t *) pQB, SB, n_ps, k_p, sel);
         } else {
+            if (!c->attr_align) { cudaFuncSetAttribute(k_align_small<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) align_small_smem(false)); c->attr_align = true; }
             k_align_small<false><<<gA, 256, align_small_smem(false), st>>>(c->dconsts, A, soA, slA, m, k, IA, (uint8_t *) pQA, SA, m_ps, k_p, sel);
             k_align_small<false><<<gB, 256, align_small_smem(false), st>>>(c->dconsts, B, soB, slB, n, k, IB, (uint8_t *) pQB, SB, n_ps, k_p, sel);
         }

@@ -124,7 +124,8 @@ __device__ __forceinline__ void align_small_entry(const int4 (&dg)[(NW + 3) / 4]
                                                      4 * w4 + 2 < NW ? x[4 * w4 + 2] : 0u, 4 * w4 + 3 < NW ? x[4 * w4 + 3] : 0u);
         return;
     }
-    // residues modulo the small moduli, times +-2^shift
+    // residues modulo the small moduli, times +-2^shift (the entry's 64-byte row of the table: L1-resident, and L1 is what this kernel
+    // lives on -- staging the rows in shared memory shrank it and cost 5x)
     const unsigned *mrow = (const unsigned *) (pws + (size_t) srow * 64);
     for (int jg = 0; 4 * jg < P; ++jg) {
         const unsigned mult4 = __ldg(mrow + jg);
@@ -196,11 +197,18 @@ __global__ void __launch_bounds__(256, 3) k_align_small(const DevConsts *Cp, SoA
     uint8_t *s_x = as_smem + align_small_smem_base();          // [256][kAXPitch]
     int *s_srow = (int *) (s_x + 256 * kAXPitch);                // [256]
     uint8_t *s_cwB = (uint8_t *) (s_srow + 256);                 // [56][kAXPitch]
-
+    // prefetch area (cp.async targets): the fields of the NEXT tile's entries, one slot per thread, and the exponent bases of its lines.
+    // Kept to 8.2 KB: three blocks must stay within the 100 KB shared-memory configuration -- the rest of the SM's 256 KB is the L1 this
+    // kernel's table rows and register spills live in (with 58 KB per block the L1 hit rate fell from 55 % to 6 % and the kernel took 5x).
+    uint8_t *pf = as_smem + align_small_smem_base() + (MMA ? 256 * kAXPitch + 256 * 4 + 56 * kAXPitch : 0);
+    int4 *s_fd0 = (int4 *) pf;                                    // [256]
+    double *s_fup = (double *) (s_fd0 + 256);                     // [256]
+    int *s_fex = (int *) (s_fup + 256), *s_fsg = s_fex + 256, *s_fem = s_fsg + 256;   // [256], [256], [kASo]
     // Persistent: a block walks the tiles blockIdx.x, blockIdx.x + gridDim.x, ... (line-block fastest); the tables are staged once and
     // the entry fields of the NEXT tile (interval bound, exponent, sign, line base, first four residues) are loaded while the current
     // tile is converted, so their DRAM latency is off the critical path.
-    struct Fields { double upf; int ex, sg, emin; long long idx; bool inside; int4 d0; };
+    // The fields travel by cp.async into this thread's shared-memory slot: held in registers across the conversion they were spilled,
+    // and the spill store waited for the load (ncu: 14 % of the kernel's stall samples on one STL).
     const int tiles_o = (int) (outer_p / kASo);
     const long long ntiles = (long long) tiles_o * (inner_p / kASl);
     int ol, ll;
@@ -208,19 +216,35 @@ __global__ void __launch_bounds__(256, 3) k_align_small(const DevConsts *Cp, SoA
     else { ll = threadIdx.x & (kASl - 1); ol = threadIdx.x / kASl; }
     const int slot = ol * kASl + ll;
     const long long xlen = X.len();
-    auto load_fields = [&](long long tile) {
-        Fields f;
+    auto entry_index = [&](long long tile, long long &idx) {
         const int o = (int) (tile % tiles_o) * kASo + ol, l = (int) (tile / tiles_o) * kASl + ll;
-        f.inside = tile < ntiles && o < outer && l < inner;
-        f.idx = f.inside ? (long long) o * so + (long long) l * sl : 0;
-        f.upf = f.inside ? X.eval[f.idx + xlen].frac : 0.0;
-        f.ex = f.inside ? X.exp[f.idx] : 0;
-        f.sg = f.inside ? X.sign[f.idx] : 0;
-        f.emin = f.inside ? info[o].emin : 0;
-        f.d0 = f.inside ? __ldg((const int4 *) (X.digits + f.idx * N)) : make_int4(0, 0, 0, 0);
-        return f;
+        const bool inside = tile < ntiles && o < outer && l < inner;
+        idx = inside ? (long long) o * so + (long long) l * sl : 0;
+        return inside;
     };
-    Fields cur = load_fields(blockIdx.x);
+    auto cp_async = [](void *dst, const void *src, auto bytes) {
+        const unsigned sa = (unsigned) __cvta_generic_to_shared(dst);
+        if (decltype(bytes)::value == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(src));
+        else if (decltype(bytes)::value == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(src));
+        else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(src));
+    };
+    auto prefetch_fields = [&](long long tile) {
+        long long idx;
+        if (entry_index(tile, idx)) {
+            cp_async(s_fd0 + threadIdx.x, X.digits + idx * N, std::integral_constant<int, 16>{});
+            cp_async(s_fup + threadIdx.x, &X.eval[idx + xlen].frac, std::integral_constant<int, 8>{});
+            cp_async(s_fex + threadIdx.x, X.exp + idx, std::integral_constant<int, 4>{});
+            cp_async(s_fsg + threadIdx.x, X.sign + idx, std::integral_constant<int, 4>{});
+        } else {
+            s_fup[threadIdx.x] = 0.0;                                // reads as an exact zero
+        }
+        if (threadIdx.x < kASo) {
+            const int o = (int) (tile % tiles_o) * kASo + threadIdx.x;
+            if (tile < ntiles && o < outer) cp_async(s_fem + threadIdx.x, &info[o].emin, std::integral_constant<int, 4>{});
+        }
+    };
+    prefetch_fields(blockIdx.x);
+    asm volatile("cp.async.wait_all;\n" ::: "memory");              // made visible to the block by the barrier below
 
     for (int t = threadIdx.x; t < ((P + 3) & ~3) * CW; t += 256) { const int j = t / CW, w = t - j * CW; s_cw[t] = SD.cw[j * 16 + w]; }
     for (int t = threadIdx.x; t < CW * CW; t += 256) { const int i = t / CW, w = t - i * CW; s_mi[t] = (i < nin && w < nin) ? SD.in_mi[((size_t) nin * 16 + i) * 16 + w] : 0u; }
@@ -242,26 +266,31 @@ __global__ void __launch_bounds__(256, 3) k_align_small(const DevConsts *Cp, SoA
 
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int o0 = (int) (tile % tiles_o) * kASo, l0 = (int) (tile / tiles_o) * kASl;
-        const Fields nxt = load_fields(tile + gridDim.x);
+        long long cur_idx;
+        const bool cur_inside = entry_index(tile, cur_idx);
+        const double cur_upf = s_fup[threadIdx.x];
+        const int4 cur_d0 = s_fd0[threadIdx.x];
         int sh16 = kShiftSentinel;
-        const bool live = cur.inside && cur.upf != 0;
+        const bool live = cur_inside && cur_upf != 0;
         int srow = 0;
         if (live) {
-            const long long sh = (long long) cur.ex - cur.emin;
+            const long long sh = (long long) s_fex[threadIdx.x] - s_fem[ol];
             const int s = sh > kSmallShiftMax ? kSmallShiftMax : (sh < 0 ? 0 : (int) sh);   // the selection guarantees sh <= kSmallShiftMax
             sh16 = s;
-            srow = 2 * s + (cur.sg ? 1 : 0);
+            srow = 2 * s + (s_fsg[threadIdx.x] ? 1 : 0);
         }
+        __syncthreads();                                                      // every thread has read its fields (and the line bases)
+        prefetch_fields(tile + gridDim.x);                                   // in flight through the conversion
         s_sh[slot] = (int16_t) sh16;
         uint8_t *xrow = s_x + threadIdx.x * kAXPitch;
         if (live) {
-            const int *dig = X.digits + cur.idx * N;
+            const int *dig = X.digits + cur_idx * N;
             uint8_t *outp = s_out + slot;
-#define MPRES_AS_CASE(NW_) case NW_: align_small_dispatch<NW_, MMA>(dig, cur.d0, nin, P, srow, s_mi, s_negmp, s_m, s_bmu, s_w, s_rcpm, s_cw, s_ppm, SD.pws, outp, xrow); break;
+#define MPRES_AS_CASE(NW_) case NW_: align_small_dispatch<NW_, MMA>(dig, cur_d0, nin, P, srow, s_mi, s_negmp, s_m, s_bmu, s_w, s_rcpm, s_cw, s_ppm, SD.pws, outp, xrow); break;
             switch (NWr) {
                 MPRES_AS_CASE(1) MPRES_AS_CASE(2) MPRES_AS_CASE(3) MPRES_AS_CASE(4) MPRES_AS_CASE(5) MPRES_AS_CASE(6) MPRES_AS_CASE(7) MPRES_AS_CASE(8)
                 MPRES_AS_CASE(12)
-                default: align_small_dispatch<16, MMA>(dig, cur.d0, nin, P, srow, s_mi, s_negmp, s_m, s_bmu, s_w, s_rcpm, s_cw, s_ppm, SD.pws, outp, xrow); break;
+                default: align_small_dispatch<16, MMA>(dig, cur_d0, nin, P, srow, s_mi, s_negmp, s_m, s_bmu, s_w, s_rcpm, s_cw, s_ppm, SD.pws, outp, xrow); break;
             }
 #undef MPRES_AS_CASE
         } else if (MMA) {
@@ -335,11 +364,13 @@ __global__ void __launch_bounds__(256, 3) k_align_small(const DevConsts *Cp, SoA
             const int oo = threadIdx.x >> 2, part = threadIdx.x & 3;
             *(uint4 *) (shifts + (long long) (o0 + oo) * inner_p + l0 + part * 8) = *(const uint4 *) (s_sh + oo * kASl + part * 8);
         }
+        asm volatile("cp.async.wait_all;\n" ::: "memory");                 // the next tile's fields have landed (issued a whole conversion ago)
         __syncthreads();
-        cur = nxt;
     }
 }
-inline size_t align_small_smem(bool mma) { return align_small_smem_base() + (mma ? 256 * kAXPitch + 256 * 4 + 56 * kAXPitch : 0); }
+inline size_t align_small_smem(bool mma) {
+    return align_small_smem_base() + (mma ? 256 * kAXPitch + 256 * 4 + 56 * kAXPitch : 0) + 256 * 16 + 256 * 8 + 2 * 256 * 4 + kASo * 4;   // + the prefetch area
+}
 
 // ---- stage 2: one u8 GEMM per small modulus on tcgen05 -----------------------------------------------------
 constexpr int kSM = 128, kSN = 256, kSK = 64, kSStages = 4;
