@@ -613,8 +613,8 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
         c->attr_fast = true;
     }
     if (small_on) {
-        const unsigned gA = (unsigned) std::min<long long>((m_ps / kASo) * (k_p / kASl), (long long) c->sm_count * 3);
-        const unsigned gB = (unsigned) std::min<long long>((n_ps / kASo) * (k_p / kASl), (long long) c->sm_count * 3);
+        const unsigned gA = (unsigned) std::min<long long>((m_ps / kASo) * (k_p / kASl), (long long) c->sm_count * MPRES_ALIGN_BLOCKS);
+        const unsigned gB = (unsigned) std::min<long long>((n_ps / kASo) * (k_p / kASl), (long long) c->sm_count * MPRES_ALIGN_BLOCKS);
         if (c->align_mma) {
             if (!c->attr_align_mma) { cudaFuncSetAttribute(k_align_small<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) align_small_smem(true)); c->attr_align_mma = true; }
             k_align_small<true><<<gA, 256, align_small_smem(true), st>>>(c->dconsts, A, soA, slA, m, k, IA, (uint8_t *) pQA, SA, m_ps, k_p, sel);
@@ -693,7 +693,7 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
     const bool f32 = c->sc.usable && c->sc.red_shift >= 24 && c->sc.red_shift <= 27 && c->norm32;
     const bool fused = small_on && have_fast && c->fuse_ext;
     if (small_on && !fused) {
-        const unsigned gx = (unsigned) ((m_p / kXT) * n);
+        const unsigned gx = (unsigned) std::min<long long>((m_p / kXT) * n, (long long) c->sm_count * 4);     // persistent: four blocks per SM
         const size_t sm = ext_small_smem(c->sc.ext_cols, N);
         if (c->sc.red_shift) k_ext_small<true><<<gx, kXT, sm, st>>>(c->dconsts, m, n, (const uint8_t *) pS8, m_p, m_ps, n_ps, (int *) pS, n_p, sel);
         else k_ext_small<false><<<gx, kXT, sm, st>>>(c->dconsts, m, n, (const uint8_t *) pS8, m_p, m_ps, n_ps, (int *) pS, n_p, sel);

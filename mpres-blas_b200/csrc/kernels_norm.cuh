@@ -399,21 +399,32 @@ __device__ __forceinline__ void norm_fast_body(const DevConsts &C, int *cds, int
         asm volatile("cp.async.commit_group;\n" ::);
     }
     okf[threadIdx.x] = 0;
+    // the entry's line descriptors and shift go out before the wait for the staged residues, and the scalar fields of C (needed after
+    // the first pass) are pulled towards L1 meanwhile: their latencies overlap instead of following one another
+    OuterInfo ra = {}, cb = {};
+    int d = 0;
+    long long ic = 0;
+    if (live) {
+        ra = ia[row]; cb = ib[col];
+        d = delta[(long long) col * m_p + row];
+        ic = row + (long long) col * ldc;
+        asm volatile("prefetch.global.L1 [%0];\n" ::"l"(Cm.eval + ic));
+        asm volatile("prefetch.global.L1 [%0];\n" ::"l"(Cm.eval + ic + Cm.len()));
+        asm volatile("prefetch.global.L1 [%0];\n" ::"l"(Cm.exp + ic));
+        asm volatile("prefetch.global.L1 [%0];\n" ::"l"(Cm.sign + ic));
+    }
     if (SMEM_S) asm volatile("cp.async.wait_group 1;\n" ::: "memory");        // the staged residues of S (an older group than the digits of C)
     __syncthreads();
     bool to_slow = false, to_todo = false, go = false;
-    int sg = 0, d = 0, sign = 0;
-    long long ic = 0;
+    int sg = 0, sign = 0;
     AddEsi p;
     Er rlo, rup;
     const int log2M = C.log2M;
     if (live) do {
         const int mp_h = C.mp_h;
-        const OuterInfo ra = ia[row], cb = ib[col];
         if (ra.win < 0 || cb.win < 0) { to_slow = true; break; }             // a line of exact zeros: S == 0
         const long long bound = (long long) ra.win + cb.win + ceil_log2(k);
         if (bound > (long long) log2M - 2) { to_todo = true; to_slow = !fallback_allowed; break; }   // window guard failed
-        d = delta[(long long) col * m_p + row];
         if (d >= kShiftSentinel) { to_slow = true; break; }                   // every term is an exact zero
         int K = log2M - (int) bound - 3;
         K = K < 0 ? 0 : K;
@@ -479,7 +490,6 @@ __device__ __forceinline__ void norm_fast_body(const DevConsts &C, int *cds, int
         const ScalarEsi al = s_al, be = s_be;
         const Er t1lo = er_md_dir<false>(lo, al.lo, C.unit_upp), t1up = er_md_dir<true>(up, al.up, C.unit_low);
         if (t1up.frac != 0 && t1up.exp >= mp_h) { to_slow = true; break; }
-        ic = row + (long long) col * ldc;
         const Er clo = Cm.eval[ic], cup = Cm.eval[ic + Cm.len()];
         const Er t2lo = er_md_dir<false>(clo, be.lo, C.unit_upp), t2up = er_md_dir<true>(cup, be.up, C.unit_low);
         if (t2up.frac != 0 && t2up.exp >= mp_h) { to_slow = true; break; }

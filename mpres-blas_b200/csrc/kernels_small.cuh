@@ -171,7 +171,10 @@ __host__ __device__ constexpr size_t align_small_smem_base() {   // output tile,
 }
 constexpr int kAXPitch = 96;      // bytes per operand row (conflict-free 64-bit fragment loads)
 template <bool MMA>
-__global__ void __launch_bounds__(256, 3) k_align_small(const DevConsts *Cp, SoA X, long long so, long long sl, int outer, int inner,
+#ifndef MPRES_ALIGN_BLOCKS
+#define MPRES_ALIGN_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(256, MPRES_ALIGN_BLOCKS) k_align_small(const DevConsts *Cp, SoA X, long long so, long long sl, int outer, int inner,
                                                         const OuterInfo *info, uint8_t *planes, int16_t *shifts,
                                                         long long outer_p, long long inner_p, const int *sel) {
     extern __shared__ __align__(16) uint8_t as_smem[];
@@ -694,27 +697,32 @@ __host__ __device__ constexpr bool ext_norm_cds_aliased(int NQ) { return (size_t
 
 // One block: the kXT consecutive rows from row0 of column col.  Leaves S mod m_q of entry e at s_S[q * kXSPitch + e].
 // Ends with a __syncthreads().
+// `first`: the block's first tile -- its one-byte residues are fetched here and the constant tables staged; later tiles of a
+// persistent block find both in place.  `next_off` >= 0: offset (in a plane of S8) of the tile this block handles next; its residues
+// are fetched as soon as the first phase has consumed the current ones, so the copy runs under the tensor-core phase.
 template <bool FASTRED>
 __device__ __forceinline__ void ext_small_block(const DevConsts &C, const SmallDev &SD, const ExtSmem &E, int P, const uint8_t *S8, long long m_ps,
-                                                long long n_ps, int col, int row0) {
+                                                long long n_ps, int col, int row0, bool first = true, long long next_off = -1) {
     const int N = C.N, cols = SD.ext_cols;
-    // the block's one-byte residues: P runs of 128 contiguous bytes, asynchronous 16-byte copies (all in flight at once)
-    {
-        const uint8_t *src = S8 + (long long) col * m_ps + row0;
+    // a tile's one-byte residues: P runs of 128 contiguous bytes, asynchronous 16-byte copies (all in flight at once)
+    auto fetch = [&](const uint8_t *src) {
         const long long plane = n_ps * m_ps;
         for (int v = threadIdx.x; v < P * (kXT / 16); v += kXT) {
             const int j = v >> 3, part = v & 7;
             cp_async16(E.X8 + j * kXT + part * 16, src + (long long) j * plane + part * 16);
         }
         cp_async_commit();
+    };
+    if (first) {
+        fetch(S8 + (long long) col * m_ps + row0);
         const uint4 *bsrc = (const uint4 *) (SD.ext_b + (size_t) P * cols * 64);
         for (int v = threadIdx.x; v < cols * 4; v += kXT) *(uint4 *) (E.Bt + (v >> 2) * kXPitch + (v & 3) * 16) = __ldg(bsrc + v);
         if (threadIdx.x < 64) {
             const int j = threadIdx.x;
             E.s_c4[j] = make_uint4((unsigned) SD.p[j], SD.mu[j], (unsigned) SD.inv[P * 64 + j], __float_as_uint(SD.rcp[j]));
         }
-        cp_async_wait<0>();
     }
+    cp_async_wait<0>();
     __syncthreads();
     // ---- phase 1: xi_i and the rank, one entry per thread ----
     {
@@ -745,7 +753,12 @@ __device__ __forceinline__ void ext_small_block(const DevConsts &C, const SmallD
 #pragma unroll
         for (int g = 0; g < 4; ++g) dst[g] = make_uint4(wds[4 * g], wds[4 * g + 1], wds[4 * g + 2], wds[4 * g + 3]);
     }
-    __syncwarp();   // a warp only reads the 32 operand rows it wrote
+    if (next_off >= 0) {
+        __syncthreads();                    // every thread has read its residues: the staging area is free for the next tile
+        fetch(S8 + next_off);
+    } else {
+        __syncwarp();                       // a warp only reads the 32 operand rows it wrote
+    }
     // ---- phase 2: (xi, R) x limbs on the tensor cores, limbs recombined and reduced per reference modulus ----
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int kred = SD.red_shift;
@@ -814,13 +827,21 @@ __global__ void __launch_bounds__(kXT, 4) k_ext_small(const DevConsts *Cp, int m
     const SmallDev &SD = *C.small;
     const ExtSmem E = ext_carve(xs_smem, SD.ext_cols);
     const int tiles = (int) (m_p / kXT);
-    const int col = blockIdx.x / tiles;
-    const int row0 = (blockIdx.x - col * tiles) * kXT;
-    ext_small_block<FASTRED>(C, SD, E, P, S8, m_ps, n_ps, col, row0);
+    const long long total = (long long) tiles * n;
     const int N = C.N;
-    for (int v = threadIdx.x; v < N * (kXT / 4); v += kXT) {
-        const int q = v >> 5, part = v & 31;
-        *(int4 *) (S + ((long long) q * n_p + col) * m_p + row0 + part * 4) = *(const int4 *) (E.s_S + q * kXSPitch + part * 4);
+    // persistent: the constant tables (8 KB at 32 moduli) are staged once per block instead of once per tile
+    bool first = true;
+    for (long long tl = blockIdx.x; tl < total; tl += gridDim.x) {
+        const int col = (int) (tl / tiles);
+        const int row0 = (int) (tl - (long long) col * tiles) * kXT;
+        const long long nx = tl + gridDim.x;
+        const long long next_off = nx < total ? (nx / tiles) * m_ps + (nx % tiles) * kXT : -1;
+        ext_small_block<FASTRED>(C, SD, E, P, S8, m_ps, n_ps, col, row0, first, next_off);
+        first = false;
+        for (int v = threadIdx.x; v < N * (kXT / 4); v += kXT) {
+            const int q = v >> 5, part = v & 31;
+            *(int4 *) (S + ((long long) q * n_p + col) * m_p + row0 + part * 4) = *(const int4 *) (E.s_S + q * kXSPitch + part * 4);
+        }
     }
 }
 
