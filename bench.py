@@ -582,6 +582,16 @@ def main():
         alpha.device2host_ptr(hal.data_ptr(), 1); beta.device2host_ptr(hbe.data_ptr(), 1)
 
         def e2e_step():
+            if args.e2e_path == "pipelined" and world > 1 and n % world == 0:
+                # every rank pulls 1/N of B through its own PCIe link, the ranks gather the rest over NVLink (five contiguous ranges of the
+                # SoA arrays), then one call over the host A / C row blocks with B resident (mpres_gemm_host_bdev)
+                cols = n // world
+                B.host2device_ptr_at(k * cols * rank, hB.data_ptr() + k * cols * rank * rs, k * cols)
+                for full, mine in zip(B.slices(0, k * n), B.slices(k * cols * rank, k * cols)):
+                    dist.all_gather_into_tensor(full, mine.clone())
+                torch.cuda.synchronize()
+                pkg.mp_gemm_host_bdev(ctx, pkg.mblas_no_trans, pkg.mblas_no_trans, mr, n, k, hal, hA, mr, B, k, hbe, hC, mr, out=hOut, panels=args.e2e_panels)
+                return
             if args.e2e_path == "pipelined":
                 # one call over the host buffers: uploads, compute and download overlapped by column panels (mpres_gemm_host)
                 pkg.mp_gemm_host(ctx, pkg.mblas_no_trans, pkg.mblas_no_trans, mr, n, k, hal, hA, mr, hB, k, hbe, hC, mr, out=hOut, panels=args.e2e_panels)
@@ -604,11 +614,14 @@ def main():
             t = torch.tensor([dt], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-        h2d = (mr * k + k * n + mr * n + 2) * rs
+        b_up = k * n // world if (args.e2e_path == "pipelined" and world > 1 and n % world == 0) else k * n
+        h2d = (mr * k + b_up + mr * n + 2) * rs
         d2h = mr * n * rs
         e2e = {"value": 2.0 * m * n * k / dt / 1e9, "unit": "MP-GFLOP/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                "ms_per_step": dt * 1e3, "steps": args.e2e_steps,
-               "path": ("mpres_gemm_host(alpha, A, B, beta, C -> out): pinned host AoS mp_float_t[], PCIe transfers pipelined with the compute by column panels"
+               "path": ("per rank: mpres_array_host2device(1/N of B) + all-gather of B over NVLink + mpres_gemm_host_bdev(alpha, A_r, B, beta, C_r -> out_r), pinned host AoS mp_float_t[]"
+                        if (args.e2e_path == "pipelined" and world > 1 and n % world == 0) else
+                        "mpres_gemm_host(alpha, A, B, beta, C -> out): pinned host AoS mp_float_t[], PCIe transfers pipelined with the compute by column panels"
                         if args.e2e_path == "pipelined" else
                         "mpres_array_host2device(A,B,C,alpha,beta) + mpres_gemm + mpres_array_device2host(C), pinned host AoS mp_float_t[]")}
 

@@ -249,6 +249,12 @@ int mpres_axpy_dot(mpres_ctx *ctx, int n, const mpres_array_t *alpha, mpres_arra
 int mpres_gemm_host(mpres_ctx *ctx, int transa, int transb, int m, int n, int k, const void *alpha, const void *A, int lda, const void *B, int ldb,
                     const void *beta, const void *Cin, void *Cout, int ldc, int panels);
 
+/* mpres_gemm_host with B already resident on the device (an mp_array_t: e.g. each rank of a row-sharded multi-GPU GEMM uploads 1/N of B
+ * and gathers the rest over NVLink instead of pulling all of B through its own PCIe link).  B must be complete before the call (the
+ * transfers run on the library's own streams: synchronise the stream that produced B first).  Panels also apply to transposed B. */
+int mpres_gemm_host_bdev(mpres_ctx *ctx, int transa, int transb, int m, int n, int k, const void *alpha, const void *A, int lda, const mpres_array_t *B,
+                         int ldb, const void *beta, const void *Cin, void *Cout, int ldc, int panels);
+
 /* The same three operations over mp_collection_t operands with explicit allocated lengths (the
  * reference only uses mp_collection_t in its sparse kernels, src/sparse/mpmtx/*.cuh; north_star asks
  * for the dense path over both containers). */

@@ -42,7 +42,7 @@ EXPORTS = [
     "mpres_set_profiling", "mpres_last_stage_ms", "mpres_set_vec_config", "mpres_last_small_base", "mpres_small_modulus", "mpres_debug_read_workspace", "mpres_last_minplus_dense_count",
     "mpres_array_init", "mpres_array_clear", "mpres_array_host2device", "mpres_array_device2host",
     "mpres_collection_init", "mpres_collection_clear", "mpres_collection_host2device", "mpres_collection_device2host",
-    "mpres_array_set_binary", "mpres_gemm", "mpres_gemv", "mpres_dot", "mpres_scal", "mpres_axpy", "mpres_waxpby", "mpres_ge_add", "mpres_ge_acc", "mpres_ger", "mpres_ge_diag_scale", "mpres_ge_lr_scale", "mpres_rot", "mpres_axpy_dot", "mpres_gemm_host", "mpres_gemm_coll", "mpres_gemv_coll",
+    "mpres_array_set_binary", "mpres_gemm", "mpres_gemv", "mpres_dot", "mpres_scal", "mpres_axpy", "mpres_waxpby", "mpres_ge_add", "mpres_ge_acc", "mpres_ger", "mpres_ge_diag_scale", "mpres_ge_lr_scale", "mpres_rot", "mpres_axpy_dot", "mpres_gemm_host", "mpres_gemm_host_bdev", "mpres_gemm_coll", "mpres_gemv_coll",
     "mpres_dot_coll", "mpres_dot_partial", "mpres_reduce_partials", "mpres_probe", "mpres_version",
 ]
 
@@ -358,6 +358,12 @@ def mp_gemm_host(ctx, transa, transb, m, n, k, alpha, A, lda, B, ldb, beta, C, l
     the result goes to `out` (default: C, in place)."""
     _check(ctx.lib.mpres_gemm_host(ctx.h, transa, transb, m, n, k, _host_ptr(alpha), _host_ptr(A), lda, _host_ptr(B), ldb, _host_ptr(beta),
                                    _host_ptr(C), _host_ptr(C if out is None else out), ldc, panels), "mpres_gemm_host")
+
+
+def mp_gemm_host_bdev(ctx, transa, transb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, out=None, panels=0):
+    """mpres_gemm_host_bdev: like mp_gemm_host, with B a device-resident mp_array_t (complete before the call)."""
+    _check(ctx.lib.mpres_gemm_host_bdev(ctx.h, transa, transb, m, n, k, _host_ptr(alpha), _host_ptr(A), lda, _ref(B), ldb, _host_ptr(beta),
+                                        _host_ptr(C), _host_ptr(C if out is None else out), ldc, panels), "mpres_gemm_host_bdev")
 
 
 def synchronize(ctx):

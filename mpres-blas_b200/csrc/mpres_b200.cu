@@ -572,10 +572,11 @@ SoA soa_offset(const SoA &a, size_t off, int N) {
 
 }  // namespace
 
-int mpres_gemm_host(mpres_ctx *c, int transa, int transb, int m, int n, int k, const void *alpha, const void *A, int lda, const void *B, int ldb,
-                    const void *beta, const void *Cin, void *Cout, int ldc, int panels) {
+// B comes from the host (Bd == nullptr) or is already resident on the device (Bd: e.g. gathered from the other ranks' slices)
+static int gemm_host_impl(mpres_ctx *c, int transa, int transb, int m, int n, int k, const void *alpha, const void *A, int lda, const void *B, const SoA *Bd,
+                          int ldb, const void *beta, const void *Cin, void *Cout, int ldc, int panels) {
     NEED_DEVICE(c);
-    if (!c || !alpha || !A || !B || !beta || !Cin || !Cout) return -1;
+    if (!c || !alpha || !A || (!B && !Bd) || !beta || !Cin || !Cout) return -1;
     if (m <= 0 || n <= 0 || k <= 0) return 0;                       // src/blas/gemm.cuh:75-78
     const bool ta = transa != MPRES_NO_TRANS, tb = transb != MPRES_NO_TRANS;
     if (transa != MPRES_NO_TRANS && transa != MPRES_TRANS && transa != MPRES_CONJ_TRANS) return -2;
@@ -594,7 +595,7 @@ int mpres_gemm_host(mpres_ctx *c, int transa, int transb, int m, int n, int k, c
     // panels: whole columns of B and C are contiguous only when B is not transposed
     int np = panels;
     if (np <= 0) { const int w = ((n + 7) / 8 + 255) / 256 * 256; np = (n + w - 1) / w; }
-    if (tb) np = 1;
+    if (tb && !Bd) np = 1;
     np = std::max(1, std::min(np, n));
     const int wcols = (n + np - 1) / np;
     np = (n + wcols - 1) / wcols;
@@ -610,7 +611,9 @@ int mpres_gemm_host(mpres_ctx *c, int transa, int transb, int m, int n, int k, c
     int rc;
     void *p;
     // (a growing workspace frees and reallocates: cudaFree synchronises, no transfer of an earlier call is in flight here anyway)
-    if ((rc = ws_soa(c, 12, lenA, &dA)) || (rc = ws_soa(c, 13, lenB, &dB)) || (rc = ws_soa(c, 14, lenC, &dC)) || (rc = ws_soa(c, 17, 2, &dS))) return rc;
+    if ((rc = ws_soa(c, 12, lenA, &dA)) || (rc = ws_soa(c, 14, lenC, &dC)) || (rc = ws_soa(c, 17, 2, &dS))) return rc;
+    if (Bd) dB = *Bd;
+    else if ((rc = ws_soa(c, 13, lenB, &dB))) return rc;
     if ((rc = ws_reserve(c, 15, (size_t) kHostRing * hp.chunk * hp.rs, &p))) return rc;
     hp.up_stage = (char *) p;
     const size_t panel_recs = (size_t) ldc * wcols;
@@ -621,15 +624,16 @@ int mpres_gemm_host(mpres_ctx *c, int transa, int transb, int m, int n, int k, c
     if ((rc = host_upload(hp, alpha, 0, 1, dS))) return rc;
     { SoA b1 = soa_offset(dS, 1, N); if ((rc = host_upload(hp, beta, 0, 1, b1))) return rc; }
     if ((rc = host_upload(hp, A, 0, extA, dA))) return rc;
-    if (tb && (rc = host_upload(hp, B, 0, extB, dB))) return rc;
+    if (tb && !Bd && (rc = host_upload(hp, B, 0, extB, dB))) return rc;
     for (int j = 0; j < np; ++j) {
         const int j0 = j * wcols, nj = std::min(wcols, n - j0);
-        if (!tb && (rc = host_upload(hp, B, (size_t) ldb * j0, (size_t) ldb * (nj - 1) + k, dB))) return rc;
+        if (!tb && !Bd && (rc = host_upload(hp, B, (size_t) ldb * j0, (size_t) ldb * (nj - 1) + k, dB))) return rc;
         const size_t coff = (size_t) ldc * j0, ccnt = (size_t) ldc * (nj - 1) + m;
         if ((rc = host_upload(hp, Cin, coff, ccnt, dC))) return rc;
         CUDA_TRY(cudaEventRecord(ev_ready, hp.s_unp));
         CUDA_TRY(cudaStreamWaitEvent(hp.s_comp, ev_ready, 0));
-        rc = gemm_impl(c, transa, transb, m, nj, k, dS, dA, lda, tb ? dB : soa_offset(dB, (size_t) ldb * j0, N), ldb, soa_offset(dS, 1, N),
+        // panel j of op(B): columns j0.. of a k x n matrix, or rows j0.. of an n x k one (whole B when it was uploaded in one piece)
+        rc = gemm_impl(c, transa, transb, m, nj, k, dS, dA, lda, soa_offset(dB, tb ? (size_t) j0 : (size_t) ldb * j0, N), ldb, soa_offset(dS, 1, N),
                        soa_offset(dC, coff, N), ldc, nullptr, hp.s_comp);
         if (rc) { cudaDeviceSynchronize(); return rc; }
         char *stage = down_stage + (size_t) (j & 1) * panel_recs * hp.rs;
@@ -647,6 +651,18 @@ int mpres_gemm_host(mpres_ctx *c, int transa, int transb, int m, int n, int k, c
     CUDA_TRY(cudaStreamSynchronize(hp.s_comp));
     CUDA_TRY(cudaStreamSynchronize(hp.s_unp));
     return 0;
+}
+
+int mpres_gemm_host(mpres_ctx *c, int transa, int transb, int m, int n, int k, const void *alpha, const void *A, int lda, const void *B, int ldb,
+                    const void *beta, const void *Cin, void *Cout, int ldc, int panels) {
+    if (!B) return -1;
+    return gemm_host_impl(c, transa, transb, m, n, k, alpha, A, lda, B, nullptr, ldb, beta, Cin, Cout, ldc, panels);
+}
+int mpres_gemm_host_bdev(mpres_ctx *c, int transa, int transb, int m, int n, int k, const void *alpha, const void *A, int lda, const mpres_array_t *B, int ldb,
+                         const void *beta, const void *Cin, void *Cout, int ldc, int panels) {
+    if (!B) return -1;
+    const SoA bd = view(B);
+    return gemm_host_impl(c, transa, transb, m, n, k, alpha, A, lda, nullptr, &bd, ldb, beta, Cin, Cout, ldc, panels);
 }
 
 int mpres_gemm_coll(mpres_ctx *c, int transa, int transb, int m, int n, int k, const mpres_collection_t *alpha,

@@ -43,6 +43,21 @@ class TorchMpArray:
         _check(self.ctx.lib.mpres_array_host2device(self.ctx.h, ctypes.byref(self.s), ctypes.c_void_p(ptr),
                                                     ctypes.c_size_t(count)), "mpres_array_host2device")
 
+    def host2device_ptr_at(self, offset, ptr, count):
+        """`count` host records into elements offset .. offset + count (a shifted view of the same arrays; `len` still gives the
+        offset of the upper interval bounds)"""
+        n = self.ctx.N
+        v = mp_array_t(self.digits.data_ptr() + 4 * n * offset, self.sign.data_ptr() + 4 * offset, self.exp.data_ptr() + 4 * offset,
+                       self.eval.data_ptr() + 16 * offset, None, self.len.data_ptr())
+        _check(self.ctx.lib.mpres_array_host2device(self.ctx.h, ctypes.byref(v), ctypes.c_void_p(ptr), ctypes.c_size_t(count)),
+               "mpres_array_host2device")
+
+    def slices(self, offset, count):
+        """the five contiguous device ranges that hold elements offset .. offset + count (digits, sign, exp, lower and upper bounds)"""
+        n, ln = self.ctx.N, max(1, self.size)
+        return [self.digits[n * offset:n * (offset + count)], self.sign[offset:offset + count], self.exp[offset:offset + count],
+                self.eval[2 * offset:2 * (offset + count)], self.eval[2 * (ln + offset):2 * (ln + offset + count)]]
+
     def device2host_ptr(self, ptr, count):
         _check(self.ctx.lib.mpres_array_device2host(self.ctx.h, ctypes.c_void_p(ptr), ctypes.byref(self.s),
                                                     ctypes.c_size_t(count)), "mpres_array_device2host")

@@ -48,6 +48,12 @@ def test_gemm_host_matches_device_sequence(pkg, N, shape, pads, ta, tb, panels):
         pad = np.array([i + j * ldc for j in range(n - 1) for i in range(m, ldc)], dtype=np.int64)
         if pad.size:
             assert diff_fields(Cio[pad], C[pad]).size == 0        # padding rows keep the caller's records
+    # B already on the device (the multi-GPU recipe: 1/N of B per PCIe link, the rest gathered over NVLink); panels also with transposed B
+    dB = ctx.mp_array_from_host(B)
+    out[:] = 0
+    pkg.mp_gemm_host_bdev(ctx, ta, tb, m, n, k, alpha, A, lda, dB, ldb, beta, C, ldc, out=out, panels=panels)
+    bad = diff_fields(out[used], want[used])
+    assert bad.size == 0, "device-resident B: %d/%d entries differ, first %d" % (bad.size, m * n, bad[0])
     # reference order through the same entry
     ctx.set_mode(pkg.MODE_REFERENCE_ORDER)
     want_ref = _device_gemm(pkg, ctx, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc)
