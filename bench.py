@@ -587,8 +587,7 @@ def main():
                 # SoA arrays), then one call over the host A / C row blocks with B resident (mpres_gemm_host_bdev)
                 cols = n // world
                 B.host2device_ptr_at(k * cols * rank, hB.data_ptr() + k * cols * rank * rs, k * cols)
-                for full, mine in zip(B.slices(0, k * n), B.slices(k * cols * rank, k * cols)):
-                    dist.all_gather_into_tensor(full, mine.clone())
+                parallel.gather_column_shards(dist, B.slices(0, k * n), B.slices(k * cols * rank, k * cols))
                 torch.cuda.synchronize()
                 pkg.mp_gemm_host_bdev(ctx, pkg.mblas_no_trans, pkg.mblas_no_trans, mr, n, k, hal, hA, mr, B, k, hbe, hC, mr, out=hOut, panels=args.e2e_panels)
                 return

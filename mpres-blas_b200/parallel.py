@@ -81,6 +81,21 @@ class LeanBroadcast:
         return small_moduli > 0 and 0 < nin_used <= self.nin and fallback_count == 0
 
 
+def soa_ranges(digits, sign, exp, ev, N, length, offset, count):
+    """The five contiguous ranges of an mp_array_t's SoA arrays that hold elements offset .. offset + count: digits, sign, exp, and
+    the lower / upper interval bounds (`ev`: int64 view of er_float_t[2 * length], lower bounds first -- src/types.cuh:85-92)."""
+    return [digits[N * offset:N * (offset + count)], sign[offset:offset + count], exp[offset:offset + count],
+            ev[2 * offset:2 * (offset + count)], ev[2 * (length + offset):2 * (length + offset + count)]]
+
+
+def gather_column_shards(dist, full_ranges, my_ranges):
+    """End-to-end recipe for the row-sharded GEMM: rank r has uploaded columns [n r / G, n (r + 1) / G) of B (elements
+    k n r / G .. of the column-major array) from host memory; every rank ends up with all of B.  One all-gather per SoA range (the
+    shards are equally long: n % G == 0), each rank contributing a copy of its own range."""
+    for full, mine in zip(full_ranges, my_ranges):
+        dist.all_gather_into_tensor(full, mine.clone())
+
+
 def dot_segment_sharded(dist, local_partial, reduce_partials):
     """local_partial() -> uint8 tensor holding one packed mp_float_t; reduce_partials(bytes, count) sums
     `count` packed records in index order and returns whatever the caller's result type is"""

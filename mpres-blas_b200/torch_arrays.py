@@ -54,9 +54,8 @@ class TorchMpArray:
 
     def slices(self, offset, count):
         """the five contiguous device ranges that hold elements offset .. offset + count (digits, sign, exp, lower and upper bounds)"""
-        n, ln = self.ctx.N, max(1, self.size)
-        return [self.digits[n * offset:n * (offset + count)], self.sign[offset:offset + count], self.exp[offset:offset + count],
-                self.eval[2 * offset:2 * (offset + count)], self.eval[2 * (ln + offset):2 * (ln + offset + count)]]
+        from .parallel import soa_ranges
+        return soa_ranges(self.digits, self.sign, self.exp, self.eval, self.ctx.N, max(1, self.size), offset, count)
 
     def device2host_ptr(self, ptr, count):
         _check(self.ctx.lib.mpres_array_device2host(self.ctx.h, ctypes.c_void_p(ptr), ctypes.byref(self.s),

@@ -104,6 +104,18 @@ def _worker(rank, world, port, tmp):
         assert bool((d.view(cnt, N)[:, 3:] == -7).all()) and bool((ev[: 2 * cnt] == -7).all())
     assert lb.nbytes(cnt) == cnt * (4 * 3 + 24)
     assert lb.verify(40, 3, 0) and not lb.verify(0, 0, 0) and not lb.verify(40, 4, 0) and not lb.verify(40, 3, 2)
+    # --- end-to-end recipe: every rank holds its column block of B (k x n2, n2 % world == 0), the five SoA ranges are all-gathered
+    n2 = 6
+    B2 = orc.random_records(k * n2, bits, 11)
+    cnt2, per = k * n2, k * n2 // world
+    full_d = torch.from_numpy(np.ascontiguousarray(B2["digits"]).reshape(-1).copy())
+    full_s, full_e = torch.from_numpy(B2["sign"].copy()), torch.from_numpy(B2["exp"].copy())
+    full_ev = torch.from_numpy(np.concatenate([B2["eval"][:, 0].copy().view(np.int64).reshape(-1), B2["eval"][:, 1].copy().view(np.int64).reshape(-1)]).copy())
+    mine_t = [torch.full_like(full_d, -7), torch.full_like(full_s, -7), torch.full_like(full_e, -7), torch.full_like(full_ev, -7)]
+    for dst, src in zip(parallel.soa_ranges(*mine_t, N, cnt2, per * rank, per), parallel.soa_ranges(full_d, full_s, full_e, full_ev, N, cnt2, per * rank, per)):
+        dst.copy_(src)                                             # "uploaded from host memory": only this rank's columns
+    parallel.gather_column_shards(dist, parallel.soa_ranges(*mine_t, N, cnt2, 0, cnt2), parallel.soa_ranges(*mine_t, N, cnt2, per * rank, per))
+    assert all(torch.equal(a, b) for a, b in zip(mine_t, [full_d, full_s, full_e, full_ev]))
     dist.barrier()
     dist.destroy_process_group()
     open(os.path.join(tmp, "ok%d" % rank), "w").write("ok")
