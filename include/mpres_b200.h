@@ -154,6 +154,9 @@ long mpres_launch_count(const mpres_ctx *ctx);
  * alignment, ms[1] = stage 2 per-modulus multiply-accumulate, ms[2] = stage 3 normalisation + epilogue. */
 int mpres_set_profiling(mpres_ctx *ctx, int on);
 int mpres_last_stage_ms(mpres_ctx *ctx, float *ms, int *stage2_launches);
+/* with profiling on: "kernel=ms;kernel=ms;..." of the last fast-path mp_gemm call, CUDA events on the caller's stream after every kernel
+ * (group) of the call; returns the bytes written or < 0.  Synchronises. */
+long mpres_last_kernel_ms(mpres_ctx *ctx, char *out, size_t cap);
 
 /* ---- containers: replace cuda::mp_array_init / clear / host2device / device2host
  *      (src/mparray.cuh:35,59,76,125) and the mp_collection_* twins (src/mpcollection.cuh:35,54,69,117).
@@ -254,6 +257,26 @@ int mpres_gemm_host(mpres_ctx *ctx, int transa, int transb, int m, int n, int k,
  * transfers run on the library's own streams: synchronise the stream that produced B first).  Panels also apply to transposed B. */
 int mpres_gemm_host_bdev(mpres_ctx *ctx, int transa, int transb, int m, int n, int k, const void *alpha, const void *A, int lda, const mpres_array_t *B,
                          int ldb, const void *beta, const void *Cin, void *Cout, int ldc, int panels);
+
+/* ---- row-sharded mp_gemm over the GPUs of one NVLink domain (BASELINE config 3; the reference has no multi-GPU code) --------------
+ * One rank per GPU (a process each, or threads of one process).  Rank r owns rows [m r / G, m (r + 1) / G) of A and C as compact
+ * arrays; every rank holds B.  Inside a call each rank converts ONE column block of B (n / G columns) into the one-byte planes of the
+ * small-modulus stage 2 and copies that package into every peer's receive buffer over NVLink (copy engines, peer-mapped memory: CUDA
+ * IPC between processes), while its tensor kernel already multiplies the panels that have arrived -- the alignment of B, which does
+ * not shrink with G when every rank converts all of B, is done once per node.  Results are identical to mpres_gemm on the row block.
+ *   mpres_shard_create   allocates the rank's receive buffer for calls with this n and k <= k_max (n % world == 0)
+ *   mpres_shard_export   writes mpres_shard_handle_size() bytes to publish to the other ranks (all-gather them in rank order)
+ *   mpres_shard_connect  maps the peers' buffers from the gathered handles (world x handle size bytes)
+ *   mpres_gemm_sharded   collective: every rank calls it with its row block (m_local rows) and its complete copy of B; the calls of
+ *                        all ranks must be made in the same order.  MPRES_PUSH_STREAMS (environment) = copy streams per rank (2). */
+typedef struct mpres_shard mpres_shard;
+size_t mpres_shard_handle_size(void);
+int mpres_shard_create(mpres_ctx *ctx, int rank, int world, int n, int k_max, mpres_shard **out);
+int mpres_shard_export(mpres_shard *s, void *handle_out);
+int mpres_shard_connect(mpres_shard *s, const void *handles);
+int mpres_shard_destroy(mpres_shard *s);
+int mpres_gemm_sharded(mpres_shard *s, int transa, int transb, int m_local, int n, int k, const mpres_array_t *alpha, const mpres_array_t *A, int lda,
+                       const mpres_array_t *B, int ldb, const mpres_array_t *beta, mpres_array_t *C, int ldc, mpres_stream_t stream);
 
 /* The same three operations over mp_collection_t operands with explicit allocated lengths (the
  * reference only uses mp_collection_t in its sparse kernels, src/sparse/mpmtx/*.cuh; north_star asks

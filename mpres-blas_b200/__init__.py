@@ -44,6 +44,8 @@ EXPORTS = [
     "mpres_collection_init", "mpres_collection_clear", "mpres_collection_host2device", "mpres_collection_device2host",
     "mpres_array_set_binary", "mpres_gemm", "mpres_gemv", "mpres_dot", "mpres_scal", "mpres_axpy", "mpres_waxpby", "mpres_ge_add", "mpres_ge_acc", "mpres_ger", "mpres_ge_diag_scale", "mpres_ge_lr_scale", "mpres_rot", "mpres_axpy_dot", "mpres_gemm_host", "mpres_gemm_host_bdev", "mpres_gemm_coll", "mpres_gemv_coll",
     "mpres_dot_coll", "mpres_dot_partial", "mpres_reduce_partials", "mpres_probe", "mpres_version",
+    "mpres_last_kernel_ms", "mpres_shard_handle_size", "mpres_shard_create", "mpres_shard_export", "mpres_shard_connect", "mpres_shard_destroy",
+    "mpres_gemm_sharded",
 ]
 
 
@@ -58,7 +60,8 @@ def load_library():
     lib = ctypes.CDLL(LIB_PATH)
     lib.mpres_version.restype = ctypes.c_char_p
     lib.mpres_sizeof_mp_float.restype = ctypes.c_size_t
-    for f in ("mpres_get_constant", "mpres_last_fallback_count", "mpres_launch_count", "mpres_last_slow_count", "mpres_last_base_size", "mpres_debug_read_workspace", "mpres_last_minplus_dense_count"):
+    lib.mpres_shard_handle_size.restype = ctypes.c_size_t
+    for f in ("mpres_last_kernel_ms", "mpres_get_constant", "mpres_last_fallback_count", "mpres_launch_count", "mpres_last_slow_count", "mpres_last_base_size", "mpres_debug_read_workspace", "mpres_last_minplus_dense_count"):
         getattr(lib, f).restype = ctypes.c_long
     _lib = lib
     return lib
@@ -167,6 +170,14 @@ class Context:
 
     def last_fallback_count(self):
         return self.lib.mpres_last_fallback_count(self.h)
+
+    def last_kernel_ms(self):
+        """[(kernel name, ms), ...] of the last fast-path mp_gemm call (profiling on), in launch order"""
+        buf = ctypes.create_string_buffer(4096)
+        n = self.lib.mpres_last_kernel_ms(self.h, buf, ctypes.c_size_t(4096))
+        if n < 0:
+            return []
+        return [(kv.split("=")[0], float(kv.split("=")[1])) for kv in buf.raw[:n].decode().split(";") if "=" in kv]
 
     def constant(self, which, dtype, count):
         out = np.zeros(count, dtype=dtype)
@@ -342,6 +353,45 @@ def mp_rot(ctx, n, x, incx, y, incy, c, s, buffer1=None, buffer2=None, stream=0)
 def mp_axpy_dot(ctx, n, alpha, w, incw, v, incv, u, incu, r, buffer=None, stream=0):
     """cuda::mp_axpy_dot (src/blas/axpydot.cuh:33): w = w - alpha*v, r[0] = u^T w."""
     _check(ctx.lib.mpres_axpy_dot(ctx.h, n, _ref(alpha), _ref(w), incw, _ref(v), incv, _ref(u), incu, _ref(r), _ref(buffer), _vp(stream)), "mpres_axpy_dot")
+
+
+class Shard:
+    """Communicator of the row-sharded mp_gemm (mpres_shard_*): this rank's receive buffer and the peer mappings.
+    `exchange(handle_bytes) -> list of every rank's handle bytes in rank order` is the caller's all-gather (torch.distributed,
+    MPI, or a plain list inside one process)."""
+
+    def __init__(self, ctx, rank, world, n, k_max):
+        self.ctx, self.rank, self.world = ctx, rank, world
+        self.h = ctypes.c_void_p()
+        _check(ctx.lib.mpres_shard_create(ctx.h, rank, world, n, k_max, ctypes.byref(self.h)), "mpres_shard_create")
+
+    def export(self):
+        size = self.ctx.lib.mpres_shard_handle_size()
+        buf = ctypes.create_string_buffer(size)
+        _check(self.ctx.lib.mpres_shard_export(self.h, buf), "mpres_shard_export")
+        return buf.raw
+
+    def connect(self, handles):
+        blob = b"".join(handles)
+        assert len(blob) == self.world * self.ctx.lib.mpres_shard_handle_size()
+        _check(self.ctx.lib.mpres_shard_connect(self.h, blob), "mpres_shard_connect")
+
+    def gemm(self, transa, transb, m_local, n, k, alpha, A, lda, B, ldb, beta, C, ldc, stream=0):
+        """collective: C_r = alpha * op(A_r) * op(B) + beta * C_r on this rank's row block; B is the rank's complete copy"""
+        _check(self.ctx.lib.mpres_gemm_sharded(self.h, transa, transb, m_local, n, k, _ref(alpha), _ref(A), lda, _ref(B), ldb, _ref(beta), _ref(C), ldc,
+                                               _vp(stream)), "mpres_gemm_sharded")
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.mpres_shard_destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            if self.ctx.h:
+                self.close()
+        except Exception:
+            pass
 
 
 def _host_ptr(a):

@@ -66,8 +66,20 @@ struct mpres_ctx {
     cudaEvent_t hev[16] = {nullptr};
     bool host_ready = false;
     std::mutex host_mu;
-    int *d_counter = nullptr;      // fallback element counter of the last call
+    // device counters of the last call, kCounterBlock ints per column panel g (one panel unless the call is sharded):
+    // [8g + 0] elements handed to the reference-order fallback, [8g + 1] elements listed for the residue-parallel normalisation,
+    // [8g + 6] (min,+) pairs recomputed densely; block 0 also holds [2] n' of the reduced base and [4], [5] the small-base selection
+    int *d_counter = nullptr;
+    int *h_sel = nullptr;          // pinned: {n', -, one-byte moduli, input residues, error} read back after the base selection
     cudaStream_t last_stream = nullptr;
+    // calls on one context share its workspaces and counters: a call on another stream than its predecessor's waits for it
+    cudaEvent_t serial_ev = nullptr;
+    cudaStream_t serial_stream = nullptr;
+    bool serial_valid = false;
+    // optional per-kernel timing (mpres_set_profiling): events recorded on the caller's stream after every kernel of the fast mp_gemm
+    std::vector<cudaEvent_t> prof_ev;
+    std::vector<const char *> prof_name;
+    int prof_used = 0;
     int sm_count = 148;
     // optional per-stage timing (events recorded on the caller's stream)
     bool profiling = false;
@@ -75,12 +87,16 @@ struct mpres_ctx {
     bool ev_valid = false;
     int last_stage2_launches = 0;
     // opt-in shared-memory sizes (cudaFuncSetAttribute) are per device: remembered per context, not per process
-    bool attr_fast = false, attr_align_mma = false, attr_align = false, attr_small = false, attr_umma = false;
+    bool attr_ext = false, attr_fast = false, attr_align_mma = false, attr_align = false, attr_small = false, attr_umma = false;
     unsigned long long attr_norm = 0;    // bit NQ / 8: k_norm_fast<NQ, *, true> (staged residues of S)
     int norm_staged = 1;                 // k_norm_fast stages the residues of S in shared memory (mpres_set_stage3_kernel(4) = off)
     unsigned long long attr_fused = 0;   // bit NQ / 8: k_ext_norm_small<NQ, *>
     std::mutex mu;
 };
+
+constexpr int kMaxPanels = 16;            // column panels of one fast-path call (ranks of a sharded call)
+constexpr int kCounterBlock = 8;
+constexpr int kCounterInts = kCounterBlock * kMaxPanels;
 
 #define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return (int) e_; } while (0)
 
@@ -96,7 +112,8 @@ int ws_reserve(mpres_ctx *c, int slot, size_t bytes, void **out) {
     if (c->ws_size[slot] < bytes) {
         if (c->ws[slot]) { cudaDeviceSynchronize(); cudaFree(c->ws[slot]); c->ws[slot] = nullptr; c->ws_size[slot] = 0; }
         size_t want = bytes + bytes / 8 + 256;
-        CUDA_TRY(cudaMalloc(&c->ws[slot], want));
+        const cudaError_t e = cudaMalloc(&c->ws[slot], want);
+        if (e != cudaSuccess) { c->ws[slot] = nullptr; cudaGetLastError(); return (int) e; }     // (the sticky last-error must not leak into the next call)
         c->ws_size[slot] = want;
     }
     *out = c->ws[slot];
@@ -128,6 +145,37 @@ int ws_soa(mpres_ctx *c, int slot, size_t len, SoA *out) {
     out->len_ptr = nullptr;
     out->len_val = (long long) len;
     return 0;
+}
+
+// Calls on one context share its workspaces and device counters.  call_begin makes the stream of this call wait for the previous
+// call when that ran on another stream; call_end records the point the next call has to wait for.
+inline int call_begin(mpres_ctx *c, cudaStream_t st) {
+    if (c->serial_valid && c->serial_stream != st) CUDA_TRY(cudaStreamWaitEvent(st, c->serial_ev, 0));
+    return 0;
+}
+inline int call_end(mpres_ctx *c, cudaStream_t st) {
+    if (!c->serial_ev) CUDA_TRY(cudaEventCreateWithFlags(&c->serial_ev, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventRecord(c->serial_ev, st));
+    c->serial_stream = st;
+    c->serial_valid = true;
+    return 0;
+}
+// per-kernel timing marks (only while profiling is on)
+inline void prof_reset(mpres_ctx *c, cudaStream_t st) {
+    c->prof_used = 0;
+    if (!c->profiling) return;
+    if (c->prof_ev.empty()) { c->prof_ev.resize(64, nullptr); c->prof_name.resize(64, nullptr); }
+    if (!c->prof_ev[0]) cudaEventCreate(&c->prof_ev[0]);
+    cudaEventRecord(c->prof_ev[0], st);
+    c->prof_name[0] = "begin";
+    c->prof_used = 1;
+}
+inline void prof_mark(mpres_ctx *c, cudaStream_t st, const char *name) {
+    if (!c->profiling || c->prof_used <= 0 || c->prof_used >= (int) c->prof_ev.size()) return;
+    const int i = c->prof_used++;
+    if (!c->prof_ev[i]) cudaEventCreate(&c->prof_ev[i]);
+    cudaEventRecord(c->prof_ev[i], st);
+    c->prof_name[i] = name;
 }
 
 inline int group_size(int N) { return N <= 8 ? 8 : N <= 16 ? 16 : 32; }

@@ -115,8 +115,24 @@ __global__ void k_outer_info(const DevConsts *Cp, SoA X, long long so, long long
 constexpr int kMaxReducedBase = 48;
 // sel[0] = number of small moduli (0: the small-modulus path is not used), sel[1] = reference moduli its input conversion reads.
 // When the small base is selected *nprime is 0 and the kernels of the reference-moduli path leave at once.
+// Sharded calls (one rank per GPU, rows of A / C split, every rank converts one column block of B): the base must be the same on every rank,
+// so the window maxima are exchanged first -- each rank stores its three maxima and the call's epoch into its slot of EVERY rank's
+// exchange array (peer-mapped memory, NVLink stores) and waits until all slots of its own array carry the epoch.  The slots are
+// double-buffered by call parity: a rank can be at most one call ahead of the slowest one.  This wait is also the rendezvous that
+// keeps a rank from overwriting receive buffers its peers still read.
+struct Xchg {
+    int world, rank, parity;
+    unsigned epoch;
+    int *peer[kMaxPanels];      // the exchange array [2][world][4] of every rank; peer[rank] is the local one
+    int *err;                   // set to 1 when a rank did not show up in time
+};
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __global__ void __launch_bounds__(256) k_choose_base(const DevConsts *Cp, const OuterInfo *ia, int m, const OuterInfo *ib, int n, int k,
-                                                     int enabled, int small_enabled, int *nprime, int *sel) {
+                                                     int enabled, int small_enabled, int *nprime, int *sel, const Xchg x) {
     __shared__ int sa[256], sb[256], sx[256];
     int wa = -1, wb = -1, xb = 0;
     for (int i = threadIdx.x; i < m; i += 256) { wa = max(wa, ia[i].win); xb = max(xb, ia[i].xb); }
@@ -131,6 +147,31 @@ __global__ void __launch_bounds__(256) k_choose_base(const DevConsts *Cp, const 
         __syncthreads();
     }
     if (threadIdx.x == 0) {
+        if (x.world > 1) {
+            const int slot = (x.parity * x.world + x.rank) * 4;
+            for (int p = 0; p < x.world; ++p) {
+                volatile int *d = x.peer[p] + slot;
+                d[0] = sa[0]; d[1] = sb[0]; d[2] = sx[0];
+            }
+            __threadfence_system();
+            for (int p = 0; p < x.world; ++p)
+                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(x.peer[p] + slot + 3), "r"(x.epoch) : "memory");
+            const unsigned long long t0 = global_ns();
+            int gwa = -1, gwb = -1, gxb = 0;
+            for (int p = 0; p < x.world; ++p) {
+                const int *src = x.peer[x.rank] + (x.parity * x.world + p) * 4;
+                for (;;) {
+                    unsigned v;
+                    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src + 3) : "memory");
+                    if (v == x.epoch) break;
+                    if (global_ns() - t0 > 60000000000ull) { *x.err = 1; break; }     // 60 s
+                    __nanosleep(500);
+                }
+                const volatile int *vs = src;
+                gwa = max(gwa, vs[0]); gwb = max(gwb, vs[1]); gxb = max(gxb, vs[2]);
+            }
+            sa[0] = gwa; sb[0] = gwb; sx[0] = gxb;
+        }
         const int N = Cp->N;
         int np = N;
         int lgk = 0;
@@ -548,241 +589,6 @@ __global__ void k_gemm_todo(const DevConsts *Cp, bool ta, bool tb, int m, int n,
 
 }  // namespace mpres
 
-// ---- host launchers ----------------------------------------------------------------------------------
-
-static inline long long round_up(long long v, long long a) { return (v + a - 1) / a * a; }
-
-// S is unused by the fast path (the epilogue is fused); *done tells the caller whether C is final.
-inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, SoA A, int lda, SoA B, int ldb,
-                          SoA alpha, SoA beta, SoA Cm, int ldc, cudaStream_t st, bool *done) {
-    *done = false;
-    const int N = c->hc.N;
-    const long long m_p = round_up(m, kBM), n_p = round_up(n, kBN), k_p = round_up(k, 128);
-    if (k_p > 32000 * 128ll) return 0;
-    // the small-modulus stage 2 (kernels_small.cuh) is offered whenever its tables exist; k_choose_base decides per call
-    const bool small_on = c->stage2 == MPRES_STAGE2_SMALL && c->sc.usable;
-    const long long m_ps = round_up(m, kSN), n_ps = round_up(n, 256);   // rows of the one-byte planes: 256 x (128 | 256) tiles of k_small_umma
-    // workspace: planes A/B (u8), S (int), shifts, delta, infos, todo
-    const size_t bytesPA = (size_t) N * 4 * m_p * k_p, bytesPB = (size_t) N * 4 * n_p * k_p;
-    const size_t bytesS = (size_t) N * n_p * m_p * 4;
-    const size_t bytesSA = (size_t) m_ps * k_p * 2, bytesSB = (size_t) n_ps * k_p * 2, bytesD = (size_t) n_p * m_p * 2;
-    const size_t bytesInfo = (size_t) (m_p + n_p) * sizeof(OuterInfo);
-    const size_t bytesTab = (size_t) (3 * c->hc.log2M + 2) * N * sizeof(int);   // alpha * 2^j, beta * 2^j (stage 3)
-    const size_t bytesTodo = (size_t) m * n * sizeof(long long);   // per list: reference-order todo, stage-3 slow list
-    void *pPA, *pPB, *pS, *pMisc, *pQA = nullptr, *pQB = nullptr, *pS8 = nullptr;
-    int rc;
-    if ((rc = ws_reserve(c, 3, bytesPA, &pPA))) return rc;
-    if ((rc = ws_reserve(c, 4, bytesPB, &pPB))) return rc;
-    if ((rc = ws_reserve(c, 5, bytesS, &pS))) return rc;
-    if ((rc = ws_reserve(c, 6, bytesSA + bytesSB + bytesD + bytesInfo + 2 * bytesTodo + bytesTab + 1024, &pMisc))) return rc;
-    if (small_on) {
-        if ((rc = ws_reserve(c, 8, (size_t) kSmallMax * m_ps * k_p, &pQA))) return rc;
-        if ((rc = ws_reserve(c, 9, (size_t) kSmallMax * n_ps * k_p, &pQB))) return rc;
-        if ((rc = ws_reserve(c, 10, (size_t) kSmallMax * n_ps * m_ps, &pS8))) return rc;
-    }
-    char *pm = (char *) pMisc;
-    int16_t *SA = (int16_t *) pm; pm += bytesSA;
-    int16_t *SB = (int16_t *) pm; pm += bytesSB;
-    int16_t *D = (int16_t *) pm; pm += (bytesD + 15) / 16 * 16;
-    OuterInfo *IA = (OuterInfo *) pm; pm += (size_t) m_p * sizeof(OuterInfo);
-    OuterInfo *IB = (OuterInfo *) pm; pm += (size_t) n_p * sizeof(OuterInfo);
-    long long *todo = (long long *) pm; pm += bytesTodo;
-    long long *slow = (long long *) pm; pm += bytesTodo;
-    pm = (char *) (((uintptr_t) pm + 15) & ~(uintptr_t) 15);   // the table rows are read as 128-bit loads
-    int *scal_tab = (int *) pm;
-    int *nprime = c->d_counter + 2, *sel = c->d_counter + 4;
-
-    // element (o, l) index strides: op(A)(i, l) and op(B)(l, j)
-    const long long soA = ta ? lda : 1, slA = ta ? 1 : lda;
-    const long long soB = tb ? 1 : ldb, slB = tb ? ldb : 1;
-    auto mark = [&](int i) { if (c->profiling) { if (!c->ev[i]) cudaEventCreate(&c->ev[i]); cudaEventRecord(c->ev[i], st); } };
-    mark(0);
-    int extra_launches = 0;
-    k_outer_info<<<(unsigned) ((m * 32ll + 255) / 256), 256, 0, st>>>(c->dconsts, A, soA, slA, m, k, IA);
-    k_outer_info<<<(unsigned) ((n * 32ll + 255) / 256), 256, 0, st>>>(c->dconsts, B, soB, slB, n, k, IB);
-    k_choose_base<<<1, 256, 0, st>>>(c->dconsts, IA, m, IB, n, k, c->reduced_base, small_on ? 1 : 0, nprime, sel);
-    const size_t smem_align = (size_t) N * 4 * (kRun + 4);
-    if (!c->attr_fast) {
-        cudaFuncSetAttribute(k_align_planes, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 4 * (kRun + 4));
-        cudaFuncSetAttribute(k_align_planes4, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 4 * (kRun + 4));
-        cudaFuncSetAttribute(k_base_extend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) base_extend_smem(128));
-        cudaFuncSetAttribute(k_limb_gemm<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
-        cudaFuncSetAttribute(k_limb_gemm<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
-        cudaFuncSetAttribute(k_ext_small<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ext_small_smem(512, 128));
-        cudaFuncSetAttribute(k_ext_small<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ext_small_smem(512, 128));
-        c->attr_fast = true;
-    }
-    if (small_on) {
-        const unsigned gA = (unsigned) std::min<long long>((m_ps / kASo) * (k_p / kASl), (long long) c->sm_count * MPRES_ALIGN_BLOCKS);
-        const unsigned gB = (unsigned) std::min<long long>((n_ps / kASo) * (k_p / kASl), (long long) c->sm_count * MPRES_ALIGN_BLOCKS);
-        if (c->align_mma) {
-            if (!c->attr_align_mma) { cudaFuncSetAttribute(k_align_small<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) align_small_smem(true)); c->attr_align_mma = true; }
-            k_align_small<true><<<gA, 256, align_small_smem(true), st>>>(c->dconsts, A, soA, slA, m, k, IA, (uint8_t *) pQA, SA, m_ps, k_p, sel);
-            k_align_small<true><<<gB, 256, align_small_smem(true), st>>>(c->dconsts, B, soB, slB, n, k, IB, (uint8_t *) pQB, SB, n_ps, k_p, sel);
-        } else {
-            if (!c->attr_align) { cudaFuncSetAttribute(k_align_small<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) align_small_smem(false)); c->attr_align = true; }
-            k_align_small<false><<<gA, 256, align_small_smem(false), st>>>(c->dconsts, A, soA, slA, m, k, IA, (uint8_t *) pQA, SA, m_ps, k_p, sel);
-            k_align_small<false><<<gB, 256, align_small_smem(false), st>>>(c->dconsts, B, soB, slB, n, k, IB, (uint8_t *) pQB, SB, n_ps, k_p, sel);
-        }
-        extra_launches += 2;
-    }
-    if (N % 4 == 0 && N <= 128 && c->stage1 == 0) {
-        k_align_planes4<<<dim3((unsigned) m_p, (unsigned) std::min<long long>(k_p / kRun, 4)), 256, smem_align, st>>>(c->dconsts, A, soA, slA, m, k, IA, (uint8_t *) pPA, SA, m_p, k_p, nprime);
-        k_align_planes4<<<dim3((unsigned) n_p, (unsigned) std::min<long long>(k_p / kRun, 4)), 256, smem_align, st>>>(c->dconsts, B, soB, slB, n, k, IB, (uint8_t *) pPB, SB, n_p, k_p, nprime);
-    } else {
-        k_align_planes<<<dim3((unsigned) m_p, (unsigned) (k_p / kRun)), 256, smem_align, st>>>(c->dconsts, A, soA, slA, m, k, IA, (uint8_t *) pPA, SA, m_p, k_p);
-        k_align_planes<<<dim3((unsigned) n_p, (unsigned) (k_p / kRun)), 256, smem_align, st>>>(c->dconsts, B, soB, slB, n, k, IB, (uint8_t *) pPB, SB, n_p, k_p);
-    }
-    if (c->minplus_sparse && k_p >= 512) {
-        // (min,+) from candidate lists (kernels_minplus.cuh); SA / SB have m_ps / n_ps allocated rows
-        const size_t bT = (size_t) k_p * (m_ps + n_ps) * 2, bD = (size_t) m_p * n_p * 2 * 2, bC = (size_t) (m_p + n_p) * kMcT * 8 + (size_t) (m_p + n_p) * 4;
-        void *pMp;
-        if ((rc = ws_reserve(c, 11, bT + bD + bC + (size_t) m * n * 8 + 256, &pMp))) return rc;
-        char *q = (char *) pMp;
-        int16_t *SAT = (int16_t *) q; q += (size_t) k_p * m_ps * 2;
-        int16_t *SBT = (int16_t *) q; q += (size_t) k_p * n_ps * 2;
-        int16_t *D1 = (int16_t *) q; q += (size_t) m_p * n_p * 2;
-        int16_t *D2 = (int16_t *) q; q += (size_t) m_p * n_p * 2;
-        int *cposA = (int *) q; q += (size_t) m_p * kMcT * 4;
-        int *cvalA = (int *) q; q += (size_t) m_p * kMcT * 4;
-        int *cposB = (int *) q; q += (size_t) n_p * kMcT * 4;
-        int *cvalB = (int *) q; q += (size_t) n_p * kMcT * 4;
-        int *thrA = (int *) q; q += (size_t) m_p * 4;
-        int *thrB = (int *) q; q += (size_t) n_p * 4;
-        q = (char *) (((uintptr_t) q + 15) & ~(uintptr_t) 15);
-        long long *mplist = (long long *) q;
-        k_mp_select<<<(unsigned) m, 256, 0, st>>>(SA, k_p, (int) k_p, m, cposA, cvalA, thrA);
-        k_mp_select<<<(unsigned) n, 256, 0, st>>>(SB, k_p, (int) k_p, n, cposB, cvalB, thrB);
-        k_mp_transpose<<<dim3((unsigned) (m_ps / 64), (unsigned) (k_p / 64)), 256, 0, st>>>(SA, k_p, SAT, m_ps);
-        k_mp_transpose<<<dim3((unsigned) (n_ps / 64), (unsigned) (k_p / 64)), 256, 0, st>>>(SB, k_p, SBT, n_ps);
-        k_mp_gather<<<(unsigned) m, 256, 0, st>>>(cposA, cvalA, SBT, n_ps, m, (int) n_p, D1, n_p);
-        k_mp_gather<<<(unsigned) n, 256, 0, st>>>(cposB, cvalB, SAT, m_ps, n, (int) m_p, D2, m_p);
-        k_mp_combine<<<dim3((unsigned) (m_p / 64), (unsigned) (n_p / 64)), 256, 0, st>>>(D1, n_p, D2, m_p, thrA, thrB, m, n, D, m_p, mplist, c->d_counter + 6);
-        k_mp_fix<<<c->sm_count * 4, 256, 0, st>>>(SA, SB, k_p, D, m_p, mplist, c->d_counter + 6);
-        extra_launches += 7;
-    } else {
-        k_minplus<<<dim3((unsigned) (m_p / kMpTI), (unsigned) (n_p / kMpTJ)), 256, 0, st>>>(SA, SB, D, k_p, m_p, n_p);
-    }
-    dim3 grid((unsigned) (n_p / kBN), (unsigned) (m_p / kBM), (unsigned) N);
-    mark(1);
-    int gemm_launches = 0;
-    if (small_on) {
-        for (long long kb = 0; kb < k_p; kb += kSmallKChunk) {
-            const int kl = (int) std::min<long long>(kSmallKChunk, k_p - kb);
-            if ((rc = launch_small_umma(c, (const uint8_t *) pQA, (const uint8_t *) pQB, (uint8_t *) pS8, m_ps, n_ps, k_p, kb, kl, kb > 0, sel, st))) return rc;
-            gemm_launches += 1;
-        }
-    }
-    for (long long kb = 0; kb < k_p; kb += 8064) {
-        const int kl = (int) std::min<long long>(8064, k_p - kb);
-        if (c->stage2 == MPRES_STAGE2_MMA_SYNC) {
-            k_limb_gemm<0><<<grid, 256, kGemmSmem, st>>>(c->dconsts, (const uint8_t *) pPA, (const uint8_t *) pPB, (int *) pS, m_p, n_p, k_p, kb, kl, kb > 0, nprime);
-            k_limb_gemm<1><<<grid, 256, kGemmSmem, st>>>(c->dconsts, (const uint8_t *) pPA, (const uint8_t *) pPB, (int *) pS, m_p, n_p, k_p, kb, kl, true, nprime);
-            gemm_launches += 2;
-        } else {
-            if ((rc = launch_limb_umma(c, c->stage2 != MPRES_STAGE2_UMMA_UNSTACKED, (const uint8_t *) pPA, (const uint8_t *) pPB, (int *) pS, m_p, n_p, k_p, kb, kl,
-                                       kb > 0, st))) return rc;
-            gemm_launches += 1;
-        }
-    }
-    mark(2);
-    const bool allow_fb = c->mode == MPRES_MODE_AUTO;
-    int stage3_launches = 0;
-    bool have_fast = c->stage3 == 0;
-    switch (N) { case 8: case 16: case 24: case 32: case 40: case 48: case 56: case 64: break; default: have_fast = false; }
-    const bool f32 = c->sc.usable && c->sc.red_shift >= 24 && c->sc.red_shift <= 27 && c->norm32;
-    const bool fused = small_on && have_fast && c->fuse_ext;
-    if (small_on && !fused) {
-        const unsigned gx = (unsigned) std::min<long long>((m_p / kXT) * n, (long long) c->sm_count * 4);     // persistent: four blocks per SM
-        const size_t sm = ext_small_smem(c->sc.ext_cols, N);
-        if (c->sc.red_shift) k_ext_small<true><<<gx, kXT, sm, st>>>(c->dconsts, m, n, (const uint8_t *) pS8, m_p, m_ps, n_ps, (int *) pS, n_p, sel);
-        else k_ext_small<false><<<gx, kXT, sm, st>>>(c->dconsts, m, n, (const uint8_t *) pS8, m_p, m_ps, n_ps, (int *) pS, n_p, sel);
-        ++extra_launches;
-    }
-    if (c->reduced_base && N % 4 == 0) {
-        const dim3 gx((unsigned) ((m + kExtThreads - 1) / kExtThreads), (unsigned) std::min(n, 256));
-        k_base_extend<<<gx, kExtThreads, base_extend_smem(N), st>>>(c->dconsts, m, n, (int *) pS, m_p, n_p, c->d_counter + 2);
-        ++stage3_launches;
-    }
-    auto norm_fast = [&](auto tag) {
-        constexpr int NQ = decltype(tag)::value;
-        const unsigned g3 = (unsigned) ((long long) ((m + kNormFastThreads - 1) / kNormFastThreads) * n);
-        const int rowsT = 3 * c->hc.log2M + 2;
-        k_scalar_tables<<<(rowsT * NQ + 255) / 256, 256, 0, st>>>(c->dconsts, alpha, beta, scal_tab);
-        const size_t sm_cds = (size_t) kNormFastThreads * (NQ + 1) * sizeof(int);
-        if (fused) {
-            // small-modulus path: base extension and normalisation in one kernel (leaves at once when the small base was not selected)
-            const unsigned gx = (unsigned) ((m_p / kXT) * n);
-            const size_t sm = ext_small_smem(c->sc.ext_cols, NQ) + (ext_norm_cds_aliased(NQ) ? 0 : sm_cds);
-            if (!(c->attr_fused >> (NQ / 8) & 1ull)) {
-                cudaFuncSetAttribute(k_ext_norm_small<NQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm);
-                cudaFuncSetAttribute(k_ext_norm_small<NQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm);
-                c->attr_fused |= 1ull << (NQ / 8);
-            }
-            if (f32)
-                k_ext_norm_small<NQ, true><<<gx, kXT, sm, st>>>(c->dconsts, m, n, k, (const uint8_t *) pS8, m_p, m_ps, n_ps, (int *) pS, n_p, sel, D, IA, IB, alpha, beta, Cm, ldc,
-                                                               scal_tab, todo, c->d_counter, slow, c->d_counter + 1, allow_fb);
-            else
-                k_ext_norm_small<NQ, false><<<gx, kXT, sm, st>>>(c->dconsts, m, n, k, (const uint8_t *) pS8, m_p, m_ps, n_ps, (int *) pS, n_p, sel, D, IA, IB, alpha, beta, Cm, ldc,
-                                                                scal_tab, todo, c->d_counter, slow, c->d_counter + 1, allow_fb);
-            ++extra_launches;
-        }
-        // limb-plane path (or unfused small path); `gate`: leave at once when the fused kernel did the work
-        const int *gate = fused ? sel : nullptr;
-        auto launch_norm = [&](auto kern, size_t smem) {
-            kern<<<g3, kNormFastThreads, smem, st>>>(c->dconsts, m, n, k, (const int *) pS, D, m_p, n_p, IA, IB, alpha, beta, Cm, ldc,
-                                                     scal_tab, todo, c->d_counter, slow, c->d_counter + 1, allow_fb, gate);
-        };
-        if (c->norm_staged) {
-            const size_t sm_st = sm_cds + (size_t) NQ * kNormFastThreads * sizeof(int);
-            if (sm_st > 48 * 1024 && !(c->attr_norm >> (NQ / 8) & 1ull)) {
-                cudaFuncSetAttribute(k_norm_fast<NQ, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm_st);
-                cudaFuncSetAttribute(k_norm_fast<NQ, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm_st);
-                c->attr_norm |= 1ull << (NQ / 8);
-            }
-            if (f32) launch_norm(k_norm_fast<NQ, true, true>, sm_st); else launch_norm(k_norm_fast<NQ, false, true>, sm_st);
-        } else {
-            if (f32) launch_norm(k_norm_fast<NQ, true, false>, sm_cds); else launch_norm(k_norm_fast<NQ, false, false>, sm_cds);
-        }
-        ++stage3_launches;
-    };
-    if (have_fast) {
-        switch (N) {
-            case 8: norm_fast(std::integral_constant<int, 8>{}); break;
-            case 16: norm_fast(std::integral_constant<int, 16>{}); break;
-            case 24: norm_fast(std::integral_constant<int, 24>{}); break;
-            case 32: norm_fast(std::integral_constant<int, 32>{}); break;
-            case 40: norm_fast(std::integral_constant<int, 40>{}); break;
-            case 48: norm_fast(std::integral_constant<int, 48>{}); break;
-            case 56: norm_fast(std::integral_constant<int, 56>{}); break;
-            case 64: norm_fast(std::integral_constant<int, 64>{}); break;
-            default: have_fast = false;
-        }
-    }
-    MPRES_DISPATCH(N, {
-        if (have_fast) {
-            k_norm_list<G, R><<<c->sm_count * 8, 256, 0, st>>>(c->dconsts, m, n, k, (const int *) pS, D, m_p, n_p, IA, IB, alpha, beta, Cm, ldc,
-                                                              slow, c->d_counter + 1);
-            stage3_launches = 2;
-        } else {
-            constexpr int kNormTile = 256 / G;
-            const unsigned g3 = (unsigned) ((long long) ((m + kNormTile - 1) / kNormTile) * n);
-            k_normalize_epilogue<G, R><<<g3, 256, (size_t) N * (kNormTile + 1) * 4, st>>>(
-                c->dconsts, m, n, k, (const int *) pS, D, m_p, n_p, IA, IB, alpha, beta, Cm, ldc, todo, c->d_counter, allow_fb);
-            stage3_launches = 1;
-        }
-        if (allow_fb) {
-            k_gemm_todo<G, R><<<c->sm_count * 8, 128, 0, st>>>(c->dconsts, ta, tb, m, n, k, A, lda, B, ldb, alpha, beta, Cm, ldc, todo, c->d_counter);
-            ++stage3_launches;
-        }
-    });
-    mark(3);
-    c->ev_valid = c->profiling;
-    c->last_stage2_launches = gemm_launches;
-    for (int i = 0; i < 6 + stage3_launches + gemm_launches + extra_launches; ++i) LAUNCHED(c);
-    CUDA_TRY(cudaGetLastError());
-    *done = true;
-    return 0;
-}
+#include "gemm_fast.cuh"
 
 #include "kernels_vec.cuh"

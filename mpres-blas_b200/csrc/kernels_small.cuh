@@ -524,16 +524,47 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
 // TJ = rows of B' per tile: 128 (one MMA per K step, two accumulators: the epilogue of a tile overlaps the next tile's MMAs) or 256
 // (two MMAs per K step share the 256-row A' operand: a third less operand traffic and twice the work per pipeline stage; both
 // accumulators belong to one tile, so its epilogue runs while the TMA ring prefetches the next tile).
+// Column panels (sharded calls): the B' planes of panel g are a separate [P][n_ps][k_p] range (4-D tensor map: k, row, plane, panel),
+// the sums go to S8 + g * s8_panel.  Panels are walked in ring order from pan.first; before the first load of a panel that another rank
+// produces, the TMA thread waits for that panel's arrival flag (written by the producing rank after its copy landed here), so the
+// multiplication of the panels already here overlaps the transfer of the others.
+struct SmallPanels {
+    int count, first, own;
+    unsigned epoch;
+    const unsigned *flags;       // [count] arrival epochs (nullptr: every panel is local)
+    long long s8_panel;          // bytes between the S8 ranges of consecutive panels
+};
+__device__ __forceinline__ void wait_arrival(const unsigned *flag, unsigned epoch) {
+    const long long t0 = clock64();
+    for (;;) {
+        unsigned v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if ((int) (v - epoch) >= 0) break;
+        if (clock64() - t0 > (1ll << 34)) asm volatile("trap;");      // ~ 8 s: a rank never delivered -- fail instead of hanging
+        __nanosleep(100);
+    }
+    asm volatile("fence.proxy.async;" ::: "memory");                   // the planes are read through the async proxy (TMA)
+}
+namespace ptx {
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t) map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+}  // namespace ptx
+
 template <int KB, int TJ>
 __global__ void __launch_bounds__(kSThreads, 1)
 k_small_umma_p(const __grid_constant__ CUtensorMap tmJ, const __grid_constant__ CUtensorMap tmI, const DevConsts *Cp, uint8_t *S8,
-               long long m_ps, long long n_ps, int k_byte0, int nk, int add_to_S, const int *sel) {
+               long long m_ps, long long n_ps, int k_byte0, int nk, int add_to_S, const int *sel, const SmallPanels pan) {
     extern __shared__ uint8_t smem_raw[];
     const int P = sel[0];
     if (P <= 0) return;
     const int tiles_i = (int) (m_ps / kSN), tiles_j = (int) (n_ps / TJ);
     const int per_z = tiles_i * tiles_j;
-    const long long total = (long long) P * per_z;
+    const long long per_panel = (long long) P * per_z;
+    const long long total = per_panel * pan.count;
     if ((long long) blockIdx.x >= total) return;
     uint8_t *smem = (uint8_t *) (((uintptr_t) smem_raw + 1023) & ~(uintptr_t) 1023);
     constexpr int kStageA = TJ * KB, kStageB = kSN * KB, kStage = kStageA + kStageB, kPStages = kPRingBytes / kStage;
@@ -564,16 +595,24 @@ k_small_umma_p(const __grid_constant__ CUtensorMap tmJ, const __grid_constant__ 
         // ===== TMA producer =====
         if (lane == 0) {
             long long g = 0;   // stage uses so far
+            int arrived = -1;
             for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
-                const int z = (int) (tile / per_z), r = (int) (tile - (long long) z * per_z);
+                const int pi = (int) (tile / per_panel);
+                const long long tp = tile - (long long) pi * per_panel;
+                const int pg = (pan.first + pi) % pan.count;
+                const int z = (int) (tp / per_z), r = (int) (tp - (long long) z * per_z);
                 const int j0 = (r / tiles_i) * TJ, i0 = (r % tiles_i) * kSN;
+                if (pg != arrived) {
+                    if (pan.flags && pg != pan.own) wait_arrival(pan.flags + pg, pan.epoch);
+                    arrived = pg;
+                }
                 for (int it = 0; it < nk; ++it, ++g) {
                     const int s = (int) (g % kPStages);
                     const uint32_t ph = (uint32_t) (g / kPStages) & 1u;
                     ptx::mbar_wait(&empty[s], ph ^ 1u);
                     ptx::mbar_expect_tx(&full[s], kStage);
                     uint8_t *dst = smem + s * kStage;
-                    ptx::tma_load_3d(dst, &tmJ, &full[s], k_byte0 + it * KB, j0, z);
+                    ptx::tma_load_4d(dst, &tmJ, &full[s], k_byte0 + it * KB, j0, z, pg);
                     ptx::tma_load_3d(dst + kStageA, &tmI, &full[s], k_byte0 + it * KB, i0, z);
                 }
             }
@@ -618,16 +657,20 @@ k_small_umma_p(const __grid_constant__ CUtensorMap tmJ, const __grid_constant__ 
         const int quad = warp & 3, half = warp >> 2;
         int lt = 0;
         for (long long tile = blockIdx.x; tile < total; tile += gridDim.x, ++lt) {
-            const int z = (int) (tile / per_z), r = (int) (tile - (long long) z * per_z);
+            const int pi = (int) (tile / per_panel);
+            const long long tp = tile - (long long) pi * per_panel;
+            const int pg = (pan.first + pi) % pan.count;
+            const int z = (int) (tp / per_z), r = (int) (tp - (long long) z * per_z);
             const int j0 = (r / tiles_i) * TJ, i0 = (r % tiles_i) * kSN;
             const unsigned p = (unsigned) SD.p[z], mu = SD.mu[z];
+            uint8_t *S8p = S8 + (long long) pg * pan.s8_panel;
             const int b = NH == 1 ? (lt & 1) : 0, use = NH == 1 ? (lt >> 1) : lt;
             ptx::mbar_wait(&acc_full[b], (uint32_t) (use & 1));
             ptx::tc_fence_after();
 #pragma unroll 1
             for (int h = 0; h < NH; ++h) {
                 const int j = j0 + h * kSM + quad * 32 + lane;
-                uint4 *dst = (uint4 *) (S8 + ((long long) z * n_ps + j) * m_ps + i0 + half * 128);
+                uint4 *dst = (uint4 *) (S8p + ((long long) z * n_ps + j) * m_ps + i0 + half * 128);
                 const uint32_t tbase = tmem + ((uint32_t) (quad * 32) << 16) + (uint32_t) ((NH == 1 ? b : h) * kSN + half * 128);
                 // all 128 columns of this thread into registers first, so the accumulator can be handed back early
                 uint32_t d[16][8];
@@ -870,29 +913,29 @@ __global__ void __launch_bounds__(kXT, 4) k_ext_norm_small(const DevConsts *Cp, 
 
 }  // namespace mpres
 
-// 3-D map (k, row, plane) over u8 planes [planes][rows_p][k_p], box 64 B x box_rows x 1 plane, 64B swizzle
-inline int small_make_map(CUtensorMap *map, const void *planes, int nplanes, long long rows_p, long long k_p, int box_rows, int box_k = mpres::kSK) {
+// map (k, row, plane[, panel]) over u8 planes [panels][planes][rows_p][k_p] (panel_stride bytes between panels), box box_k B x box_rows x 1 x 1
+inline int small_make_map(CUtensorMap *map, const void *planes, int nplanes, long long rows_p, long long k_p, int box_rows, int box_k = mpres::kSK,
+                          int npanels = 0, long long panel_stride = 0) {
     mpres_encode_tiled_fn enc = umma_encode_fn();
     if (!enc) return -30;
-    cuuint64_t dims[3] = {(cuuint64_t) k_p, (cuuint64_t) rows_p, (cuuint64_t) nplanes};
-    cuuint64_t strides[2] = {(cuuint64_t) k_p, (cuuint64_t) (rows_p * k_p)};
-    cuuint32_t box[3] = {(cuuint32_t) box_k, (cuuint32_t) box_rows, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(planes), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    cuuint64_t dims[4] = {(cuuint64_t) k_p, (cuuint64_t) rows_p, (cuuint64_t) nplanes, (cuuint64_t) (npanels > 0 ? npanels : 1)};
+    cuuint64_t strides[3] = {(cuuint64_t) k_p, (cuuint64_t) (rows_p * k_p), (cuuint64_t) (npanels > 1 ? panel_stride : rows_p * k_p * nplanes)};
+    cuuint32_t box[4] = {(cuuint32_t) box_k, (cuuint32_t) box_rows, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, npanels > 0 ? 4 : 3, const_cast<void *>(planes), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      box_k == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : -31;
 }
 
-// One launch = every small modulus (CTAs beyond the selected base leave at once), all tiles, K range [k_begin, k_begin + k_len).
-// PA: planes of A' [.][m_ps][k_p] (m_ps % 256 == 0), PB: planes of B' [.][n_ps][k_p] (n_ps % 128 == 0), S8: [.][n_ps][m_ps].
-inline int launch_small_umma(mpres_ctx *c, const uint8_t *PA, const uint8_t *PB, uint8_t *S8, long long m_ps, long long n_ps, long long k_p,
-                             long long k_begin, int k_len, bool add_to_S, const int *sel, cudaStream_t st) {
+// One launch = the P one-byte moduli of the call, all tiles of all column panels, K range [k_begin, k_begin + k_len).
+// PA: planes of A' [P][m_ps][k_p] (m_ps % 256 == 0); PB: per panel, planes of B' [P][n_ps][k_p] (n_ps % 256 == 0), consecutive panels
+// pb_panel bytes apart; S8: per panel [P][n_ps][m_ps].  P is the host's copy of sel[0].
+inline int launch_small_umma(mpres_ctx *c, int P, const uint8_t *PA, const uint8_t *PB, long long pb_panel, uint8_t *S8, long long m_ps, long long n_ps, long long k_p,
+                             long long k_begin, int k_len, bool add_to_S, const int *sel, const mpres::SmallPanels &pan, cudaStream_t st) {
     CUtensorMap tmJ, tmI;
     int rc;
     const int box_k = (c->small_persistent && c->small_kb == 128 && k_len % 128 == 0 && k_begin % 128 == 0) ? 128 : mpres::kSK;
     const int tj = (c->small_persistent && box_k == 128 && c->small_tj == 256 && n_ps % 256 == 0) ? 256 : mpres::kSM;
-    if ((rc = small_make_map(&tmJ, PB, mpres::kSmallMax, n_ps, k_p, tj, box_k))) return rc;
-    if ((rc = small_make_map(&tmI, PA, mpres::kSmallMax, m_ps, k_p, mpres::kSN, box_k))) return rc;
     if (!c->attr_small) {
         CUDA_TRY(cudaFuncSetAttribute(mpres::k_small_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, mpres::kSSmem));
         CUDA_TRY(cudaFuncSetAttribute(mpres::k_small_umma_p<64, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, mpres::kPSmem));
@@ -900,18 +943,24 @@ inline int launch_small_umma(mpres_ctx *c, const uint8_t *PA, const uint8_t *PB,
         CUDA_TRY(cudaFuncSetAttribute(mpres::k_small_umma_p<128, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, mpres::kPSmem));
         c->attr_small = true;
     }
+    if ((rc = small_make_map(&tmI, PA, P, m_ps, k_p, mpres::kSN, box_k))) return rc;
     if (c->small_persistent) {
-        const long long max_tiles = (long long) mpres::kSmallMax * (m_ps / mpres::kSN) * (n_ps / tj);
+        if ((rc = small_make_map(&tmJ, PB, P, n_ps, k_p, tj, box_k, pan.count, pb_panel))) return rc;
+        const long long max_tiles = (long long) P * (m_ps / mpres::kSN) * (n_ps / tj) * pan.count;
         const unsigned gx = (unsigned) std::min<long long>(max_tiles, (long long) c->sm_count);
         if (tj == 256)
-            mpres::k_small_umma_p<128, 256><<<gx, mpres::kSThreads, mpres::kPSmem, st>>>(tmJ, tmI, c->dconsts, S8, m_ps, n_ps, (int) k_begin, k_len / mpres::kSK, add_to_S ? 1 : 0, sel);
+            mpres::k_small_umma_p<128, 256><<<gx, mpres::kSThreads, mpres::kPSmem, st>>>(tmJ, tmI, c->dconsts, S8, m_ps, n_ps, (int) k_begin, k_len / mpres::kSK, add_to_S ? 1 : 0, sel, pan);
         else if (box_k == 128)
-            mpres::k_small_umma_p<128, 128><<<gx, mpres::kSThreads, mpres::kPSmem, st>>>(tmJ, tmI, c->dconsts, S8, m_ps, n_ps, (int) k_begin, k_len / mpres::kSK, add_to_S ? 1 : 0, sel);
+            mpres::k_small_umma_p<128, 128><<<gx, mpres::kSThreads, mpres::kPSmem, st>>>(tmJ, tmI, c->dconsts, S8, m_ps, n_ps, (int) k_begin, k_len / mpres::kSK, add_to_S ? 1 : 0, sel, pan);
         else
-            mpres::k_small_umma_p<64, 128><<<gx, mpres::kSThreads, mpres::kPSmem, st>>>(tmJ, tmI, c->dconsts, S8, m_ps, n_ps, (int) k_begin, k_len / mpres::kSK, add_to_S ? 1 : 0, sel);
+            mpres::k_small_umma_p<64, 128><<<gx, mpres::kSThreads, mpres::kPSmem, st>>>(tmJ, tmI, c->dconsts, S8, m_ps, n_ps, (int) k_begin, k_len / mpres::kSK, add_to_S ? 1 : 0, sel, pan);
         return 0;
     }
-    dim3 grid((unsigned) (m_ps / mpres::kSN), (unsigned) (n_ps / mpres::kSM), (unsigned) mpres::kSmallMax);
-    mpres::k_small_umma<<<grid, mpres::kSThreads, mpres::kSSmem, st>>>(tmJ, tmI, c->dconsts, S8, m_ps, n_ps, (int) k_begin, k_len / mpres::kSK, add_to_S ? 1 : 0, sel);
+    // one tile per CTA (A/B measurement): local panels only, one launch per panel
+    for (int g = 0; g < pan.count; ++g) {
+        if ((rc = small_make_map(&tmJ, PB + (long long) g * pb_panel, P, n_ps, k_p, tj, box_k))) return rc;
+        dim3 grid((unsigned) (m_ps / mpres::kSN), (unsigned) (n_ps / mpres::kSM), (unsigned) P);
+        mpres::k_small_umma<<<grid, mpres::kSThreads, mpres::kSSmem, st>>>(tmJ, tmI, c->dconsts, S8 + (long long) g * pan.s8_panel, m_ps, n_ps, (int) k_begin, k_len / mpres::kSK, add_to_S ? 1 : 0, sel);
+    }
     return 0;
 }

@@ -6,6 +6,7 @@
 #include "../../include/mpres_b200.h"
 
 #include <cuda_runtime.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <atomic>
@@ -26,6 +27,8 @@ static_assert(sizeof(mpres_er_float_t) == 16 && sizeof(Er) == 16, "er_float_t la
 extern "C" {
 
 const char *mpres_version(void) { return "mpres-b200 0.1 (sm_100a)"; }
+
+int mpres_finalize(mpres_ctx *c);
 
 int mpres_init_moduli(mpres_ctx **out, const int *moduli, int n, int device) {
     if (!out || !moduli) return -1;
@@ -74,7 +77,7 @@ int mpres_init_moduli(mpres_ctx **out, const int *moduli, int n, int device) {
     };
     if (up(&c->d_pow2, h.pow2) != cudaSuccess || up(&c->d_inv_pow2, h.inv_pow2_ext) != cudaSuccess ||
         up(&c->d_mrc, h.mrc_inv) != cudaSuccess || up(&c->d_prefix, h.prefix_mod) != cudaSuccess ||
-        up(&c->d_ext_w, h.ext_w) != cudaSuccess || up(&c->d_ext_t, h.ext_t) != cudaSuccess || up(&c->d_wpow2, h.wpow2) != cudaSuccess || up(&c->d_spow2, h.spow2) != cudaSuccess) { delete d; delete c; return (int) e; }
+        up(&c->d_ext_w, h.ext_w) != cudaSuccess || up(&c->d_ext_t, h.ext_t) != cudaSuccess || up(&c->d_wpow2, h.wpow2) != cudaSuccess || up(&c->d_spow2, h.spow2) != cudaSuccess) { delete d; cudaGetLastError(); mpres_finalize(c); return (int) e; }
     d->pow2 = c->d_pow2; d->inv_pow2 = c->d_inv_pow2; d->mrc_inv = c->d_mrc; d->prefix_mod = c->d_prefix; d->ext_w = c->d_ext_w; d->ext_t = c->d_ext_t; d->ext_lazy = h.ext_lazy; d->wpow2 = c->d_wpow2; d->spow2 = c->d_spow2;
     for (int i = 0; i <= h.N; ++i) d->prefix_log2[i] = h.prefix_log2[i];
     // tables of the small-modulus stage 2
@@ -110,15 +113,16 @@ int mpres_init_moduli(mpres_ctx **out, const int *moduli, int n, int device) {
         const bool ok = sd->inv && sd->ext_b && sd->cw && sd->pws && sd->in_mi && sd->in_negmp && sd->red_mu;
         const void *dev = ok ? upb(0, sd, sizeof(SmallDev)) : nullptr;
         delete sd;
-        if (!dev) { delete d; delete c; return (int) cudaErrorMemoryAllocation; }
+        if (!dev) { delete d; cudaGetLastError(); mpres_finalize(c); return (int) cudaErrorMemoryAllocation; }
         d->small = (const SmallDev *) dev;
     }
     e = cudaMalloc(&c->dconsts, sizeof(DevConsts));
     if (e == cudaSuccess) e = cudaMemcpy(c->dconsts, d, sizeof(DevConsts), cudaMemcpyHostToDevice);
     delete d;
-    if (e == cudaSuccess) e = cudaMalloc(&c->d_counter, 8 * sizeof(int));
-    if (e == cudaSuccess) e = cudaMemset(c->d_counter, 0, 8 * sizeof(int));
-    if (e != cudaSuccess) { delete c; return (int) e; }
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_counter, kCounterInts * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(c->d_counter, 0, kCounterInts * sizeof(int));
+    if (e == cudaSuccess) e = cudaHostAlloc(&c->h_sel, 8 * sizeof(int), cudaHostAllocDefault);
+    if (e != cudaSuccess) { cudaGetLastError(); mpres_finalize(c); return (int) e; }
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
     *out = c;
     return 0;
@@ -139,6 +143,10 @@ int mpres_finalize(mpres_ctx *c) {
     for (int i = 0; i < 4; ++i) if (c->hs[i]) cudaStreamDestroy(c->hs[i]);
     for (int i = 0; i < 16; ++i) if (c->hev[i]) cudaEventDestroy(c->hev[i]);
     for (int i = 0; i < 8; ++i) if (c->d_small[i]) cudaFree(c->d_small[i]);
+    if (c->serial_ev) cudaEventDestroy(c->serial_ev);
+    for (cudaEvent_t e : c->prof_ev) if (e) cudaEventDestroy(e);
+    for (int i = 0; i < 6; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->h_sel) cudaFreeHost(c->h_sel);
     cudaFree(c->d_pow2); cudaFree(c->d_inv_pow2); cudaFree(c->d_mrc); cudaFree(c->d_prefix); cudaFree(c->d_ext_w); cudaFree(c->d_ext_t); cudaFree(c->d_wpow2); cudaFree(c->d_spow2); cudaFree(c->dconsts); cudaFree(c->d_counter);
     delete c;
     return 0;
@@ -211,29 +219,35 @@ int mpres_set_stage1_kernel(mpres_ctx *c, int kind) {
 long mpres_last_minplus_dense_count(mpres_ctx *c) {
     if (!c || c->device < 0) return -1;
     DeviceGuard g(c->device);
-    int v = 0;
+    int v[kCounterInts];
     if (cudaStreamSynchronize(c->last_stream) != cudaSuccess) return -2;
-    if (cudaMemcpy(&v, c->d_counter + 6, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
-    return v;
+    if (cudaMemcpy(v, c->d_counter, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+    long t = 0;
+    for (int p = 0; p < kMaxPanels; ++p) t += v[kCounterBlock * p + 6];
+    return t;
 }
 long mpres_launch_count(const mpres_ctx *c) { return c ? c->launches.load() : -1; }
 
 long mpres_last_fallback_count(mpres_ctx *c) {
     if (!c || c->device < 0) return -1;
     DeviceGuard g(c->device);
-    int v = 0;
+    int v[kCounterInts];
     if (cudaStreamSynchronize(c->last_stream) != cudaSuccess) return -2;
-    if (cudaMemcpy(&v, c->d_counter, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
-    return v;
+    if (cudaMemcpy(v, c->d_counter, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+    long t = 0;
+    for (int p = 0; p < kMaxPanels; ++p) t += v[kCounterBlock * p + 0];
+    return t;
 }
 
 long mpres_last_slow_count(mpres_ctx *c) {
     if (!c || c->device < 0) return -1;
     DeviceGuard g(c->device);
-    int v = 0;
+    int v[kCounterInts];
     if (cudaStreamSynchronize(c->last_stream) != cudaSuccess) return -2;
-    if (cudaMemcpy(&v, c->d_counter + 1, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
-    return v;
+    if (cudaMemcpy(v, c->d_counter, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+    long t = 0;
+    for (int p = 0; p < kMaxPanels; ++p) t += v[kCounterBlock * p + 1];
+    return t;
 }
 
 int mpres_set_profiling(mpres_ctx *c, int on) { if (!c) return -1; c->profiling = on != 0; c->ev_valid = false; return 0; }
@@ -248,6 +262,23 @@ int mpres_last_stage_ms(mpres_ctx *c, float *ms, int *launches) {
     for (int i = 0; i < 3; ++i) CUDA_TRY(cudaEventElapsedTime(&ms[i], c->ev[i], c->ev[i + 1]));
     if (launches) *launches = c->last_stage2_launches;
     return 0;
+}
+
+/* "name=ms;name=ms;..." of the kernels of the last fast mp_gemm call (profiling on); returns the bytes written or < 0.  Synchronises. */
+long mpres_last_kernel_ms(mpres_ctx *c, char *out, size_t cap) {
+    if (!c || !out || cap == 0) return -1;
+    if (c->prof_used < 2) return -2;
+    DeviceGuard g(c->device);
+    if (cudaEventSynchronize(c->prof_ev[c->prof_used - 1]) != cudaSuccess) return -3;
+    size_t pos = 0;
+    for (int i = 1; i < c->prof_used; ++i) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, c->prof_ev[i - 1], c->prof_ev[i]) != cudaSuccess) return -3;
+        const int w = snprintf(out + pos, cap - pos, "%s%s=%.6f", i > 1 ? ";" : "", c->prof_name[i], ms);
+        if (w < 0 || (size_t) w >= cap - pos) return -4;
+        pos += (size_t) w;
+    }
+    return (long) pos;
 }
 
 long mpres_get_constant(const mpres_ctx *c, int which, void *out, size_t cap) {
@@ -469,7 +500,7 @@ int mpres_probe(mpres_ctx *c, int op, void *r, const void *x, const void *y, con
 /* ---- GEMM ------------------------------------------------------------------------------------------ */
 
 static int gemm_impl(mpres_ctx *c, int transa, int transb, int m, int n, int k, SoA alpha, SoA A, int lda, SoA B, int ldb,
-                     SoA beta, SoA Cm, int ldc, const SoA *buffer, cudaStream_t st) {
+                     SoA beta, SoA Cm, int ldc, const SoA *buffer, cudaStream_t st, FastShard *sh = nullptr) {
     // argument checks of src/blas/gemm.cuh:75-96 (the reference returns silently)
     if (m <= 0 || n <= 0 || k <= 0) return 0;
     const bool ta = transa != MPRES_NO_TRANS, tb = transb != MPRES_NO_TRANS;
@@ -480,37 +511,41 @@ static int gemm_impl(mpres_ctx *c, int transa, int transb, int m, int n, int k, 
     if (ldc < std::max(1, m)) return -5;
     DeviceGuard g(c->device);
     std::lock_guard<std::mutex> lk(c->mu);
+    int rc = call_begin(c, st);
+    if (rc) return rc;
     c->last_stream = st;
     const int N = c->hc.N;
-    CUDA_TRY(cudaMemsetAsync(c->d_counter, 0, 8 * sizeof(int), st));
+    CUDA_TRY(cudaMemsetAsync(c->d_counter, 0, kCounterInts * sizeof(int), st));
 
+    bool done = false;
     if (c->mode != MPRES_MODE_REFERENCE_ORDER) {
-        bool done = false;
-        int rc = gemm_fast_full(c, ta, tb, m, n, k, A, lda, B, ldb, alpha, beta, Cm, ldc, st, &done);
+        rc = gemm_fast_full(c, ta, tb, m, n, k, A, lda, B, ldb, alpha, beta, Cm, ldc, st, &done, sh);
         if (rc) return rc;
-        if (done) return 0;
     }
-    SoA S;
-    int lds = m;
-    if (buffer) S = *buffer;
-    else { int rc = ws_soa(c, 0, (size_t) m * n, &S); if (rc) return rc; }
-    MPRES_DISPATCH(N, {
-        int block = 128;
-        long long groups = (long long) m * n;
-        long long blocks = std::min<long long>((groups * G + block - 1) / block, (long long) c->sm_count * 64);
-        k_gemm_ref_order<G, R><<<(unsigned) blocks, block, 0, st>>>(c->dconsts, ta, tb, m, n, k, A, lda, B, ldb, S, lds, nullptr, nullptr);
-    });
-    LAUNCHED(c);
-    CUDA_TRY(cudaGetLastError());
-    MPRES_DISPATCH(N, {
-        int block = 128;
-        long long groups = (long long) m * n;
-        long long blocks = std::min<long long>((groups * G + block - 1) / block, (long long) c->sm_count * 32);
-        k_gemm_epilogue<G, R><<<(unsigned) blocks, block, 0, st>>>(c->dconsts, m, n, alpha, beta, S, lds, Cm, ldc);
-    });
-    LAUNCHED(c);
-    CUDA_TRY(cudaGetLastError());
-    return 0;
+    if (!done) {
+        // reference order (a sharded call holds the complete B on every rank: its row block needs no exchange here)
+        SoA S;
+        int lds = m;
+        if (buffer) S = *buffer;
+        else { rc = ws_soa(c, 0, (size_t) m * n, &S); if (rc) return rc; }
+        MPRES_DISPATCH(N, {
+            int block = 128;
+            long long groups = (long long) m * n;
+            long long blocks = std::min<long long>((groups * G + block - 1) / block, (long long) c->sm_count * 64);
+            k_gemm_ref_order<G, R><<<(unsigned) blocks, block, 0, st>>>(c->dconsts, ta, tb, m, n, k, A, lda, B, ldb, S, lds, nullptr, nullptr);
+        });
+        LAUNCHED(c);
+        CUDA_TRY(cudaGetLastError());
+        MPRES_DISPATCH(N, {
+            int block = 128;
+            long long groups = (long long) m * n;
+            long long blocks = std::min<long long>((groups * G + block - 1) / block, (long long) c->sm_count * 32);
+            k_gemm_epilogue<G, R><<<(unsigned) blocks, block, 0, st>>>(c->dconsts, m, n, alpha, beta, S, lds, Cm, ldc);
+        });
+        LAUNCHED(c);
+        CUDA_TRY(cudaGetLastError());
+    }
+    return call_end(c, st);
 }
 
 int mpres_gemm(mpres_ctx *c, int transa, int transb, int m, int n, int k, const mpres_array_t *alpha,
@@ -674,6 +709,140 @@ int mpres_gemm_coll(mpres_ctx *c, int transa, int transb, int m, int n, int k, c
                      view(Cm, lenC), ldc, nullptr, (cudaStream_t) stream);
 }
 
+/* ---- row-sharded GEMM over the GPUs of one NVLink domain ------------------------------------------------------------------
+ * The reference has no multi-GPU code; SURVEY 8(e) / BASELINE config 3: A and C split into row blocks, B needed by every rank.  One
+ * process (or thread) per GPU.  A communicator owns this rank's receive buffer (one cudaMalloc: exchange slots, arrival flags, one
+ * package slot per rank) and the peer mappings of the other ranks' buffers (CUDA IPC between processes, peer access inside one). */
+
+struct mpres_shard {
+    mpres_ctx *ctx = nullptr;
+    int rank = 0, world = 1, n = 0, k_max = 0;
+    long long nb_p = 0, k_p_max = 0;
+    size_t pkg_stride = 0, comm_bytes = 0;
+    char *comm = nullptr;
+    char *peer_comm[kMaxPanels] = {nullptr};
+    bool ipc_opened[kMaxPanels] = {false};
+    bool connected = false;
+    unsigned epoch = 0;
+    cudaStream_t push[kMaxPanels] = {nullptr};
+    cudaEvent_t ev_pkg = nullptr, ev_push[kMaxPanels] = {nullptr};
+    int npush = 0;
+};
+
+namespace {
+struct ShardHandle {          // what a rank publishes to the others (opaque to the caller)
+    int pid, device, rank, world;
+    unsigned long long bytes;
+    void *raw;
+    cudaIpcMemHandle_t mem;
+};
+constexpr size_t kShardXchgOff = 0, kShardFlagsOff = 1024, kShardPkgOff = 4096;
+}  // namespace
+
+size_t mpres_shard_handle_size(void) { return sizeof(ShardHandle); }
+
+int mpres_shard_create(mpres_ctx *c, int rank, int world, int n, int k_max, mpres_shard **out) {
+    NEED_DEVICE(c);
+    if (!c || !out || world < 1 || world > kMaxPanels || rank < 0 || rank >= world || n <= 0 || k_max <= 0 || n % world != 0) return -1;
+    DeviceGuard g(c->device);
+    mpres_shard *s = new mpres_shard();
+    s->ctx = c; s->rank = rank; s->world = world; s->n = n; s->k_max = k_max;
+    s->nb_p = round_up(n / world, 256);
+    s->k_p_max = round_up(k_max, 128);
+    s->pkg_stride = (pkg_header_bytes(s->nb_p, s->k_p_max) + (size_t) kSmallMax * s->nb_p * s->k_p_max + 4095) & ~(size_t) 4095;
+    s->comm_bytes = kShardPkgOff + (size_t) world * s->pkg_stride;
+    cudaError_t e = cudaMalloc(&s->comm, s->comm_bytes);
+    if (e == cudaSuccess) e = cudaMemset(s->comm, 0, kShardPkgOff);
+    const char *env = getenv("MPRES_PUSH_STREAMS");
+    s->npush = env ? atoi(env) : 2;
+    s->npush = std::max(1, std::min(s->npush, std::max(1, world - 1)));
+    for (int i = 0; i < s->npush && e == cudaSuccess; ++i) {
+        e = cudaStreamCreateWithFlags(&s->push[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_push[i], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_pkg, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { cudaGetLastError(); mpres_shard_destroy(s); return (int) e; }
+    s->peer_comm[rank] = s->comm;
+    s->connected = world == 1;
+    *out = s;
+    return 0;
+}
+
+int mpres_shard_export(mpres_shard *s, void *handle_out) {
+    if (!s || !handle_out) return -1;
+    DeviceGuard g(s->ctx->device);
+    ShardHandle h;
+    memset(&h, 0, sizeof(h));
+    h.pid = (int) getpid(); h.device = s->ctx->device; h.rank = s->rank; h.world = s->world; h.bytes = s->comm_bytes; h.raw = s->comm;
+    CUDA_TRY(cudaIpcGetMemHandle(&h.mem, s->comm));
+    memcpy(handle_out, &h, sizeof(h));
+    return 0;
+}
+
+int mpres_shard_connect(mpres_shard *s, const void *handles) {
+    if (!s || !handles) return -1;
+    DeviceGuard g(s->ctx->device);
+    const ShardHandle *hs = (const ShardHandle *) handles;
+    for (int p = 0; p < s->world; ++p) {
+        const ShardHandle &h = hs[p];
+        if (h.rank != p || h.world != s->world || h.bytes != s->comm_bytes) return -8;     // the ranks were created with different shapes
+        if (p == s->rank) continue;
+        if (h.pid == (int) getpid()) {
+            int can = 0;
+            CUDA_TRY(cudaDeviceCanAccessPeer(&can, s->ctx->device, h.device));
+            if (!can) return -9;
+            const cudaError_t e = cudaDeviceEnablePeerAccess(h.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return (int) e;
+            cudaGetLastError();
+            s->peer_comm[p] = (char *) h.raw;
+        } else {
+            void *ptr = nullptr;
+            CUDA_TRY(cudaIpcOpenMemHandle(&ptr, h.mem, cudaIpcMemLazyEnablePeerAccess));
+            s->peer_comm[p] = (char *) ptr;
+            s->ipc_opened[p] = true;
+        }
+    }
+    s->connected = true;
+    return 0;
+}
+
+int mpres_shard_destroy(mpres_shard *s) {
+    if (!s) return -1;
+    DeviceGuard g(s->ctx->device);
+    cudaDeviceSynchronize();
+    for (int p = 0; p < kMaxPanels; ++p) if (s->ipc_opened[p] && s->peer_comm[p]) cudaIpcCloseMemHandle(s->peer_comm[p]);
+    for (int i = 0; i < kMaxPanels; ++i) { if (s->push[i]) cudaStreamDestroy(s->push[i]); if (s->ev_push[i]) cudaEventDestroy(s->ev_push[i]); }
+    if (s->ev_pkg) cudaEventDestroy(s->ev_pkg);
+    if (s->comm) cudaFree(s->comm);
+    delete s;
+    return 0;
+}
+
+int mpres_gemm_sharded(mpres_shard *s, int transa, int transb, int m_local, int n, int k, const mpres_array_t *alpha, const mpres_array_t *A, int lda,
+                       const mpres_array_t *B, int ldb, const mpres_array_t *beta, mpres_array_t *Cm, int ldc, mpres_stream_t stream) {
+    if (!s || !alpha || !A || !B || !beta || !Cm) return -1;
+    if (!s->connected) return -10;
+    if (n != s->n || k > s->k_max) return -11;
+    mpres_ctx *c = s->ctx;
+    FastShard sh;
+    sh.rank = s->rank; sh.world = s->world;
+    sh.epoch = ++s->epoch;
+    sh.recv = s->comm + kShardPkgOff;
+    sh.pkg_stride = s->pkg_stride;
+    sh.flags = (unsigned *) (s->comm + kShardFlagsOff);
+    for (int p = 0; p < s->world; ++p) {
+        sh.peer_recv[p] = s->peer_comm[p] + kShardPkgOff;
+        sh.peer_xchg[p] = (int *) (s->peer_comm[p] + kShardXchgOff);
+        sh.peer_flags[p] = (unsigned *) (s->peer_comm[p] + kShardFlagsOff);
+    }
+    sh.npush = s->npush;
+    for (int i = 0; i < s->npush; ++i) { sh.push[i] = s->push[i]; sh.ev_push[i] = s->ev_push[i]; }
+    sh.ev_pkg = s->ev_pkg;
+    return gemm_impl(c, transa, transb, m_local, n, k, view(alpha), view(A), lda, view(B), ldb, view(beta), view(Cm), ldc, nullptr, (cudaStream_t) stream,
+                     s->world > 1 ? &sh : nullptr);
+}
+
 /* ---- GEMV ------------------------------------------------------------------------------------------ */
 
 static int gemv_impl(mpres_ctx *c, int trans, int m, int n, SoA alpha, SoA A, int lda, SoA x, int incx, SoA beta, SoA y, int incy,
@@ -685,13 +854,15 @@ static int gemv_impl(mpres_ctx *c, int trans, int m, int n, SoA alpha, SoA A, in
     const bool tr = trans != MPRES_NO_TRANS;
     DeviceGuard g(c->device);
     std::lock_guard<std::mutex> lk(c->mu);
+    int rc = call_begin(c, st);
+    if (rc) return rc;
     c->last_stream = st;
     const int N = c->hc.N;
     const int lenx = tr ? m : n, leny = tr ? n : m;
     SoA ax;
-    int rc = ws_soa(c, 1, (size_t) lenx, &ax);
+    rc = ws_soa(c, 1, (size_t) lenx, &ax);
     if (rc) return rc;
-    CUDA_TRY(cudaMemsetAsync(c->d_counter, 0, 8 * sizeof(int), st));
+    CUDA_TRY(cudaMemsetAsync(c->d_counter, 0, kCounterInts * sizeof(int), st));
     c->ev_valid = false;
     mv_mark(c, 0, st);
     MPRES_DISPATCH(N, {
@@ -717,7 +888,7 @@ static int gemv_impl(mpres_ctx *c, int trans, int m, int n, SoA alpha, SoA A, in
         LAUNCHED(c);
         CUDA_TRY(cudaGetLastError());
     }
-    return 0;
+    return call_end(c, st);
 }
 
 int mpres_gemv(mpres_ctx *c, int trans, int m, int n, const mpres_array_t *alpha, const mpres_array_t *A, int lda,
@@ -909,14 +1080,15 @@ static int dot_to_record(mpres_ctx *c, int n, SoA x, int incx, SoA y, int incy, 
     const int N = c->hc.N;
     const size_t rs = 4 * (size_t) N + 40;
     bool done = false, tried = false;
-    int rc;
-    CUDA_TRY(cudaMemsetAsync(c->d_counter, 0, 8 * sizeof(int), st));
+    int rc = call_begin(c, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemsetAsync(c->d_counter, 0, kCounterInts * sizeof(int), st));
     c->ev_valid = false;
     if (c->mode != MPRES_MODE_REFERENCE_ORDER) {
         rc = dot_fast(c, n, x, incx, y, incy, rec_out, out, st, &done, &tried);
         if (rc) return rc;
     }
-    if (done) return 0;
+    if (done) return call_end(c, st);
     // reference order: always in REFERENCE_ORDER mode; in AUTO mode gated on the fast path's guard counter
     const int *gate = tried ? c->d_counter : nullptr;
     MPRES_DISPATCH(N, {
@@ -932,7 +1104,7 @@ static int dot_to_record(mpres_ctx *c, int n, SoA x, int incx, SoA y, int incy, 
     });
     LAUNCHED(c); LAUNCHED(c);
     CUDA_TRY(cudaGetLastError());
-    return 0;
+    return call_end(c, st);
 }
 
 int mpres_dot(mpres_ctx *c, int n, const mpres_array_t *x, int incx, const mpres_array_t *y, int incy, mpres_array_t *r,

@@ -286,7 +286,43 @@ class RefLib:
                                          _ip(np.ascontiguousarray(x).reshape(-1)), _ip(np.ascontiguousarray(beta).reshape(-1)), _ip(yw))
         return yw, nt
 
+    def mpfr_gemm_timed(self, m, n, k, alpha, A, B, beta, C, prec):
+        """seconds and threads of the reference's MPFR GEMM loop (tests/blas/v2/gemm/test_mpfr_gemm.cuh:29-60) on an m x n x k problem"""
+        self.lib.ref_mpfr_gemm_timed.restype = ctypes.c_double
+        nt = ctypes.c_int()
+        secs = self.lib.ref_mpfr_gemm_timed(m, n, k, _ip(np.ascontiguousarray(alpha).reshape(-1)), _ip(np.ascontiguousarray(A).reshape(-1)),
+                                            _ip(np.ascontiguousarray(B).reshape(-1)), _ip(np.ascontiguousarray(beta).reshape(-1)),
+                                            _ip(np.ascontiguousarray(C).reshape(-1)), int(prec), ctypes.byref(nt))
+        return secs, nt.value
+
+    def to_string(self, rec, prec, digits=40):
+        buf = ctypes.create_string_buffer(4096)
+        self.lib.ref_to_string(_ip(np.ascontiguousarray(rec).reshape(1)), int(prec), int(digits), buf, 4096)
+        return buf.value.decode()
+
     # CUDA kernels of the reference (GPU box only)
+    def gpu_asum_norm(self, kind, x, n, incx=1, cfg=0):
+        """kind: 0 mp_asum, 171 one-norm, 175 inf-norm (src/blas/asum.cuh:41, norm.cuh:43)"""
+        r = self.empty(1)
+        self.lib.ref_gpu_asum_norm.restype = ctypes.c_float
+        self.lib.ref_gpu_asum_norm(int(kind), int(n), _ip(np.ascontiguousarray(x)), int(incx), _ip(r), int(cfg))
+        return r[0]
+
+    def gpu_ge_norm(self, kind, m, n, A, lda):
+        r = self.empty(1)
+        self.lib.ref_gpu_ge_norm.restype = ctypes.c_float
+        self.lib.ref_gpu_ge_norm(int(kind), int(m), int(n), _ip(np.ascontiguousarray(A).reshape(-1)), int(lda), _ip(r))
+        return r[0]
+
+    def gpu_spmv_2st(self, fmt, m, n, nnz, ptr, idx, vals, x):
+        """fmt 0: CSR (mp_spmv_mpmtx_csr2st), 1: ELLPACK (mp_spmv_mpmtx_ell2st, nnz = maxnzr)"""
+        y = self.empty(m)
+        self.lib.ref_gpu_spmv_2st.restype = ctypes.c_float
+        p = np.ascontiguousarray(ptr, dtype=np.int32) if ptr is not None else None
+        self.lib.ref_gpu_spmv_2st(int(fmt), int(m), int(n), int(nnz), _ip(p) if p is not None else None, _ip(np.ascontiguousarray(idx, dtype=np.int32)),
+                                  _ip(np.ascontiguousarray(vals).reshape(-1)), _ip(np.ascontiguousarray(x).reshape(-1)), _ip(y))
+        return y
+
     def gpu_gemm(self, m, n, k, alpha, A, B, beta, C, want_ab=False, repeat=1):
         Cw = np.ascontiguousarray(C).reshape(-1).copy()
         ab = self.empty(m * n) if want_ab else None

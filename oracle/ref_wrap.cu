@@ -30,6 +30,14 @@
 #include "blas/gemm.cuh"
 #include "blas/gemv.cuh"
 #include "blas/dot.cuh"
+#include "blas/asum.cuh"
+#include "blas/norm.cuh"
+#include "blas/genorm.cuh"
+#include "mpcollection.cuh"
+#include "sparse/mpmtx/spmv_mpmtx_csr2st.cuh"
+#include "sparse/mpmtx/spmv_mpmtx_ell2st.cuh"
+// the reference's own MPFR GEMM loop (tests/blas/v2/gemm/test_mpfr_gemm.cuh:29-60), included where it lies (-I $(REF)/tests)
+#include "blas/v2/gemm/test_mpfr_gemm.cuh"
 
 namespace v2 {
 // the v2 header defines cuda::mp_gemm as a __global__ with a different signature; include it in the
@@ -253,6 +261,43 @@ double ref_mpfr_dot_timed(const mp_float_t *x, const mp_float_t *y, long n, int 
     return t1 - t0;
 }
 
+
+/* MPFR@prec GEMM baseline: the reference's own mpfr_gemm (tests/blas/v2/gemm/test_mpfr_gemm.cuh:29-60, OpenMP over rows)
+ * on an m x n block of C with the full inner dimension k; operands pre-converted (conversion excluded, as the reference's test does).
+ * Column-major, lda = m, ldb = k, ldc = m.  Returns seconds; C (host AoS) is left untouched. */
+double ref_mpfr_gemm_timed(int m, int n, int k, const mp_float_t *alpha, const mp_float_t *A, const mp_float_t *B, const mp_float_t *beta,
+                           const mp_float_t *C, int prec, int *threads) {
+    const size_t na = (size_t) m * k, nb = (size_t) k * n, nc = (size_t) m * n;
+    mpfr_t *a = new mpfr_t[na], *b = new mpfr_t[nb], *c = new mpfr_t[nc];
+    mpfr_t al, be;
+    mpfr_init2(al, prec); mpfr_init2(be, prec);
+    to_mpfr(al, alpha); to_mpfr(be, beta);
+    #pragma omp parallel for
+    for (long i = 0; i < (long) na; i++) { mpfr_init2(a[i], prec); to_mpfr(a[i], &A[i]); }
+    #pragma omp parallel for
+    for (long i = 0; i < (long) nb; i++) { mpfr_init2(b[i], prec); to_mpfr(b[i], &B[i]); }
+    #pragma omp parallel for
+    for (long i = 0; i < (long) nc; i++) { mpfr_init2(c[i], prec); to_mpfr(c[i], &C[i]); }
+    *threads = omp_get_max_threads();
+    double t0 = omp_get_wtime();
+    mpfr_gemm(mblas_no_trans, mblas_no_trans, m, n, k, al, a, m, b, k, be, c, m);
+    double t1 = omp_get_wtime();
+    for (size_t i = 0; i < na; i++) mpfr_clear(a[i]);
+    for (size_t i = 0; i < nb; i++) mpfr_clear(b[i]);
+    for (size_t i = 0; i < nc; i++) mpfr_clear(c[i]);
+    delete[] a; delete[] b; delete[] c;
+    mpfr_clear(al); mpfr_clear(be);
+    return t1 - t0;
+}
+
+/* decimal strings ("%.*Re", `digits` significant digits) of records, through the reference's mp_get_mpfr: for accuracy checks */
+void ref_to_string(const mp_float_t *x, int prec, int digits, char *out, int cap) {
+    mpfr_t f; mpfr_init2(f, prec);
+    to_mpfr(f, x);
+    (void) cap; mpfr_sprintf(out, "%.*Re", digits, f);
+    mpfr_clear(f);
+}
+
 /* ---- reference CUDA kernels (run on the GPU box only) ----------------------------------------- */
 
 static void upload(mp_array_t &d, const mp_float_t *h, size_t n) {
@@ -384,6 +429,67 @@ float ref_gpu_dot(int n, const mp_float_t *x, const mp_float_t *y, mp_float_t *r
     cuda::mp_array_clear(dx); cuda::mp_array_clear(dy); cuda::mp_array_clear(dr); cuda::mp_array_clear(dbuf);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     return total / repeat;
+}
+
+
+/* v1 mp_asum / mp_norm (src/blas/asum.cuh:41, norm.cuh:43) with the launch configuration <grid, block> = <256, 64>
+ * (tests/blas/performance/test_asum_performance.cu:42-43) or, cfg = 1, <128, 32> (test_norm_performance.cu:49-50).
+ * kind: 0 asum, 171 one-norm, 175 inf-norm.  incx > 0; x holds 1 + (n - 1) * incx records. */
+float ref_gpu_asum_norm(int kind, int n, const mp_float_t *x, int incx, mp_float_t *r, int cfg) {
+    mp_array_t dx, dr;
+    upload(dx, x, (size_t) 1 + (size_t) (n - 1) * incx); cuda::mp_array_init(dr, 1);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    if (kind == 0) { if (cfg == 0) cuda::mp_asum<256, 64>(n, dx, incx, dr); else cuda::mp_asum<128, 32>(n, dx, incx, dr); }
+    else { if (cfg == 0) cuda::mp_norm<256, 64>((enum mblas_norm_type) kind, n, dx, incx, dr); else cuda::mp_norm<128, 32>((enum mblas_norm_type) kind, n, dx, incx, dr); }
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    download(r, dr, 1);
+    cuda::mp_array_clear(dx); cuda::mp_array_clear(dr);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return ms;
+}
+
+/* v1 mp_ge_norm (src/blas/genorm.cuh:142), <gridDim1, blockDim1> = <128, 32>; A is lda x n column-major */
+float ref_gpu_ge_norm(int kind, int m, int n, const mp_float_t *A, int lda, mp_float_t *r) {
+    mp_array_t dA, dr, dbuf;
+    upload(dA, A, (size_t) lda * n); cuda::mp_array_init(dr, 1); cuda::mp_array_init(dbuf, (size_t) (m > n ? m : n));
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    cuda::mp_ge_norm<128, 32>((enum mblas_norm_type) kind, m, n, dA, lda, dr, dbuf);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    download(r, dr, 1);
+    cuda::mp_array_clear(dA); cuda::mp_array_clear(dr); cuda::mp_array_clear(dbuf);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return ms;
+}
+
+/* two-stage SpMV over mp_collection_t (src/sparse/mpmtx/spmv_mpmtx_csr2st.cuh:106, spmv_mpmtx_ell2st.cuh:119), launch configuration
+ * <32, 32, 32, 32>.  fmt 0: CSR (ptr = irp[m + 1], idx = ja[nnz], as[nnz]); fmt 1: ELLPACK (idx = ja[m * maxnzr] column-major,
+ * as[m * maxnzr], nnz := maxnzr).  x: n records, y: m records out. */
+float ref_gpu_spmv_2st(int fmt, int m, int n, int nnz, const int *ptr, const int *idx, const mp_float_t *as, const mp_float_t *x, mp_float_t *y) {
+    const size_t cnt = fmt == 0 ? (size_t) nnz : (size_t) m * nnz;
+    mp_collection_t das, dbuf;
+    mp_array_t dx, dy;
+    cuda::mp_collection_init(das, cnt); cuda::mp_collection_init(dbuf, cnt);
+    cuda::mp_collection_host2device(das, (mp_float_ptr) as, cnt);
+    upload(dx, x, n); cuda::mp_array_init(dy, m);
+    int *dptr = nullptr, *didx = nullptr;
+    if (fmt == 0) { cudaMalloc(&dptr, sizeof(int) * (m + 1)); cudaMemcpy(dptr, ptr, sizeof(int) * (m + 1), cudaMemcpyHostToDevice); }
+    cudaMalloc(&didx, sizeof(int) * cnt); cudaMemcpy(didx, idx, sizeof(int) * cnt, cudaMemcpyHostToDevice);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    if (fmt == 0) cuda::mp_spmv_mpmtx_csr2st<32, 32, 32, 32>(m, n, nnz, dptr, didx, das, dx, dy, dbuf);
+    else cuda::mp_spmv_mpmtx_ell2st<32, 32, 32, 32>(m, n, nnz, didx, das, dx, dy, dbuf);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    download(y, dy, m);
+    cuda::mp_collection_clear(das); cuda::mp_collection_clear(dbuf); cuda::mp_array_clear(dx); cuda::mp_array_clear(dy);
+    if (dptr) cudaFree(dptr);
+    cudaFree(didx);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return ms;
 }
 
 } // extern "C"
