@@ -89,13 +89,15 @@ def test_set_binary_matches_oracle(pkg, N, full):
     got = arr.device2host()[5:]
     bad = diff_fields(got, want, ("digits", "sign", "exp"))
     assert bad.size == 0, "%d records differ, first %d\n%s\n%s" % (bad.size, bad[0], got[bad[0]], want[bad[0]])
-    # interval evaluations: bit-identical except where the refinement step's ceil(log2(x)) lands on a different (equally valid)
-    # magnification (glibc and CUDA log2 differ in the last ulp); those must still enclose X / M
-    bad = diff_fields(got, want, ("eval",))
-    assert bad.size <= count // 100, "%d interval evaluations differ" % bad.size
+    # interval evaluations: those of the reference's own cuda::rns_eval_compute (src/rns.cuh:797-868) on the same digits, bit for bit
+    # (the CPU oracle's refinement step can pick another, equally valid magnification: glibc and CUDA log2 differ in the last ulp)
+    if oracle.have_ref(N):
+        ref_ev = oracle.RefLib(N, gpu=True).gpu_probe(2, got)
+        bad = diff_fields(got, ref_ev, ("eval",))
+        assert bad.size == 0, "%d interval evaluations differ from the reference kernel, first %d\n%s\n%s" % (bad.size, bad[0], got[bad[0]], ref_ev[bad[0]])
     from fractions import Fraction
     M = orc.c["M"]
-    for i in bad:
+    for i in list(range(0, count, 97)) + [0, 1, 2]:
         X = Fraction(orc.to_int(got[i]), M)
         lo = Fraction(float(got[i]["eval"]["frac"][0])) * Fraction(2) ** int(got[i]["eval"]["exp"][0])
         up = Fraction(float(got[i]["eval"]["frac"][1])) * Fraction(2) ** int(got[i]["eval"]["exp"][1])

@@ -45,7 +45,8 @@ def test_small_path_stages_exact(pkg, N, shape, div, tiled):
     assert ctx.last_base_size() == 0
     ps = ctx.small_moduli(P)
     assert ps[0] == 256 and all(p > 1 for p in ps)
-    m_p, m_ps, k_p, n_ps, n_p = _round_up(m, 128), _round_up(m, 256), _round_up(k, 128), _round_up(n, 256), _round_up(n, 64)
+    m_p, m_ps, k_p, n_ps = _round_up(m, 128), _round_up(m, 256), _round_up(k, 128), _round_up(n, 256)
+    n_p = n_ps      # one column panel: every per-panel plane is padded to the 256-column tiles of stage 2
     a = _signed_ints(orc, A)     # column-major m x k: entry (i, l) at i + l m
     b = _signed_ints(orc, B)     # column-major k x n: entry (l, j) at l + j k
 
