@@ -216,6 +216,54 @@ def _sub_matrix(ta, ctx, src, rows_total, cols_total, rows, cols):
     return dst
 
 
+def _fractions(ctx, recs):
+    """exact values of host mp_float_t records as Fractions (CRT over the moduli of the context; plain Python integers)"""
+    from fractions import Fraction
+    mods = [int(v) for v in ctx.constant(0, "int32", ctx.N)]
+    M = 1
+    for q in mods:
+        M *= q
+    w = [(M // q) * pow(M // q, -1, q) for q in mods]
+    out = []
+    for r in recs:
+        x = sum(int(d) * wi for d, wi in zip(r["digits"], w)) % M
+        v = Fraction(x) * Fraction(2) ** int(r["exp"])
+        out.append(-v if int(r["sign"]) else v)
+    return out
+
+
+def _tolerance_check(ctx, k, alpha, beta, As, Bs, C0s, got, ref, nr, nc, take=8):
+    """p-bit inputs (single-rounding stage 3): entries (i < take, j < take) of the sampled block against exact rational arithmetic under the
+    reference's own error model |err| <= gamma_(k+3) (|alpha| sum |a||b| + |beta c|), u = 4 / sqrt(M)
+    (tests/blas/accuracy/test_dot_accuracy.cu:41-72).  Returns (entries, failures, worst ratio of ours, worst ratio of the reference-order loop)."""
+    from fractions import Fraction
+    import math
+    mods = [int(v) for v in ctx.constant(0, "int32", ctx.N)]
+    M = 1
+    for q in mods:
+        M *= q
+    u = Fraction(4, math.isqrt(M))
+    gam = (k + 3) * u / (1 - (k + 3) * u)
+    tr, tc = min(take, nr), min(take, nc)
+    hA, hB = As.device2host().reshape(k, nr), Bs.device2host().reshape(nc, k)
+    fa = [_fractions(ctx, hA[:, i]) for i in range(tr)]
+    fb = [_fractions(ctx, hB[j, :]) for j in range(tc)]
+    al, be = _fractions(ctx, alpha.device2host())[0], _fractions(ctx, beta.device2host())[0]
+    hC0, hG, hR = C0s.device2host().reshape(nc, nr), got.device2host().reshape(nc, nr), ref.device2host().reshape(nc, nr)
+    bad, worst_g, worst_r = 0, 0.0, 0.0
+    for j in range(tc):
+        c0 = _fractions(ctx, hC0[j, :tr]); g = _fractions(ctx, hG[j, :tr]); r = _fractions(ctx, hR[j, :tr])
+        for i in range(tr):
+            exact = al * sum(x * y for x, y in zip(fa[i], fb[j])) + be * c0[i]
+            bound = gam * (abs(al) * sum(abs(x * y) for x, y in zip(fa[i], fb[j])) + abs(be * c0[i]))
+            eg, er = abs(g[i] - exact), abs(r[i] - exact)
+            if eg > bound:
+                bad += 1
+            if bound:
+                worst_g = max(worst_g, float(eg / bound)); worst_r = max(worst_r, float(er / bound))
+    return tr * tc, bad, worst_g, worst_r
+
+
 def _equal_des(a, b):
     """number of entries whose digits, sign or exponent differ between two TorchMpArrays of equal size"""
     N = a.ctx.N
@@ -601,9 +649,11 @@ def run_gemm(env, workload, steps, warmup, full_precision=False, want_e2e=True, 
         g = torch.Generator(device="cpu"); g.manual_seed(4242 + rank)
         rows = sorted(torch.randperm(mr, generator=g)[:VERIFY_ROWS].tolist())
         cols = sorted(torch.randperm(n, generator=g)[:VERIFY_COLS].tolist())
+        binary = ctx.last_binary_rounding()
         As = _sub_matrix(ta, ctx, A, mr, k, rows, list(range(k)))
         Bs = _sub_matrix(ta, ctx, B, k, n, list(range(k)), cols)
         Cs = _sub_matrix(ta, ctx, C0, mr, n, rows, cols)
+        C0s = _sub_matrix(ta, ctx, C0, mr, n, rows, cols) if binary else None
         Cw = _sub_matrix(ta, ctx, state["last"], mr, n, rows, cols)
         ctx.set_mode(pkg.MODE_REFERENCE_ORDER)
         pkg.mp_gemm(ctx, pkg.mblas_no_trans, pkg.mblas_no_trans, len(rows), len(cols), k, alpha, As, len(rows), Bs, k, beta, Cs, len(rows), None, stream)
@@ -614,7 +664,15 @@ def run_gemm(env, workload, steps, warmup, full_precision=False, want_e2e=True, 
         verified = {"verified_entries": len(rows) * len(cols) * world, "verified_mismatches": bad,
                     "verified_against": "%d x %d sampled entries of the last step's C per rank, recomputed by the reference-order k-loop (mp_mul, mp_add, rounding after each) "
                                         "on the gathered rows of A / columns of B: digits, sign, exponent%s" % (len(rows), len(cols), note)}
-        del As, Bs, Cs, Cw
+        if binary:
+            # the exact sums were rounded ONCE in binary (csrc/kernels_bin.cuh): not the reference's bits, so the check is the reference's error model
+            cnt, fails, wg, wr = _tolerance_check(ctx, k, alpha, beta, As, Bs, C0s, Cw, Cs, len(rows), len(cols))
+            verified = {"verified_entries": cnt, "verified_mismatches": fails, "bitwise_differences_from_reference_order": bad,
+                        "worst_error_over_bound": wg, "worst_error_over_bound_reference_order": wr,
+                        "verified_against": "single-rounding stage 3 (p-bit inputs): %d sampled entries of the last step's C against exact rational arithmetic, |err| <= "
+                                            "gamma_(k+3) (|alpha| sum |a||b| + |beta c|) with u = 4 / sqrt(M) (the reference's model, tests/blas/accuracy/test_dot_accuracy.cu:41-72); "
+                                            "worst error / bound reported for this library and for the reference-order k-loop on the same entries" % cnt}
+        del As, Bs, Cs, Cw, C0s
 
     # ---- end-to-end through the C-ABI with host buffers ------------------------------------------------
     e2e = None

@@ -110,6 +110,10 @@ int mpres_set_stage2_kernel(mpres_ctx *ctx, int kind);
 /* Small-modulus base the last fast-path call used: *moduli = how many one-byte moduli (0: the call ran on the
  * format's own moduli), *input_moduli = how many residues of each operand entry its conversion read.  Synchronises. */
 int mpres_last_small_base(mpres_ctx *ctx, int *moduli, int *input_moduli);
+/* 1 when the last fast-path mp_gemm rebuilt its exact sums in binary and rounded them once (full-precision inputs: the sums exceed
+ * the number format but not the one-byte base; results then agree with the reference within its error model, src/arith/mul.cuh:108-110
+ * rounds every product instead), 0 when it ran in the bit-exact window, < 0 on error. */
+int mpres_last_binary_rounding(const mpres_ctx *ctx);
 /* the index-th one-byte modulus (0 when out of range or when the small base is unavailable for this moduli set) */
 int mpres_small_modulus(const mpres_ctx *ctx, int index);
 /* Test probe: copy `bytes` at `offset` of internal workspace `slot` to the host after synchronising the last stream

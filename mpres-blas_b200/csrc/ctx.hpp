@@ -32,6 +32,8 @@ struct SmallDev {
     const uint32_t *in_mi;         // [kSmallNinMax + 1][16][16]
     const uint32_t *in_negmp;      // [kSmallNinMax + 1][16]
     const uint32_t *red_mu;        // [N]
+    const uint32_t *bin_mi;        // [kSmallMax + 1][kSmallMax][kBinW]
+    const uint32_t *bin_negmp;     // [kSmallMax + 1][kBinW]
 };
 
 }  // namespace mpres
@@ -55,7 +57,7 @@ struct mpres_ctx {
     int vec_config = 0;               // tile configuration of the mp_gemv / mp_dot kernels (A/B measurement)
     HostConsts hc;
     SmallConsts sc;                   // small-modulus base of the tensor-core stage 2
-    void *d_small[8] = {nullptr};     // device copies of its tables (SmallDev first)
+    void *d_small[12] = {nullptr};     // device copies of its tables (SmallDev first)
     DevConsts *dconsts = nullptr;
     int *d_pow2 = nullptr, *d_inv_pow2 = nullptr, *d_mrc = nullptr, *d_prefix = nullptr, *d_ext_w = nullptr, *d_ext_t = nullptr, *d_wpow2 = nullptr, *d_spow2 = nullptr;
     std::atomic<long> launches{0};
@@ -86,8 +88,9 @@ struct mpres_ctx {
     cudaEvent_t ev[6] = {nullptr};
     bool ev_valid = false;
     int last_stage2_launches = 0;
+    bool last_binary = false;            // the last fast mp_gemm rounded its exact sums in binary (kernels_bin.cuh: full-precision inputs)
     // opt-in shared-memory sizes (cudaFuncSetAttribute) are per device: remembered per context, not per process
-    bool attr_ext = false, attr_fast = false, attr_align_mma = false, attr_align = false, attr_small = false, attr_umma = false;
+    bool attr_bin = false, attr_ext = false, attr_fast = false, attr_align_mma = false, attr_align = false, attr_small = false, attr_umma = false;
     unsigned long long attr_norm = 0;    // bit NQ / 8: k_norm_fast<NQ, *, true> (staged residues of S)
     int norm_staged = 1;                 // k_norm_fast stages the residues of S in shared memory (mpres_set_stage3_kernel(4) = off)
     unsigned long long attr_fused = 0;   // bit NQ / 8: k_ext_norm_small<NQ, *>

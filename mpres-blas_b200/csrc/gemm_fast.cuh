@@ -254,7 +254,7 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
     const long long m_p = round_up(m, kBM), m_ps = round_up(m, kSN), k_p = round_up(k, 128), nb_p = round_up(nb, 256);
     if (k_p > 32000 * 128ll) return 0;
     const bool small_on = c->stage2 == MPRES_STAGE2_SMALL && c->sc.usable;
-    const bool sparse_mp = c->minplus_sparse && k_p >= 512;
+    bool sparse_mp = c->minplus_sparse && k_p >= 512;
     int rc;
     // ---- workspace that does not depend on the base: windows, shift plane of A', candidate lists of A', per-panel lists and delta planes ----
     const size_t hdr = pkg_header_bytes(nb_p, k_p);
@@ -264,10 +264,12 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
     const size_t bytesList = pad1k((size_t) m * nb * sizeof(long long));          // per panel, three of them: todo, slow, (min,+) pairs
     const size_t bytesD = pad1k((size_t) nb_p * m_p * 2);                          // per panel, three of them: delta, D1, D2
     const size_t perPanel = 3 * bytesList + 3 * bytesD;
+    const size_t bytesPart = pad1k((size_t) std::max<long long>(m_ps, nb_p) * sizeof(OuterPart));
     void *pMisc;
-    if ((rc = ws_reserve(c, 6, bytesIA + bytesSA + bytesTab + bytesCandA + (size_t) W * perPanel + (sh ? 0 : hdr) + 4096, &pMisc))) return rc;
+    if ((rc = ws_reserve(c, 6, bytesIA + bytesPart + bytesSA + bytesTab + bytesCandA + (size_t) W * perPanel + (sh ? 0 : hdr) + 4096, &pMisc))) return rc;
     char *pm = (char *) pMisc;
     OuterInfo *IA = (OuterInfo *) pm; pm += bytesIA;
+    OuterPart *part = (OuterPart *) pm; pm += bytesPart;
     int16_t *SA = (int16_t *) pm; pm += bytesSA;
     int *scal_tab = (int *) pm; pm += bytesTab;
     int *cposA = (int *) pm; pm += pad1k((size_t) m_ps * kMcT * 4);
@@ -288,8 +290,24 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
     char *own_hdr = sh ? sh->recv + (size_t) rank * sh->pkg_stride : local_hdr;
     PanelPkg own = pkg_carve(own_hdr, nullptr, nb_p, k_p);
     const SoA Bown = soa_shift(B, (long long) rank * nb * soB, N);
-    k_outer_info<<<(unsigned) ((m * 32ll + 255) / 256), 256, 0, st>>>(c->dconsts, A, soA, slA, m, k, IA);
-    k_outer_info<<<(unsigned) ((nb * 32ll + 255) / 256), 256, 0, st>>>(c->dconsts, Bown, soB, slB, nb, k, own.IB);
+    // exponent base and window of every line: a warp per line when the line runs along the contiguous direction of the input, else the
+    // chunked kernel with lanes along the lines
+    auto outer_info = [&](const SoA &X, long long so, long long sl, int outer, int inner, OuterInfo *info) {
+        if (so == 1 && sl != 1 && inner >= 64) {
+            const int lineb = (outer + 31) / 32;
+            int chunks = std::max(1, std::min((c->sm_count * 8 + lineb - 1) / lineb, inner / 32));
+            const int chunk = (inner + chunks - 1) / chunks;
+            chunks = (inner + chunk - 1) / chunk;
+            k_outer_part_init<<<(outer + 255) / 256, 256, 0, st>>>(part, outer);
+            k_outer_part<<<dim3((unsigned) lineb, (unsigned) chunks), 256, 0, st>>>(X, sl, outer, inner, chunk, part);
+            k_outer_part_final<<<(outer + 255) / 256, 256, 0, st>>>(c->dconsts, part, outer, info);
+            launches += 2;
+        } else {
+            k_outer_info<<<(unsigned) ((outer * 32ll + 255) / 256), 256, 0, st>>>(c->dconsts, X, so, sl, outer, inner, info);
+        }
+    };
+    outer_info(A, soA, slA, m, k, IA);
+    outer_info(Bown, soB, slB, nb, k, own.IB);
     prof_mark(c, st, "k_outer_info");
     Xchg x;
     memset(&x, 0, sizeof(x));
@@ -302,9 +320,13 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
     k_choose_base<<<1, 256, 0, st>>>(c->dconsts, IA, m, own.IB, nb, k, c->reduced_base, small_on ? 1 : 0, nprime, sel, x);
     launches += 3;
     // the host needs the choice: which kernels to launch, how many planes to reserve and to send
-    CUDA_TRY(cudaMemcpyAsync(c->h_sel, c->d_counter + 2, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(c->h_sel, c->d_counter + 2, 6 * sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     const int P = c->h_sel[2], nin = c->h_sel[3];
+    // full-precision inputs: the exact sums exceed the number format (window guard of kernels_norm.cuh) but not the one-byte base --
+    // stage 3 rebuilds them in binary and rounds once (kernels_bin.cuh); the (min,+) exponent product is not needed then
+    const bool binary = P > 0 && c->h_sel[5] > c->hc.log2M - 2;
+    c->last_binary = binary;
     if (sh && c->h_sel[1]) return -50;                       // a rank did not reach the call
     prof_mark(c, st, "k_choose_base");
     (void) nin;
@@ -318,12 +340,14 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
         *done = true;
         return 0;
     }
+    if (binary) sparse_mp = false;
     // ---- workspace that depends on the base ----
     void *pQA, *pS8, *pS, *pSAT = nullptr, *pPl = nullptr;
     if ((rc = ws_reserve(c, 8, (size_t) P * m_ps * k_p, &pQA))) return rc;
     const size_t s8_panel = (size_t) P * nb_p * m_ps, s_panel = (size_t) N * nb_p * m_p * 4;
     if ((rc = ws_reserve(c, 10, (size_t) W * s8_panel, &pS8))) return rc;
-    if ((rc = ws_reserve(c, 5, (size_t) W * s_panel, &pS))) return rc;
+    if (binary) pS = nullptr;
+    else if ((rc = ws_reserve(c, 5, (size_t) W * s_panel, &pS))) return rc;
     if (sparse_mp && (rc = ws_reserve(c, 11, (size_t) k_p * m_ps * 2 + 256, &pSAT))) return rc;
     if (!sh && (rc = ws_reserve(c, 9, (size_t) P * nb_p * k_p, &pPl))) return rc;
     const size_t planes_bytes = (size_t) P * nb_p * k_p;
@@ -389,7 +413,7 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
     switch (N) { case 8: case 16: case 24: case 32: case 40: case 48: case 56: case 64: break; default: have_fast = false; }
     const bool f32 = c->sc.usable && c->sc.red_shift >= 24 && c->sc.red_shift <= 27 && c->norm32;
     const bool fused = have_fast && c->fuse_ext;
-    if (have_fast) {
+    if (have_fast && !binary) {
         const int rowsT = 3 * c->hc.log2M + 2;
         k_scalar_tables<<<(rowsT * N + 255) / 256, 256, 0, st>>>(c->dconsts, alpha, beta, scal_tab);
         ++launches;
@@ -438,7 +462,7 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
         return 0;
     };
     if (!sh) {
-        minplus_panel(0);
+        if (!binary) minplus_panel(0);
         prof_mark(c, st, "k_mp_gather+combine+fix");
         mark(1);
         if ((rc = stage2())) return rc;
@@ -462,8 +486,19 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
         int *Sg = (int *) ((char *) pS + (size_t) g * s_panel);
         if (sh) {
             if (g != rank) { k_wait_flag<<<1, 1, 0, st>>>(sh->flags + g, sh->epoch); ++launches; }
-            minplus_panel(g);
+            if (!binary) minplus_panel(g);
             if (pi == 0) prof_mark(c, st, "k_mp_gather+combine+fix");
+        }
+        if (binary) {
+            const size_t smb = bin_smem_bytes(N);
+            const unsigned gx = (unsigned) std::min<long long>((long long) ((m + kBinT - 1) / kBinT) * nb, (long long) c->sm_count * 4);
+            MPRES_DISPATCH(N, {
+                if (!c->attr_bin) { CUDA_TRY(cudaFuncSetAttribute(k_bin_norm<G, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smb)); c->attr_bin = true; }
+                k_bin_norm<G, R><<<gx, kBinT, smb, st>>>(c->dconsts, m, nb, S8g, m_ps, nb_p, sel, IA, pk.IB, alpha, beta, Cg, ldc);
+            });
+            ++launches;
+            if (pi == 0) prof_mark(c, st, "k_bin_norm");
+            continue;
         }
         if (!fused) {
             const unsigned gx = (unsigned) std::min<long long>((m_p / kXT) * nb, (long long) c->sm_count * 4);     // persistent: four blocks per SM

@@ -256,6 +256,7 @@ constexpr int kSmallMax = 54;          // small moduli available (product ~ 2^36
 constexpr int kSmallK = 64;            // K extent of the base-extension MMA: residues, rank, zero padding
 constexpr int kSmallNinMax = 16;       // reference moduli the input conversion may read
 constexpr int kSmallShiftMax = 400;    // alignment shifts the +-2^s table covers (> log2 of the product)
+constexpr int kBinW = 12;              // 32-bit words of a sum rebuilt in binary from the one-byte base (2^384 > 54 M')
 static const int kSmallModuli[kSmallMax] = {
     256, 251, 243, 241, 239, 233, 229, 227, 223, 211, 199, 197, 193, 191, 181, 179, 173, 169, 167, 163, 157, 151, 149, 139, 137, 131, 127,
     125, 121, 113, 109, 107, 103, 101, 97,  89,  83,  79,  73,  71,  67,  61,  59,  53,  49,  47,  43,  41,  37,  31,  29,  23,  19,  17};
@@ -274,6 +275,9 @@ struct SmallConsts {
     std::vector<uint32_t> in_negmp;      // [kSmallNinMax + 1][16]      words of 2^(32 c) - m_0 ... m_{c-1}
     std::vector<int> in_log2_milli;      // [kSmallNinMax + 1]  floor(1024 log2(m_0 ... m_{c-1})) - 1
     std::vector<uint32_t> red_mu;        // [N]  floor(2^(k + 30) / m_q), k = red_shift: one-correction 32-bit Barrett constant (barrett_k in mp_device.cuh)
+    // binary reconstruction of a sum from its one-byte residues (kernels_bin.cuh): 32-bit words of M'_c / p_i and of 2^(32 kBinW) - M'_c
+    std::vector<uint32_t> bin_mi;        // [kSmallMax + 1][kSmallMax][kBinW]
+    std::vector<uint32_t> bin_negmp;     // [kSmallMax + 1][kBinW]
     double log2M_up = 0;                 // log2(M), rounded up a little
 };
 
@@ -385,6 +389,26 @@ inline void compute_small_consts(const HostConsts &c, SmallConsts &s) {
         BigUInt M(1);
         for (int i = 0; i < N; ++i) M.mul_small((uint32_t) c.moduli[i]);
         s.log2M_up = biguint_log2(M) + 1e-9;
+    }
+    s.bin_mi.assign((size_t) (P + 1) * P * kBinW, 0);
+    s.bin_negmp.assign((size_t) (P + 1) * kBinW, 0);
+    {
+        BigUInt prod(1);
+        for (int cc = 1; cc <= P; ++cc) {
+            prod.mul_small((uint32_t) kSmallModuli[cc - 1]);
+            uint64_t borrow = 0;
+            for (int w = 0; w < kBinW; ++w) {
+                const uint64_t pw = w < (int) prod.limb.size() ? prod.limb[w] : 0;
+                const uint64_t sub = pw + borrow;
+                s.bin_negmp[(size_t) cc * kBinW + w] = (uint32_t) (0ull - sub);
+                borrow = (sub != 0) ? 1 : 0;
+            }
+            for (int i = 0; i < cc; ++i) {
+                BigUInt mi = prod;
+                mi.div_small((uint32_t) kSmallModuli[i]);
+                for (int w = 0; w < kBinW && w < (int) mi.limb.size(); ++w) s.bin_mi[((size_t) cc * P + i) * kBinW + w] = mi.limb[w];
+            }
+        }
     }
 }
 

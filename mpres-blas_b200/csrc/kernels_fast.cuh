@@ -107,6 +107,81 @@ __global__ void k_outer_info(const DevConsts *Cp, SoA X, long long so, long long
     }
 }
 
+// The same for lines that are the CONTIGUOUS direction of the input (so == 1: rows of a non-transposed A, columns of a transposed B):
+// a warp per line would read with stride sl.  Here a block takes 32 consecutive lines x a chunk of inner positions, lanes along the lines
+// (coalesced), combines its eight inner sub-groups in shared memory and folds the chunk into per-line partials with atomics
+// (k_outer_part_init before, k_outer_part_final after).  The largest interval bound travels as one 64-bit key: (exponent, mantissa
+// rounded up to 45 bits) -- an upper bound like the one above, at most 2^-44 larger.
+struct OuterPart { int emin; int pad; long long top; unsigned long long key; };
+constexpr long long kOuterKeyBias = 120000;
+__global__ void k_outer_part_init(OuterPart *part, int outer) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o < outer) { OuterPart p; p.emin = INT_MAX; p.pad = 0; p.top = LLONG_MIN; p.key = 0ull; part[o] = p; }
+}
+__global__ void __launch_bounds__(256) k_outer_part(SoA X, long long sl, int outer, int inner, int chunk, OuterPart *part) {
+    __shared__ int s_emin[8][32];
+    __shared__ long long s_top[8][32];
+    __shared__ unsigned long long s_key[8][32];
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+    const int o = blockIdx.x * 32 + lx;
+    const int l0 = blockIdx.y * chunk, l1 = min(inner, l0 + chunk);
+    const long long len = X.len();
+    int emin = INT_MAX;
+    long long top = LLONG_MIN;
+    unsigned long long key = 0ull;
+    if (o < outer) {
+        for (int l = l0 + ly; l < l1; l += 8) {
+            const long long idx = (long long) o + (long long) l * sl;
+            const Er up = X.eval[idx + len];
+            if (up.frac != 0) {
+                const int e = X.exp[idx];
+                emin = min(emin, e);
+                const long long t = (long long) e + up.exp;
+                top = t > top ? t : top;
+                const unsigned long long fb = (unsigned long long) __double_as_longlong(fabs(up.frac));
+                const long long ue = (up.exp > 100000 ? 100000 : (up.exp < -100000 ? -100000 : up.exp)) + (long long) (fb >> 52);
+                const unsigned long long k2 = ((unsigned long long) (ue + kOuterKeyBias) << 45) + (((fb & 0xfffffffffffffull) >> 8) + 1ull);
+                key = k2 > key ? k2 : key;
+            }
+        }
+    }
+    s_emin[ly][lx] = emin; s_top[ly][lx] = top; s_key[ly][lx] = key;
+    __syncthreads();
+    if (ly == 0 && o < outer) {
+#pragma unroll
+        for (int g = 1; g < 8; ++g) {
+            emin = min(emin, s_emin[g][lx]);
+            top = s_top[g][lx] > top ? s_top[g][lx] : top;
+            key = s_key[g][lx] > key ? s_key[g][lx] : key;
+        }
+        if (emin != INT_MAX) {
+            atomicMin(&part[o].emin, emin);
+            atomicMax(&part[o].top, top);
+            atomicMax(&part[o].key, key);
+        }
+    }
+}
+__global__ void k_outer_part_final(const DevConsts *Cp, const OuterPart *part, int outer, OuterInfo *info) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= outer) return;
+    const OuterPart p = part[o];
+    const int log2M = Cp->log2M;
+    OuterInfo r;
+    r.pad = 0;
+    if (p.emin == INT_MAX) { r.emin = 0; r.win = -1; r.xb = 0; }
+    else {
+        const long long be = (long long) (p.key >> 45) - kOuterKeyBias;
+        const unsigned long long bm = (p.key & ((1ull << 45) - 1ull)) << 8;            // <= 2^52: a carry into the exponent is a mantissa of 1.0 more
+        const double lx = (double) (be - 1023) + log2(1.0 + (double) bm * 2.220446049250313e-16);
+        long long w = p.top - p.emin + log2M + 2;
+        r.emin = p.emin;
+        r.win = w > 1000000 ? 1000000 : (w < 0 ? 0 : (int) w);
+        const double b = (lx + (Cp->small ? Cp->small->log2M_up : (double) (log2M + 1))) * 1024.0;
+        r.xb = b > 1.0e8 ? 100000000 : (b < 0 ? 0 : (int) ceil(b) + 2);
+    }
+    info[o] = r;
+}
+
 // ---- stage 1a': how many moduli the exact sums need ---------------------------------------------------
 // Every exact sum satisfies |S| < 2^(win_a + win_b + ceil(log2 k)); the first n' moduli determine it when
 // their product M' obeys |S| < M'/4.  n' = smallest such count (or N when more than kMaxReducedBase would be
@@ -193,6 +268,7 @@ __global__ void __launch_bounds__(256) k_choose_base(const DevConsts *Cp, const 
             if (P == 0 || nin == 0) { P = 0; nin = 0; }
         }
         sel[0] = P; sel[1] = nin;
+        sel[3] = need > 2000000000ll ? 2000000000 : (int) need - 2;      // |S| < 2^sel[3] for every entry of the call
         *nprime = P > 0 ? 0 : np;
     }
 }
@@ -549,6 +625,7 @@ __global__ void __launch_bounds__(256, 1) k_limb_gemm(const DevConsts *Cp, const
 
 #include "kernels_norm.cuh"
 #include "kernels_small.cuh"
+#include "kernels_bin.cuh"
 #include "kernels_minplus.cuh"
 
 namespace mpres {

@@ -35,7 +35,7 @@ struct Er {
 
 // Device-resident constants of one moduli set (one copy per device of a context).
 struct DevConsts {
-    int N, log2M, mp_h, mp_j, ref_factor, pad0;
+    int N, log2M, mp_h, mp_j, ref_factor, precision;   // precision = MP_PRECISION (src/arith/arith_utils.cuh:44-61)
     double accuracy;
     Er unit_low, unit_upp, inv_low, inv_upp;
     int moduli[kMaxN];

@@ -54,7 +54,7 @@ int mpres_init_moduli(mpres_ctx **out, const int *moduli, int n, int device) {
     const HostConsts &h = c->hc;
     DevConsts *d = new DevConsts();
     memset(d, 0, sizeof(*d));
-    d->N = h.N; d->log2M = h.log2M; d->mp_h = h.mp_h; d->mp_j = h.mp_j; d->ref_factor = h.ref_factor;
+    d->N = h.N; d->log2M = h.log2M; d->mp_h = h.mp_h; d->mp_j = h.mp_j; d->ref_factor = h.ref_factor; d->precision = h.mp_precision;
     d->accuracy = h.accuracy;
     d->unit_low = {h.unit_low.frac, h.unit_low.exp}; d->unit_upp = {h.unit_upp.frac, h.unit_upp.exp};
     d->inv_low = {h.inv_low.frac, h.inv_low.exp}; d->inv_upp = {h.inv_upp.frac, h.inv_upp.exp};
@@ -110,7 +110,9 @@ int mpres_init_moduli(mpres_ctx **out, const int *moduli, int n, int device) {
         sd->in_mi = (const uint32_t *) upb(5, sc.in_mi.data(), sc.in_mi.size() * 4);
         sd->in_negmp = (const uint32_t *) upb(6, sc.in_negmp.data(), sc.in_negmp.size() * 4);
         sd->red_mu = (const uint32_t *) upb(7, sc.red_mu.data(), sc.red_mu.size() * 4);
-        const bool ok = sd->inv && sd->ext_b && sd->cw && sd->pws && sd->in_mi && sd->in_negmp && sd->red_mu;
+        sd->bin_mi = (const uint32_t *) upb(8, sc.bin_mi.data(), sc.bin_mi.size() * 4);
+        sd->bin_negmp = (const uint32_t *) upb(9, sc.bin_negmp.data(), sc.bin_negmp.size() * 4);
+        const bool ok = sd->inv && sd->ext_b && sd->cw && sd->pws && sd->in_mi && sd->in_negmp && sd->red_mu && sd->bin_mi && sd->bin_negmp;
         const void *dev = ok ? upb(0, sd, sizeof(SmallDev)) : nullptr;
         delete sd;
         if (!dev) { delete d; cudaGetLastError(); mpres_finalize(c); return (int) cudaErrorMemoryAllocation; }
@@ -142,7 +144,7 @@ int mpres_finalize(mpres_ctx *c) {
     for (int i = 0; i < 18; ++i) if (c->ws[i]) cudaFree(c->ws[i]);
     for (int i = 0; i < 4; ++i) if (c->hs[i]) cudaStreamDestroy(c->hs[i]);
     for (int i = 0; i < 16; ++i) if (c->hev[i]) cudaEventDestroy(c->hev[i]);
-    for (int i = 0; i < 8; ++i) if (c->d_small[i]) cudaFree(c->d_small[i]);
+    for (int i = 0; i < 12; ++i) if (c->d_small[i]) cudaFree(c->d_small[i]);
     if (c->serial_ev) cudaEventDestroy(c->serial_ev);
     for (cudaEvent_t e : c->prof_ev) if (e) cudaEventDestroy(e);
     for (int i = 0; i < 6; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -196,6 +198,7 @@ int mpres_last_small_base(mpres_ctx *c, int *moduli, int *input_moduli) {
     if (input_moduli) *input_moduli = v[1];
     return 0;
 }
+int mpres_last_binary_rounding(const mpres_ctx *c) { return c ? (c->last_binary ? 1 : 0) : -1; }
 int mpres_small_modulus(const mpres_ctx *c, int index) {
     if (!c || !c->sc.usable || index < 0 || index >= kSmallMax) return 0;
     return kSmallModuli[index];
@@ -514,6 +517,7 @@ static int gemm_impl(mpres_ctx *c, int transa, int transb, int m, int n, int k, 
     int rc = call_begin(c, st);
     if (rc) return rc;
     c->last_stream = st;
+    c->last_binary = false;
     const int N = c->hc.N;
     CUDA_TRY(cudaMemsetAsync(c->d_counter, 0, kCounterInts * sizeof(int), st));
 
