@@ -282,6 +282,39 @@ int mpres_shard_destroy(mpres_shard *s);
 int mpres_gemm_sharded(mpres_shard *s, int transa, int transb, int m_local, int n, int k, const mpres_array_t *alpha, const mpres_array_t *A, int lda,
                        const mpres_array_t *B, int ldb, const mpres_array_t *beta, mpres_array_t *C, int ldc, mpres_stream_t stream);
 
+/* ---- sums of magnitudes and norms -----------------------------------------------------------------------
+ * mpres_asum     r[0] = |x_0| + ... + |x_(n-1)|                                   cuda::mp_asum<gridDim1, blockDim1>(n, x, incx, r), src/blas/asum.cuh:41
+ * mpres_norm     norm = MPRES_ONE_NORM: the same; MPRES_INF_NORM: max |x_i|        cuda::mp_norm<...>(norm, n, x, incx, r), src/blas/norm.cuh:43
+ * mpres_ge_norm  one norm (largest column sum) / infinity norm (largest row sum)  cuda::mp_ge_norm<...>(norm, m, n, A, lda, r, buffer), src/blas/genorm.cuh:142
+ * n <= 0 or incx <= 0 return without touching r, as the reference does.  The sums run on the exact-window accumulators of mp_dot (one
+ * pass over the data, one rounding); whenever the reference's own additions do not round (its p/4-bit benchmark inputs) the digits,
+ * sign and exponent are the reference's.  The maximum is the element itself with its sign cleared (src/mpreduct.cuh:247-250); among
+ * entries of equal magnitude any one of them may be returned.  buffer (n or m elements) may be NULL. */
+#define MPRES_ONE_NORM 171   /* mblas_one_norm, src/blas/mblas_enum.cuh:41-44 */
+#define MPRES_INF_NORM 175   /* mblas_inf_norm */
+int mpres_asum(mpres_ctx *ctx, int n, const mpres_array_t *x, int incx, mpres_array_t *r, mpres_stream_t stream);
+int mpres_norm(mpres_ctx *ctx, int norm, int n, const mpres_array_t *x, int incx, mpres_array_t *r, mpres_stream_t stream);
+int mpres_ge_norm(mpres_ctx *ctx, int norm, int m, int n, const mpres_array_t *A, int lda, mpres_array_t *r, mpres_array_t *buffer, mpres_stream_t stream);
+
+/* ---- sparse matrix-vector product with multiple-precision entries ------------------------------------------
+ * y = A x, A in CSR (irp[m + 1], ja[nnz], as[nnz]) or ELLPACK (column-major m x maxnzr arrays ja / as, padding marked by ja < 0), the
+ * entries of A in an mp_collection_t:  cuda::mp_spmv_mpmtx_csr2st<...>(m, n, nnz, irp, ja, as, x, y, buffer), src/sparse/mpmtx/spmv_mpmtx_csr2st.cuh:106;
+ * cuda::mp_spmv_mpmtx_ell2st<...>(m, n, maxnzr, ja, as, x, y, buffer), src/sparse/mpmtx/spmv_mpmtx_ell2st.cuh:119.  One pass: a lane group
+ * per row forms round(a x_j) and adds it to the running sum in the reference's order -- the same mp_mul / mp_add sequence, so the same
+ * records; `buffer` (the reference's nnz-element scratch) is accepted and unused, may be NULL.  irp, ja: device pointers. */
+int mpres_spmv_csr2st(mpres_ctx *ctx, int m, int n, int nnz, const int *irp, const int *ja, const mpres_collection_t *as, const mpres_array_t *x,
+                      mpres_array_t *y, mpres_collection_t *buffer, mpres_stream_t stream);
+int mpres_spmv_ell2st(mpres_ctx *ctx, int m, int n, int maxnzr, const int *ja, const mpres_collection_t *as, const mpres_array_t *x, mpres_array_t *y,
+                      mpres_collection_t *buffer, mpres_stream_t stream);
+
+/* ---- conversions either side of the path ---------------------------------------------------------------------
+ * mpres_array_set_d: dst[offset + i] = src[i] exactly (sign, exponent, odd significand reduced modulo every m_q: digits, sign and exponent
+ * as mp_set_d, src/arith/assign.cuh:54-81; interval evaluation by the device rns_eval_compute).  mpres_array_get_d: dst[i] = the double
+ * nearest to src[offset + i] (ties to even; mp_get_d, src/arith/assign.cuh:154-180, rounds the exact value the same way through MPFR).
+ * src / dst doubles are DEVICE pointers. */
+int mpres_array_set_d(mpres_ctx *ctx, mpres_array_t *dst, size_t offset, const double *src, size_t n, mpres_stream_t stream);
+int mpres_array_get_d(mpres_ctx *ctx, double *dst, const mpres_array_t *src, size_t offset, size_t n, mpres_stream_t stream);
+
 /* The same three operations over mp_collection_t operands with explicit allocated lengths (the
  * reference only uses mp_collection_t in its sparse kernels, src/sparse/mpmtx/*.cuh; north_star asks
  * for the dense path over both containers). */

@@ -45,7 +45,7 @@ EXPORTS = [
     "mpres_array_set_binary", "mpres_gemm", "mpres_gemv", "mpres_dot", "mpres_scal", "mpres_axpy", "mpres_waxpby", "mpres_ge_add", "mpres_ge_acc", "mpres_ger", "mpres_ge_diag_scale", "mpres_ge_lr_scale", "mpres_rot", "mpres_axpy_dot", "mpres_gemm_host", "mpres_gemm_host_bdev", "mpres_gemm_coll", "mpres_gemv_coll",
     "mpres_dot_coll", "mpres_dot_partial", "mpres_reduce_partials", "mpres_probe", "mpres_version",
     "mpres_last_kernel_ms", "mpres_shard_handle_size", "mpres_shard_create", "mpres_shard_export", "mpres_shard_connect", "mpres_shard_destroy",
-    "mpres_gemm_sharded",
+    "mpres_gemm_sharded", "mpres_asum", "mpres_norm", "mpres_ge_norm", "mpres_spmv_csr2st", "mpres_spmv_ell2st", "mpres_array_set_d", "mpres_array_get_d",
 ]
 
 
@@ -304,6 +304,49 @@ def mp_dot(ctx, n, x, incx, y, incy, r, buffer=None, stream=0):
                                       _ref(r), _vp(stream)), "mpres_dot_coll")
         return
     _check(ctx.lib.mpres_dot(ctx.h, n, _ref(x), incx, _ref(y), incy, _ref(r), _ref(buffer), _vp(stream)), "mpres_dot")
+
+
+mblas_one_norm, mblas_inf_norm = 171, 175   # src/blas/mblas_enum.cuh:41-44
+
+
+def mp_asum(ctx, n, x, incx, r, stream=0):
+    """cuda::mp_asum (src/blas/asum.cuh:41): r[0] = sum |x_i|."""
+    _check(ctx.lib.mpres_asum(ctx.h, n, _ref(x), incx, _ref(r), _vp(stream)), "mpres_asum")
+
+
+def mp_norm(ctx, norm, n, x, incx, r, stream=0):
+    """cuda::mp_norm (src/blas/norm.cuh:43): one norm (sum of magnitudes) or infinity norm (largest magnitude) of a vector."""
+    _check(ctx.lib.mpres_norm(ctx.h, norm, n, _ref(x), incx, _ref(r), _vp(stream)), "mpres_norm")
+
+
+def mp_ge_norm(ctx, norm, m, n, A, lda, r, buffer=None, stream=0):
+    """cuda::mp_ge_norm (src/blas/genorm.cuh:142): one norm (largest column sum) or infinity norm (largest row sum) of a matrix."""
+    _check(ctx.lib.mpres_ge_norm(ctx.h, norm, m, n, _ref(A), lda, _ref(r), _ref(buffer), _vp(stream)), "mpres_ge_norm")
+
+
+def _dev_ptr(t):
+    """device address of a torch CUDA tensor (or a raw integer address)"""
+    return ctypes.c_void_p(t if isinstance(t, int) else t.data_ptr())
+
+
+def mp_spmv_mpmtx_csr2st(ctx, m, n, nnz, irp, ja, As, x, y, buffer=None, stream=0):
+    """cuda::mp_spmv_mpmtx_csr2st (src/sparse/mpmtx/spmv_mpmtx_csr2st.cuh:106): y = A x, A in CSR with mp_collection_t entries; irp, ja: int32 device tensors."""
+    _check(ctx.lib.mpres_spmv_csr2st(ctx.h, m, n, nnz, _dev_ptr(irp), _dev_ptr(ja), _ref(As), _ref(x), _ref(y), _ref(buffer), _vp(stream)), "mpres_spmv_csr2st")
+
+
+def mp_spmv_mpmtx_ell2st(ctx, m, n, maxnzr, ja, As, x, y, buffer=None, stream=0):
+    """cuda::mp_spmv_mpmtx_ell2st (src/sparse/mpmtx/spmv_mpmtx_ell2st.cuh:119): y = A x, A in ELLPACK (column-major m x maxnzr, ja < 0 = padding)."""
+    _check(ctx.lib.mpres_spmv_ell2st(ctx.h, m, n, maxnzr, _dev_ptr(ja), _ref(As), _ref(x), _ref(y), _ref(buffer), _vp(stream)), "mpres_spmv_ell2st")
+
+
+def mp_array_set_d(ctx, dst, offset, src, n, stream=0):
+    """dst[offset + i] = src[i] (mp_set_d, src/arith/assign.cuh:54-81); src: float64 device tensor."""
+    _check(ctx.lib.mpres_array_set_d(ctx.h, _ref(dst), ctypes.c_size_t(offset), _dev_ptr(src), ctypes.c_size_t(n), _vp(stream)), "mpres_array_set_d")
+
+
+def mp_array_get_d(ctx, dst, src, offset, n, stream=0):
+    """dst[i] = nearest double of src[offset + i] (mp_get_d, src/arith/assign.cuh:154-180); dst: float64 device tensor."""
+    _check(ctx.lib.mpres_array_get_d(ctx.h, _dev_ptr(dst), _ref(src), ctypes.c_size_t(offset), ctypes.c_size_t(n), _vp(stream)), "mpres_array_get_d")
 
 
 def mp_scal(ctx, n, alpha, x, incx, stream=0):

@@ -62,8 +62,8 @@ struct mpres_ctx {
     int *d_pow2 = nullptr, *d_inv_pow2 = nullptr, *d_mrc = nullptr, *d_prefix = nullptr, *d_ext_w = nullptr, *d_ext_t = nullptr, *d_wpow2 = nullptr, *d_spow2 = nullptr;
     std::atomic<long> launches{0};
     // workspace pool (grown on demand, never freed per call)
-    void *ws[18] = {nullptr};            // 12..17: device operands and staging rings of mpres_gemm_host
-    size_t ws_size[18] = {0};
+    void *ws[24] = {nullptr};            // 12..17: device operands and staging rings of mpres_gemm_host; 18..23: mpres_ops.cu
+    size_t ws_size[24] = {0};
     cudaStream_t hs[4] = {nullptr};      // mpres_gemm_host: upload, unpack, compute, download
     cudaEvent_t hev[16] = {nullptr};
     bool host_ready = false;
@@ -100,6 +100,10 @@ struct mpres_ctx {
 constexpr int kMaxPanels = 16;            // column panels of one fast-path call (ranks of a sharded call)
 constexpr int kCounterBlock = 8;
 constexpr int kCounterInts = kCounterBlock * kMaxPanels;
+
+// internal entry points shared between the translation units (not part of the C-ABI)
+extern "C" int mpres_internal_maxabs(mpres_ctx *c, long long n, const mpres::SoA *x, int incx, const mpres::SoA *r, cudaStream_t st);
+extern "C" void mpres_ops_release(mpres_ctx *c);
 
 #define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return (int) e_; } while (0)
 

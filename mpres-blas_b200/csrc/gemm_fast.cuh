@@ -240,6 +240,331 @@ inline int gemm_fast_limb(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
     return 0;
 }
 
+// ---- sharded call, flat layout -------------------------------------------------------------------------------------------------------
+// When the ranks' column blocks are whole 256-column tiles (nb % 256 == 0) the B-side stage-1 results of ALL blocks live in ONE set of
+// arrays in every rank's receive buffer -- windows [n], candidate lists [n][64], shift plane [n][k_p], one-byte planes [P][n][k_p] -- and a
+// rank copies its block of each array into the same position of every peer's buffer (copy engines over NVLink; the planes as one 2-D
+// copy).  Everything downstream is then the single-GPU code on column SEGMENTS: the panels are multiplied and normalised in groups (ring
+// order from the rank's own block), so the normalisation of the first group runs while the blocks of the next are still arriving, and
+// every stage-3 kernel runs once per segment instead of once per panel.
+struct FlatLayout { size_t oIB, oThr, oCpos, oCval, oSB, oQB, total; };
+static inline FlatLayout flat_layout(long long n, long long k_p, int planes) {
+    FlatLayout f;
+    size_t o = 0;
+    f.oIB = o; o += pad1k((size_t) n * sizeof(OuterInfo));
+    f.oThr = o; o += pad1k((size_t) n * 4);
+    f.oCpos = o; o += pad1k((size_t) n * kMcT * 4);
+    f.oCval = o; o += pad1k((size_t) n * kMcT * 4);
+    f.oSB = o; o += pad1k((size_t) n * k_p * 2);
+    f.oQB = o; o += (size_t) planes * n * k_p;
+    f.total = o;
+    return f;
+}
+
+inline int gemm_fast_flat(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, SoA A, int lda, SoA B, int ldb,
+                          SoA alpha, SoA beta, SoA Cm, int ldc, cudaStream_t st, bool *done, FastShard *sh) {
+    *done = false;
+    const int N = c->hc.N;
+    const int W = sh->world, rank = sh->rank;
+    const int nb = n / W;
+    const long long m_p = round_up(m, kBM), m_ps = round_up(m, kSN), k_p = round_up(k, 128);
+    if (k_p > 32000 * 128ll) return 0;
+    const bool small_on = c->stage2 == MPRES_STAGE2_SMALL && c->sc.usable;
+    bool sparse_mp = c->minplus_sparse && k_p >= 512;
+    int rc;
+    const FlatLayout fl = flat_layout(n, k_p, kSmallMax);
+    if (fl.total > (size_t) W * sh->pkg_stride) return -7;
+    char *rb = sh->recv;
+    OuterInfo *IB = (OuterInfo *) (rb + fl.oIB);
+    int *thrB = (int *) (rb + fl.oThr), *cposB = (int *) (rb + fl.oCpos), *cvalB = (int *) (rb + fl.oCval);
+    int16_t *SB = (int16_t *) (rb + fl.oSB);
+    uint8_t *QB = (uint8_t *) (rb + fl.oQB);
+    // ---- workspace that does not depend on the base ----
+    const size_t bytesIA = pad1k((size_t) m_ps * sizeof(OuterInfo)), bytesSA = pad1k((size_t) m_ps * k_p * 2);
+    const size_t bytesPart = pad1k((size_t) std::max<long long>(m_ps, nb) * sizeof(OuterPart));
+    const size_t bytesTab = pad1k((size_t) (3 * c->hc.log2M + 2) * N * sizeof(int));
+    const size_t bytesCandA = 2 * pad1k((size_t) m_ps * kMcT * 4) + pad1k((size_t) m_ps * 4);
+    const size_t bytesList = pad1k((size_t) m * n * sizeof(long long));
+    const size_t bytesD = pad1k((size_t) n * m_p * 2);
+    void *pMisc;
+    if ((rc = ws_reserve(c, 6, bytesIA + bytesPart + bytesSA + bytesTab + bytesCandA + 3 * bytesList + 3 * bytesD + 4096, &pMisc))) return rc;
+    char *pm = (char *) pMisc;
+    OuterInfo *IA = (OuterInfo *) pm; pm += bytesIA;
+    OuterPart *part = (OuterPart *) pm; pm += bytesPart;
+    int16_t *SA = (int16_t *) pm; pm += bytesSA;
+    int *scal_tab = (int *) pm; pm += bytesTab;
+    int *cposA = (int *) pm; pm += pad1k((size_t) m_ps * kMcT * 4);
+    int *cvalA = (int *) pm; pm += pad1k((size_t) m_ps * kMcT * 4);
+    int *thrA = (int *) pm; pm += pad1k((size_t) m_ps * 4);
+    long long *todo = (long long *) pm; pm += bytesList;
+    long long *slow = (long long *) pm; pm += bytesList;
+    long long *mplist = (long long *) pm; pm += bytesList;
+    int16_t *D = (int16_t *) pm; pm += bytesD;
+    int16_t *D1 = (int16_t *) pm; pm += bytesD;
+    int16_t *D2 = (int16_t *) pm;
+    int *nprime = c->d_counter + 2, *sel = c->d_counter + 4;
+    const long long soA = ta ? lda : 1, slA = ta ? 1 : lda;
+    const long long soB = tb ? 1 : ldb, slB = tb ? ldb : 1;
+    auto mark = [&](int i) { if (c->profiling) { if (!c->ev[i]) cudaEventCreate(&c->ev[i]); cudaEventRecord(c->ev[i], st); } };
+    prof_reset(c, st);
+    mark(0);
+    int launches = 0;
+    const long long col_own = (long long) rank * nb;
+    const SoA Bown = soa_shift(B, col_own * soB, N);
+    auto outer_info = [&](const SoA &X, long long so, long long sl, int outer, int inner, OuterInfo *info) {
+        if (so == 1 && sl != 1 && inner >= 64) {
+            const int lineb = (outer + 31) / 32;
+            int chunks = std::max(1, std::min((c->sm_count * 8 + lineb - 1) / lineb, inner / 32));
+            const int chunk = (inner + chunks - 1) / chunks;
+            chunks = (inner + chunk - 1) / chunk;
+            k_outer_part_init<<<(outer + 255) / 256, 256, 0, st>>>(part, outer);
+            k_outer_part<<<dim3((unsigned) lineb, (unsigned) chunks), 256, 0, st>>>(X, sl, outer, inner, chunk, part);
+            k_outer_part_final<<<(outer + 255) / 256, 256, 0, st>>>(c->dconsts, part, outer, info);
+            launches += 2;
+        } else {
+            k_outer_info<<<(unsigned) ((outer * 32ll + 255) / 256), 256, 0, st>>>(c->dconsts, X, so, sl, outer, inner, info);
+        }
+        ++launches;
+    };
+    // the previous call's copies have left this rank's block of the arrays (safeguard: the rendezvous below already implies it)
+    for (int si = 0; si < sh->npush && si < W - 1; ++si) CUDA_TRY(cudaStreamWaitEvent(st, sh->ev_push[si], 0));
+    outer_info(A, soA, slA, m, k, IA);
+    outer_info(Bown, soB, slB, nb, k, IB + col_own);
+    prof_mark(c, st, "k_outer_info");
+    Xchg x;
+    memset(&x, 0, sizeof(x));
+    x.world = W; x.rank = rank;
+    x.epoch = sh->epoch; x.parity = (int) (sh->epoch & 1u);
+    for (int p = 0; p < W; ++p) x.peer[p] = sh->peer_xchg[p];
+    x.err = c->d_counter + 3;
+    k_choose_base<<<1, 256, 0, st>>>(c->dconsts, IA, m, IB + col_own, nb, k, c->reduced_base, small_on ? 1 : 0, nprime, sel, x);
+    ++launches;
+    CUDA_TRY(cudaMemcpyAsync(c->h_sel, c->d_counter + 2, 6 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    const int P = c->h_sel[2];
+    if (c->h_sel[1]) return -50;                                  // a rank did not reach the call
+    const bool binary = P > 0 && c->h_sel[5] > c->hc.log2M - 2;
+    c->last_binary = binary;
+    prof_mark(c, st, "k_choose_base");
+    if (P <= 0) {
+        rc = gemm_fast_limb(c, ta, tb, m, n, k, A, lda, B, ldb, alpha, beta, Cm, ldc, st, IA);
+        if (rc) return rc;
+        mark(3);
+        c->ev_valid = c->profiling;
+        for (int i = 0; i < launches; ++i) LAUNCHED(c);
+        CUDA_TRY(cudaGetLastError());
+        *done = true;
+        return 0;
+    }
+    if (binary) sparse_mp = false;
+    // ---- workspace that depends on the base ----
+    void *pQA, *pS8, *pS = nullptr, *pT = nullptr;
+    if ((rc = ws_reserve(c, 8, (size_t) P * m_ps * k_p, &pQA))) return rc;
+    if ((rc = ws_reserve(c, 10, (size_t) P * n * m_ps, &pS8))) return rc;
+    if (!binary && (rc = ws_reserve(c, 5, (size_t) N * n * m_p * 4, &pS))) return rc;
+    if (sparse_mp && (rc = ws_reserve(c, 11, (size_t) k_p * (m_ps + n) * 2 + 512, &pT))) return rc;
+    int16_t *SAT = (int16_t *) pT, *SBT = sparse_mp ? SAT + (size_t) k_p * m_ps : nullptr;
+    if (!c->attr_ext) {
+        cudaFuncSetAttribute(k_ext_small<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ext_small_smem(512, 128));
+        cudaFuncSetAttribute(k_ext_small<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ext_small_smem(512, 128));
+        c->attr_ext = true;
+    }
+    if (!c->attr_align) { cudaFuncSetAttribute(k_align_small<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) align_small_smem(false)); c->attr_align = true; }
+    // ---- stage 1: the rank's column block of B first (it has to travel), then its rows of A ----
+    {
+        const unsigned gB = (unsigned) std::min<long long>((nb / kASo) * (k_p / kASl), (long long) c->sm_count * MPRES_ALIGN_BLOCKS);
+        const unsigned gA = (unsigned) std::min<long long>((m_ps / kASo) * (k_p / kASl), (long long) c->sm_count * MPRES_ALIGN_BLOCKS);
+        k_align_small<false><<<gB, 256, align_small_smem(false), st>>>(c->dconsts, Bown, soB, slB, nb, k, IB + col_own, QB + col_own * k_p, SB + col_own * k_p,
+                                                                       nb, k_p, sel, n);
+        ++launches;
+        prof_mark(c, st, "k_align_small(B)");
+        if (sparse_mp) {
+            k_mp_select<<<(unsigned) nb, 256, 0, st>>>(SB + col_own * k_p, k_p, (int) k_p, nb, cposB + col_own * kMcT, cvalB + col_own * kMcT, thrB + col_own);
+            ++launches;
+            prof_mark(c, st, "k_mp_select(B)");
+        }
+        CUDA_TRY(cudaEventRecord(sh->ev_pkg, st));
+        k_align_small<false><<<gA, 256, align_small_smem(false), st>>>(c->dconsts, A, soA, slA, m, k, IA, (uint8_t *) pQA, SA, m_ps, k_p, sel);
+        ++launches;
+        prof_mark(c, st, "k_align_small(A)");
+        if (sparse_mp) {
+            k_mp_select<<<(unsigned) m, 256, 0, st>>>(SA, k_p, (int) k_p, m, cposA, cvalA, thrA);
+            k_mp_transpose<<<dim3((unsigned) (m_ps / 64), (unsigned) (k_p / 64)), 256, 0, st>>>(SA, k_p, SAT, m_ps);
+            launches += 2;
+            prof_mark(c, st, "k_mp_select+transpose(A)");
+        }
+        // the block's share of every array to every peer, peers in the order they will need it (rank - 1 multiplies it second)
+        for (int d = 1; d < W; ++d) {
+            const int peer = (rank - d + W) % W;
+            const int si = (d - 1) % sh->npush;
+            cudaStream_t ps = sh->push[si];
+            if (d - 1 < sh->npush) CUDA_TRY(cudaStreamWaitEvent(ps, sh->ev_pkg, 0));
+            char *dst = sh->peer_recv[peer];
+            auto push = [&](size_t off, size_t per_col) -> cudaError_t {
+                const size_t o = off + (size_t) col_own * per_col;
+                return cudaMemcpyAsync(dst + o, rb + o, (size_t) nb * per_col, cudaMemcpyDeviceToDevice, ps);
+            };
+            CUDA_TRY(push(fl.oIB, sizeof(OuterInfo)));
+            if (sparse_mp) { CUDA_TRY(push(fl.oThr, 4)); CUDA_TRY(push(fl.oCpos, kMcT * 4)); CUDA_TRY(push(fl.oCval, kMcT * 4)); }
+            if (!binary) CUDA_TRY(push(fl.oSB, (size_t) k_p * 2));
+            {
+                const size_t o = fl.oQB + (size_t) col_own * k_p;
+                if ((size_t) n * k_p < ((size_t) 1 << 31)) {
+                    CUDA_TRY(cudaMemcpy2DAsync(dst + o, (size_t) n * k_p, rb + o, (size_t) n * k_p, (size_t) nb * k_p, (size_t) P, cudaMemcpyDeviceToDevice, ps));
+                } else {                                   // beyond the pitch limit of 2-D copies: plane by plane
+                    for (int z = 0; z < P; ++z)
+                        CUDA_TRY(cudaMemcpyAsync(dst + o + (size_t) z * n * k_p, rb + o + (size_t) z * n * k_p, (size_t) nb * k_p, cudaMemcpyDeviceToDevice, ps));
+                }
+            }
+            k_set_flag<<<1, 1, 0, ps>>>(sh->peer_flags[peer] + rank, sh->epoch);
+            ++launches;
+        }
+        for (int si = 0; si < sh->npush && si < W - 1; ++si) CUDA_TRY(cudaEventRecord(sh->ev_push[si], sh->push[si]));
+    }
+    const bool allow_fb = c->mode == MPRES_MODE_AUTO;
+    bool have_fast = c->stage3 == 0;
+    switch (N) { case 8: case 16: case 24: case 32: case 40: case 48: case 56: case 64: break; default: have_fast = false; }
+    const bool f32 = c->sc.usable && c->sc.red_shift >= 24 && c->sc.red_shift <= 27 && c->norm32;
+    if (have_fast && !binary) {
+        const int rowsT = 3 * c->hc.log2M + 2;
+        k_scalar_tables<<<(rowsT * N + 255) / 256, 256, 0, st>>>(c->dconsts, alpha, beta, scal_tab);
+        ++launches;
+    }
+    mark(1);
+    // ---- groups of panels in ring order: multiply, then normalise the group's column segments ----
+    int NG = W >= 4 ? 2 : 1;
+    if (const char *env = getenv("MPRES_SHARD_GROUPS")) NG = std::max(1, std::min(atoi(env), W));
+    int gemm_launches = 0, seg_index = 0;
+    bool first_seg = true;
+    for (int gi = 0; gi < NG; ++gi) {
+        const int pb = (int) ((long long) W * gi / NG), pe = (int) ((long long) W * (gi + 1) / NG);
+        if (pe <= pb) continue;
+        SmallPanels pan;
+        pan.count = pe - pb; pan.first = (rank + pb) % W; pan.own = rank; pan.epoch = sh->epoch; pan.flags = sh->flags;
+        pan.s8_panel = (long long) nb * m_ps; pan.ring = W; pan.plane_rows = n;
+        for (long long kb = 0; kb < k_p; kb += kSmallKChunk) {
+            const int kl = (int) std::min<long long>(kSmallKChunk, k_p - kb);
+            if ((rc = launch_small_umma(c, P, (const uint8_t *) pQA, QB, (long long) nb * k_p, (uint8_t *) pS8, m_ps, nb, k_p, kb, kl, kb > 0, sel, pan, st, n))) return rc;
+            gemm_launches += 1;
+        }
+        if (gi == 0) { prof_mark(c, st, "k_small_umma_p"); mark(2); }
+        // the group's panels as maximal runs of consecutive column blocks
+        int pi = pb;
+        while (pi < pe) {
+            const int g0 = (rank + pi) % W;
+            int cnt = 1;
+            while (pi + cnt < pe && g0 + cnt < W) ++cnt;                   // (ring order wraps at W: a new segment starts at block 0)
+            const long long col0 = (long long) g0 * nb;
+            const int nc = cnt * nb;
+            for (int q = 0; q < cnt; ++q)
+                if (g0 + q != rank) { k_wait_flag<<<1, 1, 0, st>>>(sh->flags + g0 + q, sh->epoch); ++launches; }
+            const SoA Cg = soa_shift(Cm, col0 * ldc, N);
+            const SoA Bg = soa_shift(B, col0 * soB, N);
+            int *cnt_s = c->d_counter + kCounterBlock * seg_index;
+            long long *todo_s = todo + (size_t) col0 * m, *slow_s = slow + (size_t) col0 * m, *mpl_s = mplist + (size_t) col0 * m;
+            int16_t *Ds = D + col0 * m_p;
+            uint8_t *S8s = (uint8_t *) pS8 + col0 * m_ps;
+            if (binary) {
+                const size_t smb = bin_smem_bytes(N);
+                const unsigned gx = (unsigned) std::min<long long>((long long) ((m + kBinT - 1) / kBinT) * nc, (long long) c->sm_count * 4);
+                MPRES_DISPATCH(N, {
+                    if (!c->attr_bin) { CUDA_TRY(cudaFuncSetAttribute(k_bin_norm<G, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smb)); c->attr_bin = true; }
+                    k_bin_norm<G, R><<<gx, kBinT, smb, st>>>(c->dconsts, m, nc, S8s, m_ps, n, sel, IA, IB + col0, alpha, beta, Cg, ldc);
+                });
+                ++launches;
+                if (first_seg) prof_mark(c, st, "k_bin_norm");
+            } else {
+                int *Ss = (int *) pS + col0 * m_p;
+                if (sparse_mp) {
+                    int16_t *D1s = D1 + col0 * m_p, *D2s = D2 + col0 * m_p;
+                    k_mp_transpose<<<dim3((unsigned) (nc / 64), (unsigned) (k_p / 64)), 256, 0, st>>>(SB + col0 * k_p, k_p, SBT + col0, n);
+                    k_mp_gather<<<(unsigned) m, 256, 0, st>>>(cposA, cvalA, SBT + col0, n, m, nc, D1s, nc);
+                    k_mp_gather<<<(unsigned) nc, 256, 0, st>>>(cposB + col0 * kMcT, cvalB + col0 * kMcT, SAT, m_ps, nc, (int) m_p, D2s, m_p);
+                    k_mp_combine<<<dim3((unsigned) (m_p / 64), (unsigned) (nc / 64)), 256, 0, st>>>(D1s, nc, D2s, m_p, thrA, thrB + col0, m, nc, Ds, m_p, mpl_s, cnt_s + 6);
+                    k_mp_fix<<<c->sm_count * 4, 256, 0, st>>>(SA, SB + col0 * k_p, k_p, Ds, m_p, mpl_s, cnt_s + 6);
+                    launches += 5;
+                } else {
+                    k_minplus<<<dim3((unsigned) (m_p / kMpTI), (unsigned) (nc / kMpTJ)), 256, 0, st>>>(SA, SB + col0 * k_p, Ds, k_p, m_p, nc);
+                    ++launches;
+                }
+                if (first_seg) prof_mark(c, st, "k_mp_transpose(B)+gather+combine+fix");
+                {
+                    const unsigned gx = (unsigned) std::min<long long>((m_p / kXT) * nc, (long long) c->sm_count * 4);
+                    const size_t sm = ext_small_smem(c->sc.ext_cols, N);
+                    if (c->sc.red_shift) k_ext_small<true><<<gx, kXT, sm, st>>>(c->dconsts, m, nc, S8s, m_p, m_ps, n, Ss, n, sel);
+                    else k_ext_small<false><<<gx, kXT, sm, st>>>(c->dconsts, m, nc, S8s, m_p, m_ps, n, Ss, n, sel);
+                    ++launches;
+                    if (first_seg) prof_mark(c, st, "k_ext_small");
+                }
+                auto norm_fast = [&](auto tag) {
+                    constexpr int NQ = decltype(tag)::value;
+                    const unsigned g3 = (unsigned) ((long long) ((m + kNormFastThreads - 1) / kNormFastThreads) * nc);
+                    const size_t sm_cds = (size_t) kNormFastThreads * (NQ + 1) * sizeof(int);
+                    auto launch_norm = [&](auto kern, size_t smem) {
+                        kern<<<g3, kNormFastThreads, smem, st>>>(c->dconsts, m, nc, k, (const int *) Ss, Ds, m_p, n, IA, IB + col0, alpha, beta, Cg, ldc,
+                                                                 scal_tab, todo_s, cnt_s, slow_s, cnt_s + 1, allow_fb, nullptr);
+                    };
+                    if (c->norm_staged) {
+                        const size_t sm_st = sm_cds + (size_t) NQ * kNormFastThreads * sizeof(int);
+                        if (sm_st > 48 * 1024 && !(c->attr_norm >> (NQ / 8) & 1ull)) {
+                            cudaFuncSetAttribute(k_norm_fast<NQ, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm_st);
+                            cudaFuncSetAttribute(k_norm_fast<NQ, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm_st);
+                            c->attr_norm |= 1ull << (NQ / 8);
+                        }
+                        if (f32) launch_norm(k_norm_fast<NQ, true, true>, sm_st); else launch_norm(k_norm_fast<NQ, false, true>, sm_st);
+                    } else {
+                        if (f32) launch_norm(k_norm_fast<NQ, true, false>, sm_cds); else launch_norm(k_norm_fast<NQ, false, false>, sm_cds);
+                    }
+                    ++launches;
+                };
+                bool hf = have_fast;
+                if (hf) {
+                    switch (N) {
+                        case 8: norm_fast(std::integral_constant<int, 8>{}); break;
+                        case 16: norm_fast(std::integral_constant<int, 16>{}); break;
+                        case 24: norm_fast(std::integral_constant<int, 24>{}); break;
+                        case 32: norm_fast(std::integral_constant<int, 32>{}); break;
+                        case 40: norm_fast(std::integral_constant<int, 40>{}); break;
+                        case 48: norm_fast(std::integral_constant<int, 48>{}); break;
+                        case 56: norm_fast(std::integral_constant<int, 56>{}); break;
+                        case 64: norm_fast(std::integral_constant<int, 64>{}); break;
+                        default: hf = false;
+                    }
+                    if (first_seg) prof_mark(c, st, "k_norm_fast");
+                }
+                MPRES_DISPATCH(N, {
+                    if (hf) {
+                        k_norm_list<G, R><<<c->sm_count * 8, 256, 0, st>>>(c->dconsts, m, nc, k, (const int *) Ss, Ds, m_p, n, IA, IB + col0, alpha, beta, Cg, ldc,
+                                                                          slow_s, cnt_s + 1);
+                    } else {
+                        constexpr int kNormTile = 256 / G;
+                        const unsigned g3 = (unsigned) ((long long) ((m + kNormTile - 1) / kNormTile) * nc);
+                        k_normalize_epilogue<G, R><<<g3, 256, (size_t) N * (kNormTile + 1) * 4, st>>>(
+                            c->dconsts, m, nc, k, (const int *) Ss, Ds, m_p, n, IA, IB + col0, alpha, beta, Cg, ldc, todo_s, cnt_s, allow_fb);
+                    }
+                    ++launches;
+                    if (allow_fb) {
+                        k_gemm_todo<G, R><<<c->sm_count * 8, 128, 0, st>>>(c->dconsts, ta, tb, m, nc, k, A, lda, Bg, ldb, alpha, beta, Cg, ldc, todo_s, cnt_s);
+                        ++launches;
+                    }
+                });
+                if (first_seg) prof_mark(c, st, "k_norm_list+k_gemm_todo");
+            }
+            first_seg = false;
+            ++seg_index;
+            pi += cnt;
+        }
+    }
+    mark(3);
+    prof_mark(c, st, "end");
+    c->ev_valid = c->profiling;
+    c->last_stage2_launches = gemm_launches;
+    for (int i = 0; i < launches + gemm_launches; ++i) LAUNCHED(c);
+    CUDA_TRY(cudaGetLastError());
+    *done = true;
+    return 0;
+}
+
 // ---- the fast path -----------------------------------------------------------------------------------------------------------------------
 // *done tells the caller whether C is final (false: the call has to run in reference order).  sh != nullptr: sharded call -- m, A, Cm are
 // this rank's row block, B is the rank's complete copy of B (the rank converts columns [rank n / world, (rank + 1) n / world) of it and
@@ -251,6 +576,11 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
     const int W = sh ? sh->world : 1, rank = sh ? sh->rank : 0;      // W column panels
     if (W > kMaxPanels || n % W != 0) return -6;
     const int nb = n / W;                                   // columns per panel
+    if (sh && W > 1 && nb % 256 == 0 && c->stage2 == MPRES_STAGE2_SMALL && c->small_persistent && c->small_kb == 128 && c->small_tj == 256 &&
+        !c->align_mma && !c->fuse_ext) {
+        const char *env = getenv("MPRES_SHARD_FLAT");
+        if (!env || atoi(env) != 0) return gemm_fast_flat(c, ta, tb, m, n, k, A, lda, B, ldb, alpha, beta, Cm, ldc, st, done, sh);
+    }
     const long long m_p = round_up(m, kBM), m_ps = round_up(m, kSN), k_p = round_up(k, 128), nb_p = round_up(nb, 256);
     if (k_p > 32000 * 128ll) return 0;
     const bool small_on = c->stage2 == MPRES_STAGE2_SMALL && c->sc.usable;
@@ -449,6 +779,7 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
     // ---- stage 2: one u8 GEMM per one-byte modulus, all panels in one persistent launch ----
     SmallPanels pan;
     pan.count = W; pan.first = rank; pan.own = rank; pan.epoch = sh ? sh->epoch : 0u; pan.flags = sh ? sh->flags : nullptr; pan.s8_panel = (long long) s8_panel;
+    pan.ring = 0; pan.plane_rows = 0;
     const uint8_t *PB0 = sh ? (const uint8_t *) (sh->recv + hdr) : own.QB;
     const long long pb_panel = sh ? (long long) sh->pkg_stride : (long long) planes_bytes;
     int gemm_launches = 0;

@@ -338,8 +338,13 @@ __global__ void k_dot_partial(const DevConsts *Cp, long long n, SoA x, int incx,
     num_zero(sum);
     for (long long i = grp; i < n; i += ngrp) {
         load_num<G, R>(C, L, x, inc_index(i, n, incx), a);
-        load_num<G, R>(C, L, y, inc_index(i, n, incy), b);
-        mp_mul<G, R, true>(C, L, prod, a, b);
+        if (y.digits) {
+            load_num<G, R>(C, L, y, inc_index(i, n, incy), b);
+            mp_mul<G, R, true>(C, L, prod, a, b);
+        } else {                                        // no second operand: sum of magnitudes (mp_asum, src/mpreduct.cuh:120-149)
+            prod = a;
+            prod.sign = 0;
+        }
         mp_add<G, R, true>(C, L, sum, sum, prod);
     }
     store_rec<G, R>(C, L, partials, grp, sum);

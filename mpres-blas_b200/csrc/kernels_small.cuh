@@ -176,10 +176,11 @@ template <bool MMA>
 #endif
 __global__ void __launch_bounds__(256, MPRES_ALIGN_BLOCKS) k_align_small(const DevConsts *Cp, SoA X, long long so, long long sl, int outer, int inner,
                                                         const OuterInfo *info, uint8_t *planes, int16_t *shifts,
-                                                        long long outer_p, long long inner_p, const int *sel) {
+                                                        long long outer_p, long long inner_p, const int *sel, long long plane_rows = 0) {
     extern __shared__ __align__(16) uint8_t as_smem[];
     const int P = sel[0], nin = sel[1];
     if (P <= 0) return;
+    if (plane_rows == 0) plane_rows = outer_p;      // rows between consecutive planes (> outer_p: the lines are a block of a larger plane set)
     const DevConsts &C = *Cp;
     const SmallDev &SD = *C.small;
     const int N = C.N;
@@ -361,7 +362,7 @@ __global__ void __launch_bounds__(256, MPRES_ALIGN_BLOCKS) k_align_small(const D
             const int j = v / (kASo * 2), rem = v - j * (kASo * 2);
             const int oo = rem >> 1, h = rem & 1;
             const uint4 val = *(const uint4 *) (s_out + j * (kASo * kASl) + oo * kASl + h * 16);
-            *(uint4 *) (planes + ((long long) j * outer_p + o0 + oo) * inner_p + l0 + h * 16) = val;
+            *(uint4 *) (planes + ((long long) j * plane_rows + o0 + oo) * inner_p + l0 + h * 16) = val;
         }
         if (threadIdx.x < kASo * 4) {
             const int oo = threadIdx.x >> 2, part = threadIdx.x & 3;
@@ -529,10 +530,12 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
 // produces, the TMA thread waits for that panel's arrival flag (written by the producing rank after its copy landed here), so the
 // multiplication of the panels already here overlaps the transfer of the others.
 struct SmallPanels {
-    int count, first, own;
+    int count, first, own;       // panels of this launch: first, first + 1, ... (mod ring)
     unsigned epoch;
-    const unsigned *flags;       // [count] arrival epochs (nullptr: every panel is local)
+    const unsigned *flags;       // [ring] arrival epochs (nullptr: every panel is local)
     long long s8_panel;          // bytes between the S8 ranges of consecutive panels
+    int ring;                    // panels of the call (0: count)
+    long long plane_rows;        // rows of one S8 plane (0: n_ps -- every panel has its own plane set)
 };
 __device__ __forceinline__ void wait_arrival(const unsigned *flag, unsigned epoch) {
     const long long t0 = clock64();
@@ -599,7 +602,7 @@ k_small_umma_p(const __grid_constant__ CUtensorMap tmJ, const __grid_constant__ 
             for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
                 const int pi = (int) (tile / per_panel);
                 const long long tp = tile - (long long) pi * per_panel;
-                const int pg = (pan.first + pi) % pan.count;
+                const int pg = (pan.first + pi) % (pan.ring ? pan.ring : pan.count);
                 const int z = (int) (tp / per_z), r = (int) (tp - (long long) z * per_z);
                 const int j0 = (r / tiles_i) * TJ, i0 = (r % tiles_i) * kSN;
                 if (pg != arrived) {
@@ -612,7 +615,8 @@ k_small_umma_p(const __grid_constant__ CUtensorMap tmJ, const __grid_constant__ 
                     ptx::mbar_wait(&empty[s], ph ^ 1u);
                     ptx::mbar_expect_tx(&full[s], kStage);
                     uint8_t *dst = smem + s * kStage;
-                    ptx::tma_load_4d(dst, &tmJ, &full[s], k_byte0 + it * KB, j0, z, pg);
+                    if (pan.plane_rows) ptx::tma_load_4d(dst, &tmJ, &full[s], k_byte0 + it * KB, j0, pg, z);     // (k, row, panel, plane): one plane set
+                    else ptx::tma_load_4d(dst, &tmJ, &full[s], k_byte0 + it * KB, j0, z, pg);
                     ptx::tma_load_3d(dst + kStageA, &tmI, &full[s], k_byte0 + it * KB, i0, z);
                 }
             }
@@ -659,18 +663,19 @@ k_small_umma_p(const __grid_constant__ CUtensorMap tmJ, const __grid_constant__ 
         for (long long tile = blockIdx.x; tile < total; tile += gridDim.x, ++lt) {
             const int pi = (int) (tile / per_panel);
             const long long tp = tile - (long long) pi * per_panel;
-            const int pg = (pan.first + pi) % pan.count;
+            const int pg = (pan.first + pi) % (pan.ring ? pan.ring : pan.count);
             const int z = (int) (tp / per_z), r = (int) (tp - (long long) z * per_z);
             const int j0 = (r / tiles_i) * TJ, i0 = (r % tiles_i) * kSN;
             const unsigned p = (unsigned) SD.p[z], mu = SD.mu[z];
             uint8_t *S8p = S8 + (long long) pg * pan.s8_panel;
+            const long long s8_rows = pan.plane_rows ? pan.plane_rows : n_ps;
             const int b = NH == 1 ? (lt & 1) : 0, use = NH == 1 ? (lt >> 1) : lt;
             ptx::mbar_wait(&acc_full[b], (uint32_t) (use & 1));
             ptx::tc_fence_after();
 #pragma unroll 1
             for (int h = 0; h < NH; ++h) {
                 const int j = j0 + h * kSM + quad * 32 + lane;
-                uint4 *dst = (uint4 *) (S8p + ((long long) z * n_ps + j) * m_ps + i0 + half * 128);
+                uint4 *dst = (uint4 *) (S8p + ((long long) z * s8_rows + j) * m_ps + i0 + half * 128);
                 const uint32_t tbase = tmem + ((uint32_t) (quad * 32) << 16) + (uint32_t) ((NH == 1 ? b : h) * kSN + half * 128);
                 // all 128 columns of this thread into registers first, so the accumulator can be handed back early
                 uint32_t d[16][8];
@@ -914,12 +919,17 @@ __global__ void __launch_bounds__(kXT, 4) k_ext_norm_small(const DevConsts *Cp, 
 }  // namespace mpres
 
 // map (k, row, plane[, panel]) over u8 planes [panels][planes][rows_p][k_p] (panel_stride bytes between panels), box box_k B x box_rows x 1 x 1
+// plane_rows > 0: the planes are plane_rows rows apart (the panels are row blocks of ONE plane set: panel_stride = rows_p * k_p)
 inline int small_make_map(CUtensorMap *map, const void *planes, int nplanes, long long rows_p, long long k_p, int box_rows, int box_k = mpres::kSK,
-                          int npanels = 0, long long panel_stride = 0) {
+                          int npanels = 0, long long panel_stride = 0, long long plane_rows = 0) {
     mpres_encode_tiled_fn enc = umma_encode_fn();
     if (!enc) return -30;
     cuuint64_t dims[4] = {(cuuint64_t) k_p, (cuuint64_t) rows_p, (cuuint64_t) nplanes, (cuuint64_t) (npanels > 0 ? npanels : 1)};
     cuuint64_t strides[3] = {(cuuint64_t) k_p, (cuuint64_t) (rows_p * k_p), (cuuint64_t) (npanels > 1 ? panel_stride : rows_p * k_p * nplanes)};
+    if (plane_rows > 0) {     // (k, row, panel, plane)
+        dims[2] = (cuuint64_t) (npanels > 0 ? npanels : 1); dims[3] = (cuuint64_t) nplanes;
+        strides[1] = (cuuint64_t) (rows_p * k_p); strides[2] = (cuuint64_t) (plane_rows * k_p);
+    }
     cuuint32_t box[4] = {(cuuint32_t) box_k, (cuuint32_t) box_rows, 1, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, npanels > 0 ? 4 : 3, const_cast<void *>(planes), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -931,7 +941,7 @@ inline int small_make_map(CUtensorMap *map, const void *planes, int nplanes, lon
 // PA: planes of A' [P][m_ps][k_p] (m_ps % 256 == 0); PB: per panel, planes of B' [P][n_ps][k_p] (n_ps % 256 == 0), consecutive panels
 // pb_panel bytes apart; S8: per panel [P][n_ps][m_ps].  P is the host's copy of sel[0].
 inline int launch_small_umma(mpres_ctx *c, int P, const uint8_t *PA, const uint8_t *PB, long long pb_panel, uint8_t *S8, long long m_ps, long long n_ps, long long k_p,
-                             long long k_begin, int k_len, bool add_to_S, const int *sel, const mpres::SmallPanels &pan, cudaStream_t st) {
+                             long long k_begin, int k_len, bool add_to_S, const int *sel, const mpres::SmallPanels &pan, cudaStream_t st, long long pb_plane_rows = 0) {
     CUtensorMap tmJ, tmI;
     int rc;
     const int box_k = (c->small_persistent && c->small_kb == 128 && k_len % 128 == 0 && k_begin % 128 == 0) ? 128 : mpres::kSK;
@@ -945,7 +955,7 @@ inline int launch_small_umma(mpres_ctx *c, int P, const uint8_t *PA, const uint8
     }
     if ((rc = small_make_map(&tmI, PA, P, m_ps, k_p, mpres::kSN, box_k))) return rc;
     if (c->small_persistent) {
-        if ((rc = small_make_map(&tmJ, PB, P, n_ps, k_p, tj, box_k, pan.count, pb_panel))) return rc;
+        if ((rc = small_make_map(&tmJ, PB, P, n_ps, k_p, tj, box_k, pan.ring ? pan.ring : pan.count, pb_panel, pb_plane_rows))) return rc;
         const long long max_tiles = (long long) P * (m_ps / mpres::kSN) * (n_ps / tj) * pan.count;
         const unsigned gx = (unsigned) std::min<long long>(max_tiles, (long long) c->sm_count);
         if (tj == 256)

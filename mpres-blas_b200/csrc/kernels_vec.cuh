@@ -133,9 +133,11 @@ constexpr int kVecExpLimit = 1 << 28;   // exponents beyond this magnitude make 
 // pd[(split m + row) N + q] digits, plab label, pmin smallest term exponent, ptop window top.
 // SMALL: every modulus has bit length kb <= 27.
 // (forcing three blocks per SM through __launch_bounds__ was measured: 6.0 ms against 5.4 ms at config 4 -- the default allocation stays)
-template <bool SMALL, int CB, int STAGES>
+// ABS: the signs of both factors are ignored (sums of magnitudes: mp_ge_norm, src/blas/genorm.cuh:39-75).  vs = 0: every column
+// uses v[0] (a vector of equal entries without the memory), vs = 1: v[j].
+template <bool SMALL, int CB, int STAGES, bool ABS = false>
 __global__ void __launch_bounds__(256) k_mv_acc_n(const DevConsts *Cp, SoA A, int lda, int m, int n, SoA v, int lgRB, int cols_per_split,
-                                                  int *pd, int *plab, int *pmin, int *ptop) {
+                                                  int *pd, int *plab, int *pmin, int *ptop, int vs = 1) {
     extern __shared__ __align__(16) unsigned char vsm[];
     typedef typename VecAcc<SMALL>::type acc_t;
     static_assert((CB & (CB - 1)) == 0 && CB >= 2 && CB <= 32, "columns per stage: power of two (phase A reduces over CB lanes)");
@@ -203,11 +205,12 @@ __global__ void __launch_bounds__(256) k_mv_acc_n(const DevConsts *Cp, SoA A, in
             }
         }
         if (r < nc) {   // vector entry j0 + r: thread (r, q4) copies its four digits, q4 == 0 the scalar fields
-            cp16(S + oAxd + (r * N + 4 * q4) * 4, v.digits + (long long) (j0 + r) * N + 4 * q4);
+            const long long jv = (long long) (j0 + r) * vs;
+            cp16(S + oAxd + (r * N + 4 * q4) * 4, v.digits + jv * N + 4 * q4);
             if (q4 == 0) {
-                cp4(S + oAxe + r * 4, v.exp + j0 + r);
-                cp4(S + oAxg + r * 4, v.sign + j0 + r);
-                cp16(S + oAxu + r * 16, v.eval + (j0 + r + lenv));
+                cp4(S + oAxe + r * 4, v.exp + jv);
+                cp4(S + oAxg + r * 4, v.sign + jv);
+                cp16(S + oAxu + r * 16, v.eval + (jv + lenv));
             }
         }
     };
@@ -250,7 +253,7 @@ __global__ void __launch_bounds__(256) k_mv_acc_n(const DevConsts *Cp, SoA A, in
                         tp = tp > (1 << 30) ? (1 << 30) : (tp < -(1 << 30) ? -(1 << 30) : tp);
                         if (abs(ea) > kVecExpLimit || abs(ex) > kVecExpLimit) tp = 1 << 30;   // keeps the 32-bit shift arithmetic exact
                         mn = et; mx = (int) tp;
-                        code = et * 2 + ((sgnA[c * pitchE + rr] ^ axg[c]) & 1);
+                        code = et * 2 + (ABS ? 0 : ((sgnA[c * pitchE + rr] ^ axg[c]) & 1));
                     }
                 }
                 code_s[rr * (CB + 1) + c] = code;
@@ -336,9 +339,10 @@ __host__ __device__ inline size_t mv_t_stage_bytes(int RS, int T, int RT) {
 // ---- y = A^T x and x . y: one block = one column of M (blockIdx.x; ncols = 1, ldm = 0 for DOT) and the rows of one
 //      split (blockIdx.y).  All threads of the block accumulate the same output under one block-wide label.
 // pd[(split ncols + col) N + q], plab / pmin / ptop[split ncols + col].  kb: common bit length of the moduli (SMALL).
-template <bool SMALL, int RT, int STAGES>
+// ABS / vs as in k_mv_acc_n (mp_asum, column sums of mp_ge_norm: V = one entry "1", vs = 0).
+template <bool SMALL, int RT, int STAGES, bool ABS = false>
 __global__ void __launch_bounds__(256) k_mv_acc_t(const DevConsts *Cp, SoA M, long long ldm, long long nrows, int ncols, SoA V, int lgRB,
-                                                  long long rows_per_split, int kb, int *pd, int *plab, int *pmin, int *ptop) {
+                                                  long long rows_per_split, int kb, int *pd, int *plab, int *pmin, int *ptop, int vs = 1) {
     extern __shared__ __align__(16) unsigned char vsm[];
     typedef typename VecAcc<SMALL>::type acc_t;
     __shared__ int s_min, s_top;
@@ -371,9 +375,9 @@ __global__ void __launch_bounds__(256) k_mv_acc_t(const DevConsts *Cp, SoA M, lo
     for (int i = t; i < N; i += T) s_sum[i] = 0ull;
     // rbeg and RS are multiples of four: 16-byte copies of four exponents / signs need aligned bases
     const bool quadsM = (mbase & 3) == 0 && ((((size_t) M.exp) | ((size_t) M.sign)) & 15) == 0;
-    const bool quadsV = ((((size_t) V.exp) | ((size_t) V.sign)) & 15) == 0;
+    const bool quadsV = vs != 0 && ((((size_t) V.exp) | ((size_t) V.sign)) & 15) == 0;
     const unsigned smem0 = (unsigned) __cvta_generic_to_shared(vsm);
-    const int *gM = M.digits + (mbase + rbeg) * N + 4 * t, *gV = V.digits + rbeg * N + 4 * t;   // + chunk * RS * N + u * 4 T
+    const int *gM = M.digits + (mbase + rbeg) * N + 4 * t, *gV = V.digits + (vs ? rbeg * N + 4 * t : 4 * q4);   // + chunk * RS * N + u * 4 T
 
     auto cp16 = [](unsigned dst, const void *src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src)); };
     auto cp4 = [](unsigned dst, const void *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst), "l"(src)); };
@@ -387,13 +391,13 @@ __global__ void __launch_bounds__(256) k_mv_acc_t(const DevConsts *Cp, SoA M, lo
         for (int u = 0; u < RT; ++u) {
             if (rl + (u << lgRB) < nr) {                // 16-byte chunk t + T u: row rl + RB u, moduli 4 q4 ..
                 cp16(S + (t + T * u) * 16, gM + doff + 4 * T * u);
-                cp16(S + oDigV + (t + T * u) * 16, gV + doff + 4 * T * u);
+                cp16(S + oDigV + (t + T * u) * 16, gV + (doff + 4 * T * u) * vs);
             }
         }
         for (int e = t; e < RS; e += T) {
             if (e < nr) {
                 cp16(S + oUppM + e * 16, M.eval + (mbase + r0 + e + lenM));
-                cp16(S + oUppV + e * 16, V.eval + (r0 + e + lenV));
+                cp16(S + oUppV + e * 16, V.eval + ((r0 + e) * vs + lenV));
             }
         }
         for (int e = t; e < (RS >> 2); e += T) {   // exponents and signs, four rows per item
@@ -411,7 +415,7 @@ __global__ void __launch_bounds__(256) k_mv_acc_t(const DevConsts *Cp, SoA M, lo
                     cp16(S + oExpV + e * 16, V.exp + row);
                     cp16(S + oSgnV + e * 16, V.sign + row);
                 } else {
-                    for (int k = 0; k < 4 && e4 + k < nr; ++k) { cp4(S + oExpV + e * 16 + 4 * k, V.exp + row + k); cp4(S + oSgnV + e * 16 + 4 * k, V.sign + row + k); }
+                    for (int k = 0; k < 4 && e4 + k < nr; ++k) { cp4(S + oExpV + e * 16 + 4 * k, V.exp + (row + k) * vs); cp4(S + oSgnV + e * 16 + 4 * k, V.sign + (row + k) * vs); }
                 }
             }
         }
@@ -446,7 +450,7 @@ __global__ void __launch_bounds__(256) k_mv_acc_t(const DevConsts *Cp, SoA M, lo
                         tp = tp > (1 << 30) ? (1 << 30) : (tp < -(1 << 30) ? -(1 << 30) : tp);
                         if (abs(ea) > kVecExpLimit || abs(ex) > kVecExpLimit) tp = 1 << 30;
                         mn = min(mn, et); mx = max(mx, (int) tp);
-                        code = et * 2 + ((sgnM[e] ^ sgnV[e]) & 1);
+                        code = et * 2 + (ABS ? 0 : ((sgnM[e] ^ sgnV[e]) & 1));
                     }
                 }
                 code_s[e] = code;
@@ -573,10 +577,10 @@ __global__ void __launch_bounds__(256) k_mv_combine(const DevConsts *Cp, int nou
 
 // ---- combine the splits, normalise, apply --------------------------------------------------------------------
 // add_to_y: y[o] = round(y[o] + S_o) (y already holds round(beta y), src/blas/gemv.cuh:199-218); otherwise r = S
-// (stored to out[0] or to the AoS record rec_out).  nterms: length of every sum (for the magnitude bound).
+// (stored to out[0] or to the AoS record rec_out; store_each: to y[o]).  nterms: length of every sum (for the magnitude bound).
 template <int G, int R>
 __global__ void __launch_bounds__(256) k_mv_finalize(const DevConsts *Cp, int nout, int nsplit, MvParts in, long long nterms, bool add_to_y, SoA y,
-                                                     int incy, char *rec_out, int *todo, int *todo_count, bool fallback_allowed) {
+                                                     int incy, char *rec_out, int *todo, int *todo_count, bool fallback_allowed, bool store_each = false) {
     const DevConsts &C = *Cp;
     Lane<R> L;
     lane_init<G, R>(C, L);
@@ -651,7 +655,7 @@ __global__ void __launch_bounds__(256) k_mv_finalize(const DevConsts *Cp, int no
     } else if (rec_out) {
         store_rec<G, R>(C, L, rec_out, 0, s);
     } else {
-        store_num<G, R>(C, L, y, 0, s);
+        store_num<G, R>(C, L, y, store_each ? inc_index(o, nout, incy) : 0, s);
     }
 }
 
@@ -723,6 +727,23 @@ static inline void mv_launch_t(mpres_ctx *c, dim3 grid, int T, int lgRB, SoA M, 
     const size_t smem = STAGES * mv_t_stage_bytes(RS, T, RT) + (size_t) RS * 4;
     cudaFuncSetAttribute(k_mv_acc_t<SMALL, RT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     k_mv_acc_t<SMALL, RT, STAGES><<<grid, T, smem, st>>>(c->dconsts, M, ldm, nrows, ncols, V, lgRB, rows_per, kb, o.pd, o.lab, o.mn, o.top);
+}
+// sums of magnitudes against the single entry `one`
+template <bool SMALL>
+static inline void mv_launch_t_abs(mpres_ctx *c, dim3 grid, int T, int lgRB, SoA M, long long ldm, long long nrows, int ncols, SoA one, long long rows_per,
+                                   int kb, const MvParts &o, cudaStream_t st) {
+    constexpr int RT = 4, STAGES = 2;
+    const int RS = RT << lgRB;
+    const size_t smem = STAGES * mv_t_stage_bytes(RS, T, RT) + (size_t) RS * 4;
+    cudaFuncSetAttribute(k_mv_acc_t<SMALL, RT, STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    k_mv_acc_t<SMALL, RT, STAGES, true><<<grid, T, smem, st>>>(c->dconsts, M, ldm, nrows, ncols, one, lgRB, rows_per, kb, o.pd, o.lab, o.mn, o.top, 0);
+}
+template <bool SMALL>
+static inline void mv_launch_n_abs(mpres_ctx *c, dim3 grid, int T, int lgRB, SoA A, int lda, int m, int n, SoA one, int cols_per, const MvParts &o, cudaStream_t st) {
+    constexpr int CB = 8, STAGES = 2;
+    const size_t smem = STAGES * mv_n_stage_bytes(c->hc.N, 1 << lgRB, T, CB) + mv_n_common_bytes(1 << lgRB, CB);
+    cudaFuncSetAttribute(k_mv_acc_n<SMALL, CB, STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    k_mv_acc_n<SMALL, CB, STAGES, true><<<grid, T, smem, st>>>(c->dconsts, A, lda, m, n, one, lgRB, cols_per, o.pd, o.lab, o.mn, o.top, 0);
 }
 
 // tile configurations (A/B switch mpres_set_vec_config): columns (N) / row tiles (T) per stage x ring depth
@@ -859,5 +880,108 @@ inline int dot_fast(mpres_ctx *c, int n, SoA x, int incx, SoA y, int incy, char 
     c->last_stage2_launches = 1;
     *launched = true;
     *done = !allow_fb;   // AUTO: the caller still launches the reference-order kernels, gated on d_counter[0]
+    return 0;
+}
+
+// ---- sums of magnitudes (mp_asum, the row / column sums of mp_ge_norm) on the exact-window accumulators ------------------------------
+namespace mpres {
+
+// the number 1 as a one-element SoA (digits 1, exponent 0, interval evaluation of 1 / M)
+__global__ void k_make_one(const DevConsts *Cp, SoA one) {
+    const DevConsts &C = *Cp;
+    const int t = threadIdx.x;
+    if (t < C.N) one.digits[t] = 1;
+    if (t == 0) {
+        one.sign[0] = 0; one.exp[0] = 0;
+        Er lo = C.unit_low, up = C.unit_upp;
+        er_adjust(lo); er_adjust(up);
+        one.eval[0] = lo; one.eval[1] = up;
+    }
+}
+
+// reference-order fallback: out[o] = sum_l |X(o, l)| for the listed outputs (or all of them), one lane group each, sequential mp_add
+// with the rounding of src/arith/add.cuh:197-199.  Element (o, l) at o * so + l * sl.
+template <int G, int R>
+__global__ void k_abs_sum_ref(const DevConsts *Cp, SoA X, long long so, long long sl, int nout, long long nterms, SoA out, int inco,
+                              const int *todo, const int *todo_count) {
+    const DevConsts &C = *Cp;
+    Lane<R> L;
+    lane_init<G, R>(C, L);
+    long long grp = ((long long) blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const long long ngrp = (long long) gridDim.x * blockDim.x / G;
+    const long long total = todo ? (long long) *todo_count : (long long) nout;
+    for (; grp < total; grp += ngrp) {
+        const long long o = todo ? todo[grp] : grp;
+        Num<R> sum, a;
+        num_zero(sum);
+        for (long long l = 0; l < nterms; ++l) {
+            load_num<G, R>(C, L, X, o * so + l * sl, a);
+            a.sign = 0;
+            mp_add<G, R, true>(C, L, sum, sum, a);
+        }
+        store_num<G, R>(C, L, out, inc_index(o, nout, inco), sum);
+    }
+}
+
+}  // namespace mpres
+
+// out[o] = sum over l of |X(o, l)|, o < nout, l < nterms; X(o, l) at o * so + l * sl with so == 1 (lines strided: row sums of a column-major
+// matrix) or sl == 1 (lines contiguous: column sums, a vector).  One pass over X at HBM speed; outputs whose window guard fails
+// (exponent spreads beyond the format) are recomputed in reference order.
+inline int abs_sums_fast(mpres_ctx *c, SoA X, long long so, long long sl, int nout, long long nterms, SoA out, cudaStream_t st, bool *done) {
+    *done = false;
+    const int N = c->hc.N;
+    if (N % 4 != 0 || N > kMaxN || nterms > 0x7fffffffll) return 0;
+    const int lgRB = mv_log2_rows_per_block(N);
+    if (lgRB < 0) return 0;
+    const int RB = 1 << lgRB, Q4 = N / 4, T = RB * Q4;
+    const int kb = mv_small_moduli_bits(c);
+    SoA one;
+    int rc;
+    if ((rc = ws_soa(c, 19, 1, &one))) return rc;
+    k_make_one<<<1, 128, 0, st>>>(c->dconsts, one);
+    LAUNCHED(c);
+    MvWork w;
+    int nsplit;
+    const int target = c->sm_count * 8;
+    if (sl == 1) {
+        constexpr int RT = 4;
+        const int RS = RT * RB;
+        nsplit = (int) std::max<long long>(1, std::min<long long>((target + nout - 1) / nout, (nterms + 4 * RS - 1) / (4 * RS)));
+        long long rows_per = (nterms + nsplit - 1) / nsplit;
+        rows_per = (rows_per + RS - 1) / RS * RS;
+        nsplit = (int) ((nterms + rows_per - 1) / rows_per);
+        if ((rc = mv_workspace(c, nout, nsplit, &w))) return rc;
+        const dim3 grid((unsigned) nout, (unsigned) nsplit);
+        if (kb) mv_launch_t_abs<true>(c, grid, T, lgRB, X, so, nterms, nout, one, rows_per, kb, w.parts, st);
+        else mv_launch_t_abs<false>(c, grid, T, lgRB, X, so, nterms, nout, one, rows_per, kb, w.parts, st);
+    } else if (so == 1) {
+        constexpr int CB = 8;
+        const int nrb = (nout + RB - 1) / RB;
+        nsplit = (int) std::max<long long>(1, std::min<long long>((target + nrb - 1) / nrb, (nterms + 8 * CB - 1) / (8 * CB)));
+        int cols_per = (int) ((nterms + nsplit - 1) / nsplit);
+        cols_per = (cols_per + CB - 1) / CB * CB;
+        nsplit = (int) ((nterms + cols_per - 1) / cols_per);
+        if ((rc = mv_workspace(c, nout, nsplit, &w))) return rc;
+        const dim3 grid((unsigned) nrb, (unsigned) nsplit);
+        if (kb) mv_launch_n_abs<true>(c, grid, T, lgRB, X, (int) sl, nout, (int) nterms, one, cols_per, w.parts, st);
+        else mv_launch_n_abs<false>(c, grid, T, lgRB, X, (int) sl, nout, (int) nterms, one, cols_per, w.parts, st);
+    } else {
+        return 0;
+    }
+    LAUNCHED(c);
+    CUDA_TRY(cudaGetLastError());
+    const bool allow_fb = c->mode == MPRES_MODE_AUTO;
+    MPRES_DISPATCH(N, {
+        const unsigned blocks = (unsigned) (((long long) nout * G + 255) / 256);
+        k_mv_finalize<G, R><<<blocks, 256, 0, st>>>(c->dconsts, nout, nsplit, w.parts, nterms, false, out, 1, nullptr, w.todo, c->d_counter, allow_fb, true);
+        LAUNCHED(c);
+        if (allow_fb) {
+            k_abs_sum_ref<G, R><<<c->sm_count * 4, 128, 0, st>>>(c->dconsts, X, so, sl, nout, nterms, out, 1, w.todo, c->d_counter);
+            LAUNCHED(c);
+        }
+    });
+    CUDA_TRY(cudaGetLastError());
+    *done = true;
     return 0;
 }

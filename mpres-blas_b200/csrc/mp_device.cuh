@@ -101,7 +101,7 @@ __device__ __forceinline__ int submod(int a, int b, int m) {  // a, b in [0, m)
     return t < 0 ? t + m : t;
 }
 // 2^j mod m for j outside the table (the reference reads out of bounds there)
-__device__ __noinline__ int pow2_slow(long long j, int m, unsigned long long mu) {
+static __device__ __noinline__ int pow2_slow(long long j, int m, unsigned long long mu) {
     int r = 1, b = 2 % m;
     while (j > 0) {
         if (j & 1) r = mulmod(r, b, m, mu);

@@ -141,7 +141,8 @@ int mpres_finalize(mpres_ctx *c) {
     if (c->device < 0) { delete c; return 0; }
     DeviceGuard g(c->device);
     cudaDeviceSynchronize();
-    for (int i = 0; i < 18; ++i) if (c->ws[i]) cudaFree(c->ws[i]);
+    mpres_ops_release(c);
+    for (int i = 0; i < 24; ++i) if (c->ws[i]) cudaFree(c->ws[i]);
     for (int i = 0; i < 4; ++i) if (c->hs[i]) cudaStreamDestroy(c->hs[i]);
     for (int i = 0; i < 16; ++i) if (c->hev[i]) cudaEventDestroy(c->hev[i]);
     for (int i = 0; i < 12; ++i) if (c->d_small[i]) cudaFree(c->d_small[i]);
@@ -1153,6 +1154,85 @@ int mpres_axpy_dot(mpres_ctx *c, int n, const mpres_array_t *alpha, mpres_array_
     }
     return mpres_dot(c, n, u, incu, w, incw, r, buffer, stream);      // src/blas/axpydot.cuh:67
 }
+/* ---- sums of magnitudes and norms (src/blas/asum.cuh:41, genorm.cuh:142) ------------------------------------------------- */
+
+// out[o] = sum_l |X(o, l)|: the exact-window accumulators when they apply, else the reference-order loops.  The caller holds the lock.
+static int abs_sums(mpres_ctx *c, SoA X, long long so, long long sl, int nout, long long nterms, SoA out, cudaStream_t st) {
+    const int N = c->hc.N;
+    bool done = false;
+    CUDA_TRY(cudaMemsetAsync(c->d_counter, 0, kCounterInts * sizeof(int), st));
+    if (c->mode != MPRES_MODE_REFERENCE_ORDER && (sl == 1 || so == 1)) {
+        int rc = abs_sums_fast(c, X, so, sl, nout, nterms, out, st, &done);
+        if (rc) return rc;
+    }
+    if (!done) {
+        if (nout == 1 && nterms > 4096) {
+            // one long sum: partial sums per lane group, then a tree (the structure of src/mpreduct.cuh:120-149)
+            const size_t rs = 4 * (size_t) N + 40;
+            int rc = 0;
+            SoA none;
+            memset(&none, 0, sizeof(none));
+            MPRES_DISPATCH(N, {
+                const int block = 128;
+                const long long gpb = block / G;
+                const long long blocks = std::min<long long>((nterms + gpb - 1) / gpb, (long long) c->sm_count * 8);
+                const long long groups = blocks * gpb;
+                void *parts;
+                rc = ws_reserve(c, 2, (size_t) groups * rs, &parts);
+                if (rc) return rc;
+                k_dot_partial<G, R><<<(unsigned) blocks, block, 0, st>>>(c->dconsts, nterms, X, (int) sl, none, 1, (char *) parts, nullptr);
+                k_tree_records<G, R><<<1, 256, 0, st>>>(c->dconsts, (char *) parts, groups, out, 0, nullptr, nullptr);
+            });
+            LAUNCHED(c); LAUNCHED(c);
+        } else {
+            MPRES_DISPATCH(N, {
+                const long long blocks = std::max<long long>(1, std::min<long long>(((long long) nout * G + 127) / 128, (long long) c->sm_count * 8));
+                k_abs_sum_ref<G, R><<<(unsigned) blocks, 128, 0, st>>>(c->dconsts, X, so, sl, nout, nterms, out, 1, nullptr, nullptr);
+            });
+            LAUNCHED(c);
+        }
+        CUDA_TRY(cudaGetLastError());
+    }
+    return 0;
+}
+
+int mpres_asum(mpres_ctx *c, int n, const mpres_array_t *x, int incx, mpres_array_t *r, mpres_stream_t stream) {
+    NEED_DEVICE(c);
+    if (!c || !x || !r) return -1;
+    if (n <= 0 || incx <= 0) return 0;   // src/blas/asum.cuh:44-46
+    DeviceGuard g(c->device);
+    std::lock_guard<std::mutex> lk(c->mu);
+    cudaStream_t st = (cudaStream_t) stream;
+    int rc = call_begin(c, st);
+    if (rc) return rc;
+    c->last_stream = st;
+    if ((rc = abs_sums(c, view(x), 0, incx, 1, n, view(r), st))) return rc;
+    return call_end(c, st);
+}
+
+int mpres_ge_norm(mpres_ctx *c, int norm, int m, int n, const mpres_array_t *A, int lda, mpres_array_t *r, mpres_array_t *buffer, mpres_stream_t stream) {
+    NEED_DEVICE(c);
+    if (!c || !A || !r) return -1;
+    if (norm != MPRES_ONE_NORM && norm != MPRES_INF_NORM) return -2;
+    if (m <= 0 || n <= 0) return 0;      // src/blas/genorm.cuh:145-151
+    if (lda < std::max(1, m)) return -3;
+    DeviceGuard g(c->device);
+    std::lock_guard<std::mutex> lk(c->mu);
+    cudaStream_t st = (cudaStream_t) stream;
+    int rc = call_begin(c, st);
+    if (rc) return rc;
+    c->last_stream = st;
+    const bool one = norm == MPRES_ONE_NORM;         // one norm: largest column sum; infinity norm: largest row sum
+    const int nout = one ? n : m;
+    SoA sums;
+    if (buffer && buffer->digits) sums = view(buffer);
+    else if ((rc = ws_soa(c, 20, (size_t) nout, &sums))) return rc;
+    if ((rc = abs_sums(c, view(A), one ? lda : 1, one ? 1 : lda, nout, one ? m : n, sums, st))) return rc;
+    const SoA rv = view(r);
+    if ((rc = mpres_internal_maxabs(c, nout, &sums, 1, &rv, st))) return rc;
+    return call_end(c, st);
+}
+
 int mpres_dot_partial(mpres_ctx *c, int n, const mpres_array_t *x, int incx, const mpres_array_t *y, int incy, void *partial,
                       mpres_stream_t stream) {
     NEED_DEVICE(c);
