@@ -70,7 +70,7 @@ def read_peaks():
 
 
 def read_int8_peak(bf16_peak):
-    """dense int8 tensor peak in TOP/s: measured (tools/int8_peak.py: cuBLASLt CUDA_R_8I 8192^3, profiles/r02_int8_peak.json) when that
+    """dense int8 tensor peak in TOP/s: measured (tools/int8_peak.cu: cuBLAS s8 x s8 -> s32 8192^3, profiles/r02_int8_peak.json) when that
     file exists, else 2 x the measured bf16 burst peak (int8 dense = 2 x bf16 dense on the same tensor cores)"""
     p = os.path.join(ROOT, "profiles", "r02_int8_peak.json")
     if os.path.exists(p):

@@ -57,7 +57,7 @@ struct mpres_ctx {
     int vec_config = 0;               // tile configuration of the mp_gemv / mp_dot kernels (A/B measurement)
     HostConsts hc;
     SmallConsts sc;                   // small-modulus base of the tensor-core stage 2
-    void *d_small[12] = {nullptr};     // device copies of its tables (SmallDev first)
+    void *d_small[16] = {nullptr};     // device copies of its tables (SmallDev first)
     DevConsts *dconsts = nullptr;
     int *d_pow2 = nullptr, *d_inv_pow2 = nullptr, *d_mrc = nullptr, *d_prefix = nullptr, *d_ext_w = nullptr, *d_ext_t = nullptr, *d_wpow2 = nullptr, *d_spow2 = nullptr;
     std::atomic<long> launches{0};
@@ -94,12 +94,14 @@ struct mpres_ctx {
     unsigned long long attr_norm = 0;    // bit NQ / 8: k_norm_fast<NQ, *, true> (staged residues of S)
     int norm_staged = 1;                 // k_norm_fast stages the residues of S in shared memory (mpres_set_stage3_kernel(4) = off)
     unsigned long long attr_fused = 0;   // bit NQ / 8: k_ext_norm_small<NQ, *>
+    unsigned long long attr_bin2 = 0;    // bit NQ / 8: k_bin_norm2<NQ, ...>
     std::mutex mu;
 };
 
 constexpr int kMaxPanels = 16;            // column panels of one fast-path call (ranks of a sharded call)
 constexpr int kCounterBlock = 8;
-constexpr int kCounterInts = kCounterBlock * kMaxPanels;
+constexpr int kCounterInts = kCounterBlock * kMaxPanels;        // (+ kCounterExtra ints behind them: slices, slice width of the last call)
+constexpr int kCounterExtra = 8;
 
 // internal entry points shared between the translation units (not part of the C-ABI)
 extern "C" int mpres_internal_maxabs(mpres_ctx *c, long long n, const mpres::SoA *x, int incx, const mpres::SoA *r, cudaStream_t st);

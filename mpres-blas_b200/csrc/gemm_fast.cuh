@@ -441,7 +441,7 @@ inline int gemm_fast_flat(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
         if (pe <= pb) continue;
         SmallPanels pan;
         pan.count = pe - pb; pan.first = (rank + pb) % W; pan.own = rank; pan.epoch = sh->epoch; pan.flags = sh->flags;
-        pan.s8_panel = (long long) nb * m_ps; pan.ring = W; pan.plane_rows = n;
+        pan.s8_panel = (long long) nb * m_ps; pan.ring = W; pan.plane_rows = n; pan.slices = 1;
         for (long long kb = 0; kb < k_p; kb += kSmallKChunk) {
             const int kl = (int) std::min<long long>(kSmallKChunk, k_p - kb);
             if ((rc = launch_small_umma(c, P, (const uint8_t *) pQA, QB, (long long) nb * k_p, (uint8_t *) pS8, m_ps, nb, k_p, kb, kl, kb > 0, sel, pan, st, n))) return rc;
@@ -465,13 +465,7 @@ inline int gemm_fast_flat(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
             int16_t *Ds = D + col0 * m_p;
             uint8_t *S8s = (uint8_t *) pS8 + col0 * m_ps;
             if (binary) {
-                const size_t smb = bin_smem_bytes(N);
-                const unsigned gx = (unsigned) std::min<long long>((long long) ((m + kBinT - 1) / kBinT) * nc, (long long) c->sm_count * 4);
-                MPRES_DISPATCH(N, {
-                    if (!c->attr_bin) { CUDA_TRY(cudaFuncSetAttribute(k_bin_norm<G, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smb)); c->attr_bin = true; }
-                    k_bin_norm<G, R><<<gx, kBinT, smb, st>>>(c->dconsts, m, nc, S8s, m_ps, n, sel, IA, IB + col0, alpha, beta, Cg, ldc);
-                });
-                ++launches;
+                if ((rc = bin_norm_segment(c, first_seg, m, nc, S8s, m_ps, n, sel, IA, IB + col0, alpha, beta, Cg, ldc, st, &launches))) return rc;
                 if (first_seg) prof_mark(c, st, "k_bin_norm");
             } else {
                 int *Ss = (int *) pS + col0 * m_p;
@@ -647,12 +641,16 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
         for (int p = 0; p < W; ++p) x.peer[p] = sh->peer_xchg[p];
         x.err = c->d_counter + 3;
     }
-    k_choose_base<<<1, 256, 0, st>>>(c->dconsts, IA, m, own.IB, nb, k, c->reduced_base, small_on ? 1 : 0, nprime, sel, x);
+    // (2: the significands may be cut into slices when the sums exceed the one-byte base -- single-GPU calls of a format with a binary epilogue)
+    const int small_mode = !small_on ? 0 : ((!sh && bin2_variant(c) && c->small_persistent && !c->align_mma) ? 2 : 1);
+    k_choose_base<<<1, 256, 0, st>>>(c->dconsts, IA, m, own.IB, nb, k, c->reduced_base, small_mode, nprime, sel, x);
     launches += 3;
     // the host needs the choice: which kernels to launch, how many planes to reserve and to send
     CUDA_TRY(cudaMemcpyAsync(c->h_sel, c->d_counter + 2, 6 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(c->h_sel + 6, sel + kSelSlices, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     const int P = c->h_sel[2], nin = c->h_sel[3];
+    const int slices = std::max(1, c->h_sel[6]), ND = 2 * slices - 1;
     // full-precision inputs: the exact sums exceed the number format (window guard of kernels_norm.cuh) but not the one-byte base --
     // stage 3 rebuilds them in binary and rounds once (kernels_bin.cuh); the (min,+) exponent product is not needed then
     const bool binary = P > 0 && c->h_sel[5] > c->hc.log2M - 2;
@@ -673,14 +671,14 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
     if (binary) sparse_mp = false;
     // ---- workspace that depends on the base ----
     void *pQA, *pS8, *pS, *pSAT = nullptr, *pPl = nullptr;
-    if ((rc = ws_reserve(c, 8, (size_t) P * m_ps * k_p, &pQA))) return rc;
-    const size_t s8_panel = (size_t) P * nb_p * m_ps, s_panel = (size_t) N * nb_p * m_p * 4;
+    if ((rc = ws_reserve(c, 8, (size_t) slices * P * m_ps * k_p, &pQA))) return rc;
+    const size_t s8_panel = (size_t) ND * P * nb_p * m_ps, s_panel = (size_t) N * nb_p * m_p * 4;
     if ((rc = ws_reserve(c, 10, (size_t) W * s8_panel, &pS8))) return rc;
     if (binary) pS = nullptr;
     else if ((rc = ws_reserve(c, 5, (size_t) W * s_panel, &pS))) return rc;
     if (sparse_mp && (rc = ws_reserve(c, 11, (size_t) k_p * m_ps * 2 + 256, &pSAT))) return rc;
-    if (!sh && (rc = ws_reserve(c, 9, (size_t) P * nb_p * k_p, &pPl))) return rc;
-    const size_t planes_bytes = (size_t) P * nb_p * k_p;
+    if (!sh && (rc = ws_reserve(c, 9, (size_t) slices * P * nb_p * k_p, &pPl))) return rc;
+    const size_t planes_bytes = (size_t) slices * P * nb_p * k_p;
     if (sh && hdr + planes_bytes > sh->pkg_stride) return -7;
     own.QB = sh ? (uint8_t *) (own_hdr + hdr) : (uint8_t *) pPl;
     auto panel_pkg = [&](int g) { return sh ? pkg_carve(sh->recv + (size_t) g * sh->pkg_stride, sh->recv + (size_t) g * sh->pkg_stride + hdr, nb_p, k_p) : own; };
@@ -702,8 +700,13 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
             if (!c->attr_align_mma) { cudaFuncSetAttribute(k_align_small<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) align_small_smem(true)); c->attr_align_mma = true; }
             k_align_small<true><<<gB, 256, align_small_smem(true), st>>>(c->dconsts, Bown, soB, slB, nb, k, own.IB, own.QB, own.SB, nb_p, k_p, sel);
         } else {
-            if (!c->attr_align) { cudaFuncSetAttribute(k_align_small<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) align_small_smem(false)); c->attr_align = true; }
-            k_align_small<false><<<gB, 256, align_small_smem(false), st>>>(c->dconsts, Bown, soB, slB, nb, k, own.IB, own.QB, own.SB, nb_p, k_p, sel);
+            if (!c->attr_align) {
+                cudaFuncSetAttribute(k_align_small<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) align_small_smem(false));
+                cudaFuncSetAttribute(k_align_small<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) align_small_smem(false));
+                c->attr_align = true;
+            }
+            if (slices > 1) k_align_small<false, true><<<gB, 256, align_small_smem(false), st>>>(c->dconsts, Bown, soB, slB, nb, k, own.IB, own.QB, own.SB, nb_p, k_p, sel);
+            else k_align_small<false><<<gB, 256, align_small_smem(false), st>>>(c->dconsts, Bown, soB, slB, nb, k, own.IB, own.QB, own.SB, nb_p, k_p, sel);
         }
         prof_mark(c, st, "k_align_small(B)");
         if (sparse_mp) {
@@ -728,6 +731,7 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
             for (int si = 0; si < sh->npush && si < W - 1; ++si) CUDA_TRY(cudaEventRecord(sh->ev_push[si], sh->push[si]));
         }
         if (c->align_mma) k_align_small<true><<<gA, 256, align_small_smem(true), st>>>(c->dconsts, A, soA, slA, m, k, IA, (uint8_t *) pQA, SA, m_ps, k_p, sel);
+        else if (slices > 1) k_align_small<false, true><<<gA, 256, align_small_smem(false), st>>>(c->dconsts, A, soA, slA, m, k, IA, (uint8_t *) pQA, SA, m_ps, k_p, sel);
         else k_align_small<false><<<gA, 256, align_small_smem(false), st>>>(c->dconsts, A, soA, slA, m, k, IA, (uint8_t *) pQA, SA, m_ps, k_p, sel);
         launches += 2;
         prof_mark(c, st, "k_align_small(A)");
@@ -779,13 +783,14 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
     // ---- stage 2: one u8 GEMM per one-byte modulus, all panels in one persistent launch ----
     SmallPanels pan;
     pan.count = W; pan.first = rank; pan.own = rank; pan.epoch = sh ? sh->epoch : 0u; pan.flags = sh ? sh->flags : nullptr; pan.s8_panel = (long long) s8_panel;
-    pan.ring = 0; pan.plane_rows = 0;
+    pan.ring = 0; pan.plane_rows = 0; pan.slices = slices;
     const uint8_t *PB0 = sh ? (const uint8_t *) (sh->recv + hdr) : own.QB;
     const long long pb_panel = sh ? (long long) sh->pkg_stride : (long long) planes_bytes;
     int gemm_launches = 0;
     auto stage2 = [&]() -> int {
-        for (long long kb = 0; kb < k_p; kb += kSmallKChunk) {
-            const int kl = (int) std::min<long long>(kSmallKChunk, k_p - kb);
+        const long long chunk = slices > 1 ? (kSmallKChunk / slices) / 128 * 128 : kSmallKChunk;     // pairs x 255^2 x chunk < 2^31
+        for (long long kb = 0; kb < k_p; kb += chunk) {
+            const int kl = (int) std::min<long long>(chunk, k_p - kb);
             int r2 = launch_small_umma(c, P, (const uint8_t *) pQA, PB0, pb_panel, (uint8_t *) pS8, m_ps, nb_p, k_p, kb, kl, kb > 0, sel, pan, st);
             if (r2) return r2;
             gemm_launches += 1;
@@ -821,14 +826,14 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
             if (pi == 0) prof_mark(c, st, "k_mp_gather+combine+fix");
         }
         if (binary) {
-            const size_t smb = bin_smem_bytes(N);
-            const unsigned gx = (unsigned) std::min<long long>((long long) ((m + kBinT - 1) / kBinT) * nb, (long long) c->sm_count * 4);
-            MPRES_DISPATCH(N, {
-                if (!c->attr_bin) { CUDA_TRY(cudaFuncSetAttribute(k_bin_norm<G, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smb)); c->attr_bin = true; }
-                k_bin_norm<G, R><<<gx, kBinT, smb, st>>>(c->dconsts, m, nb, S8g, m_ps, nb_p, sel, IA, pk.IB, alpha, beta, Cg, ldc);
-            });
-            ++launches;
+            if ((rc = bin_norm_segment(c, pi == 0, m, nb, S8g, m_ps, nb_p, sel, IA, pk.IB, alpha, beta, Cg, ldc, st, &launches, slices, w.todo, w.cnt))) return rc;
             if (pi == 0) prof_mark(c, st, "k_bin_norm");
+            if (slices > 1) {
+                MPRES_DISPATCH(N, {
+                    k_gemm_todo<G, R><<<c->sm_count * 8, 128, 0, st>>>(c->dconsts, ta, tb, m, nb, k, A, lda, Bg, ldb, alpha, beta, Cg, ldc, w.todo, w.cnt);
+                });
+                ++launches;
+            }
             continue;
         }
         if (!fused) {

@@ -278,6 +278,9 @@ struct SmallConsts {
     // binary reconstruction of a sum from its one-byte residues (kernels_bin.cuh): 32-bit words of M'_c / p_i and of 2^(32 kBinW) - M'_c
     std::vector<uint32_t> bin_mi;        // [kSmallMax + 1][kSmallMax][kBinW]
     std::vector<uint32_t> bin_negmp;     // [kSmallMax + 1][kBinW]
+    // binary reconstruction of a number of the format (CRT over all N moduli): words of M / m_i, of 2^(32 full_nw) - M and of M
+    int full_nw = 0;                     // words of M + 1
+    std::vector<uint32_t> full_mi, full_negm, full_m;   // [N][full_nw], [full_nw], [full_nw]
     double log2M_up = 0;                 // log2(M), rounded up a little
 };
 
@@ -389,6 +392,26 @@ inline void compute_small_consts(const HostConsts &c, SmallConsts &s) {
         BigUInt M(1);
         for (int i = 0; i < N; ++i) M.mul_small((uint32_t) c.moduli[i]);
         s.log2M_up = biguint_log2(M) + 1e-9;
+    }
+    {
+        BigUInt M(1);
+        for (int i = 0; i < N; ++i) M.mul_small((uint32_t) c.moduli[i]);
+        s.full_nw = (int) M.limb.size() + 1;
+        s.full_mi.assign((size_t) N * s.full_nw, 0);
+        s.full_negm.assign(s.full_nw, 0);
+        s.full_m.assign(s.full_nw, 0);
+        for (int w = 0; w < (int) M.limb.size(); ++w) s.full_m[w] = M.limb[w];
+        uint64_t borrow = 0;
+        for (int w = 0; w < s.full_nw; ++w) {
+            const uint64_t sub = (uint64_t) s.full_m[w] + borrow;
+            s.full_negm[w] = (uint32_t) (0ull - sub);
+            borrow = sub != 0 ? 1 : 0;
+        }
+        for (int i = 0; i < N; ++i) {
+            BigUInt q = M;
+            q.div_small((uint32_t) c.moduli[i]);
+            for (int w = 0; w < (int) q.limb.size(); ++w) s.full_mi[(size_t) i * s.full_nw + w] = q.limb[w];
+        }
     }
     s.bin_mi.assign((size_t) (P + 1) * P * kBinW, 0);
     s.bin_negmp.assign((size_t) (P + 1) * kBinW, 0);

@@ -48,7 +48,7 @@ struct OuterInfo {   // per row of op(A) / column of op(B)
     int emin;        // min exponent over non-zero entries (0 if none)
     int win;         // max over non-zero entries of (e - emin + bit bound of X); <0 if the line is all zero
     int xb;          // upper bound of 1024 log2(X) over the non-zero entries (significand size, for the small-modulus path)
-    int pad;
+    int smax;        // largest alignment shift e - emin over the non-zero entries
 };
 
 // ---- stage 1a: exponent base and magnitude window of every line -----------------------------------
@@ -59,7 +59,7 @@ __global__ void k_outer_info(const DevConsts *Cp, SoA X, long long so, long long
     const long long warp = ((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (warp >= outer) return;
     const long long len = X.len();
-    int emin = INT_MAX;
+    int emin = INT_MAX, emax = INT_MIN;
     long long top = LLONG_MIN;
     // largest upper bound of X / M over the line, compared without floating point: (binary exponent of the bound, fraction bits) is
     // monotone in the value for positive doubles; its log2 is taken once per line
@@ -70,7 +70,7 @@ __global__ void k_outer_info(const DevConsts *Cp, SoA X, long long so, long long
         const Er up = X.eval[idx + len];
         if (up.frac != 0) {
             const int e = X.exp[idx];
-            emin = min(emin, e);
+            emin = min(emin, e); emax = max(emax, e);
             // X/M < 2^(up.exp+1) and M < 2^(log2M+1)  =>  X < 2^(log2M + up.exp + 2)
             long long t = (long long) e + up.exp;
             top = t > top ? t : top;
@@ -83,6 +83,7 @@ __global__ void k_outer_info(const DevConsts *Cp, SoA X, long long so, long long
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) {
         emin = min(emin, __shfl_xor_sync(0xffffffffu, emin, o));
+        emax = max(emax, __shfl_xor_sync(0xffffffffu, emax, o));
         long long t = __shfl_xor_sync(0xffffffffu, top, o);
         top = t > top ? t : top;
         const long long oe = __shfl_xor_sync(0xffffffffu, be, o);
@@ -93,11 +94,13 @@ __global__ void k_outer_info(const DevConsts *Cp, SoA X, long long so, long long
     const double lx = (double) (be - 1023) + log2(__longlong_as_double((long long) (bm | 0x3ff0000000000000ull)));
     if (lane == 0) {
         OuterInfo r;
-        r.pad = 0;
+        r.smax = 0;
         if (emin == INT_MAX) { r.emin = 0; r.win = -1; r.xb = 0; }
         else {
             long long w = top - emin + log2M + 2;
             r.emin = emin;
+            const long long sm = (long long) emax - emin;
+            r.smax = sm > 1000000 ? 1000000 : (int) sm;
             r.win = w > 1000000 ? 1000000 : (w < 0 ? 0 : (int) w);
             // X <= up * M:  1024 log2 X <= 1024 (lx + log2 M), rounded up with a margin
             const double b = (lx + (Cp->small ? Cp->small->log2M_up : (double) (log2M + 1))) * 1024.0;
@@ -112,21 +115,21 @@ __global__ void k_outer_info(const DevConsts *Cp, SoA X, long long so, long long
 // (coalesced), combines its eight inner sub-groups in shared memory and folds the chunk into per-line partials with atomics
 // (k_outer_part_init before, k_outer_part_final after).  The largest interval bound travels as one 64-bit key: (exponent, mantissa
 // rounded up to 45 bits) -- an upper bound like the one above, at most 2^-44 larger.
-struct OuterPart { int emin; int pad; long long top; unsigned long long key; };
+struct OuterPart { int emin; int emax; long long top; unsigned long long key; };
 constexpr long long kOuterKeyBias = 120000;
 __global__ void k_outer_part_init(OuterPart *part, int outer) {
     const int o = blockIdx.x * blockDim.x + threadIdx.x;
-    if (o < outer) { OuterPart p; p.emin = INT_MAX; p.pad = 0; p.top = LLONG_MIN; p.key = 0ull; part[o] = p; }
+    if (o < outer) { OuterPart p; p.emin = INT_MAX; p.emax = INT_MIN; p.top = LLONG_MIN; p.key = 0ull; part[o] = p; }
 }
 __global__ void __launch_bounds__(256) k_outer_part(SoA X, long long sl, int outer, int inner, int chunk, OuterPart *part) {
-    __shared__ int s_emin[8][32];
+    __shared__ int s_emin[8][32], s_emax[8][32];
     __shared__ long long s_top[8][32];
     __shared__ unsigned long long s_key[8][32];
     const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
     const int o = blockIdx.x * 32 + lx;
     const int l0 = blockIdx.y * chunk, l1 = min(inner, l0 + chunk);
     const long long len = X.len();
-    int emin = INT_MAX;
+    int emin = INT_MAX, emax = INT_MIN;
     long long top = LLONG_MIN;
     unsigned long long key = 0ull;
     if (o < outer) {
@@ -135,7 +138,7 @@ __global__ void __launch_bounds__(256) k_outer_part(SoA X, long long sl, int out
             const Er up = X.eval[idx + len];
             if (up.frac != 0) {
                 const int e = X.exp[idx];
-                emin = min(emin, e);
+                emin = min(emin, e); emax = max(emax, e);
                 const long long t = (long long) e + up.exp;
                 top = t > top ? t : top;
                 const unsigned long long fb = (unsigned long long) __double_as_longlong(fabs(up.frac));
@@ -145,17 +148,18 @@ __global__ void __launch_bounds__(256) k_outer_part(SoA X, long long sl, int out
             }
         }
     }
-    s_emin[ly][lx] = emin; s_top[ly][lx] = top; s_key[ly][lx] = key;
+    s_emin[ly][lx] = emin; s_emax[ly][lx] = emax; s_top[ly][lx] = top; s_key[ly][lx] = key;
     __syncthreads();
     if (ly == 0 && o < outer) {
 #pragma unroll
         for (int g = 1; g < 8; ++g) {
-            emin = min(emin, s_emin[g][lx]);
+            emin = min(emin, s_emin[g][lx]); emax = max(emax, s_emax[g][lx]);
             top = s_top[g][lx] > top ? s_top[g][lx] : top;
             key = s_key[g][lx] > key ? s_key[g][lx] : key;
         }
         if (emin != INT_MAX) {
             atomicMin(&part[o].emin, emin);
+            atomicMax(&part[o].emax, emax);
             atomicMax(&part[o].top, top);
             atomicMax(&part[o].key, key);
         }
@@ -167,9 +171,11 @@ __global__ void k_outer_part_final(const DevConsts *Cp, const OuterPart *part, i
     const OuterPart p = part[o];
     const int log2M = Cp->log2M;
     OuterInfo r;
-    r.pad = 0;
+    r.smax = 0;
     if (p.emin == INT_MAX) { r.emin = 0; r.win = -1; r.xb = 0; }
     else {
+        const long long sm = (long long) p.emax - p.emin;
+        r.smax = sm > 1000000 ? 1000000 : (int) sm;
         const long long be = (long long) (p.key >> 45) - kOuterKeyBias;
         const unsigned long long bm = (p.key & ((1ull << 45) - 1ull)) << 8;            // <= 2^52: a carry into the exponent is a mantissa of 1.0 more
         const double lx = (double) (be - 1023) + log2(1.0 + (double) bm * 2.220446049250313e-16);
@@ -188,6 +194,9 @@ __global__ void k_outer_part_final(const DevConsts *Cp, const OuterPart *part, i
 // needed).  Stage 1b then aligns the first ceil4(n') moduli (it works on groups of four), stage 2 multiplies
 // n' of them and k_base_extend reconstructs the residues q >= n'.  One block.
 constexpr int kMaxReducedBase = 48;
+constexpr int kMaxSlices = 4;          // pieces a significand may be cut into when the exact sums exceed the one-byte base
+constexpr int kBinBig = 32;            // 32-bit words of an exact sum put together from slice sums (kernels_bin.cuh)
+constexpr int kSelSlices = kCounterInts - 4, kSelWidth = kCounterInts - 3;     // offsets from sel = d_counter + 4: the two ints behind the counter blocks
 // sel[0] = number of small moduli (0: the small-modulus path is not used), sel[1] = reference moduli its input conversion reads.
 // When the small base is selected *nprime is 0 and the kernels of the reference-moduli path leave at once.
 // Sharded calls (one rank per GPU, rows of A / C split, every rank converts one column block of B): the base must be the same on every rank,
@@ -198,7 +207,7 @@ constexpr int kMaxReducedBase = 48;
 struct Xchg {
     int world, rank, parity;
     unsigned epoch;
-    int *peer[kMaxPanels];      // the exchange array [2][world][4] of every rank; peer[rank] is the local one
+    int *peer[kMaxPanels];      // the exchange array [2][world][8] of every rank; peer[rank] is the local one
     int *err;                   // set to 1 when a rank did not show up in time
 };
 __device__ __forceinline__ unsigned long long global_ns() {
@@ -208,33 +217,34 @@ __device__ __forceinline__ unsigned long long global_ns() {
 }
 __global__ void __launch_bounds__(256) k_choose_base(const DevConsts *Cp, const OuterInfo *ia, int m, const OuterInfo *ib, int n, int k,
                                                      int enabled, int small_enabled, int *nprime, int *sel, const Xchg x) {
-    __shared__ int sa[256], sb[256], sx[256];
-    int wa = -1, wb = -1, xb = 0;
-    for (int i = threadIdx.x; i < m; i += 256) { wa = max(wa, ia[i].win); xb = max(xb, ia[i].xb); }
-    for (int j = threadIdx.x; j < n; j += 256) { wb = max(wb, ib[j].win); xb = max(xb, ib[j].xb); }
-    sa[threadIdx.x] = wa; sb[threadIdx.x] = wb; sx[threadIdx.x] = xb;
+    __shared__ int sa[256], sb[256], sx[256], ssa[256], ssb[256];
+    int wa = -1, wb = -1, xb = 0, sha = 0, shb = 0;
+    for (int i = threadIdx.x; i < m; i += 256) { wa = max(wa, ia[i].win); xb = max(xb, ia[i].xb); sha = max(sha, ia[i].smax); }
+    for (int j = threadIdx.x; j < n; j += 256) { wb = max(wb, ib[j].win); xb = max(xb, ib[j].xb); shb = max(shb, ib[j].smax); }
+    sa[threadIdx.x] = wa; sb[threadIdx.x] = wb; sx[threadIdx.x] = xb; ssa[threadIdx.x] = sha; ssb[threadIdx.x] = shb;
     __syncthreads();
     for (int o = 128; o >= 1; o >>= 1) {
         if (threadIdx.x < o) {
             sa[threadIdx.x] = max(sa[threadIdx.x], sa[threadIdx.x + o]); sb[threadIdx.x] = max(sb[threadIdx.x], sb[threadIdx.x + o]);
             sx[threadIdx.x] = max(sx[threadIdx.x], sx[threadIdx.x + o]);
+            ssa[threadIdx.x] = max(ssa[threadIdx.x], ssa[threadIdx.x + o]); ssb[threadIdx.x] = max(ssb[threadIdx.x], ssb[threadIdx.x + o]);
         }
         __syncthreads();
     }
     if (threadIdx.x == 0) {
         if (x.world > 1) {
-            const int slot = (x.parity * x.world + x.rank) * 4;
+            const int slot = (x.parity * x.world + x.rank) * 8;
             for (int p = 0; p < x.world; ++p) {
                 volatile int *d = x.peer[p] + slot;
-                d[0] = sa[0]; d[1] = sb[0]; d[2] = sx[0];
+                d[0] = sa[0]; d[1] = sb[0]; d[2] = sx[0]; d[4] = ssa[0]; d[5] = ssb[0];
             }
             __threadfence_system();
             for (int p = 0; p < x.world; ++p)
                 asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(x.peer[p] + slot + 3), "r"(x.epoch) : "memory");
             const unsigned long long t0 = global_ns();
-            int gwa = -1, gwb = -1, gxb = 0;
+            int gwa = -1, gwb = -1, gxb = 0, gsa = 0, gsb = 0;
             for (int p = 0; p < x.world; ++p) {
-                const int *src = x.peer[x.rank] + (x.parity * x.world + p) * 4;
+                const int *src = x.peer[x.rank] + (x.parity * x.world + p) * 8;
                 for (;;) {
                     unsigned v;
                     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src + 3) : "memory");
@@ -243,9 +253,9 @@ __global__ void __launch_bounds__(256) k_choose_base(const DevConsts *Cp, const 
                     __nanosleep(500);
                 }
                 const volatile int *vs = src;
-                gwa = max(gwa, vs[0]); gwb = max(gwb, vs[1]); gxb = max(gxb, vs[2]);
+                gwa = max(gwa, vs[0]); gwb = max(gwb, vs[1]); gxb = max(gxb, vs[2]); gsa = max(gsa, vs[4]); gsb = max(gsb, vs[5]);
             }
-            sa[0] = gwa; sb[0] = gwb; sx[0] = gxb;
+            sa[0] = gwa; sb[0] = gwb; sx[0] = gxb; ssa[0] = gsa; ssb[0] = gsb;
         }
         const int N = Cp->N;
         int np = N;
@@ -257,17 +267,38 @@ __global__ void __launch_bounds__(256) k_choose_base(const DevConsts *Cp, const 
                 if ((long long) Cp->prefix_log2[c] >= need) { np = c; break; }
             if (np > kMaxReducedBase) np = N;
         }
-        int P = 0, nin = 0;
+        int P = 0, nin = 0, slices = 1, width = 0;
         const SmallDev *SD = Cp->small;
-        if (small_enabled && SD && SD->usable && sa[0] >= 0 && sb[0] >= 0 && sa[0] <= kSmallShiftMax && sb[0] <= kSmallShiftMax) {
+        if (small_enabled && SD && SD->usable && sa[0] >= 0 && sb[0] >= 0 && ssa[0] <= kSmallShiftMax && ssb[0] <= kSmallShiftMax) {   // (shifts index the +-2^s table)
             for (int c = 1; c <= kSmallMax; ++c)
                 if ((long long) SD->prefix_log2[c] >= need) { P = c; break; }
             const int cmax = min(kSmallNinMax, N - 1);
             for (int c = 1; c <= cmax; ++c)
                 if (SD->in_log2_milli[c] >= sx[0]) { nin = c; break; }   // X < m_0 ... m_{c-1}
-            if (P == 0 || nin == 0) { P = 0; nin = 0; }
+            if (P == 0 || nin == 0) { P = 0; }
+            // Sums beyond the one-byte base (full-precision inputs at more than 8 moduli): the significands are cut into `slices` pieces of
+            // `width` bits, X = sum_t X_t 2^(width t); the sums S_d = sum over t + u = d of sum_l X_a,t X_b,u 2^shift fit the base again and
+            // S = sum_d S_d 2^(width d) is put together in binary by stage 3 (kernels_bin.cuh).  small_enabled == 2: the caller can run it.
+            if (P == 0 && nin > 0 && small_enabled == 2 && need - 2 > (long long) Cp->log2M - 2 && need <= 32 * kBinBig - 40) {
+                const int xbits = (sx[0] + 1023) >> 10;
+                long long best = -1;
+                for (int s = 2; s <= kMaxSlices; ++s) {
+                    const int w = (xbits + s - 1) / s;
+                    int lgs = 0;
+                    while ((1 << lgs) < s) ++lgs;
+                    const long long need_s = 2ll * w + ssa[0] + ssb[0] + lgk + lgs + 4;
+                    int Ps = 0;
+                    for (int c = 1; c <= kSmallMax; ++c)
+                        if ((long long) SD->prefix_log2[c] >= need_s) { Ps = c; break; }
+                    if (Ps == 0) continue;
+                    const long long cost = (long long) s * s * Ps;
+                    if (best < 0 || cost < best) { best = cost; P = Ps; slices = s; width = w; }
+                }
+            }
+            if (P == 0) nin = 0;
         }
         sel[0] = P; sel[1] = nin;
+        sel[kSelSlices] = slices; sel[kSelWidth] = width;
         sel[3] = need > 2000000000ll ? 2000000000 : (int) need - 2;      // |S| < 2^sel[3] for every entry of the call
         *nprime = P > 0 ? 0 : np;
     }

@@ -51,13 +51,36 @@ __device__ __forceinline__ void mma_u8_frag(int (&c)[4], const unsigned (&a)[4],
 // A block handles kASo lines x kASl inner positions, one entry per thread.
 constexpr int kASo = 8, kASl = 32;
 
+// bits [sh, sh + width) of x, in place (width > 0)
+template <int N>
+__device__ __forceinline__ void slice_extract(unsigned (&x)[N], int sh, int width) {
+    const int ws = sh >> 5, bs = sh & 31;
+#pragma unroll
+    for (int step = 1; step < N; step <<= 1)
+        if (ws & step) {
+#pragma unroll
+            for (int w = 0; w < N; ++w) x[w] = (w + step < N) ? x[w + step] : 0u;
+        }
+    if (ws >= N) {
+#pragma unroll
+        for (int w = 0; w < N; ++w) x[w] = 0u;
+    }
+#pragma unroll
+    for (int w = 0; w < N; ++w) {
+        unsigned v = __funnelshift_r(x[w], w + 1 < N ? x[w + 1] : 0u, bs);
+        const int rem = width - 32 * w;              // bits of this word inside the slice
+        v = rem >= 32 ? v : (rem <= 0 ? 0u : (v & ((1u << rem) - 1u)));
+        x[w] = v;
+    }
+}
+
 // NW: words of the binary significand = reference residues read (>= n_in); CW = NW rounded up to a multiple of four
-// is the row pitch of the staged tables.
+// is the row pitch of the staged tables.  width > 0: only bits [slice width, (slice + 1) width) of the significand are converted.
 template <int NW, bool MMA>
 __device__ __forceinline__ void align_small_entry(const int4 (&dg)[(NW + 3) / 4], int nin, int P, int srow, const unsigned *s_mi, const unsigned *s_negmp,
                                                   const int *s_m, const unsigned long long *s_bmu, const int *s_w, const double *s_rcpm,
                                                   const unsigned *s_cw, const unsigned *s_ppm, const uint8_t *pws,
-                                                  uint8_t *out, uint8_t *xrow) {
+                                                  uint8_t *out, uint8_t *xrow, int slice = 0, int width = 0) {
     constexpr int CW = (NW + 3) & ~3;
     // CRT over the first nin residues: X = sum xi_i M'_i - R M' with R = floor(sum xi_i / m_i).  The double sum can miss R
     // by one when X / M' is within 2^-48 of an integer; then the result is off by exactly M' and is put right below.
@@ -116,6 +139,7 @@ __device__ __forceinline__ void align_small_entry(const int4 (&dg)[(NW + 3) / 4]
             for (int w = 0; w < NW; ++w) x[w] = t[w];
         }
     }
+    if (width > 0) slice_extract<NW>(x, slice * width, width);
     if (MMA) {
         // the binary significand goes to this entry's operand row; the residues follow on the tensor cores (k_align_small<true>)
 #pragma unroll
@@ -153,12 +177,13 @@ __device__ __forceinline__ void align_small_entry(const int4 (&dg)[(NW + 3) / 4]
 template <int NW, bool MMA>
 __device__ __forceinline__ void align_small_dispatch(const int *dig, const int4 &d0, int nin, int P, int srow, const unsigned *s_mi, const unsigned *s_negmp,
                                                      const int *s_m, const unsigned long long *s_bmu, const int *s_w, const double *s_rcpm,
-                                                     const unsigned *s_cw, const unsigned *s_ppm, const uint8_t *pws, uint8_t *out, uint8_t *xrow) {
+                                                     const unsigned *s_cw, const unsigned *s_ppm, const uint8_t *pws, uint8_t *out, uint8_t *xrow,
+                                                     int slice = 0, int width = 0) {
     int4 dg[(NW + 3) / 4];
     dg[0] = d0;                                   // prefetched with the entry's other fields
 #pragma unroll
     for (int g = 1; g < (NW + 3) / 4; ++g) dg[g] = (4 * g < nin) ? __ldg((const int4 *) dig + g) : make_int4(0, 0, 0, 0);
-    align_small_entry<NW, MMA>(dg, nin, P, srow, s_mi, s_negmp, s_m, s_bmu, s_w, s_rcpm, s_cw, s_ppm, pws, out, xrow);
+    align_small_entry<NW, MMA>(dg, nin, P, srow, s_mi, s_negmp, s_m, s_bmu, s_w, s_rcpm, s_cw, s_ppm, pws, out, xrow, slice, width);
 }
 
 // MMA = true: the residues modulo the one-byte moduli are computed on the tensor cores -- per warp, the 32 binary significands
@@ -170,10 +195,11 @@ __host__ __device__ constexpr size_t align_small_smem_base() {   // output tile,
     return 64 * kASo * kASl + kASo * kASl * 2 + 64 * 16 * 4 + 16 * 16 * 4 + 16 * 4 + 16 * 8 + 16 * 8 + 16 * 4 * 2 + 64 * 4 * 2 + 64;
 }
 constexpr int kAXPitch = 96;      // bytes per operand row (conflict-free 64-bit fragment loads)
-template <bool MMA>
 #ifndef MPRES_ALIGN_BLOCKS
 #define MPRES_ALIGN_BLOCKS 3
 #endif
+// SLICED: the instantiation for significands cut into pieces (kept apart: the default one is tuned to its register budget)
+template <bool MMA, bool SLICED = false>
 __global__ void __launch_bounds__(256, MPRES_ALIGN_BLOCKS) k_align_small(const DevConsts *Cp, SoA X, long long so, long long sl, int outer, int inner,
                                                         const OuterInfo *info, uint8_t *planes, int16_t *shifts,
                                                         long long outer_p, long long inner_p, const int *sel, long long plane_rows = 0) {
@@ -181,6 +207,8 @@ __global__ void __launch_bounds__(256, MPRES_ALIGN_BLOCKS) k_align_small(const D
     const int P = sel[0], nin = sel[1];
     if (P <= 0) return;
     if (plane_rows == 0) plane_rows = outer_p;      // rows between consecutive planes (> outer_p: the lines are a block of a larger plane set)
+    const int slices = SLICED ? max(1, sel[kSelSlices]) : 1;   // > 1: planes [slice][P] of the significand's pieces (k_choose_base)
+    const int width = (SLICED && slices > 1) ? sel[kSelWidth] : 0;
     const DevConsts &C = *Cp;
     const SmallDev &SD = *C.small;
     const int N = C.N;
@@ -287,14 +315,16 @@ __global__ void __launch_bounds__(256, MPRES_ALIGN_BLOCKS) k_align_small(const D
         prefetch_fields(tile + gridDim.x);                                   // in flight through the conversion
         s_sh[slot] = (int16_t) sh16;
         uint8_t *xrow = s_x + threadIdx.x * kAXPitch;
+        for (int slice = 0; slice < slices; ++slice) {
+        if (slice > 0) __syncthreads();                                       // the previous slice's planes have left the output tile
         if (live) {
             const int *dig = X.digits + cur_idx * N;
             uint8_t *outp = s_out + slot;
-#define MPRES_AS_CASE(NW_) case NW_: align_small_dispatch<NW_, MMA>(dig, cur_d0, nin, P, srow, s_mi, s_negmp, s_m, s_bmu, s_w, s_rcpm, s_cw, s_ppm, SD.pws, outp, xrow); break;
+#define MPRES_AS_CASE(NW_) case NW_: align_small_dispatch<NW_, MMA>(dig, cur_d0, nin, P, srow, s_mi, s_negmp, s_m, s_bmu, s_w, s_rcpm, s_cw, s_ppm, SD.pws, outp, xrow, SLICED ? slice : 0, SLICED ? width : 0); break;
             switch (NWr) {
                 MPRES_AS_CASE(1) MPRES_AS_CASE(2) MPRES_AS_CASE(3) MPRES_AS_CASE(4) MPRES_AS_CASE(5) MPRES_AS_CASE(6) MPRES_AS_CASE(7) MPRES_AS_CASE(8)
                 MPRES_AS_CASE(12)
-                default: align_small_dispatch<16, MMA>(dig, cur_d0, nin, P, srow, s_mi, s_negmp, s_m, s_bmu, s_w, s_rcpm, s_cw, s_ppm, SD.pws, outp, xrow); break;
+                default: align_small_dispatch<16, MMA>(dig, cur_d0, nin, P, srow, s_mi, s_negmp, s_m, s_bmu, s_w, s_rcpm, s_cw, s_ppm, SD.pws, outp, xrow, SLICED ? slice : 0, SLICED ? width : 0); break;
             }
 #undef MPRES_AS_CASE
         } else if (MMA) {
@@ -362,8 +392,9 @@ __global__ void __launch_bounds__(256, MPRES_ALIGN_BLOCKS) k_align_small(const D
             const int j = v / (kASo * 2), rem = v - j * (kASo * 2);
             const int oo = rem >> 1, h = rem & 1;
             const uint4 val = *(const uint4 *) (s_out + j * (kASo * kASl) + oo * kASl + h * 16);
-            *(uint4 *) (planes + ((long long) j * plane_rows + o0 + oo) * inner_p + l0 + h * 16) = val;
+            *(uint4 *) (planes + ((long long) (slice * P + j) * plane_rows + o0 + oo) * inner_p + l0 + h * 16) = val;
         }
+        }   // slices
         if (threadIdx.x < kASo * 4) {
             const int oo = threadIdx.x >> 2, part = threadIdx.x & 3;
             *(uint4 *) (shifts + (long long) (o0 + oo) * inner_p + l0 + part * 8) = *(const uint4 *) (s_sh + oo * kASl + part * 8);
@@ -536,6 +567,7 @@ struct SmallPanels {
     long long s8_panel;          // bytes between the S8 ranges of consecutive panels
     int ring;                    // panels of the call (0: count)
     long long plane_rows;        // rows of one S8 plane (0: n_ps -- every panel has its own plane set)
+    int slices;                  // > 1: operand planes [slice][P]; sums S_d, d = t + u, into planes [d][P] (K runs over the pairs of d)
 };
 __device__ __forceinline__ void wait_arrival(const unsigned *flag, unsigned epoch) {
     const long long t0 = clock64();
@@ -566,7 +598,9 @@ k_small_umma_p(const __grid_constant__ CUtensorMap tmJ, const __grid_constant__ 
     if (P <= 0) return;
     const int tiles_i = (int) (m_ps / kSN), tiles_j = (int) (n_ps / TJ);
     const int per_z = tiles_i * tiles_j;
-    const long long per_panel = (long long) P * per_z;
+    const int SL = pan.slices > 1 ? pan.slices : 1, ND = 2 * SL - 1;
+    const long long per_d = (long long) P * per_z;
+    const long long per_panel = per_d * ND;
     const long long total = per_panel * pan.count;
     if ((long long) blockIdx.x >= total) return;
     uint8_t *smem = (uint8_t *) (((uintptr_t) smem_raw + 1023) & ~(uintptr_t) 1023);
@@ -603,21 +637,27 @@ k_small_umma_p(const __grid_constant__ CUtensorMap tmJ, const __grid_constant__ 
                 const int pi = (int) (tile / per_panel);
                 const long long tp = tile - (long long) pi * per_panel;
                 const int pg = (pan.first + pi) % (pan.ring ? pan.ring : pan.count);
-                const int z = (int) (tp / per_z), r = (int) (tp - (long long) z * per_z);
+                const int dd = (int) (tp / per_d);
+                const long long tq = tp - (long long) dd * per_d;
+                const int z = (int) (tq / per_z), r = (int) (tq - (long long) z * per_z);
                 const int j0 = (r / tiles_i) * TJ, i0 = (r % tiles_i) * kSN;
                 if (pg != arrived) {
                     if (pan.flags && pg != pan.own) wait_arrival(pan.flags + pg, pan.epoch);
                     arrived = pg;
                 }
-                for (int it = 0; it < nk; ++it, ++g) {
-                    const int s = (int) (g % kPStages);
-                    const uint32_t ph = (uint32_t) (g / kPStages) & 1u;
-                    ptx::mbar_wait(&empty[s], ph ^ 1u);
-                    ptx::mbar_expect_tx(&full[s], kStage);
-                    uint8_t *dst = smem + s * kStage;
-                    if (pan.plane_rows) ptx::tma_load_4d(dst, &tmJ, &full[s], k_byte0 + it * KB, j0, pg, z);     // (k, row, panel, plane): one plane set
-                    else ptx::tma_load_4d(dst, &tmJ, &full[s], k_byte0 + it * KB, j0, z, pg);
-                    ptx::tma_load_3d(dst + kStageA, &tmI, &full[s], k_byte0 + it * KB, i0, z);
+                const int t0 = max(0, dd - (SL - 1)), t1 = min(dd, SL - 1);      // slice pairs (t, dd - t) of this sum
+                for (int t = t0; t <= t1; ++t) {
+                    const int za = t * P + z, zb = (dd - t) * P + z;
+                    for (int it = 0; it < nk; ++it, ++g) {
+                        const int s = (int) (g % kPStages);
+                        const uint32_t ph = (uint32_t) (g / kPStages) & 1u;
+                        ptx::mbar_wait(&empty[s], ph ^ 1u);
+                        ptx::mbar_expect_tx(&full[s], kStage);
+                        uint8_t *dst = smem + s * kStage;
+                        if (pan.plane_rows) ptx::tma_load_4d(dst, &tmJ, &full[s], k_byte0 + it * KB, j0, pg, zb);     // (k, row, panel, plane): one plane set
+                        else ptx::tma_load_4d(dst, &tmJ, &full[s], k_byte0 + it * KB, j0, zb, pg);
+                        ptx::tma_load_3d(dst + kStageA, &tmI, &full[s], k_byte0 + it * KB, i0, za);
+                    }
                 }
             }
         }
@@ -633,7 +673,12 @@ k_small_umma_p(const __grid_constant__ CUtensorMap tmJ, const __grid_constant__ 
                 ptx::mbar_wait(&acc_empty[b], (uint32_t) ((use & 1) ^ 1));   // the epilogue has drained this accumulator
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem + (uint32_t) (b * kSN);
-                for (int it = 0; it < nk; ++it, ++g) {
+                int nkt = nk;
+                if (SL > 1) {
+                    const int dd = (int) ((tile % per_panel) / per_d);
+                    nkt = nk * (min(dd, SL - 1) - max(0, dd - (SL - 1)) + 1);
+                }
+                for (int it = 0; it < nkt; ++it, ++g) {
                     const int s = (int) (g % kPStages);
                     const uint32_t ph = (uint32_t) (g / kPStages) & 1u;
                     ptx::mbar_wait(&full[s], ph);
@@ -664,9 +709,12 @@ k_small_umma_p(const __grid_constant__ CUtensorMap tmJ, const __grid_constant__ 
             const int pi = (int) (tile / per_panel);
             const long long tp = tile - (long long) pi * per_panel;
             const int pg = (pan.first + pi) % (pan.ring ? pan.ring : pan.count);
-            const int z = (int) (tp / per_z), r = (int) (tp - (long long) z * per_z);
+            const int dd = (int) (tp / per_d);
+            const long long tq = tp - (long long) dd * per_d;
+            const int zm = (int) (tq / per_z), r = (int) (tq - (long long) zm * per_z);
+            const int z = dd * P + zm;                                   // output plane
             const int j0 = (r / tiles_i) * TJ, i0 = (r % tiles_i) * kSN;
-            const unsigned p = (unsigned) SD.p[z], mu = SD.mu[z];
+            const unsigned p = (unsigned) SD.p[zm], mu = SD.mu[zm];
             uint8_t *S8p = S8 + (long long) pg * pan.s8_panel;
             const long long s8_rows = pan.plane_rows ? pan.plane_rows : n_ps;
             const int b = NH == 1 ? (lt & 1) : 0, use = NH == 1 ? (lt >> 1) : lt;
@@ -942,6 +990,7 @@ inline int small_make_map(CUtensorMap *map, const void *planes, int nplanes, lon
 // pb_panel bytes apart; S8: per panel [P][n_ps][m_ps].  P is the host's copy of sel[0].
 inline int launch_small_umma(mpres_ctx *c, int P, const uint8_t *PA, const uint8_t *PB, long long pb_panel, uint8_t *S8, long long m_ps, long long n_ps, long long k_p,
                              long long k_begin, int k_len, bool add_to_S, const int *sel, const mpres::SmallPanels &pan, cudaStream_t st, long long pb_plane_rows = 0) {
+    const int SLc = pan.slices > 1 ? pan.slices : 1;
     CUtensorMap tmJ, tmI;
     int rc;
     const int box_k = (c->small_persistent && c->small_kb == 128 && k_len % 128 == 0 && k_begin % 128 == 0) ? 128 : mpres::kSK;
@@ -953,10 +1002,10 @@ inline int launch_small_umma(mpres_ctx *c, int P, const uint8_t *PA, const uint8
         CUDA_TRY(cudaFuncSetAttribute(mpres::k_small_umma_p<128, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, mpres::kPSmem));
         c->attr_small = true;
     }
-    if ((rc = small_make_map(&tmI, PA, P, m_ps, k_p, mpres::kSN, box_k))) return rc;
+    if ((rc = small_make_map(&tmI, PA, P * SLc, m_ps, k_p, mpres::kSN, box_k))) return rc;
     if (c->small_persistent) {
-        if ((rc = small_make_map(&tmJ, PB, P, n_ps, k_p, tj, box_k, pan.ring ? pan.ring : pan.count, pb_panel, pb_plane_rows))) return rc;
-        const long long max_tiles = (long long) P * (m_ps / mpres::kSN) * (n_ps / tj) * pan.count;
+        if ((rc = small_make_map(&tmJ, PB, P * SLc, n_ps, k_p, tj, box_k, pan.ring ? pan.ring : pan.count, pb_panel, pb_plane_rows))) return rc;
+        const long long max_tiles = (long long) P * (2 * SLc - 1) * (m_ps / mpres::kSN) * (n_ps / tj) * pan.count;
         const unsigned gx = (unsigned) std::min<long long>(max_tiles, (long long) c->sm_count);
         if (tj == 256)
             mpres::k_small_umma_p<128, 256><<<gx, mpres::kSThreads, mpres::kPSmem, st>>>(tmJ, tmI, c->dconsts, S8, m_ps, n_ps, (int) k_begin, k_len / mpres::kSK, add_to_S ? 1 : 0, sel, pan);

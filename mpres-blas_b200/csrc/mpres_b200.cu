@@ -112,7 +112,9 @@ int mpres_init_moduli(mpres_ctx **out, const int *moduli, int n, int device) {
         sd->red_mu = (const uint32_t *) upb(7, sc.red_mu.data(), sc.red_mu.size() * 4);
         sd->bin_mi = (const uint32_t *) upb(8, sc.bin_mi.data(), sc.bin_mi.size() * 4);
         sd->bin_negmp = (const uint32_t *) upb(9, sc.bin_negmp.data(), sc.bin_negmp.size() * 4);
-        const bool ok = sd->inv && sd->ext_b && sd->cw && sd->pws && sd->in_mi && sd->in_negmp && sd->red_mu && sd->bin_mi && sd->bin_negmp;
+        const bool okf = upb(10, sc.full_mi.data(), sc.full_mi.size() * 4) && upb(11, sc.full_negm.data(), sc.full_negm.size() * 4) &&
+                         upb(12, sc.full_m.data(), sc.full_m.size() * 4);
+        const bool ok = okf && sd->inv && sd->ext_b && sd->cw && sd->pws && sd->in_mi && sd->in_negmp && sd->red_mu && sd->bin_mi && sd->bin_negmp;
         const void *dev = ok ? upb(0, sd, sizeof(SmallDev)) : nullptr;
         delete sd;
         if (!dev) { delete d; cudaGetLastError(); mpres_finalize(c); return (int) cudaErrorMemoryAllocation; }
@@ -121,8 +123,8 @@ int mpres_init_moduli(mpres_ctx **out, const int *moduli, int n, int device) {
     e = cudaMalloc(&c->dconsts, sizeof(DevConsts));
     if (e == cudaSuccess) e = cudaMemcpy(c->dconsts, d, sizeof(DevConsts), cudaMemcpyHostToDevice);
     delete d;
-    if (e == cudaSuccess) e = cudaMalloc(&c->d_counter, kCounterInts * sizeof(int));
-    if (e == cudaSuccess) e = cudaMemset(c->d_counter, 0, kCounterInts * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_counter, (kCounterInts + kCounterExtra) * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(c->d_counter, 0, (kCounterInts + kCounterExtra) * sizeof(int));
     if (e == cudaSuccess) e = cudaHostAlloc(&c->h_sel, 8 * sizeof(int), cudaHostAllocDefault);
     if (e != cudaSuccess) { cudaGetLastError(); mpres_finalize(c); return (int) e; }
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
@@ -145,7 +147,7 @@ int mpres_finalize(mpres_ctx *c) {
     for (int i = 0; i < 24; ++i) if (c->ws[i]) cudaFree(c->ws[i]);
     for (int i = 0; i < 4; ++i) if (c->hs[i]) cudaStreamDestroy(c->hs[i]);
     for (int i = 0; i < 16; ++i) if (c->hev[i]) cudaEventDestroy(c->hev[i]);
-    for (int i = 0; i < 12; ++i) if (c->d_small[i]) cudaFree(c->d_small[i]);
+    for (int i = 0; i < 16; ++i) if (c->d_small[i]) cudaFree(c->d_small[i]);
     if (c->serial_ev) cudaEventDestroy(c->serial_ev);
     for (cudaEvent_t e : c->prof_ev) if (e) cudaEventDestroy(e);
     for (int i = 0; i < 6; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);

@@ -132,11 +132,11 @@ def test_gemm_fast_path_transposes(pkg):
     ctx.close()
 
 
-@pytest.mark.parametrize("N", [32])
+@pytest.mark.parametrize("N", [40])
 def test_gemm_full_precision_inputs(pkg, N):
     """p-bit inputs: every product needs a rounding in the reference, the exact window does not fit in
-    M.  Where the sums do not fit the one-byte base either (N >= 16) AUTO must route those elements to the
-    reference-order fallback (bit-exact again); N = 8 is tests/test_gpu_fullprec.py."""
+    M.  Formats without the single-rounding stage 3 (more than 32 moduli) must route those elements to the
+    reference-order fallback (bit-exact again); N <= 32 is tests/test_gpu_fullprec.py."""
     ctx = pkg.Context(N, 0)
     orc = get_oracle(N, oracle.DEVICE)
     bits = orc.precision

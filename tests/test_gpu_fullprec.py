@@ -3,7 +3,9 @@ one-byte base and rounds ONCE (csrc/kernels_bin.cuh) where the reference rounds 
 (src/arith/mul.cuh:108-110, src/arith/add.cuh:197-199).  Checked here:
   * alpha = 1, beta = 0: digits, sign, exponent == the exact integer sum rounded to nearest at MP_PRECISION bits (Python integers), the
     interval evaluation encloses T / M tightly;
-  * general alpha, beta: the reference's epilogue (mp_mul, mp_mul, mp_add of the DEVICE oracle) applied to those rounded sums, bit for bit;
+  * general alpha, beta: C = rn(rn(alpha rn(S)) + rn(beta C)), every rn the rounding to nearest of the exact value at MP_PRECISION bits,
+    against a Python-integer model bit for bit (the binary epilogue, k_bin_norm2); with MPRES_BIN_EPILOGUE=0 the residue-parallel
+    epilogue: the reference's mp_mul, mp_mul, mp_add (DEVICE oracle) applied to the rounded sums, bit for bit;
   * against exact rationals within the reference's own error model |err| <= gamma_k sum |a||b|, u = 4 / sqrt(M)
     (tests/blas/accuracy/test_dot_accuracy.cu:41-72), and at least as close as the reference-order k-loop on average."""
 from fractions import Fraction
@@ -75,8 +77,11 @@ def _round_nearest(s, base, prec):
     return sign, mag, base + drop
 
 
-@pytest.mark.parametrize("N,shape,spread", [(8, (40, 24, 70), 0), (8, (130, 70, 300), 6), (8, (24, 20, 1100), 3)])
+@pytest.mark.parametrize("N,shape,spread", [(8, (40, 24, 70), 0), (8, (130, 70, 300), 6), (8, (24, 20, 1100), 3),
+                                            (16, (40, 24, 70), 0), (24, (20, 30, 130), 4), (32, (33, 20, 50), 0), (32, (130, 40, 300), 9)])
 def test_rounded_sums_match_exact_integers(pkg, N, shape, spread):
+    """N >= 16: the sums exceed the one-byte base too -- the significands are cut into slices (k_choose_base), stage 2 forms the slice sums
+    and stage 3 puts them together in binary"""
     ctx = pkg.Context(N, 0)
     orc = get_oracle(N, oracle.DEVICE)
     prec = orc.precision
@@ -115,8 +120,82 @@ def test_rounded_sums_match_exact_integers(pkg, N, shape, spread):
     ctx.close()
 
 
+def _rn(mag, e, prec):
+    L = mag.bit_length()
+    drop = max(0, L - prec)
+    if drop:
+        mag = (mag + (1 << (drop - 1))) >> drop
+    return mag, e + drop
+
+
+def _model_entry(s, base, al, be, c, prec):
+    """(sign, significand, exponent) of rn(rn(alpha rn(S)) + rn(beta C)); al, be, c = (sign, integer, exponent)"""
+    m1 = e1 = s1 = 0
+    if s and al[1]:
+        t, et = _rn(abs(s), base, prec)
+        m1, e1 = _rn(t * al[1], et + al[2], prec)
+        s1 = (1 if s < 0 else 0) ^ al[0]
+    m2 = e2 = s2 = 0
+    if be[1] and c[1]:
+        m2, e2 = _rn(c[1] * be[1], c[2] + be[2], prec)
+        s2 = c[0] ^ be[0]
+    if m1 == 0 and m2 == 0:
+        return 0, 0, 0
+    top1, top2 = e1 + m1.bit_length(), e2 + m2.bit_length()
+    if m1 == 0 or (m2 and top2 - top1 > prec + 2):
+        return s2, m2, e2
+    if m2 == 0 or top1 - top2 > prec + 2:
+        return s1, m1, e1
+    emin = min(e1, e2)
+    v = (-1 if s1 else 1) * (m1 << (e1 - emin)) + (-1 if s2 else 1) * (m2 << (e2 - emin))
+    if v == 0:
+        return 0, 0, 0
+    mr, er = _rn(abs(v), emin, prec)
+    return (1 if v < 0 else 0), mr, er
+
+
+@pytest.mark.parametrize("N,shape,bits_c,spread", [(8, (33, 21, 64), None, 0), (8, (64, 40, 200), 26, 5), (8, (130, 24, 90), None, 40),
+                                                   (16, (33, 21, 64), None, 60), (32, (30, 18, 40), None, 0), (32, (20, 12, 600), 106, 200)])
+def test_binary_epilogue_matches_the_integer_model(pkg, N, shape, bits_c, spread):
+    ctx = pkg.Context(N, 0)
+    orc = get_oracle(N, oracle.DEVICE)
+    prec = orc.precision
+    m, n, k = shape
+    A, B = random_records(N, m * k, prec, 931), random_records(N, k * n, prec, 932)
+    C = random_records(N, m * n, bits_c or prec, 933)
+    rng = np.random.RandomState(934)
+    if spread:
+        C["exp"] += rng.randint(-spread, spread, size=C.shape).astype(np.int32)     # t2 dominant / negligible / cancelling against t1
+    C[2::11] = orc.set_ints([0], [0], [0])[0]
+    A[7 + np.arange(k) * m] = orc.set_ints([0], [0], [0])[0]                           # a zero row of A: C = rn(beta C)
+    alpha, beta = random_records(N, 1, prec, 935), random_records(N, 1, prec, 936)
+    S = _exact_sums(orc, A, B, m, n, k)
+    mods = orc.c["moduli"]
+    triple = lambda r: (int(r["sign"]), orc.to_int(r), int(r["exp"]))
+    for al_, be_ in ((alpha, beta), (alpha, orc.set_ints([0], [0], [0])), (orc.set_ints([1], [3], [-1]), beta)):
+        got = _gemm(pkg, ctx, m, n, k, al_, A, B, be_, C, pkg.MODE_AUTO)
+        assert ctx.last_binary_rounding() and ctx.last_fallback_count() == 0
+        al, be = triple(al_[0]), triple(be_[0])
+        for j in range(n):
+            for i in range(m):
+                s, base = S[i, j]
+                sg, mant, ex = _model_entry(s, base, al, be, triple(C[i + j * m]), prec)
+                g = got[i + j * m]
+                assert (int(g["sign"]), int(g["exp"])) == (sg, ex), (i, j, g, sg, mant, ex)
+                assert [int(d) for d in g["digits"]] == [mant % q for q in mods], (i, j)
+                if mant:
+                    lo = Fraction(float(g["eval"]["frac"][0])) * Fraction(2) ** int(g["eval"]["exp"][0])
+                    up = Fraction(float(g["eval"]["frac"][1])) * Fraction(2) ** int(g["eval"]["exp"][1])
+                    x = Fraction(mant, orc.c["M"])
+                    assert lo <= x <= up and (up - lo) <= x / 2 ** 45, (i, j)
+                else:
+                    assert g["eval"]["frac"][1] == 0
+    ctx.close()
+
+
 @pytest.mark.parametrize("N,shape,bits_c", [(8, (33, 21, 64), None), (8, (64, 40, 200), 26)])
-def test_epilogue_is_the_reference_sequence_on_the_rounded_sums(pkg, N, shape, bits_c):
+def test_epilogue_is_the_reference_sequence_on_the_rounded_sums(pkg, N, shape, bits_c, monkeypatch):
+    monkeypatch.setenv("MPRES_BIN_EPILOGUE", "0")          # the residue-parallel epilogue (also the fallback for scalars wider than the precision)
     ctx = pkg.Context(N, 0)
     orc = get_oracle(N, oracle.DEVICE)
     prec = orc.precision
@@ -135,7 +214,7 @@ def test_epilogue_is_the_reference_sequence_on_the_rounded_sums(pkg, N, shape, b
     ctx.close()
 
 
-@pytest.mark.parametrize("N,shape,trans", [(8, (20, 16, 128), (111, 111)), (8, (17, 13, 90), (112, 112))])
+@pytest.mark.parametrize("N,shape,trans", [(8, (20, 16, 128), (111, 111)), (8, (17, 13, 90), (112, 112)), (32, (12, 10, 64), (112, 111)), (24, (9, 8, 40), (111, 112))])
 def test_accuracy_against_exact_rationals(pkg, N, shape, trans):
     ctx = pkg.Context(N, 0)
     orc = get_oracle(N, oracle.DEVICE)
