@@ -313,6 +313,16 @@ int mpres_spmv_ell2st(mpres_ctx *ctx, int m, int n, int maxnzr, const int *ja, c
  * nearest to src[offset + i] (ties to even; mp_get_d, src/arith/assign.cuh:154-180, rounds the exact value the same way through MPFR).
  * src / dst doubles are DEVICE pointers. */
 int mpres_array_set_d(mpres_ctx *ctx, mpres_array_t *dst, size_t offset, const double *src, size_t n, mpres_stream_t stream);
+/* r[0] = x[0] / y[0] rounded to nearest (ties to even) at MP_PRECISION bits, on the device.  The reference's cuda::mp_div copies both numbers
+ * to the host and divides with MPFR_RNDN at MP_PRECISION bits (src/arith/div.cuh:33-66): the same value.  A zero divisor leaves r untouched. */
+int mpres_div(mpres_ctx *ctx, mpres_array_t *r, const mpres_array_t *x, const mpres_array_t *y, mpres_stream_t stream);
+/* Conjugate gradients for A x = b, A symmetric positive definite in CSR with double entries (mp_cg_csr, src/sparse/solver/cg_csr.cuh:53; with
+ * M != NULL the diagonally preconditioned iteration mp_pcg_csr, pcg_csr.cuh:57, M = n doubles).  The iteration is the reference's, operation for
+ * operation, in this library's kernels: the matrix is converted once to multiple precision (exactly) and multiplied by the two-stage SpMV,
+ * mpres_dot, mpres_div, fused a x + y.  irp, ja, as, M: device pointers; b, x: n elements (x: initial guess in, solution out); tol: relative
+ * residual; *iters: iterations done; resvec: maxit + 1 doubles on the host (relative residual history) or NULL.  Synchronises. */
+int mpres_cg_csr(mpres_ctx *ctx, int n, int nnz, const int *irp, const int *ja, const double *as, const mpres_array_t *b, double tol, int maxit,
+                 const double *M, mpres_array_t *x, int *iters, double *resvec, mpres_stream_t stream);
 int mpres_array_get_d(mpres_ctx *ctx, double *dst, const mpres_array_t *src, size_t offset, size_t n, mpres_stream_t stream);
 
 /* The same three operations over mp_collection_t operands with explicit allocated lengths (the

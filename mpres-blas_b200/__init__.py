@@ -45,7 +45,7 @@ EXPORTS = [
     "mpres_array_set_binary", "mpres_gemm", "mpres_gemv", "mpres_dot", "mpres_scal", "mpres_axpy", "mpres_waxpby", "mpres_ge_add", "mpres_ge_acc", "mpres_ger", "mpres_ge_diag_scale", "mpres_ge_lr_scale", "mpres_rot", "mpres_axpy_dot", "mpres_gemm_host", "mpres_gemm_host_bdev", "mpres_gemm_coll", "mpres_gemv_coll",
     "mpres_dot_coll", "mpres_dot_partial", "mpres_reduce_partials", "mpres_probe", "mpres_version",
     "mpres_last_kernel_ms", "mpres_shard_handle_size", "mpres_shard_create", "mpres_shard_export", "mpres_shard_connect", "mpres_shard_destroy",
-    "mpres_gemm_sharded", "mpres_asum", "mpres_norm", "mpres_ge_norm", "mpres_spmv_csr2st", "mpres_spmv_ell2st", "mpres_array_set_d", "mpres_array_get_d",
+    "mpres_gemm_sharded", "mpres_asum", "mpres_norm", "mpres_ge_norm", "mpres_spmv_csr2st", "mpres_spmv_ell2st", "mpres_array_set_d", "mpres_array_get_d", "mpres_div", "mpres_cg_csr",
 ]
 
 
@@ -347,6 +347,21 @@ def mp_array_set_d(ctx, dst, offset, src, n, stream=0):
 def mp_array_get_d(ctx, dst, src, offset, n, stream=0):
     """dst[i] = nearest double of src[offset + i] (mp_get_d, src/arith/assign.cuh:154-180); dst: float64 device tensor."""
     _check(ctx.lib.mpres_array_get_d(ctx.h, _dev_ptr(dst), _ref(src), ctypes.c_size_t(offset), ctypes.c_size_t(n), _vp(stream)), "mpres_array_get_d")
+
+
+def mp_div(ctx, r, x, y, stream=0):
+    """cuda::mp_div (src/arith/div.cuh:56-65): r[0] = x[0] / y[0], rounded to nearest at the working precision."""
+    _check(ctx.lib.mpres_div(ctx.h, _ref(r), _ref(x), _ref(y), _vp(stream)), "mpres_div")
+
+
+def mp_cg_csr(ctx, n, nnz, irp, ja, vals, b, tol, maxit, x, M=None, stream=0):
+    """mp_cg_csr / mp_pcg_csr (src/sparse/solver/cg_csr.cuh:53, pcg_csr.cuh:57): returns (iterations, relative residual history)."""
+    it = ctypes.c_int(0)
+    res = (ctypes.c_double * (maxit + 1))()
+    ctx.lib.mpres_cg_csr.argtypes = None
+    _check(ctx.lib.mpres_cg_csr(ctx.h, n, nnz, _dev_ptr(irp), _dev_ptr(ja), _dev_ptr(vals), _ref(b), ctypes.c_double(tol), maxit,
+                                _dev_ptr(M) if M is not None else None, _ref(x), ctypes.byref(it), res, _vp(stream)), "mpres_cg_csr")
+    return it.value, list(res)[: it.value + 1]
 
 
 def mp_scal(ctx, n, alpha, x, incx, stream=0):

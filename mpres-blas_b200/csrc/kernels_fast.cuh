@@ -165,6 +165,58 @@ __global__ void __launch_bounds__(256) k_outer_part(SoA X, long long sl, int out
         }
     }
 }
+// ... and for lines that run along the contiguous direction of the input (sl == 1) when there are too few of them to fill the GPU with one
+// warp per line (a rank's column block of B in a sharded call): block (line, chunk), lanes along the line
+__global__ void __launch_bounds__(256) k_outer_part_l(SoA X, long long so, int outer, int inner, int chunk, OuterPart *part) {
+    __shared__ int s_emin[8], s_emax[8];
+    __shared__ long long s_top[8];
+    __shared__ unsigned long long s_key[8];
+    const int o = blockIdx.x;
+    const int l0 = blockIdx.y * chunk, l1 = min(inner, l0 + chunk);
+    const long long len = X.len();
+    int emin = INT_MAX, emax = INT_MIN;
+    long long top = LLONG_MIN;
+    unsigned long long key = 0ull;
+    for (int l = l0 + threadIdx.x; l < l1; l += 256) {
+        const long long idx = (long long) o * so + l;
+        const Er up = X.eval[idx + len];
+        if (up.frac != 0) {
+            const int e = X.exp[idx];
+            emin = min(emin, e); emax = max(emax, e);
+            const long long t = (long long) e + up.exp;
+            top = t > top ? t : top;
+            const unsigned long long fb = (unsigned long long) __double_as_longlong(fabs(up.frac));
+            const long long ue = (up.exp > 100000 ? 100000 : (up.exp < -100000 ? -100000 : up.exp)) + (long long) (fb >> 52);
+            const unsigned long long k2 = ((unsigned long long) (ue + kOuterKeyBias) << 45) + (((fb & 0xfffffffffffffull) >> 8) + 1ull);
+            key = k2 > key ? k2 : key;
+        }
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        emin = min(emin, __shfl_xor_sync(0xffffffffu, emin, d));
+        emax = max(emax, __shfl_xor_sync(0xffffffffu, emax, d));
+        const long long t = __shfl_xor_sync(0xffffffffu, top, d);
+        top = t > top ? t : top;
+        const unsigned long long k2 = __shfl_xor_sync(0xffffffffu, key, d);
+        key = k2 > key ? k2 : key;
+    }
+    const int warp = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { s_emin[warp] = emin; s_emax[warp] = emax; s_top[warp] = top; s_key[warp] = key; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int g = 1; g < 8; ++g) {
+            emin = min(emin, s_emin[g]); emax = max(emax, s_emax[g]);
+            top = s_top[g] > top ? s_top[g] : top;
+            key = s_key[g] > key ? s_key[g] : key;
+        }
+        if (emin != INT_MAX) {
+            atomicMin(&part[o].emin, emin);
+            atomicMax(&part[o].emax, emax);
+            atomicMax(&part[o].top, top);
+            atomicMax(&part[o].key, key);
+        }
+    }
+}
 __global__ void k_outer_part_final(const DevConsts *Cp, const OuterPart *part, int outer, OuterInfo *info) {
     const int o = blockIdx.x * blockDim.x + threadIdx.x;
     if (o >= outer) return;

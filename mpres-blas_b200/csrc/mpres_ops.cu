@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "ctx.hpp"
+#include "kernels_ref_order.cuh"
 
 #define NEED_DEVICE(c) do { if ((c) && (c)->device < 0) return -100; } while (0)
 
@@ -224,6 +225,208 @@ __global__ void __launch_bounds__(128) k_get_d(const DevConsts *Cp, GetDTab T, l
     }
 }
 
+// ---- division (src/arith/div.cuh:33-66: the reference copies both numbers to the host and divides with MPFR at MP_PRECISION bits) ----------
+// Here: one thread rebuilds both significands in binary (CRT over all moduli), divides by shift-and-subtract, rounds the quotient to nearest
+// (ties to even, MPFR_RNDN) at `prec` bits and trims its trailing zeros as mp_set_mpfr does (assign.cuh:95-111); the lane group then forms
+// the digits' interval evaluation.  r[0] = x[0] / y[0]; a zero divisor leaves r untouched and sets *status.
+__device__ __forceinline__ void ops_crt(const DevConsts &C, const int *dg, const GetDTab &T, unsigned *x) {
+    const int N = C.N, nw = T.nw;
+    double sum = 0.0;
+    for (int q = 0; q < N; ++q) sum += (double) mulmod(dg[q], C.part_inverse[q], C.moduli[q], C.barrett[q]) / (double) C.moduli[q];
+    long long Rk = (long long) floor(sum);
+    for (int pass = 0; pass < 3; ++pass) {
+        unsigned long long clo = 0, chi = 0;
+        for (int w = 0; w < nw; ++w) {
+            unsigned long long lo = clo, hi = chi;
+            for (int q = 0; q < N; ++q) {
+                const unsigned long long xi = (unsigned long long) (unsigned) mulmod(dg[q], C.part_inverse[q], C.moduli[q], C.barrett[q]);
+                const unsigned long long p = xi * T.mi[(size_t) q * nw + w];
+                lo += p; hi += lo < p ? 1ull : 0ull;
+            }
+            const unsigned long long p = (unsigned long long) Rk * T.negm[w];
+            lo += p; hi += lo < p ? 1ull : 0ull;
+            x[w] = (unsigned) lo;
+            clo = (lo >> 32) | (hi << 32); chi = hi >> 32;
+        }
+        bool ge = true;
+        for (int w = nw - 1; w >= 0; --w) { if (x[w] != T.mw[w]) { ge = x[w] > T.mw[w]; break; } }
+        if (!ge) break;
+        if ((int) x[nw - 1] < 0) --Rk; else ++Rk;
+    }
+}
+__device__ __forceinline__ int ops_bitlen(const unsigned *x, int nw) {
+    int L = 0;
+    for (int w = 0; w < nw; ++w) if (x[w]) L = 32 * w + 32 - __clz(x[w]);
+    return L;
+}
+constexpr int kDivW = 2 * (kMaxN + 2) + 2;
+template <int G, int R>
+__global__ void k_div(const DevConsts *Cp, GetDTab T, SoA xs, SoA ys, SoA rs, int *status) {
+    const DevConsts &C = *Cp;
+    Lane<R> L;
+    lane_init<G, R>(C, L);
+    __shared__ unsigned q[kMaxN + 4];
+    __shared__ int s_exp, s_sign, s_nw, s_ok;
+    if (threadIdx.x == 0) {
+        s_ok = 0;
+        const bool xz = xs.eval[xs.len()].frac == 0, yz = ys.eval[ys.len()].frac == 0;
+        if (yz) { if (status) *status = 1; }
+        else if (xz) { s_ok = 2; }
+        else {
+            unsigned X[kMaxN + 2], Y[kMaxN + 2], Nn[kDivW], Rm[kMaxN + 3];
+            const int nw = T.nw, prec = C.precision;
+            ops_crt(C, xs.digits, T, X);
+            ops_crt(C, ys.digits, T, Y);
+            const int Lx = ops_bitlen(X, nw), Ly = ops_bitlen(Y, nw);
+            const int s = prec + 2 + Ly - Lx;                       // the quotient of X 2^s / Y has prec + 2 or prec + 3 bits
+            // numerator X 2^max(s, 0), divisor Y 2^max(-s, 0) (Ly + |s| bits: at most 2 nw words)
+            const int nn = 2 * nw + 2;
+            for (int w = 0; w < nn; ++w) Nn[w] = 0u;
+            const int sx = s > 0 ? s : 0;
+            const int nxw = (Lx + 31) >> 5, nyw = (Ly + 31) >> 5;
+            for (int w = 0; w < nxw; ++w) {
+                const unsigned long long v = (unsigned long long) X[w] << (sx & 31);
+                Nn[w + (sx >> 5)] |= (unsigned) v;
+                Nn[w + (sx >> 5) + 1] |= (unsigned) (v >> 32);
+            }
+            unsigned D[kMaxN + 4];
+            const int nd = nw + 2;                                    // s < 0 only when Lx > prec + 2 + Ly: |s| < Lx: fits
+            for (int w = 0; w < nd; ++w) D[w] = 0u;
+            const int sy = s < 0 ? -s : 0;
+            {
+                for (int w = 0; w < nyw; ++w) {
+                    const unsigned long long v = (unsigned long long) Y[w] << (sy & 31);
+                    D[w + (sy >> 5)] |= (unsigned) v;
+                    D[w + (sy >> 5) + 1] |= (unsigned) (v >> 32);
+                }
+                const int Ln = ops_bitlen(Nn, nn);
+                for (int w = 0; w < nd + 1; ++w) Rm[w] = 0u;
+                for (int w = 0; w < nw + 2; ++w) q[w] = 0u;
+                for (int b = Ln - 1; b >= 0; --b) {
+                    // R = 2 R + bit b of the numerator
+                    unsigned cy = (Nn[b >> 5] >> (b & 31)) & 1u;
+                    for (int w = 0; w < nd + 1; ++w) { const unsigned nx = Rm[w] >> 31; Rm[w] = (Rm[w] << 1) | cy; cy = nx; }
+                    bool ge = Rm[nd] != 0;
+                    if (!ge) { ge = true; for (int w = nd - 1; w >= 0; --w) { if (Rm[w] != D[w]) { ge = Rm[w] > D[w]; break; } } }
+                    if (ge) {
+                        long long bw = 0;
+                        for (int w = 0; w < nd; ++w) { const long long df = (long long) Rm[w] - D[w] - bw; Rm[w] = (unsigned) df; bw = df < 0 ? 1 : 0; }
+                        Rm[nd] -= (unsigned) bw;
+                        if (b < 32 * (nw + 2)) q[b >> 5] |= 1u << (b & 31);
+                    }
+                }
+                bool sticky = false;
+                for (int w = 0; w < nd + 1; ++w) sticky |= Rm[w] != 0;
+                int Lq = ops_bitlen(q, nw + 2);
+                int ex = xs.exp[0] - ys.exp[0] - s;
+                const int d = Lq - prec;
+                if (d > 0) {
+                    const int hw = (d - 1) >> 5;
+                    const unsigned hb = 1u << ((d - 1) & 31);
+                    // remainder below the cut against one half
+                    bool above = false, half = (q[hw] & hb) != 0;
+                    for (int w = 0; w <= hw; ++w) {
+                        const unsigned mask = w < hw ? 0xffffffffu : (hb - 1u);
+                        if (q[w] & mask) above = true;
+                    }
+                    // shift right by d
+                    const int ws = d >> 5, bs = d & 31;
+                    for (int w = 0; w < nw + 2; ++w) {
+                        const unsigned lo = w + ws < nw + 2 ? q[w + ws] : 0u, hi = w + ws + 1 < nw + 2 ? q[w + ws + 1] : 0u;
+                        q[w] = bs ? (lo >> bs) | (hi << (32 - bs)) : lo;
+                    }
+                    if (half && (above || sticky || (q[0] & 1u))) {
+                        unsigned long long cy2 = 1;
+                        for (int w = 0; w < nw + 2 && cy2; ++w) { cy2 += q[w]; q[w] = (unsigned) cy2; cy2 >>= 32; }
+                    }
+                    ex += d;
+                }
+                // trailing zeros into the exponent
+                Lq = ops_bitlen(q, nw + 2);
+                int tz = 0;
+                while (tz < Lq && !((q[tz >> 5] >> (tz & 31)) & 1u)) ++tz;
+                if (tz) {
+                    const int ws = tz >> 5, bs = tz & 31;
+                    for (int w = 0; w < nw + 2; ++w) {
+                        const unsigned lo = w + ws < nw + 2 ? q[w + ws] : 0u, hi = w + ws + 1 < nw + 2 ? q[w + ws + 1] : 0u;
+                        q[w] = bs ? (lo >> bs) | (hi << (32 - bs)) : lo;
+                    }
+                    ex += tz;
+                }
+                s_exp = ex; s_sign = (xs.sign[0] ^ ys.sign[0]) & 1; s_nw = nw + 2; s_ok = 1;
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x >= G) return;
+    Num<R> v;
+    if (s_ok == 2) { num_zero(v); store_num<G, R>(C, L, rs, 0, v); return; }
+    if (s_ok != 1) return;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        unsigned long long acc = 0;
+        if (L.act[r]) {
+            for (int w = 0; w < s_nw; ++w) {
+                if (q[w] == 0u) continue;
+                const int pw = 32 * w <= C.log2M ? __ldg(C.pow2 + (long long) (32 * w) * C.N + L.idx[r]) : pow2_slow(32 * w, L.m[r], L.mu[r]);
+                acc += (unsigned long long) q[w] * (unsigned) pw;
+                acc = (unsigned long long) (unsigned) reduce64(acc, L.m[r], L.mu[r]);
+            }
+        }
+        v.d[r] = (int) acc;
+    }
+    v.sign = s_sign; v.exp = s_exp;
+    eval_compute<G, R, false>(C, L, v.d, v.lo, v.up);
+    store_num<G, R>(C, L, rs, 0, v);
+}
+
+// r = a x + y element-wise with the roundings of mp_mul / mp_add (cuda::mp_axpy of src/blas/v2/axpy_v2.cuh; negate: cuda::mp_maxpy, maxpy_v2.cuh:39-53)
+template <int G, int R>
+__global__ void k_axpy_out(const DevConsts *Cp, long long n, SoA a, bool negate, SoA x, SoA y, SoA r) {
+    const DevConsts &C = *Cp;
+    Lane<R> L;
+    lane_init<G, R>(C, L);
+    const long long ngrp = (long long) gridDim.x * blockDim.x / G;
+    Num<R> s, xv, yv, t;
+    load_num<G, R>(C, L, a, 0, s);
+    if (negate) s.sign ^= 1;
+    for (long long i = ((long long) blockIdx.x * blockDim.x + threadIdx.x) / G; i < n; i += ngrp) {
+        load_num<G, R>(C, L, x, i, xv);
+        load_num<G, R>(C, L, y, i, yv);
+        mp_mul<G, R, true>(C, L, t, s, xv);
+        mp_add<G, R, true>(C, L, t, t, yv);
+        store_num<G, R>(C, L, r, i, t);
+    }
+}
+// r = x - y (cuda::mp_diff, src/blas/v2/diff_v2.cuh) and r = x * y element-wise (cuda::mp_prod_d with the doubles converted once)
+template <int G, int R, bool MUL>
+__global__ void k_elementwise(const DevConsts *Cp, long long n, SoA x, SoA y, SoA r) {
+    const DevConsts &C = *Cp;
+    Lane<R> L;
+    lane_init<G, R>(C, L);
+    const long long ngrp = (long long) gridDim.x * blockDim.x / G;
+    Num<R> xv, yv, t;
+    for (long long i = ((long long) blockIdx.x * blockDim.x + threadIdx.x) / G; i < n; i += ngrp) {
+        load_num<G, R>(C, L, x, i, xv);
+        load_num<G, R>(C, L, y, i, yv);
+        if (MUL) mp_mul<G, R, true>(C, L, t, xv, yv);
+        else { yv.sign ^= 1; mp_add<G, R, true>(C, L, t, xv, yv); }
+        store_num<G, R>(C, L, r, i, t);
+    }
+}
+template <int G, int R>
+__global__ void k_copy(const DevConsts *Cp, long long n, SoA x, SoA r) {
+    const DevConsts &C = *Cp;
+    Lane<R> L;
+    lane_init<G, R>(C, L);
+    const long long ngrp = (long long) gridDim.x * blockDim.x / G;
+    Num<R> xv;
+    for (long long i = ((long long) blockIdx.x * blockDim.x + threadIdx.x) / G; i < n; i += ngrp) {
+        load_num<G, R>(C, L, x, i, xv);
+        store_num<G, R>(C, L, r, i, xv);
+    }
+}
+
 }  // namespace mpres
 
 namespace {
@@ -371,6 +574,126 @@ int mpres_array_set_d(mpres_ctx *c, mpres_array_t *dst, size_t offset, const dou
     });
     LAUNCHED(c);
     CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+static int ops_gettab(mpres_ctx *c, GetDTab *T) {
+    OpsTables t;
+    int rc = ops_tables(c, &t);
+    if (rc) return rc;
+    if (t.nw > kMaxN + 2) return -4;
+    T->nw = t.nw; T->mi = t.d_mi; T->negm = t.d_negm; T->mw = t.d_mw;
+    return 0;
+}
+
+int mpres_div(mpres_ctx *c, mpres_array_t *r, const mpres_array_t *x, const mpres_array_t *y, mpres_stream_t stream) {
+    NEED_DEVICE(c);
+    if (!c || !r || !x || !y) return -1;
+    DeviceGuard g(c->device);
+    GetDTab T;
+    int rc = ops_gettab(c, &T);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t) stream;
+    MPRES_DISPATCH(c->hc.N, { k_div<G, R><<<1, 32, 0, st>>>(c->dconsts, T, view(x), view(y), view(r), nullptr); });
+    LAUNCHED(c);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// Conjugate gradients, optionally with a diagonal preconditioner (src/sparse/solver/cg_csr.cuh:53-110, pcg_csr.cuh:57-130), built from this
+// library's operations: two-stage SpMV over the matrix converted once to multiple precision, mpres_dot, division, fused a x + y.
+// A: CSR with double entries (irp, ja, as: device pointers, as in the reference's csr_t), b, x: mp_array_t of n elements (x: initial guess in,
+// solution out), M: n doubles (device; the inverse diagonal) or NULL, tol: relative residual, resvec: maxit + 1 doubles on the host or NULL.
+int mpres_cg_csr(mpres_ctx *c, int n, int nnz, const int *irp, const int *ja, const double *as, const mpres_array_t *b, double tol, int maxit, const double *M,
+                 mpres_array_t *x, int *iters, double *resvec, mpres_stream_t stream) {
+    NEED_DEVICE(c);
+    if (!c || !irp || !ja || !as || !b || !x || n <= 0 || nnz < 0) return -1;
+    DeviceGuard g(c->device);
+    cudaStream_t st = (cudaStream_t) stream;
+    const int N = c->hc.N;
+    mpres_array_t r, p, q, z, sc, Mv;                     // sc: rho, rhop, alpha, beta, pq, nrm as six one-element views of one array
+    mpres_collection_t Am;
+    memset(&z, 0, sizeof(z)); memset(&Mv, 0, sizeof(Mv));
+    int rc;
+    if ((rc = mpres_array_init(c, &r, n)) || (rc = mpres_array_init(c, &p, n)) || (rc = mpres_array_init(c, &q, n)) || (rc = mpres_array_init(c, &sc, 6)) ||
+        (rc = mpres_collection_init(c, &Am, nnz ? nnz : 1))) return rc;
+    if (M && ((rc = mpres_array_init(c, &z, n)) || (rc = mpres_array_init(c, &Mv, n)))) return rc;
+    auto scalar = [&](int i) {                               // element i of sc as a length-1 array (same allocated length: same offset of the upper bounds)
+        mpres_array_t v = sc;
+        v.digits += (size_t) i * N; v.sign += i; v.exp += i; v.eval += i;
+        return v;
+    };
+    mpres_array_t rho = scalar(0), rhop = scalar(1), alpha = scalar(2), beta = scalar(3), pq = scalar(4), nrm = scalar(5);
+    double *d_nrm = nullptr;
+    CUDA_TRY(cudaMalloc(&d_nrm, sizeof(double)));
+    auto cleanup = [&]() {
+        cudaStreamSynchronize(st);
+        mpres_array_clear(c, &r); mpres_array_clear(c, &p); mpres_array_clear(c, &q); mpres_array_clear(c, &sc); mpres_collection_clear(c, &Am);
+        if (M) { mpres_array_clear(c, &z); mpres_array_clear(c, &Mv); }
+        cudaFree(d_nrm);
+    };
+    auto grid = [&](long long items, int G_) { return (unsigned) std::max<long long>(1, std::min<long long>((items * G_ + 127) / 128, (long long) c->sm_count * 16)); };
+    // the matrix (and the preconditioner) in multiple precision, exactly
+    {
+        mpres_array_t av;                                    // the collection's arrays as an array view for the conversion kernel
+        memset(&av, 0, sizeof(av));
+        av.digits = Am.digits; av.sign = Am.sign; av.exp = Am.exp; av.eval = Am.eval;
+        SoA dstv = view(&Am, (size_t) (nnz ? nnz : 1));
+        if (nnz) { MPRES_DISPATCH(N, { k_set_d<G, R><<<grid(nnz, G), 128, 0, st>>>(c->dconsts, (long long) nnz, as, dstv, 0); }); LAUNCHED(c); }
+        if (M && (rc = mpres_array_set_d(c, &Mv, 0, M, (size_t) n, stream))) { cleanup(); return rc; }
+    }
+    auto norm2 = [&](const mpres_array_t *v, double *out) -> int {   // sqrt(v . v) as a double (cuda::mp_norm2, src/blas/v2/norm2_v2.cuh:108-118)
+        int e = mpres_dot(c, n, v, 1, v, 1, &nrm, nullptr, stream);
+        if (e) return e;
+        if ((e = mpres_array_get_d(c, d_nrm, &nrm, 0, 1, stream))) return e;
+        double h = 0;
+        CUDA_TRY(cudaMemcpyAsync(&h, d_nrm, sizeof(double), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        *out = sqrt(h);
+        return 0;
+    };
+    auto fail = [&](int e) { cleanup(); return e; };
+    // r = b - A x
+    if ((rc = mpres_spmv_csr2st(c, n, n, nnz, irp, ja, &Am, x, &r, nullptr, stream))) return fail(rc);
+    MPRES_DISPATCH(N, { k_elementwise<G, R, false><<<grid(n, G), 128, 0, st>>>(c->dconsts, (long long) n, view(b), view(&r), view(&r)); });
+    LAUNCHED(c);
+    double norm0 = 0, normk = 0;
+    if ((rc = norm2(&r, &norm0))) return fail(rc);
+    const double eps = norm0 * tol;
+    normk = norm0;
+    int k = 0;
+    if (resvec) resvec[0] = norm0 > 0 ? 1.0 : 0.0;
+    while (normk > eps && k < maxit) {
+        const mpres_array_t *zz = &r;
+        if (M) {
+            MPRES_DISPATCH(N, { k_elementwise<G, R, true><<<grid(n, G), 128, 0, st>>>(c->dconsts, (long long) n, view(&r), view(&Mv), view(&z)); });
+            LAUNCHED(c);
+            zz = &z;
+        }
+        MPRES_DISPATCH(N, { k_copy<G, R><<<1, 32, 0, st>>>(c->dconsts, 1, view(&rho), view(&rhop)); });
+        if ((rc = mpres_dot(c, n, &r, 1, zz, 1, &rho, nullptr, stream))) return fail(rc);
+        if (k == 0) {
+            MPRES_DISPATCH(N, { k_copy<G, R><<<grid(n, G), 128, 0, st>>>(c->dconsts, (long long) n, view(zz), view(&p)); });
+        } else {
+            if ((rc = mpres_div(c, &beta, &rho, &rhop, stream))) return fail(rc);
+            MPRES_DISPATCH(N, { k_axpy_out<G, R><<<grid(n, G), 128, 0, st>>>(c->dconsts, (long long) n, view(&beta), false, view(&p), view(zz), view(&p)); });
+        }
+        LAUNCHED(c);
+        if ((rc = mpres_spmv_csr2st(c, n, n, nnz, irp, ja, &Am, &p, &q, nullptr, stream))) return fail(rc);
+        if ((rc = mpres_dot(c, n, &p, 1, &q, 1, &pq, nullptr, stream))) return fail(rc);
+        if ((rc = mpres_div(c, &alpha, &rho, &pq, stream))) return fail(rc);
+        MPRES_DISPATCH(N, {
+            k_axpy_out<G, R><<<grid(n, G), 128, 0, st>>>(c->dconsts, (long long) n, view(&alpha), false, view(&p), view(x), view(x));
+            k_axpy_out<G, R><<<grid(n, G), 128, 0, st>>>(c->dconsts, (long long) n, view(&alpha), true, view(&q), view(&r), view(&r));
+        });
+        LAUNCHED(c); LAUNCHED(c);
+        if ((rc = norm2(&r, &normk))) return fail(rc);
+        ++k;
+        if (resvec) resvec[k] = norm0 > 0 ? normk / norm0 : 0.0;
+    }
+    if (iters) *iters = k;
+    CUDA_TRY(cudaGetLastError());
+    cleanup();
     return 0;
 }
 

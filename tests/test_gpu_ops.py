@@ -207,3 +207,109 @@ def test_double_conversions(pkg, N):
         want = fr.numerator / fr.denominator              # Python: correctly rounded (ties to even) division of integers
         assert struct.pack("<d", v) == struct.pack("<d", want), (v, want)
     ctx.close()
+
+
+def _rne(num, den, prec):
+    """(mantissa, exponent) of num / den rounded to nearest even at prec bits, trailing zeros trimmed (num, den > 0)"""
+    L = num.bit_length() - den.bit_length()
+    sh = prec + 2 - L
+    n2, d2 = (num << sh, den) if sh >= 0 else (num, den << -sh)
+    q, r = divmod(n2, d2)
+    e = -sh
+    d = q.bit_length() - prec
+    if d > 0:
+        half, rem = 1 << (d - 1), q & ((1 << d) - 1)
+        q >>= d
+        if rem > half or (rem == half and (r or (q & 1))):
+            q += 1
+        elif rem == half and not r and not (q & 1):
+            pass
+        e += d
+    elif r:
+        raise AssertionError("quotient shorter than the precision with a remainder")
+    while q and not q & 1:
+        q >>= 1
+        e += 1
+    return q, e
+
+
+@pytest.mark.parametrize("N", [8, 16, 32, 64])
+def test_div_is_correctly_rounded(pkg, N):
+    ctx = pkg.Context(N, 0)
+    orc = get_oracle(N, oracle.DEVICE)
+    prec = orc.precision
+    xs = random_records(N, 24, prec, 1261)
+    ys = random_records(N, 24, prec // 3, 1262)
+    xs[3] = orc.set_ints([1], [12], [5])[0]; ys[3] = orc.set_ints([0], [3], [-2])[0]       # exact quotient
+    xs[4] = orc.set_ints([0], [1], [0])[0]; ys[4] = orc.set_ints([0], [3], [0])[0]        # 1 / 3
+    xs[5] = orc.set_ints([0], [0], [0])[0]                                                   # 0 / y
+    mods = orc.c["moduli"]
+    r = ctx.mp_array_init(1)
+    for x, y in zip(xs, ys):
+        pkg.mp_div(ctx, r, ctx.mp_array_from_host(x.reshape(1)), ctx.mp_array_from_host(y.reshape(1)))
+        g = r.device2host()[0]
+        xi, yi = orc.to_int(x), orc.to_int(y)
+        if xi == 0:
+            assert not g["digits"].any() and g["eval"]["frac"][1] == 0
+            continue
+        q, e = _rne(xi, yi, prec)
+        assert int(g["sign"]) == int(x["sign"]) ^ int(y["sign"])
+        assert int(g["exp"]) == int(x["exp"]) - int(y["exp"]) + e, (g, e)
+        assert [int(d) for d in g["digits"]] == [q % m for m in mods]
+        lo = Fraction(float(g["eval"]["frac"][0])) * Fraction(2) ** int(g["eval"]["exp"][0])
+        up = Fraction(float(g["eval"]["frac"][1])) * Fraction(2) ** int(g["eval"]["exp"][1])
+        assert lo <= Fraction(q, orc.c["M"]) <= up
+    ctx.close()
+
+
+@pytest.mark.parametrize("N,precond", [(8, False), (32, False), (32, True)])
+def test_conjugate_gradients(pkg, N, precond):
+    """a 1-D beam-like SPD band matrix (the structure of the reference's fixture tests/sparse/matrices/LF10.mtx): in exact arithmetic CG ends after
+    n steps; at 106 / 424 bits the residual must fall far below double precision and the solution must match the exact rational one"""
+    ctx = pkg.Context(N, 0)
+    orc = get_oracle(N, oracle.DEVICE)
+    n = 24
+    rng = np.random.RandomState(1271)
+    A = np.zeros((n, n))
+    for i in range(n):
+        A[i, i] = 4.0 + rng.randint(0, 8) / 4.0
+        if i + 1 < n:
+            A[i, i + 1] = A[i + 1, i] = -1.0 - rng.randint(0, 4) / 8.0
+        if i + 2 < n:
+            A[i, i + 2] = A[i + 2, i] = 0.25
+    bvec = rng.randint(-8, 9, size=n) / 4.0
+    irp, ja, vals = [0], [], []
+    for i in range(n):
+        for j in range(n):
+            if A[i, j] != 0:
+                ja.append(j); vals.append(A[i, j])
+        irp.append(len(ja))
+    dev = torch.device("cuda", 0)
+    d_irp = torch.as_tensor(np.array(irp, dtype=np.int32), device=dev)
+    d_ja = torch.as_tensor(np.array(ja, dtype=np.int32), device=dev)
+    d_vals = torch.as_tensor(np.array(vals, dtype=np.float64), device=dev)
+    b = ctx.mp_array_init(n)
+    pkg.mp_array_set_d(ctx, b, 0, torch.as_tensor(bvec, device=dev), n)
+    x = ctx.mp_array_init(n)
+    pkg.mp_array_set_d(ctx, x, 0, torch.zeros(n, dtype=torch.float64, device=dev), n)
+    M = torch.as_tensor(1.0 / np.diag(A), device=dev) if precond else None
+    tol = 2.0 ** -(orc.precision - 30)
+    iters, res = pkg.mp_cg_csr(ctx, n, len(ja), d_irp, d_ja, d_vals, b, tol, 3 * n, x, M)
+    assert 0 < iters <= 3 * n and res[-1] <= tol, (iters, res[-3:])
+    # exact solution by rational Gaussian elimination
+    Af = [[Fraction(float(v)) for v in row] for row in A]
+    bf = [Fraction(float(v)) for v in bvec]
+    for c in range(n):
+        piv = Af[c][c]
+        for rr in range(c + 1, n):
+            f = Af[rr][c] / piv
+            if f:
+                Af[rr] = [a - f * p for a, p in zip(Af[rr], Af[c])]
+                bf[rr] -= f * bf[c]
+    sol = [Fraction(0)] * n
+    for c in range(n - 1, -1, -1):
+        sol[c] = (bf[c] - sum(Af[c][j] * sol[j] for j in range(c + 1, n))) / Af[c][c]
+    got = [orc.to_fraction(v) for v in x.device2host()]
+    err = max(abs(g - s) for g, s in zip(got, sol)) / max(abs(s) for s in sol)
+    assert err < Fraction(2) ** -(orc.precision - 40), float(err)
+    ctx.close()
