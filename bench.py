@@ -926,12 +926,15 @@ def main():
                     subs.append({"name": name, "error": repr(e)})
         if env.world > 1:
             sub("config3_B_on_rank0_broadcast_inside_step", lambda: run_gemm(env, DEFAULT_WORKLOAD, 3, 3, want_e2e=False, want_cpu=False, bcast_inside=True))
-        sub("config2_gemm1024_106bit", lambda: run_gemm(env, "gemm1024_106bit", 10, 3, want_e2e=(env.world == 1), want_cpu=False, ref_gpu=True))
-        sub("config2_gemm1024_106bit_full_precision_inputs", lambda: run_gemm(env, "gemm1024_106bit", 5, 3, full_precision=True, want_e2e=False, want_cpu=False, ref_gpu=True))
+        if env.world == 1:       # (configs 2 and 5 are single-GPU configurations: 1024 / 2048 columns leave a rank of 8 only one or two tensor tiles)
+            sub("config2_gemm1024_106bit", lambda: run_gemm(env, "gemm1024_106bit", 10, 3, want_e2e=True, want_cpu=False, ref_gpu=True))
+            sub("config2_gemm1024_106bit_full_precision_inputs", lambda: run_gemm(env, "gemm1024_106bit", 5, 3, full_precision=True, want_e2e=False, want_cpu=False, ref_gpu=True))
+            sub("config3_gemm4096_424bit_full_precision_inputs", lambda: run_gemm(env, DEFAULT_WORKLOAD, 3, 3, full_precision=True, want_e2e=False, want_cpu=False))
         for w in ("gemv16384_212bit", "gemvt16384_212bit", "dot16m_212bit"):
             sub("config4_" + w, lambda w=w: run_vec(env, w, 5, 3, want_e2e=False, want_cpu=False))
         for w in ("gemm2048_106bit", "gemm2048_212bit", "gemm2048_318bit", "gemm2048_424bit", "gemm2048_530bit", "gemm2048_636bit", "gemm2048_742bit", "gemm2048_848bit"):
-            sub("config5_" + w, lambda w=w: run_gemm(env, w, 5, 3, want_e2e=False, want_cpu=False))
+            if env.world == 1:
+                sub("config5_" + w, lambda w=w: run_gemm(env, w, 5, 3, want_e2e=False, want_cpu=False))
     if env.rank == 0:
         if subs:
             line["sub_results"] = subs

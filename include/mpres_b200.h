@@ -72,7 +72,8 @@ typedef void *mpres_stream_t; /* cudaStream_t */
 /* moduli_size selects one of the predefined sets of src/params/32-bit-n-double-moduli/
  * (8, 16, 24, 32, 40, 48, 56, 64 or 128 moduli); constants are uploaded to `device`. */
 int mpres_init(mpres_ctx **ctx, int moduli_size, int device);
-/* any pairwise-coprime odd moduli < 2^31 (what overwriting src/params.h does in the reference) */
+/* any pairwise-coprime odd moduli < 2^31 (what overwriting src/params.h does in the reference); 2 <= moduli_size <= 128 and even
+ * (an odd count would pad the reference's mp_float_t to 4N + 44 bytes: -15), more than 128 moduli: -11 */
 int mpres_init_moduli(mpres_ctx **ctx, const int *moduli, int moduli_size, int device);
 int mpres_finalize(mpres_ctx *ctx);
 

@@ -44,6 +44,7 @@ typedef mpres_collection_t mp_collection_t;
 
 enum mblas_trans_type { mblas_no_trans = 111, mblas_trans = 112, mblas_conj_trans = 113 }; /* src/blas/mblas_enum.cuh:25-29 */
 enum mblas_side_type { mblas_left_side = 141, mblas_right_side = 142 };                    /* src/blas/mblas_enum.cuh:37-40 */
+enum mblas_norm_type { mblas_one_norm = 171, mblas_inf_norm = 175 };                       /* src/blas/mblas_enum.cuh:41-44 */
 
 namespace mpres_compat {
 inline mpres_ctx *&ctx() { static mpres_ctx *c = nullptr; return c; }
@@ -158,6 +159,31 @@ template <int gridDim1, int blockDim1, int gridDim2, int gridDim3, int blockDim3
 void mp_axpy_dot(const int n, mp_array_t &alpha, mp_array_t &w, const int incw, mp_array_t &v, const int incv, mp_array_t &u, const int incu,
                  mp_array_t &r, mp_array_t &buffer) {
     mpres_compat::status() = mpres_axpy_dot(mpres_compat::ctx(), n, &alpha, &w, incw, &v, incv, &u, incu, &r, &buffer, nullptr);
+}
+
+/* src/blas/asum.cuh:40-41, norm.cuh:42-43, genorm.cuh:141-142 */
+template <int gridDim1, int blockDim1>
+void mp_asum(const int n, mp_array_t &x, const int incx, mp_array_t &r) {
+    mpres_compat::status() = mpres_asum(mpres_compat::ctx(), n, &x, incx, &r, nullptr);
+}
+template <int gridDim1, int blockDim1>
+void mp_norm(enum mblas_norm_type norm, const int n, mp_array_t &x, const int incx, mp_array_t &r) {
+    mpres_compat::status() = mpres_norm(mpres_compat::ctx(), norm, n, &x, incx, &r, nullptr);
+}
+template <int gridDim1, int blockDim1>
+void mp_ge_norm(enum mblas_norm_type norm, const int m, const int n, mp_array_t &A, const int lda, mp_array_t &r, mp_array_t &buffer) {
+    mpres_compat::status() = mpres_ge_norm(mpres_compat::ctx(), norm, m, n, &A, lda, &r, &buffer, nullptr);
+}
+
+/* src/sparse/mpmtx/spmv_mpmtx_csr2st.cuh:105-106, spmv_mpmtx_ell2st.cuh:118-119 */
+template <int gridDim1, int blockDim1, int gridDim2, int blockDim3>
+void mp_spmv_mpmtx_csr2st(const int m, const int n, const int nnz, const int *irp, const int *ja, mp_collection_t &as, mp_array_t &x, mp_array_t &y,
+                          mp_collection_t &buffer) {
+    mpres_compat::status() = mpres_spmv_csr2st(mpres_compat::ctx(), m, n, nnz, irp, ja, &as, &x, &y, &buffer, nullptr);
+}
+template <int gridDim1, int blockDim1, int gridDim2, int blockDim3>
+void mp_spmv_mpmtx_ell2st(const int m, const int n, const int maxnzr, const int *ja, mp_collection_t &as, mp_array_t &x, mp_array_t &y, mp_collection_t &buffer) {
+    mpres_compat::status() = mpres_spmv_ell2st(mpres_compat::ctx(), m, n, maxnzr, ja, &as, &x, &y, &buffer, nullptr);
 }
 
 }  // namespace cuda

@@ -449,7 +449,7 @@ inline int gemm_fast_flat(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
         if (pe <= pb) continue;
         SmallPanels pan;
         pan.count = pe - pb; pan.first = (rank + pb) % W; pan.own = rank; pan.epoch = sh->epoch; pan.flags = sh->flags;
-        pan.s8_panel = (long long) nb * m_ps; pan.ring = W; pan.plane_rows = n; pan.slices = 1;
+        pan.s8_panel = (long long) nb * m_ps; pan.ring = W; pan.plane_rows = n; pan.slices = 1; pan.pair = -1;
         for (long long kb = 0; kb < k_p; kb += kSmallKChunk) {
             const int kl = (int) std::min<long long>(kSmallKChunk, k_p - kb);
             if ((rc = launch_small_umma(c, P, (const uint8_t *) pQA, QB, (long long) nb * k_p, (uint8_t *) pS8, m_ps, nb, k_p, kb, kl, kb > 0, sel, pan, st, n))) return rc;
@@ -799,17 +799,24 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
     // ---- stage 2: one u8 GEMM per one-byte modulus, all panels in one persistent launch ----
     SmallPanels pan;
     pan.count = W; pan.first = rank; pan.own = rank; pan.epoch = sh ? sh->epoch : 0u; pan.flags = sh ? sh->flags : nullptr; pan.s8_panel = (long long) s8_panel;
-    pan.ring = 0; pan.plane_rows = 0; pan.slices = slices;
+    pan.ring = 0; pan.plane_rows = 0; pan.slices = slices; pan.pair = -1;
     const uint8_t *PB0 = sh ? (const uint8_t *) (sh->recv + hdr) : own.QB;
     const long long pb_panel = sh ? (long long) sh->pkg_stride : (long long) planes_bytes;
     int gemm_launches = 0;
     auto stage2 = [&]() -> int {
-        const long long chunk = slices > 1 ? (kSmallKChunk / slices) / 128 * 128 : kSmallKChunk;     // pairs x 255^2 x chunk < 2^31
-        for (long long kb = 0; kb < k_p; kb += chunk) {
-            const int kl = (int) std::min<long long>(chunk, k_p - kb);
-            int r2 = launch_small_umma(c, P, (const uint8_t *) pQA, PB0, pb_panel, (uint8_t *) pS8, m_ps, nb_p, k_p, kb, kl, kb > 0, sel, pan, st);
-            if (r2) return r2;
-            gemm_launches += 1;
+        // sliced significands: all slice pairs of a sum in ONE K loop (pairs x 255^2 x chunk < 2^31).  Measured at config 3 with p-bit inputs:
+        // 31.9 ms; one launch per pair index with the launches adding up in S8 (MPRES_SLICE_PASSES=1: two planes per modulus in flight
+        // instead of six) took 56.6 ms -- nine short K loops per tile set expose the epilogue and the pipeline fill nine times
+        const bool passes = slices > 1 && getenv("MPRES_SLICE_PASSES") && atoi(getenv("MPRES_SLICE_PASSES")) != 0;
+        const long long chunk = (slices > 1 && !passes) ? (kSmallKChunk / slices) / 128 * 128 : kSmallKChunk;
+        for (int pr = 0; pr < (passes ? slices : 1); ++pr) {
+            pan.pair = passes ? pr : -1;
+            for (long long kb = 0; kb < k_p; kb += chunk) {
+                const int kl = (int) std::min<long long>(chunk, k_p - kb);
+                int r2 = launch_small_umma(c, P, (const uint8_t *) pQA, PB0, pb_panel, (uint8_t *) pS8, m_ps, nb_p, k_p, kb, kl, kb > 0 || pr > 0, sel, pan, st);
+                if (r2) return r2;
+                gemm_launches += 1;
+            }
         }
         return 0;
     };

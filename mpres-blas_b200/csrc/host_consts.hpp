@@ -94,7 +94,8 @@ struct HostConsts {
 
 // returns 0 on success, negative on unusable moduli
 inline int compute_constants(const int *mods, int N, HostConsts &c) {
-    if (N < 2 || N > kMaxModuli) return -1;
+    if (N < 2 || N > kMaxModuli) return -1;        // (the reference ships sets of up to 160 moduli; this library stops at 128)
+    if (N & 1) return -5;                             // odd N: the reference's mp_float_t is padded to 4N + 44 bytes; only even counts are laid out here
     for (int i = 0; i < N; ++i) {
         if (mods[i] < 3 || (mods[i] & 1) == 0) return -2;  // power-of-two scaling needs odd moduli
         for (int j = 0; j < i; ++j) if (std::__gcd(mods[i], mods[j]) != 1) return -3;

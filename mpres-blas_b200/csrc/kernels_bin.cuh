@@ -488,32 +488,30 @@ __global__ void __launch_bounds__(kBinT) k_bin_norm2(const DevConsts *Cp, BinTab
                 }
                 if (line_ok) {
                     uint8_t *xs = X8 + threadIdx.x;
-                    float sum = 0.f;
-                    for (int j = 0; j < P; ++j) {
-                        const uint4 cj = c4[j];
-                        const unsigned tj = (unsigned) xs[j * kBinT] * cj.z;
-                        const unsigned rj = tj - __umulhi(tj, cj.y) * cj.x;
-                        const unsigned xi = min(rj, rj - cj.x);
-                        sum = fmaf((float) xi, __uint_as_float(cj.w), sum);
-                        xs[j * kBinT] = (uint8_t) xi;
-                    }
-                    const unsigned Rk = (unsigned) __float2int_rn(sum);
+                    // xi_i = x_i (M'/p_i)^-1 mod p_i, the rank R = nearest integer of sum xi_i / p_i, and the column sums of xi_i (M'/p_i) - R M' word by word:
+                    // one pass over the moduli, twelve accumulators (each below 2^46), carries at the end
                     unsigned x[SW];
-                    unsigned long long carry = 0;
+                    {
+                        float sum = 0.f;
+                        unsigned long long cw[SW];
 #pragma unroll
-                    for (int w4 = 0; w4 < SW / 4; ++w4) {
-                        unsigned long long c0 = (unsigned long long) Rk * negmp[4 * w4], c1 = (unsigned long long) Rk * negmp[4 * w4 + 1],
-                                           c2 = (unsigned long long) Rk * negmp[4 * w4 + 2], c3 = (unsigned long long) Rk * negmp[4 * w4 + 3];
+                        for (int w = 0; w < SW; ++w) cw[w] = 0ull;
                         for (int j = 0; j < P; ++j) {
-                            const unsigned long long xi = xs[j * kBinT];
-                            const uint4 mm = mi4[j * (kBinW / 4) + w4];
-                            c0 += xi * mm.x; c1 += xi * mm.y; c2 += xi * mm.z; c3 += xi * mm.w;
+                            const uint4 cj = c4[j];
+                            const unsigned tj = (unsigned) xs[j * kBinT] * cj.z;
+                            const unsigned rj = tj - __umulhi(tj, cj.y) * cj.x;
+                            const unsigned long long xi = min(rj, rj - cj.x);
+                            sum = fmaf((float) (unsigned) xi, __uint_as_float(cj.w), sum);
+#pragma unroll
+                            for (int w4 = 0; w4 < SW / 4; ++w4) {
+                                const uint4 mm = mi4[j * (kBinW / 4) + w4];
+                                cw[4 * w4] += xi * mm.x; cw[4 * w4 + 1] += xi * mm.y; cw[4 * w4 + 2] += xi * mm.z; cw[4 * w4 + 3] += xi * mm.w;
+                            }
                         }
-                        c0 += carry; x[4 * w4] = (unsigned) c0;
-                        c1 += c0 >> 32; x[4 * w4 + 1] = (unsigned) c1;
-                        c2 += c1 >> 32; x[4 * w4 + 2] = (unsigned) c2;
-                        c3 += c2 >> 32; x[4 * w4 + 3] = (unsigned) c3;
-                        carry = c3 >> 32;
+                        const unsigned long long Rk = (unsigned) __float2int_rn(sum);
+                        unsigned long long carry = 0;
+#pragma unroll
+                        for (int w = 0; w < SW; ++w) { cw[w] += carry + Rk * negmp[w]; x[w] = (unsigned) cw[w]; carry = cw[w] >> 32; }
                     }
                     if (BW == SW) {
 #pragma unroll
@@ -704,6 +702,327 @@ __global__ void k_fill_todo(long long *todo, int *todo_count, int m, int nc, con
     if (blockIdx.x == 0 && threadIdx.x == 0) *todo_count = (int) total;
 }
 
+// ---- the same epilogue for the wider formats (N >= 16) -----------------------------------------------------------------------------------
+// k_bin_norm2 keeps every multiword value in registers; from N = 16 on (28-word significands of C, 42-word products, 32-word slice-sum
+// accumulators) that no longer fits: the compiler spilled 8.5 KB per thread and the kernel took 127 of 193 ms at 4096^3 / 424 bit.  Here
+// the long values live in a per-thread column of shared memory (word w of thread t at [w][t]: conflict-free), walked by short run-time
+// loops; only the MP_PRECISION-sized values (T, t1, t2, the result) and the 2 PW-word product alpha T stay in registers.
+constexpr int kBin3RA = 2 * kBinBig - 20;        // words of scratch region A (slice-sum accumulator 33, then the product beta C: NWF + PW <= 44, then a)
+constexpr int kBin3RB = 32;                     // region B: C in binary [NWF <= 28] (the xi_q overwrite the entry's staged digits); then b
+template <int NQ, int PW, int NWF>
+__global__ void __launch_bounds__(kBinT, 3) k_bin_norm3(const DevConsts *Cp, BinTabs T, int m, int n, const uint8_t *S8, long long m_ps, long long n_ps, const int *sel,
+                                                        const OuterInfo *ia, const OuterInfo *ib, SoA Cm, int ldc) {
+    extern __shared__ __align__(16) uint8_t bin_smem[];
+    static_assert(NWF + PW <= kBin3RA && 2 * PW + 2 <= kBin3RA && 2 * PW + 2 <= kBin3RB && NWF <= kBin3RB && kBinBig + 1 <= kBin3RA, "scratch regions");
+    const int P = sel[0];
+    if (P <= 0 || *T.ok == 0) return;
+    const DevConsts &C = *Cp;
+    const SmallDev &SD = *C.small;
+    constexpr int SW = kBinW, BW = kBinBig, AW = 2 * PW + 2;
+    const int slices = max(1, sel[kSelSlices]), ND = 2 * slices - 1;
+    const int width = slices > 1 ? sel[kSelWidth] : 0;
+    uint8_t *X8 = bin_smem;
+    uint4 *mi4 = (uint4 *) (X8 + 56 * kBinT);
+    uint4 *c4 = mi4 + kSmallMax * (kBinW / 4);
+    unsigned *negmp = (unsigned *) (c4 + 64);
+    unsigned *fmi = negmp + kBinW;
+    unsigned *fneg = fmi + NQ * NWF, *fmw = fneg + NWF;
+    unsigned *p32 = fmw + NWF;
+    unsigned *s_al = p32 + PW * NQ, *s_be = s_al + PW;
+    int *cd = (int *) (s_be + PW);
+    unsigned *RA = (unsigned *) (cd + kBinT * (NQ + 1)), *RB = RA + kBin3RA * kBinT;
+    __shared__ int s_meta[8];
+    __shared__ double s_rcpm[NQ];
+    for (int v = threadIdx.x; v < P * (kBinW / 4); v += kBinT) mi4[v] = __ldg((const uint4 *) (SD.bin_mi + (size_t) P * kSmallMax * kBinW) + v);
+    if (threadIdx.x < kBinW) negmp[threadIdx.x] = SD.bin_negmp[P * kBinW + threadIdx.x];
+    if (threadIdx.x < 64) {
+        const int j = threadIdx.x;
+        c4[j] = make_uint4((unsigned) SD.p[j], SD.mu[j], (unsigned) SD.inv[P * 64 + j], __float_as_uint(SD.rcp[j]));
+    }
+    for (int v = threadIdx.x; v < NQ * NWF; v += kBinT) fmi[v] = T.fmi[v];
+    for (int v = threadIdx.x; v < NWF; v += kBinT) { fneg[v] = T.fneg[v]; fmw[v] = T.fmw[v]; }
+    for (int v = threadIdx.x; v < PW * NQ; v += kBinT) { const int w = v / NQ, q = v - w * NQ; p32[v] = (unsigned) C.pow2[(long long) (32 * w) * NQ + q]; }
+    for (int v = threadIdx.x; v < PW; v += kBinT) { s_al[v] = T.scal[0].w[v]; s_be[v] = T.scal[1].w[v]; }
+    for (int v = threadIdx.x; v < NQ; v += kBinT) s_rcpm[v] = 1.0 / (double) C.moduli[v];
+    if (threadIdx.x == 0) {
+        s_meta[0] = T.scal[0].len; s_meta[1] = T.scal[0].exp; s_meta[2] = T.scal[0].sign;
+        s_meta[3] = T.scal[1].len; s_meta[4] = T.scal[1].exp; s_meta[5] = T.scal[1].sign;
+    }
+    const int prec = C.precision;
+    const int tiles = (m + kBinT - 1) / kBinT;
+    const long long total = (long long) tiles * n;
+    const long long plane = n_ps * m_ps;
+    constexpr int CP = NQ + 1;
+    unsigned *ra = RA + threadIdx.x, *rb = RB + threadIdx.x;            // word w at ra[w * kBinT]
+    // helpers on a scratch column
+    auto bitlen_s = [](const unsigned *col, int nw) { int L = 0; for (int w = nw - 1; w >= 0; --w) { const unsigned v = col[w * kBinT]; if (v) { L = 32 * w + 32 - __clz(v); break; } } return L; };
+    // round the magnitude in col (nw words, bit length L < 32 nw) to prec bits, nearest, ties away; the kept bits to out[PW]; returns the bits dropped
+    auto round_s = [&](unsigned *col, int nw, int L, unsigned (&out)[PW]) {
+        int drop = L - prec;
+        if (drop > 0) {
+            unsigned long long cy = 1ull << ((drop - 1) & 31);
+            for (int w = (drop - 1) >> 5; w < nw && cy; ++w) { cy += col[w * kBinT]; col[w * kBinT] = (unsigned) cy; cy >>= 32; }
+        } else {
+            drop = 0;
+        }
+        const int ws = drop >> 5, bs = drop & 31;
+#pragma unroll
+        for (int w = 0; w < PW; ++w) {
+            const unsigned lo = w + ws < nw ? col[(w + ws) * kBinT] : 0u, hi = w + ws + 1 < nw ? col[(w + ws + 1) * kBinT] : 0u;
+            out[w] = __funnelshift_r(lo, hi, bs);
+        }
+        return drop;
+    };
+    // col (nw words, zeroed by the caller) = v << sh, v of PW words
+    auto place_s = [](unsigned *col, int nw, const unsigned (&v)[PW], int sh) {
+        const int ws = sh >> 5, bs = sh & 31;
+#pragma unroll
+        for (int j = 0; j <= PW; ++j) {
+            const unsigned cur = j < PW ? v[j] : 0u, prev = j > 0 ? v[j - 1] : 0u;
+            if (ws + j < nw) col[(ws + j) * kBinT] = __funnelshift_l(prev, cur, bs);
+        }
+    };
+    for (long long tl = blockIdx.x; tl < total; tl += gridDim.x) {
+        const int col = (int) (tl / tiles);
+        const int row0 = (int) (tl - (long long) col * tiles) * kBinT;
+        const int rows_live = min(kBinT, m - row0);
+        __syncthreads();
+        {
+            const uint8_t *src = S8 + (long long) col * m_ps + row0;
+            for (int v = threadIdx.x; v < P * (kBinT / 16); v += kBinT) {
+                const int j = v >> 3, part = v & 7;
+                cp_async16(X8 + j * kBinT + part * 16, src + (long long) j * plane + part * 16);
+            }
+            const int *csrc = Cm.digits + (row0 + (long long) col * ldc) * NQ;
+            for (int v = threadIdx.x; v < rows_live * NQ; v += kBinT) {
+                const unsigned sa = (unsigned) __cvta_generic_to_shared(cd + (v / NQ) * CP + v % NQ);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(csrc + v));
+            }
+            cp_async_commit();
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const int row = row0 + threadIdx.x;
+        OuterInfo ra0 = {}, cb0 = {};
+        bool line_ok = false;
+        if (row < m) { ra0 = ia[row]; cb0 = ib[col]; line_ok = ra0.win >= 0 && cb0.win >= 0 && s_meta[0] > 0; }
+        // ---- the exact sum: S = sum_d S_d 2^(width d) in region A (two's complement, BW words) ----
+        for (int w = 0; w <= BW; ++w) ra[w * kBinT] = 0u;
+        for (int d = 0; d < ND; ++d) {
+            if (d > 0) {
+                __syncthreads();
+                const uint8_t *src = S8 + (long long) col * m_ps + row0;
+                for (int v = threadIdx.x; v < P * (kBinT / 16); v += kBinT) {
+                    const int j = v >> 3, part = v & 7;
+                    cp_async16(X8 + j * kBinT + part * 16, src + (long long) (d * P + j) * plane + part * 16);
+                }
+                cp_async_commit();
+                cp_async_wait<0>();
+                __syncthreads();
+            }
+            if (line_ok) {
+                uint8_t *xs = X8 + threadIdx.x;
+                // xi_i = x_i (M'/p_i)^-1 mod p_i, the rank R = nearest integer of sum xi_i / p_i, and the column sums of xi_i (M'/p_i) - R M' word by word:
+                // one pass over the moduli, twelve accumulators (each below 2^46), carries at the end
+                unsigned x[SW];
+                {
+                    float sum = 0.f;
+                    unsigned long long cw[SW];
+#pragma unroll
+                    for (int w = 0; w < SW; ++w) cw[w] = 0ull;
+                    for (int j = 0; j < P; ++j) {
+                        const uint4 cj = c4[j];
+                        const unsigned tj = (unsigned) xs[j * kBinT] * cj.z;
+                        const unsigned rj = tj - __umulhi(tj, cj.y) * cj.x;
+                        const unsigned long long xi = min(rj, rj - cj.x);
+                        sum = fmaf((float) (unsigned) xi, __uint_as_float(cj.w), sum);
+#pragma unroll
+                        for (int w4 = 0; w4 < SW / 4; ++w4) {
+                            const uint4 mm = mi4[j * (kBinW / 4) + w4];
+                            cw[4 * w4] += xi * mm.x; cw[4 * w4 + 1] += xi * mm.y; cw[4 * w4 + 2] += xi * mm.z; cw[4 * w4 + 3] += xi * mm.w;
+                        }
+                    }
+                    const unsigned long long Rk = (unsigned) __float2int_rn(sum);
+                    unsigned long long carry = 0;
+#pragma unroll
+                    for (int w = 0; w < SW; ++w) { cw[w] += carry + Rk * negmp[w]; x[w] = (unsigned) cw[w]; carry = cw[w] >> 32; }
+                }
+                // S += sign-extended x << (width d), modulo 2^(32 BW)
+                const int sh = d * width, ws = sh >> 5, bs = sh & 31;
+                const unsigned ext = (x[SW - 1] >> 31) ? 0xffffffffu : 0u;
+                unsigned long long cy = 0;
+#pragma unroll
+                for (int j = 0; j <= SW; ++j) {
+                    const unsigned cur = j < SW ? x[j] : ext, prev = j > 0 ? x[j - 1] : 0u;
+                    if (ws + j < BW) { cy += (unsigned long long) ra[(ws + j) * kBinT] + __funnelshift_l(prev, cur, bs); ra[(ws + j) * kBinT] = (unsigned) cy; cy >>= 32; }
+                }
+                for (int w = ws + SW + 1; w < BW; ++w) { cy += (unsigned long long) ra[w * kBinT] + ext; ra[w * kBinT] = (unsigned) cy; cy >>= 32; }
+            }
+        }
+        if (row < m) {
+            const long long ic = row + (long long) col * ldc;
+            int *mycd = cd + threadIdx.x * CP;
+            // ---- t1 = rn(alpha rn(S)) ----
+            unsigned t1[PW];
+            int e1 = 0, s1 = 0, L1 = 0;
+#pragma unroll
+            for (int w = 0; w < PW; ++w) t1[w] = 0u;
+            if (line_ok) {
+                const int sS = (int) (ra[(BW - 1) * kBinT] >> 31);
+                if (sS) {
+                    unsigned long long cy = 1;
+                    for (int w = 0; w < BW; ++w) { cy += (unsigned long long) (~ra[w * kBinT]); ra[w * kBinT] = (unsigned) cy; cy >>= 32; }
+                }
+                const int Ls = bitlen_s(ra, BW);
+                if (Ls > 0) {
+                    unsigned tt[PW], al[PW], pr[2 * PW];
+                    const int dS = round_s(ra, BW + 1, Ls, tt);
+#pragma unroll
+                    for (int w = 0; w < PW; ++w) al[w] = s_al[w];
+                    mw::mul<PW, PW>(tt, al, pr);
+                    const int Lp = mw::bitlen<2 * PW>(pr);
+                    const int d1 = mw::round_to<2 * PW>(pr, Lp, prec);
+#pragma unroll
+                    for (int w = 0; w < PW; ++w) t1[w] = pr[w];
+                    L1 = mw::bitlen<PW>(t1);
+                    e1 = ra0.emin + cb0.emin + dS + s_meta[1] + d1;
+                    s1 = sS ^ s_meta[2];
+                }
+            }
+            // ---- t2 = rn(beta C): C in binary (region B: xi, then the words), the product in region A ----
+            unsigned t2[PW];
+            int e2 = 0, s2 = 0, L2 = 0;
+#pragma unroll
+            for (int w = 0; w < PW; ++w) t2[w] = 0u;
+            if (s_meta[3] > 0 && Cm.eval[ic + Cm.len()].frac != 0) {
+                double sum = 0.0;
+#pragma unroll 4
+                for (int q = 0; q < NQ; ++q) {
+                    const unsigned xi = (unsigned) mulmod(mycd[q], C.part_inverse[q], C.moduli[q], C.barrett[q]);
+                    mycd[q] = (int) xi;                                  // (the digits are not needed again)
+                    sum += (double) xi * s_rcpm[q];
+                }
+                long long Rk = (long long) floor(sum);
+                unsigned *cx = rb;
+                for (int pass = 0; pass < 3; ++pass) {
+                    unsigned long long clo = 0, chi = 0;
+                    for (int w = 0; w < NWF; ++w) {
+                        unsigned long long lo = clo, hi = chi;
+#pragma unroll 4
+                        for (int q = 0; q < NQ; ++q) {
+                            const unsigned long long p = (unsigned long long) (unsigned) mycd[q] * fmi[q * NWF + w];
+                            lo += p; hi += lo < p ? 1ull : 0ull;
+                        }
+                        const unsigned long long p = (unsigned long long) Rk * fneg[w];
+                        lo += p; hi += lo < p ? 1ull : 0ull;
+                        cx[w * kBinT] = (unsigned) lo;
+                        clo = (lo >> 32) | (hi << 32); chi = hi >> 32;
+                    }
+                    int ge = 1;
+                    for (int w = NWF - 1; w >= 0; --w) { const unsigned v = cx[w * kBinT]; if (v != fmw[w]) { ge = v > fmw[w] ? 1 : -1; break; } }
+                    if (ge < 0) break;
+                    if ((int) cx[(NWF - 1) * kBinT] < 0) --Rk; else ++Rk;
+                }
+                const int ncw = (bitlen_s(cx, NWF) + 31) >> 5;
+                unsigned be[PW];
+#pragma unroll
+                for (int w = 0; w < PW; ++w) be[w] = s_be[w];
+                for (int w = 0; w < NWF + PW; ++w) ra[w * kBinT] = 0u;
+                for (int i = 0; i < ncw; ++i) {
+                    const unsigned long long ci = cx[i * kBinT];
+                    unsigned long long cy = 0;
+#pragma unroll
+                    for (int j = 0; j < PW; ++j) {
+                        const unsigned long long t = ci * be[j] + ra[(i + j) * kBinT] + cy;
+                        ra[(i + j) * kBinT] = (unsigned) t;
+                        cy = t >> 32;
+                    }
+                    ra[(i + PW) * kBinT] = (unsigned) cy;
+                }
+                const int Lp = bitlen_s(ra, NWF + PW);
+                if (Lp > 0) {
+                    const int d2 = round_s(ra, NWF + PW, Lp, t2);
+                    L2 = mw::bitlen<PW>(t2);
+                    e2 = Cm.exp[ic] + s_meta[4] + d2;
+                    s2 = (Cm.sign[ic] ^ s_meta[5]) & 1;
+                }
+            }
+            // ---- C = rn(t1 + t2) ----
+            unsigned r[PW];
+            int er = 0, sr = 0, Lr = 0;
+            if (L1 == 0 || (L2 > 0 && (e2 + L2) - (e1 + L1) > prec + 2)) {
+#pragma unroll
+                for (int w = 0; w < PW; ++w) r[w] = t2[w];
+                er = e2; sr = s2; Lr = L2;
+            } else if (L2 == 0 || (e1 + L1) - (e2 + L2) > prec + 2) {
+#pragma unroll
+                for (int w = 0; w < PW; ++w) r[w] = t1[w];
+                er = e1; sr = s1; Lr = L1;
+            } else {
+                const int emin = min(e1, e2);
+                for (int w = 0; w < AW; ++w) { ra[w * kBinT] = 0u; rb[w * kBinT] = 0u; }
+                place_s(ra, AW, t1, e1 - emin);
+                place_s(rb, AW, t2, e2 - emin);
+                if (s1 == s2) {
+                    unsigned long long cy = 0;
+                    for (int w = 0; w < AW; ++w) { cy += (unsigned long long) ra[w * kBinT] + rb[w * kBinT]; ra[w * kBinT] = (unsigned) cy; cy >>= 32; }
+                    sr = s1;
+                } else {
+                    int cm = 0;
+                    for (int w = AW - 1; w >= 0; --w) { const unsigned a = ra[w * kBinT], b = rb[w * kBinT]; if (a != b) { cm = a > b ? 1 : -1; break; } }
+                    long long bw = 0;
+                    for (int w = 0; w < AW; ++w) {
+                        const long long a = ra[w * kBinT], b = rb[w * kBinT];
+                        const long long df = cm >= 0 ? a - b - bw : b - a - bw;
+                        ra[w * kBinT] = (unsigned) df;
+                        bw = df < 0 ? 1 : 0;
+                    }
+                    sr = cm >= 0 ? s1 : s2;
+                }
+                const int La = bitlen_s(ra, AW);
+                const int dr = round_s(ra, AW, La, r);
+                Lr = mw::bitlen<PW>(r);
+                er = emin + dr;
+            }
+            Er lo, up;
+            lo.frac = 0; lo.exp = 0; up.frac = 0; up.exp = 0;
+            if (Lr == 0) {
+                er = 0; sr = 0;
+#pragma unroll 8
+                for (int q = 0; q < NQ; ++q) mycd[q] = 0;
+            } else {
+                bin_eval<PW>(C, r, Lr, lo, up);
+#pragma unroll 2
+                for (int q = 0; q < NQ; ++q) {
+                    unsigned long long acc = 0;
+#pragma unroll
+                    for (int w = 0; w < PW; ++w) {
+                        acc += (unsigned long long) r[w] * p32[w * NQ + q];
+                        if ((w & 7) == 7) acc = (unsigned long long) (unsigned) reduce64(acc, C.moduli[q], C.barrett[q]);
+                    }
+                    mycd[q] = reduce64(acc, C.moduli[q], C.barrett[q]);
+                }
+            }
+            Cm.sign[ic] = sr;
+            Cm.exp[ic] = er;
+            Cm.eval[ic] = lo;
+            Cm.eval[ic + Cm.len()] = up;
+        }
+        __syncthreads();
+        int4 *cd4 = (int4 *) (Cm.digits + (row0 + (long long) col * ldc) * NQ);
+        for (int v = threadIdx.x; v < rows_live * (NQ / 4); v += kBinT) {
+            const int ent = (4 * v) / NQ;
+            const int *src = cd + ent * CP + (4 * v) % NQ;
+            cd4[v] = make_int4(src[0], src[1], src[2], src[3]);
+        }
+    }
+}
+template <int NQ, int PW, int NWF>
+__host__ __device__ inline size_t bin3_smem_bytes() {
+    return (size_t) 56 * kBinT + (size_t) kSmallMax * kBinW * 4 + 64 * 16 + kBinW * 4 + ((size_t) NQ * NWF + 2 * NWF + (size_t) PW * NQ + 2 * PW) * 4 +
+           (size_t) kBinT * (NQ + 1) * 4 + (size_t) (kBin3RA + kBin3RB) * kBinT * 4 + 64;
+}
+
 template <int NQ, int PW, int NWF>
 __host__ __device__ inline size_t bin2_smem_bytes() {
     return (size_t) 56 * kBinT + (size_t) kSmallMax * kBinW * 4 + 64 * 16 + kBinW * 4 + ((size_t) NQ * NWF + 2 * NWF + (size_t) PW * NQ + 2 * PW) * 4 +
@@ -726,6 +1045,18 @@ static inline void bin2_launch(mpres_ctx *c, bool sliced, const mpres::BinTabs &
     }
     if (sliced) mpres::k_bin_norm2<NQ, PW, NWF, mpres::kBinBig><<<gx, mpres::kBinT, sm, st>>>(c->dconsts, T, m, nc, S8s, m_ps, n_ps, sel, IA, IBs, Cg, ldc);
     else mpres::k_bin_norm2<NQ, PW, NWF, mpres::kBinW><<<gx, mpres::kBinT, sm, st>>>(c->dconsts, T, m, nc, S8s, m_ps, n_ps, sel, IA, IBs, Cg, ldc);
+}
+// the shared-memory scratch variant (formats of 16 moduli and more)
+template <int NQ, int PW, int NWF>
+static inline void bin3_launch(mpres_ctx *c, const mpres::BinTabs &T, int m, int nc, const uint8_t *S8s, long long m_ps, long long n_ps,
+                               const int *sel, const mpres::OuterInfo *IA, const mpres::OuterInfo *IBs, mpres::SoA Cg, int ldc, cudaStream_t st) {
+    const size_t sm = mpres::bin3_smem_bytes<NQ, PW, NWF>();
+    if (!(c->attr_bin2 >> (NQ / 8) & 1ull)) {
+        cudaFuncSetAttribute(mpres::k_bin_norm3<NQ, PW, NWF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm);
+        c->attr_bin2 |= 1ull << (NQ / 8);
+    }
+    const unsigned gx = (unsigned) std::min<long long>((long long) ((m + mpres::kBinT - 1) / mpres::kBinT) * nc, (long long) c->sm_count * 3);
+    mpres::k_bin_norm3<NQ, PW, NWF><<<gx, mpres::kBinT, sm, st>>>(c->dconsts, T, m, nc, S8s, m_ps, n_ps, sel, IA, IBs, Cg, ldc);
 }
 
 // the formats the binary epilogue is instantiated for (0: none)
@@ -774,9 +1105,9 @@ inline int bin_norm_segment(mpres_ctx *c, bool first, int m, int nc, const uint8
         const bool sl = slices > 1;
         switch (variant) {
             case 8: bin2_launch<8, 4, 8>(c, sl, T, gx, m, nc, S8s, m_ps, n_ps, sel, IA, IBs, Cg, ldc, st); break;
-            case 16: bin2_launch<16, 7, 15>(c, sl, T, gx, m, nc, S8s, m_ps, n_ps, sel, IA, IBs, Cg, ldc, st); break;
-            case 24: bin2_launch<24, 10, 21>(c, sl, T, gx, m, nc, S8s, m_ps, n_ps, sel, IA, IBs, Cg, ldc, st); break;
-            default: bin2_launch<32, 14, 28>(c, sl, T, gx, m, nc, S8s, m_ps, n_ps, sel, IA, IBs, Cg, ldc, st); break;
+            case 16: bin3_launch<16, 7, 15>(c, T, m, nc, S8s, m_ps, n_ps, sel, IA, IBs, Cg, ldc, st); break;
+            case 24: bin3_launch<24, 10, 21>(c, T, m, nc, S8s, m_ps, n_ps, sel, IA, IBs, Cg, ldc, st); break;
+            default: bin3_launch<32, 14, 28>(c, T, m, nc, S8s, m_ps, n_ps, sel, IA, IBs, Cg, ldc, st); break;
         }
         ++*launches;
     }

@@ -151,6 +151,7 @@ __device__ __forceinline__ void align_small_entry(const int4 (&dg)[(NW + 3) / 4]
     // residues modulo the small moduli, times +-2^shift (the entry's 64-byte row of the table: L1-resident, and L1 is what this kernel
     // lives on -- staging the rows in shared memory shrank it and cost 5x)
     const unsigned *mrow = (const unsigned *) (pws + (size_t) srow * 64);
+    const int nq4 = width > 0 ? (((width + 31) >> 5) + 3) >> 2 : CW / 4;      // word quads that can be non-zero (a slice is short)
     for (int jg = 0; 4 * jg < P; ++jg) {
         const unsigned mult4 = __ldg(mrow + jg);
 #pragma unroll
@@ -159,6 +160,7 @@ __device__ __forceinline__ void align_small_entry(const int4 (&dg)[(NW + 3) / 4]
             unsigned v = 0;
 #pragma unroll
             for (int w4 = 0; w4 < CW / 4; ++w4) {
+                if (w4 >= nq4) break;
                 const uint4 c4 = *(const uint4 *) (s_cw + j * CW + 4 * w4);
                 v = __dp4a(x[4 * w4], c4.x, v);
                 if (4 * w4 + 1 < NW) v = __dp4a(x[4 * w4 + 1], c4.y, v);
@@ -568,6 +570,8 @@ struct SmallPanels {
     int ring;                    // panels of the call (0: count)
     long long plane_rows;        // rows of one S8 plane (0: n_ps -- every panel has its own plane set)
     int slices;                  // > 1: operand planes [slice][P]; sums S_d, d = t + u, into planes [d][P] (K runs over the pairs of d)
+    int pair;                    // >= 0: this launch multiplies only the pair-th slice pair of every d (the launches add up in S8) -- two planes
+                                 // per (d, modulus) in flight instead of 2 npairs: the tiles of a modulus stay in L2
 };
 __device__ __forceinline__ void wait_arrival(const unsigned *flag, unsigned epoch) {
     const long long t0 = clock64();
@@ -645,7 +649,8 @@ k_small_umma_p(const __grid_constant__ CUtensorMap tmJ, const __grid_constant__ 
                     if (pan.flags && pg != pan.own) wait_arrival(pan.flags + pg, pan.epoch);
                     arrived = pg;
                 }
-                const int t0 = max(0, dd - (SL - 1)), t1 = min(dd, SL - 1);      // slice pairs (t, dd - t) of this sum
+                int t0 = max(0, dd - (SL - 1)), t1 = min(dd, SL - 1);      // slice pairs (t, dd - t) of this sum
+                if (pan.pair >= 0) { t0 += pan.pair; if (t0 > t1) continue; t1 = t0; }
                 for (int t = t0; t <= t1; ++t) {
                     const int za = t * P + z, zb = (dd - t) * P + z;
                     for (int it = 0; it < nk; ++it, ++g) {
@@ -668,16 +673,19 @@ k_small_umma_p(const __grid_constant__ CUtensorMap tmJ, const __grid_constant__ 
             constexpr uint32_t idesc = ptx::idesc_u8(kSM, kSN);
             long long g = 0;
             int lt = 0;
-            for (long long tile = blockIdx.x; tile < total; tile += gridDim.x, ++lt) {
-                const int b = NH == 1 ? (lt & 1) : 0, use = NH == 1 ? (lt >> 1) : lt;
-                ptx::mbar_wait(&acc_empty[b], (uint32_t) ((use & 1) ^ 1));   // the epilogue has drained this accumulator
-                ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem + (uint32_t) (b * kSN);
+            for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
                 int nkt = nk;
                 if (SL > 1) {
                     const int dd = (int) ((tile % per_panel) / per_d);
-                    nkt = nk * (min(dd, SL - 1) - max(0, dd - (SL - 1)) + 1);
+                    const int np = min(dd, SL - 1) - max(0, dd - (SL - 1)) + 1;
+                    if (pan.pair >= 0) { if (pan.pair >= np) continue; }
+                    else nkt = nk * np;
                 }
+                const int b = NH == 1 ? (lt & 1) : 0, use = NH == 1 ? (lt >> 1) : lt;
+                ++lt;
+                ptx::mbar_wait(&acc_empty[b], (uint32_t) ((use & 1) ^ 1));   // the epilogue has drained this accumulator
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem + (uint32_t) (b * kSN);
                 for (int it = 0; it < nkt; ++it, ++g) {
                     const int s = (int) (g % kPStages);
                     const uint32_t ph = (uint32_t) (g / kPStages) & 1u;
@@ -705,11 +713,12 @@ k_small_umma_p(const __grid_constant__ CUtensorMap tmJ, const __grid_constant__ 
         const SmallDev &SD = *Cp->small;
         const int quad = warp & 3, half = warp >> 2;
         int lt = 0;
-        for (long long tile = blockIdx.x; tile < total; tile += gridDim.x, ++lt) {
+        for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
             const int pi = (int) (tile / per_panel);
             const long long tp = tile - (long long) pi * per_panel;
             const int pg = (pan.first + pi) % (pan.ring ? pan.ring : pan.count);
             const int dd = (int) (tp / per_d);
+            if (SL > 1 && pan.pair >= 0 && pan.pair >= min(dd, SL - 1) - max(0, dd - (SL - 1)) + 1) continue;
             const long long tq = tp - (long long) dd * per_d;
             const int zm = (int) (tq / per_z), r = (int) (tq - (long long) zm * per_z);
             const int z = dd * P + zm;                                   // output plane
@@ -718,6 +727,7 @@ k_small_umma_p(const __grid_constant__ CUtensorMap tmJ, const __grid_constant__ 
             uint8_t *S8p = S8 + (long long) pg * pan.s8_panel;
             const long long s8_rows = pan.plane_rows ? pan.plane_rows : n_ps;
             const int b = NH == 1 ? (lt & 1) : 0, use = NH == 1 ? (lt >> 1) : lt;
+            ++lt;
             ptx::mbar_wait(&acc_full[b], (uint32_t) (use & 1));
             ptx::tc_fence_after();
 #pragma unroll 1

@@ -44,6 +44,20 @@ int main(int argc, char **argv) {
     cuda::mp_rot<128, 64, 128>(k, dx, 1, dy, 1, dal, dbe, dbuf2, dbuf2);
     cuda::mp_ge_diag_scale<128, 64, 128>(mblas_right_side, m, n, dy, 1, dC, m);     /* n <= k elements of y as the diagonal */
     cuda::mp_ge_lr_scale<128, 64, 128>(m, n, dx, 1, dy, 1, dC, m);
+    cuda::mp_asum<64, 64>(k, dx, 1, dr);                               /* ... and the norms and the two-stage SpMV */
+    cuda::mp_norm<64, 64>(mblas_inf_norm, k, dx, 1, dr);
+    cuda::mp_ge_norm<64, 64>(mblas_one_norm, m, n, dC, m, dr, dbuf2);
+    {
+        mp_collection_t as, cbuf;
+        cuda::mp_collection_init(as, 1); cuda::mp_collection_init(cbuf, 1);
+        cuda::mp_collection_host2device(as, x.data(), 1);
+        int h_irp[2] = {0, 1}, h_ja[1] = {0}, *irp, *ja;
+        cudaMalloc(&irp, sizeof(h_irp)); cudaMalloc(&ja, sizeof(h_ja));
+        cudaMemcpy(irp, h_irp, sizeof(h_irp), cudaMemcpyHostToDevice); cudaMemcpy(ja, h_ja, sizeof(h_ja), cudaMemcpyHostToDevice);
+        cuda::mp_spmv_mpmtx_csr2st<32, 64, 32, 64>(1, 1, 1, irp, ja, as, dx, dr, cbuf);
+        cuda::mp_spmv_mpmtx_ell2st<32, 64, 32, 64>(1, 1, 1, ja, as, dx, dr, cbuf);
+        cuda::mp_collection_clear(as); cuda::mp_collection_clear(cbuf);
+    }
     if (mpres_compat_last_status() != 0) return 9;
     cuda::mp_array_clear(dA); cuda::mp_array_clear(dB); cuda::mp_array_clear(dC);
     printf("MP_PRECISION %d MP_H %d\n", MP_PRECISION, MP_H);

@@ -22,3 +22,20 @@ for r in rows[2:]:
     print('---')
     for i in idx:
         print('%-85s %-12s %s' % (hdr[i], units[i], r[i][:110]))
+
+# --json <workload> <out.json>: per kernel (first captured launch) the DRAM bytes and the time, for bench.py's roofline.traffic
+if len(sys.argv) >= 5 and sys.argv[2] == '--json':
+    import json
+    import re
+    col = {w: hdr.index(w) for w in ('Kernel Name', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__time_duration.sum') if w in hdr}
+    scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+    kernels = {}
+    for r in rows[2:]:
+        name = re.split(r'[<(]', r[col['Kernel Name']])[0]
+        if name in kernels:
+            continue
+        rd = float(r[col['dram__bytes_read.sum']].replace(',', '')) * scale.get(units[col['dram__bytes_read.sum']], 1.0)
+        wr = float(r[col['dram__bytes_write.sum']].replace(',', '')) * scale.get(units[col['dram__bytes_write.sum']], 1.0)
+        kernels[name] = {'dram_bytes_read': rd, 'dram_bytes_write': wr, 'gpu_time': r[col['gpu__time_duration.sum']] + ' ' + units[col['gpu__time_duration.sum']]}
+    json.dump({'workload': sys.argv[3], 'source': 'ncu --set full --clock-control none, first captured launch of every kernel (tools/gpu_final.sh)', 'kernels': kernels},
+              open(sys.argv[4], 'w'), indent=1)
