@@ -720,10 +720,15 @@ def run_gemm(env, workload, steps, warmup, full_precision=False, want_e2e=True, 
         env.barrier()
         dt = env.max_over_ranks((time.perf_counter() - t0) / e2e_steps)
         b_up = k * n // world if split_b else k * n
-        h2d = (mr * k + b_up + mr * n + 2) * rs
+        # what crossed the PCIe link: mpres_gemm_host cuts the records of A (and of B when it uploads B) down to the fields the fast path reads
+        lean = ctx.last_host_upload_residues() if args.e2e_path == "pipelined" else 0
+        ls = (4 * lean + 24) if lean > 0 else rs
+        h2d = mr * k * ls + b_up * (rs if split_b else ls) + (mr * n + 2) * rs
         d2h = mr * n * rs
         e2e = {"value": 2.0 * m * n * k / dt / 1e9, "unit": "MP-GFLOP/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
-               "ms_per_step": dt * 1e3, "steps": e2e_steps,
+               "ms_per_step": dt * 1e3, "steps": e2e_steps, "operand_residues_uploaded": lean if lean > 0 else N,
+               "host_pack": ("A and B cross the link as %d-byte records (first %d residues, sign, exponent, upper interval bound of the %d-byte mp_float_t), cut down by the "
+                             "host cores inside the call; C travels in full both ways" % (ls, lean, rs)) if lean > 0 else "full records",
                "path": ("per rank: mpres_array_host2device(1/N of B) + all-gather of B over NVLink + mpres_gemm_host_bdev(alpha, A_r, B, beta, C_r -> out_r), pinned host AoS mp_float_t[]"
                         if split_b else
                         "mpres_gemm_host(alpha, A, B, beta, C -> out): pinned host AoS mp_float_t[], PCIe transfers pipelined with the compute by column panels"

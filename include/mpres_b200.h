@@ -260,6 +260,11 @@ int mpres_gemm_host(mpres_ctx *ctx, int transa, int transb, int m, int n, int k,
 /* mpres_gemm_host with B already resident on the device (an mp_array_t: e.g. each rank of a row-sharded multi-GPU GEMM uploads 1/N of B
  * and gathers the rest over NVLink instead of pulling all of B through its own PCIe link).  B must be complete before the call (the
  * transfers run on the library's own streams: synchronise the stream that produced B first).  Panels also apply to transposed B. */
+/* Residues per entry of A / B the last mpres_gemm_host[_bdev] call moved to the device: the host cores cut the operand records down to what the
+ * fast path reads (first n_in residues, sign, exponent, upper interval bound: 4 n_in + 24 of 4N + 40 bytes) before they cross the PCIe link; the
+ * count is guessed from a sample, checked against every record while packing and against the call's own choice on the device, and anything that does
+ * not fit goes up in full.  0: full records (reference-order mode, formats without the one-byte base, MPRES_HOST_LEAN=0, or a fallback). */
+int mpres_last_host_upload_residues(const mpres_ctx *ctx);
 int mpres_gemm_host_bdev(mpres_ctx *ctx, int transa, int transb, int m, int n, int k, const void *alpha, const void *A, int lda, const mpres_array_t *B,
                          int ldb, const void *beta, const void *Cin, void *Cout, int ldc, int panels);
 

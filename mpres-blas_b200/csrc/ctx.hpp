@@ -88,6 +88,10 @@ struct mpres_ctx {
     cudaEvent_t ev[6] = {nullptr};
     bool ev_valid = false;
     int last_stage2_launches = 0;
+    void *lean_host = nullptr;           // pinned host slots of the lean uploads of mpres_gemm_host
+    int last_host_lean = 0;              // residues per entry the last mpres_gemm_host uploaded of A / B (0: full records)
+    bool last_fast_ok = false;           // the last fast mp_gemm ran on the one-byte base without the limb planes or the reference-order fallback
+    int last_nin = 0;                    // ... reading this many residues per operand entry
     bool last_binary = false;            // the last fast mp_gemm rounded its exact sums in binary (kernels_bin.cuh: full-precision inputs)
     // opt-in shared-memory sizes (cudaFuncSetAttribute) are per device: remembered per context, not per process
     bool attr_bin = false, attr_ext = false, attr_fast = false, attr_align_mma = false, attr_align = false, attr_small = false, attr_umma = false;

@@ -353,6 +353,8 @@ inline int gemm_fast_flat(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
     if (c->h_sel[1]) return -50;                                  // a rank did not reach the call
     const bool binary = P > 0 && c->h_sel[5] > c->hc.log2M - 2;
     c->last_binary = binary;
+    c->last_fast_ok = P > 0;
+    c->last_nin = c->h_sel[3];
     prof_mark(c, st, "k_choose_base");
     if (P <= 0) {
         rc = gemm_fast_limb(c, ta, tb, m, n, k, A, lda, B, ldb, alpha, beta, Cm, ldc, st, IA);
@@ -671,6 +673,8 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
     // stage 3 rebuilds them in binary and rounds once (kernels_bin.cuh); the (min,+) exponent product is not needed then
     const bool binary = P > 0 && c->h_sel[5] > c->hc.log2M - 2;
     c->last_binary = binary;
+    c->last_fast_ok = P > 0;
+    c->last_nin = c->h_sel[3];
     if (sh && c->h_sel[1]) return -50;                       // a rank did not reach the call
     prof_mark(c, st, "k_choose_base");
     (void) nin;

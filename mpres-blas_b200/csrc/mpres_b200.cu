@@ -12,7 +12,9 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <cmath>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "ctx.hpp"
@@ -23,6 +25,34 @@
 #define NEED_DEVICE(c) do { if ((c) && (c)->device < 0) return -100; } while (0)
 
 static_assert(sizeof(mpres_er_float_t) == 16 && sizeof(Er) == 16, "er_float_t layout (src/types.cuh:46-49)");
+
+// host-side helpers of the lean upload (mpres_gemm_host): templates cannot live inside the extern "C" block
+namespace {
+struct BoundKey { long long e; unsigned long long m; };       // largest upper interval bound seen: (exponent incl. the double's, mantissa bits)
+inline void bound_key_update(BoundKey &k, double frac, long long ex) {
+    if (frac == 0) return;
+    unsigned long long fb;
+    const double a = frac < 0 ? -frac : frac;
+    memcpy(&fb, &a, 8);
+    const long long ue = (ex > 100000 ? 100000 : (ex < -100000 ? -100000 : ex)) + (long long) (fb >> 52);
+    const unsigned long long fm = fb & 0xfffffffffffffull;
+    if (ue > k.e || (ue == k.e && fm > k.m)) { k.e = ue; k.m = fm; }
+}
+template <int W>
+void pack_lean_range(const unsigned long long *src, size_t rw, size_t Nw, size_t b, size_t e, unsigned long long *dst, BoundKey &k) {
+    for (size_t i = b; i < e; ++i) {
+        const unsigned long long *r = src + i * rw;
+        unsigned long long *o = dst + i * (W + 3);
+        for (int w = 0; w < W; ++w) o[w] = r[w];
+        o[W] = r[Nw];                                  // sign, exponent
+        const unsigned long long fr = r[Nw + 3], ex = r[Nw + 4];
+        o[W + 1] = fr; o[W + 2] = ex;                  // eval[1]
+        double f; long long x;
+        memcpy(&f, &fr, 8); memcpy(&x, &ex, 8);
+        bound_key_update(k, f, x);
+    }
+}
+}  // namespace
 
 extern "C" {
 
@@ -152,6 +182,7 @@ int mpres_finalize(mpres_ctx *c) {
     for (cudaEvent_t e : c->prof_ev) if (e) cudaEventDestroy(e);
     for (int i = 0; i < 6; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     if (c->h_sel) cudaFreeHost(c->h_sel);
+    if (c->lean_host) cudaFreeHost(c->lean_host);
     cudaFree(c->d_pow2); cudaFree(c->d_inv_pow2); cudaFree(c->d_mrc); cudaFree(c->d_prefix); cudaFree(c->d_ext_w); cudaFree(c->d_ext_t); cudaFree(c->d_wpow2); cudaFree(c->d_spow2); cudaFree(c->dconsts); cudaFree(c->d_counter);
     delete c;
     return 0;
@@ -201,6 +232,7 @@ int mpres_last_small_base(mpres_ctx *c, int *moduli, int *input_moduli) {
     if (input_moduli) *input_moduli = v[1];
     return 0;
 }
+int mpres_last_host_upload_residues(const mpres_ctx *c) { return c ? c->last_host_lean : -1; }
 int mpres_last_binary_rounding(const mpres_ctx *c) { return c ? (c->last_binary ? 1 : 0) : -1; }
 int mpres_small_modulus(const mpres_ctx *c, int index) {
     if (!c || !c->sc.usable || index < 0 || index >= kSmallMax) return 0;
@@ -380,6 +412,20 @@ __global__ void k_aos_to_soa(int N, const char *recs, long long n, int *digits, 
         }
     }
 }
+// lean records (what the fast mp_gemm path reads of an operand entry): nin residues | sign | exponent | upper interval bound
+__global__ void k_lean_to_soa(int N, int nin, const char *recs, long long n, int *digits, int *sign, int *exp, Er *eval, long long len) {
+    const long long ls = 4ll * nin + 24;
+    const int F = nin + 4;                      // work items per record: residues, sign, exponent, two words of the bound
+    for (long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x; t < n * F; t += (long long) gridDim.x * blockDim.x) {
+        const long long i = t / F;
+        const int f = (int) (t % F);
+        const char *p = recs + i * ls;
+        if (f < nin) digits[i * N + f] = ((const int *) p)[f];
+        else if (f == nin) sign[i] = ((const int *) p)[nin];
+        else if (f == nin + 1) exp[i] = ((const int *) p)[nin + 1];
+        else ((long long *) (eval + i + len))[f - nin - 2] = ((const long long *) (p + 4 * nin + 8))[f - nin - 2];
+    }
+}
 __global__ void k_soa_to_aos(int N, char *recs, long long n, const int *digits, const int *sign, const int *exp, const Er *eval, long long len) {
     const long long rs = 4ll * N + 40;
     for (long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x; t < n * (N + 6); t += (long long) gridDim.x * blockDim.x) {
@@ -521,6 +567,8 @@ static int gemm_impl(mpres_ctx *c, int transa, int transb, int m, int n, int k, 
     if (rc) return rc;
     c->last_stream = st;
     c->last_binary = false;
+    c->last_fast_ok = false;
+    c->last_nin = 0;
     const int N = c->hc.N;
     CUDA_TRY(cudaMemsetAsync(c->d_counter, 0, kCounterInts * sizeof(int), st));
 
@@ -578,6 +626,7 @@ struct HostPipe {
     mpres_ctx *c;
     size_t rs, chunk;           // record size, records per staging chunk
     char *up_stage;             // kHostRing chunks
+    char *lean_host = nullptr;  // pinned host slots (kHostRing x 64 MiB) the lean records are packed into
     int seq = 0;
     cudaStream_t s_up, s_unp, s_comp, s_down;
 };
@@ -604,6 +653,113 @@ int host_upload(HostPipe &hp, const void *host, size_t off, size_t cnt, const So
         off += now; cnt -= now;
     }
     return 0;
+}
+
+// ---- lean upload of A and B ------------------------------------------------------------------------------------------------------
+// The fast path reads of an operand entry its first n_in residues, sign, exponent and upper interval bound: 40 of the 168 bytes of a
+// 424-bit record with the reference's benchmark inputs.  The host cores cut the records down (16 threads: 117 GB/s of source records on
+// the GPU box, tools/host_pack_bench.cpp), so the PCIe link carries 4.2 instead of 8.5 GB per step at config 3.  n_in is guessed from a
+// sample of the interval bounds, the packing pass sees every bound and reports the largest; gemm_impl's own choice is checked after every
+// panel (HostPipe::lean_*), and whatever does not fit is uploaded in full.
+// residues an entry with this bound needs (the rule of k_outer_info / k_choose_base, with one unit of slack), kSmallNinMax + 1 if more than the tables hold
+int nin_for_bound(const mpres_ctx *c, const BoundKey &k) {
+    if (k.e == LLONG_MIN) return 1;
+    double mant;
+    const unsigned long long mb = k.m | 0x3ff0000000000000ull;
+    memcpy(&mant, &mb, 8);
+    const double lx = (double) (k.e - 1023) + std::log2(mant);
+    const double b = (lx + c->sc.log2M_up) * 1024.0;
+    const long long xb = b > 1.0e8 ? 100000000 : (b < 0 ? 0 : (long long) std::ceil(b) + 4);
+    const int cmax = std::min(kSmallNinMax, c->hc.N - 1);
+    for (int q = 1; q <= cmax; ++q)
+        if (c->sc.in_log2_milli[q] >= xb) return q;
+    return kSmallNinMax + 1;
+}
+int host_threads() {
+    static int t = 0;
+    if (t == 0) {
+        const char *env = getenv("MPRES_HOST_THREADS");
+        t = env ? atoi(env) : (int) std::thread::hardware_concurrency();
+        t = std::max(1, std::min(t, 64));
+    }
+    return t;
+}
+// records [0, cnt) at src (rs bytes each) -> lean records at dst; returns the largest bound.  nin even: everything moves as 8-byte words
+// (records are 4N + 40 bytes with N even).
+BoundKey pack_lean(const char *src, size_t cnt, int N, int nin, char *dst) {
+    const size_t rw = (4 * (size_t) N + 40) / 8, Nw = (size_t) N / 2;
+    const int T = (int) std::min<size_t>((size_t) host_threads(), std::max<size_t>(1, cnt / 4096));
+    std::vector<BoundKey> keys((size_t) T, BoundKey{LLONG_MIN, 0ull});
+    auto work = [&](int t) {
+        BoundKey k{LLONG_MIN, 0ull};
+        const size_t b = cnt * (size_t) t / T, e = cnt * (size_t) (t + 1) / T;
+        const unsigned long long *s8 = (const unsigned long long *) src;
+        unsigned long long *d8 = (unsigned long long *) dst;
+        switch (nin / 2) {
+            case 1: pack_lean_range<1>(s8, rw, Nw, b, e, d8, k); break;
+            case 2: pack_lean_range<2>(s8, rw, Nw, b, e, d8, k); break;
+            case 3: pack_lean_range<3>(s8, rw, Nw, b, e, d8, k); break;
+            case 4: pack_lean_range<4>(s8, rw, Nw, b, e, d8, k); break;
+            case 5: pack_lean_range<5>(s8, rw, Nw, b, e, d8, k); break;
+            case 6: pack_lean_range<6>(s8, rw, Nw, b, e, d8, k); break;
+            case 7: pack_lean_range<7>(s8, rw, Nw, b, e, d8, k); break;
+            default: pack_lean_range<8>(s8, rw, Nw, b, e, d8, k); break;
+        }
+        keys[(size_t) t] = k;
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto &x : th) x.join();
+    BoundKey k{LLONG_MIN, 0ull};
+    for (const BoundKey &q : keys) if (q.e > k.e || (q.e == k.e && q.m > k.m)) k = q;
+    return k;
+}
+// records [off, off + cnt) of a host AoS array into the same positions of a device SoA, as lean records with nin residues.  *need = residues
+// the largest entry requires (> nin: the caller has to upload this range in full)
+int host_upload_lean(HostPipe &hp, const void *host, size_t off, size_t cnt, const SoA &dst, int nin, int *need) {
+    mpres_ctx *c = hp.c;
+    const int N = c->hc.N;
+    const size_t ls = 4 * (size_t) nin + 24;
+    const size_t chunk = std::max<size_t>(1, std::min(hp.chunk * hp.rs, (size_t) 64 << 20) / ls);   // records per staging slot (device: hp.chunk records of hp.rs bytes; host: 64 MiB)
+    BoundKey key{LLONG_MIN, 0ull};
+    while (cnt) {
+        const size_t now = std::min(cnt, chunk);
+        const int slot = hp.seq % kHostRing;
+        cudaEvent_t done = c->hev[slot], freed = c->hev[kHostRing + slot], hfree = c->hev[10 + slot];
+        char *hstage = hp.lean_host + (size_t) slot * ((size_t) 64 << 20);
+        char *stage = hp.up_stage + (size_t) slot * hp.chunk * hp.rs;
+        CUDA_TRY(cudaEventSynchronize(hfree));                                   // the copy that last read this host slot has finished
+        const BoundKey k2 = pack_lean((const char *) host + off * hp.rs, now, N, nin, hstage);
+        if (k2.e > key.e || (k2.e == key.e && k2.m > key.m)) key = k2;
+        CUDA_TRY(cudaStreamWaitEvent(hp.s_up, freed, 0));
+        CUDA_TRY(cudaMemcpyAsync(stage, hstage, now * ls, cudaMemcpyHostToDevice, hp.s_up));
+        CUDA_TRY(cudaEventRecord(done, hp.s_up));
+        CUDA_TRY(cudaEventRecord(hfree, hp.s_up));
+        CUDA_TRY(cudaStreamWaitEvent(hp.s_unp, done, 0));
+        k_lean_to_soa<<<c->sm_count * 4, 256, 0, hp.s_unp>>>(N, nin, stage, (long long) now, dst.digits + off * N, dst.sign + off, dst.exp + off, dst.eval + off,
+                                                             dst.len_val);
+        LAUNCHED(c);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaEventRecord(freed, hp.s_unp));
+        ++hp.seq;
+        off += now; cnt -= now;
+    }
+    *need = nin_for_bound(c, key);
+    return 0;
+}
+// n_in guessed from up to 4096 records spread over an operand
+int sample_nin(const mpres_ctx *c, const void *host, size_t cnt) {
+    const size_t rs = 4 * (size_t) c->hc.N + 40;
+    BoundKey k{LLONG_MIN, 0ull};
+    const size_t step = std::max<size_t>(1, cnt / 4096);
+    for (size_t i = 0; i < cnt; i += step) {
+        const char *r = (const char *) host + i * rs;
+        double fr; long long ex;
+        memcpy(&fr, r + 4 * c->hc.N + 24, 8); memcpy(&ex, r + 4 * c->hc.N + 32, 8);
+        bound_key_update(k, fr, ex);
+    }
+    return nin_for_bound(c, k);
 }
 
 SoA soa_offset(const SoA &a, size_t off, int N) {
@@ -663,21 +819,98 @@ static int gemm_host_impl(mpres_ctx *c, int transa, int transb, int m, int n, in
     char *down_stage = (char *) p;
     cudaEvent_t ev_ready = c->hev[6], ev_packed = c->hev[7], ev_dfree[2] = {c->hev[8], c->hev[9]};
 
+    // lean upload of A and B (see host_upload_lean): only in the fast modes, on formats with the one-byte base
+    int lean_nin = 0;                    // residues the lean uploads carry (0: everything goes up in full)
+    bool A_full = true;
+    const bool dbg = getenv("MPRES_DEBUG_LEAN") != nullptr;
+    {
+        const char *env = getenv("MPRES_HOST_LEAN");
+        const char *envmin = getenv("MPRES_HOST_LEAN_MIN");                   // smallest operand (entries) worth the packing threads
+        const bool want = c->mode != MPRES_MODE_REFERENCE_ORDER && c->sc.usable && c->stage2 == MPRES_STAGE2_SMALL && (!env || atoi(env) != 0) &&
+                          (size_t) m * k >= (size_t) (envmin ? atoll(envmin) : 65536);
+        if (want) {
+            lean_nin = sample_nin(c, A, extA);
+            if (!Bd) lean_nin = std::max(lean_nin, sample_nin(c, B, extB));
+            lean_nin = (lean_nin + 1) & ~1;                                                         // whole 8-byte words per record
+            if (lean_nin > kSmallNinMax || 4 * lean_nin + 24 > (int) hp.rs / 2) lean_nin = 0;      // no gain
+        }
+        if (lean_nin) {
+            if (!c->lean_host) {
+                if (cudaHostAlloc(&c->lean_host, (size_t) kHostRing * ((size_t) 64 << 20), cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); c->lean_host = nullptr; lean_nin = 0; }
+                else for (int i = 0; i < kHostRing; ++i) CUDA_TRY(cudaEventRecord(c->hev[10 + i], hp.s_up));
+            }
+            hp.lean_host = (char *) c->lean_host;
+        }
+    }
+    c->last_host_lean = 0;
     if ((rc = host_upload(hp, alpha, 0, 1, dS))) return rc;
     { SoA b1 = soa_offset(dS, 1, N); if ((rc = host_upload(hp, beta, 0, 1, b1))) return rc; }
-    if ((rc = host_upload(hp, A, 0, extA, dA))) return rc;
-    if (tb && !Bd && (rc = host_upload(hp, B, 0, extB, dB))) return rc;
+    if (lean_nin) {
+        int need = 0;
+        if ((rc = host_upload_lean(hp, A, 0, extA, dA, lean_nin, &need))) return rc;
+        if (dbg) fprintf(stderr, "[mpres lean] sample says %d residues, A needs %d\n", lean_nin, need);
+        A_full = false;
+        if (need > lean_nin) { if ((rc = host_upload(hp, A, 0, extA, dA))) return rc; A_full = true; }      // the sample missed the largest entries
+    } else if ((rc = host_upload(hp, A, 0, extA, dA))) return rc;
+    bool B_lean_ok = true;               // the panels of B uploaded so far fit lean_nin
+    auto upload_B = [&](size_t off, size_t cnt) -> int {
+        if (!lean_nin) return host_upload(hp, B, off, cnt, dB);
+        int need = 0, e = host_upload_lean(hp, B, off, cnt, dB, lean_nin, &need);
+        if (e) return e;
+        if (dbg) fprintf(stderr, "[mpres lean] B range %zu + %zu: needs %d residues (lean %d)\n", off, cnt, need, lean_nin);
+        if (need > lean_nin) {
+            B_lean_ok = false;
+            if ((e = host_upload(hp, B, off, cnt, dB))) return e;
+            if (!A_full) { if ((e = host_upload(hp, A, 0, extA, dA))) return e; A_full = true; }           // the call will read more residues of A too
+            lean_nin = 0;                                                                                   // (no further attempts in this call)
+        }
+        return 0;
+    };
+    if (tb && !Bd && (rc = upload_B(0, extB))) return rc;
+    cudaEvent_t ev_in[2] = {ev_ready, c->hev[13]};
+    // the inputs of panel j: C first (its copy runs while the host cores pack the panel of B), then B
+    auto issue_inputs = [&](int j) -> int {
+        const int j0 = j * wcols, nj = std::min(wcols, n - j0);
+        const size_t coff = (size_t) ldc * j0, ccnt = (size_t) ldc * (nj - 1) + m;
+        int e = host_upload(hp, Cin, coff, ccnt, dC);
+        if (e) return e;
+        if (!tb && !Bd && (e = upload_B((size_t) ldb * j0, (size_t) ldb * (nj - 1) + k))) return e;
+        CUDA_TRY(cudaEventRecord(ev_in[j & 1], hp.s_unp));
+        return 0;
+    };
+    if ((rc = issue_inputs(0))) return rc;
     for (int j = 0; j < np; ++j) {
         const int j0 = j * wcols, nj = std::min(wcols, n - j0);
-        if (!tb && !Bd && (rc = host_upload(hp, B, (size_t) ldb * j0, (size_t) ldb * (nj - 1) + k, dB))) return rc;
+        const size_t boff = (size_t) ldb * j0;
         const size_t coff = (size_t) ldc * j0, ccnt = (size_t) ldc * (nj - 1) + m;
-        if ((rc = host_upload(hp, Cin, coff, ccnt, dC))) return rc;
-        CUDA_TRY(cudaEventRecord(ev_ready, hp.s_unp));
-        CUDA_TRY(cudaStreamWaitEvent(hp.s_comp, ev_ready, 0));
+        // one panel ahead: the next panel's inputs travel (and are packed) while this one is multiplied -- gemm_impl waits on the host for its
+        // base choice, which would otherwise leave the link idle
+        if (j + 1 < np && (rc = issue_inputs(j + 1))) return rc;
+        CUDA_TRY(cudaStreamWaitEvent(hp.s_comp, ev_in[j & 1], 0));
         // panel j of op(B): columns j0.. of a k x n matrix, or rows j0.. of an n x k one (whole B when it was uploaded in one piece)
         rc = gemm_impl(c, transa, transb, m, nj, k, dS, dA, lda, soa_offset(dB, tb ? (size_t) j0 : (size_t) ldb * j0, N), ldb, soa_offset(dS, 1, N),
                        soa_offset(dC, coff, N), ldc, nullptr, hp.s_comp);
         if (rc) { cudaDeviceSynchronize(); return rc; }
+        if (lean_nin && (!A_full || (!Bd && B_lean_ok))) {
+            // the call chose its base and its residue count on the device (gemm_impl read them back): anything but the one-byte base with at
+            // most lean_nin residues has read fields that were never uploaded -- upload everything that is still to be used and run the panel
+            // again (C from the host: its results have not been downloaded yet)
+            const bool ok = c->last_fast_ok && c->last_nin > 0 && c->last_nin <= lean_nin;
+            if (dbg) fprintf(stderr, "[mpres lean] panel %d: the call read %d residues on the one-byte base %s\n", j, c->last_nin, c->last_fast_ok ? "(ok)" : "(NOT chosen)");
+            if (!ok) {
+                if (!A_full) { if ((rc = host_upload(hp, A, 0, extA, dA))) return rc; A_full = true; }
+                if (!Bd) { if ((rc = host_upload(hp, B, tb ? 0 : boff, tb ? extB : extB - boff, dB))) return rc; }       // this panel and all later ones
+                if ((rc = host_upload(hp, Cin, coff, ccnt, dC))) return rc;
+                lean_nin = 0;
+                CUDA_TRY(cudaEventRecord(ev_in[j & 1], hp.s_unp));
+                CUDA_TRY(cudaStreamWaitEvent(hp.s_comp, ev_in[j & 1], 0));
+                rc = gemm_impl(c, transa, transb, m, nj, k, dS, dA, lda, soa_offset(dB, tb ? (size_t) j0 : (size_t) ldb * j0, N), ldb, soa_offset(dS, 1, N),
+                               soa_offset(dC, coff, N), ldc, nullptr, hp.s_comp);
+                if (rc) { cudaDeviceSynchronize(); return rc; }
+            } else {
+                c->last_host_lean = lean_nin;
+            }
+        }
         char *stage = down_stage + (size_t) (j & 1) * panel_recs * hp.rs;
         CUDA_TRY(cudaStreamWaitEvent(hp.s_comp, ev_dfree[j & 1], 0));
         k_soa_to_aos<<<c->sm_count * 4, 256, 0, hp.s_comp>>>(N, stage, (long long) ccnt, dC.digits + coff * N, dC.sign + coff, dC.exp + coff, dC.eval + coff,
