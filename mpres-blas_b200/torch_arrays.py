@@ -47,6 +47,8 @@ class TorchMpArray:
         """`count` host records into elements offset .. offset + count (a shifted view of the same arrays; `len` still gives the
         offset of the upper interval bounds)"""
         n = self.ctx.N
+        if offset < 0 or count < 0 or offset + count > max(1, self.size):
+            raise ValueError("records %d .. %d do not fit an array of %d" % (offset, offset + count, self.size))
         v = mp_array_t(self.digits.data_ptr() + 4 * n * offset, self.sign.data_ptr() + 4 * offset, self.exp.data_ptr() + 4 * offset,
                        self.eval.data_ptr() + 16 * offset, None, self.len.data_ptr())
         _check(self.ctx.lib.mpres_array_host2device(self.ctx.h, ctypes.byref(v), ctypes.c_void_p(ptr), ctypes.c_size_t(count)),
