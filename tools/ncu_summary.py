@@ -31,7 +31,7 @@ if len(sys.argv) >= 5 and sys.argv[2] == '--json':
     scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
     kernels = {}
     for r in rows[2:]:
-        name = re.split(r'[<(]', r[col['Kernel Name']])[0]
+        name = re.split(r'[<(]', r[col['Kernel Name']])[0].replace('void ', '').strip()
         if name in kernels:
             continue
         rd = float(r[col['dram__bytes_read.sum']].replace(',', '')) * scale.get(units[col['dram__bytes_read.sum']], 1.0)
