@@ -115,6 +115,15 @@ int mpres_last_small_base(mpres_ctx *ctx, int *moduli, int *input_moduli);
  * the number format but not the one-byte base; results then agree with the reference within its error model, src/arith/mul.cuh:108-110
  * rounds every product instead), 0 when it ran in the bit-exact window, < 0 on error. */
 int mpres_last_binary_rounding(const mpres_ctx *ctx);
+/* Workspace budget.  The fast mp_gemm keeps its planes (one-byte residues of A', B' and of the sums, shift planes, lists) in a per-context
+ * pool that grows on demand: about (P + 2) k (m + n) + (P + 4 N + 10) m n bytes for P one-byte moduli, against the m x n scratch matrix the
+ * reference needs (src/blas/gemm.cuh:98-139).  mpres_set_workspace_limit caps the pool (0 = no cap): a call whose reservation would
+ * exceed the cap -- or that the device cannot satisfy -- is served in reference order instead (same results as MPRES_MODE_REFERENCE_ORDER,
+ * one m x n scratch matrix) and counted by mpres_workspace_fallbacks; a sharded call returns cudaErrorMemoryAllocation (2) instead,
+ * because its peers wait for this rank's planes.  mpres_workspace_bytes = bytes the pool holds now. */
+int mpres_set_workspace_limit(mpres_ctx *ctx, size_t bytes);
+long mpres_workspace_fallbacks(const mpres_ctx *ctx);
+size_t mpres_workspace_bytes(const mpres_ctx *ctx);
 /* the index-th one-byte modulus (0 when out of range or when the small base is unavailable for this moduli set) */
 int mpres_small_modulus(const mpres_ctx *ctx, int index);
 /* Test probe: copy `bytes` at `offset` of internal workspace `slot` to the host after synchronising the last stream

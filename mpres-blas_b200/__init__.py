@@ -39,7 +39,7 @@ EXPORTS = [
     "mpres_init", "mpres_init_moduli", "mpres_finalize", "mpres_moduli_size", "mpres_moduli_product_log2",
     "mpres_precision", "mpres_mp_h", "mpres_mp_j", "mpres_device", "mpres_sizeof_mp_float", "mpres_get_constant",
     "mpres_set_mode", "mpres_get_mode", "mpres_set_stage2_kernel", "mpres_set_stage3_kernel", "mpres_set_stage1_kernel", "mpres_set_reduced_base", "mpres_last_base_size", "mpres_last_slow_count", "mpres_last_fallback_count", "mpres_launch_count",
-    "mpres_set_profiling", "mpres_last_stage_ms", "mpres_set_vec_config", "mpres_last_small_base", "mpres_last_binary_rounding", "mpres_last_host_upload_residues", "mpres_small_modulus", "mpres_debug_read_workspace", "mpres_last_minplus_dense_count",
+    "mpres_set_profiling", "mpres_last_stage_ms", "mpres_set_vec_config", "mpres_last_small_base", "mpres_last_binary_rounding", "mpres_last_host_upload_residues", "mpres_set_workspace_limit", "mpres_workspace_fallbacks", "mpres_workspace_bytes", "mpres_small_modulus", "mpres_debug_read_workspace", "mpres_last_minplus_dense_count",
     "mpres_array_init", "mpres_array_clear", "mpres_array_host2device", "mpres_array_device2host",
     "mpres_collection_init", "mpres_collection_clear", "mpres_collection_host2device", "mpres_collection_device2host",
     "mpres_array_set_binary", "mpres_gemm", "mpres_gemv", "mpres_dot", "mpres_scal", "mpres_axpy", "mpres_waxpby", "mpres_ge_add", "mpres_ge_acc", "mpres_ger", "mpres_ge_diag_scale", "mpres_ge_lr_scale", "mpres_rot", "mpres_axpy_dot", "mpres_gemm_host", "mpres_gemm_host_bdev", "mpres_gemm_coll", "mpres_gemv_coll",
@@ -61,8 +61,10 @@ def load_library():
     lib.mpres_version.restype = ctypes.c_char_p
     lib.mpres_sizeof_mp_float.restype = ctypes.c_size_t
     lib.mpres_shard_handle_size.restype = ctypes.c_size_t
-    for f in ("mpres_last_kernel_ms", "mpres_get_constant", "mpres_last_fallback_count", "mpres_launch_count", "mpres_last_slow_count", "mpres_last_base_size", "mpres_debug_read_workspace", "mpres_last_minplus_dense_count"):
+    for f in ("mpres_last_kernel_ms", "mpres_get_constant", "mpres_last_fallback_count", "mpres_launch_count", "mpres_last_slow_count", "mpres_last_base_size", "mpres_debug_read_workspace", "mpres_last_minplus_dense_count", "mpres_workspace_fallbacks"):
         getattr(lib, f).restype = ctypes.c_long
+    lib.mpres_workspace_bytes.restype = ctypes.c_size_t
+    lib.mpres_set_workspace_limit.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
     _lib = lib
     return lib
 
@@ -137,6 +139,16 @@ class Context:
     def last_binary_rounding(self):
         """True when the last fast mp_gemm rounded its exact sums once in binary (full-precision inputs)"""
         return self.lib.mpres_last_binary_rounding(self.h) == 1
+
+    def set_workspace_limit(self, nbytes):
+        """cap the workspace pool of the fast mp_gemm (0: no cap); calls that would exceed it run in reference order instead"""
+        _check(self.lib.mpres_set_workspace_limit(self.h, int(nbytes)), "mpres_set_workspace_limit")
+
+    def workspace_fallbacks(self):
+        return self.lib.mpres_workspace_fallbacks(self.h)
+
+    def workspace_bytes(self):
+        return self.lib.mpres_workspace_bytes(self.h)
 
     def last_host_upload_residues(self):
         """residues per entry of A / B the last mp_gemm_host call uploaded (0: full records)"""

@@ -64,6 +64,8 @@ struct mpres_ctx {
     // workspace pool (grown on demand, never freed per call)
     void *ws[24] = {nullptr};            // 12..17: device operands and staging rings of mpres_gemm_host; 18..23: mpres_ops.cu
     size_t ws_size[24] = {0};
+    size_t ws_limit = 0;                 // mpres_set_workspace_limit: reservations beyond this many bytes in total fail like a device out of memory (0: no limit)
+    long ws_fallbacks = 0;               // mp_gemm calls served in reference order because the fast path's workspaces did not fit
     cudaStream_t hs[4] = {nullptr};      // mpres_gemm_host: upload, unpack, compute, download
     cudaEvent_t hev[16] = {nullptr};
     bool host_ready = false;
@@ -125,6 +127,11 @@ int ws_reserve(mpres_ctx *c, int slot, size_t bytes, void **out) {
     if (c->ws_size[slot] < bytes) {
         if (c->ws[slot]) { cudaDeviceSynchronize(); cudaFree(c->ws[slot]); c->ws[slot] = nullptr; c->ws_size[slot] = 0; }
         size_t want = bytes + bytes / 8 + 256;
+        if (c->ws_limit) {
+            size_t held = 0;
+            for (int i = 0; i < 24; ++i) held += c->ws_size[i];
+            if (held + want > c->ws_limit) return (int) cudaErrorMemoryAllocation;
+        }
         const cudaError_t e = cudaMalloc(&c->ws[slot], want);
         if (e != cudaSuccess) { c->ws[slot] = nullptr; cudaGetLastError(); return (int) e; }     // (the sticky last-error must not leak into the next call)
         c->ws_size[slot] = want;

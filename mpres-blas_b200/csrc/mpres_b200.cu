@@ -240,6 +240,18 @@ int mpres_last_small_base(mpres_ctx *c, int *moduli, int *input_moduli) {
 }
 int mpres_last_host_upload_residues(const mpres_ctx *c) { return c ? c->last_host_lean : -1; }
 int mpres_last_binary_rounding(const mpres_ctx *c) { return c ? (c->last_binary ? 1 : 0) : -1; }
+int mpres_set_workspace_limit(mpres_ctx *c, size_t bytes) {
+    if (!c) return -1;
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->ws_limit = bytes;
+    return 0;
+}
+long mpres_workspace_fallbacks(const mpres_ctx *c) { return c ? c->ws_fallbacks : -1; }
+size_t mpres_workspace_bytes(const mpres_ctx *c) {
+    size_t held = 0;
+    if (c) for (int i = 0; i < 24; ++i) held += c->ws_size[i];
+    return held;
+}
 int mpres_small_modulus(const mpres_ctx *c, int index) {
     if (!c || !c->sc.usable || index < 0 || index >= kSmallMax) return 0;
     return kSmallModuli[index];
@@ -581,6 +593,14 @@ static int gemm_impl(mpres_ctx *c, int transa, int transb, int m, int n, int k, 
     bool done = false;
     if (c->mode != MPRES_MODE_REFERENCE_ORDER) {
         rc = gemm_fast_full(c, ta, tb, m, n, k, A, lda, B, ldb, alpha, beta, Cm, ldc, st, &done, sh);
+        if (rc == (int) cudaErrorMemoryAllocation && !sh) {
+            // the fast path's workspaces did not fit: every reservation precedes the first write to C, so the call can still be served in
+            // reference order, which needs one m x n scratch matrix like the reference itself (a sharded call cannot: its peers wait for this rank)
+            CUDA_TRY(cudaMemsetAsync(c->d_counter, 0, kCounterInts * sizeof(int), st));
+            c->last_binary = false; c->last_fast_ok = false; c->last_nin = 0;
+            c->ws_fallbacks++;
+            done = false; rc = 0;
+        }
         if (rc) return rc;
     }
     if (!done) {

@@ -320,3 +320,30 @@ def test_gemm_reduced_base_identical(pkg, N, bits_div, shape):
     if bits_div >= 4 and N >= 16:
         assert base[1] < N, "p/%d-bit inputs must not need all %d moduli (got %d)" % (bits_div, N, base[1])
     ctx.close()
+
+
+def test_gemm_workspace_limit_falls_back_to_reference_order(pkg):
+    """A fast-path call whose workspaces do not fit the pool's budget is served in reference order (the m x n scratch matrix of
+    src/blas/gemm.cuh:98-139) instead of failing with an allocation error; the next call without the cap takes the fast path again."""
+    N = 8
+    ctx = pkg.Context(N, 0)
+    orc = get_oracle(N, oracle.DEVICE)
+    bits = orc.precision // 4
+    m, n, k = 96, 80, 160
+    A = random_records(N, m * k, bits, 71)
+    B = random_records(N, k * n, bits, 72)
+    C = random_records(N, m * n, bits, 73)
+    alpha = random_records(N, 1, bits, 74)
+    beta = random_records(N, 1, bits, 75)
+    want = _gemm(pkg, ctx, m, n, k, alpha, A, B, beta, C, pkg.MODE_REFERENCE_ORDER)
+    held = ctx.workspace_bytes()
+    ctx.set_workspace_limit(held + 4096)              # room for nothing beyond the reference-order scratch already held
+    got = _gemm(pkg, ctx, m, n, k, alpha, A, B, beta, C, pkg.MODE_AUTO)
+    assert ctx.workspace_fallbacks() == 1
+    assert diff_fields(got, want).size == 0
+    ctx.set_workspace_limit(0)
+    got = _gemm(pkg, ctx, m, n, k, alpha, A, B, beta, C, pkg.MODE_AUTO)
+    assert ctx.workspace_fallbacks() == 1 and ctx.last_fallback_count() == 0
+    assert ctx.workspace_bytes() > held
+    assert diff_fields(got, want, ("digits", "sign", "exp")).size == 0
+    ctx.close()
