@@ -10,6 +10,7 @@ import ctypes
 import json
 import os
 import subprocess
+import time
 
 import numpy as np
 
@@ -319,8 +320,10 @@ class RefLib:
         y = self.empty(m)
         self.lib.ref_gpu_spmv_2st.restype = ctypes.c_float
         p = np.ascontiguousarray(ptr, dtype=np.int32) if ptr is not None else None
-        self.lib.ref_gpu_spmv_2st(int(fmt), int(m), int(n), int(nnz), _ip(p) if p is not None else None, _ip(np.ascontiguousarray(idx, dtype=np.int32)),
-                                  _ip(np.ascontiguousarray(vals).reshape(-1)), _ip(np.ascontiguousarray(x).reshape(-1)), _ip(y))
+        t0 = time.time()
+        self.last_kernel_ms = self.lib.ref_gpu_spmv_2st(int(fmt), int(m), int(n), int(nnz), _ip(p) if p is not None else None, _ip(np.ascontiguousarray(idx, dtype=np.int32)),
+                                                        _ip(np.ascontiguousarray(vals).reshape(-1)), _ip(np.ascontiguousarray(x).reshape(-1)), _ip(y))
+        self.last_wall_s = time.time() - t0
         return y
 
     def gpu_gemm(self, m, n, k, alpha, A, B, beta, C, want_ab=False, repeat=1):

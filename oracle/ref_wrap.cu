@@ -473,6 +473,10 @@ float ref_gpu_spmv_2st(int fmt, int m, int n, int nnz, const int *ptr, const int
     mp_collection_t das, dbuf;
     mp_array_t dx, dy;
     cuda::mp_collection_init(das, cnt); cuda::mp_collection_init(dbuf, cnt);
+    /* the reference rounds EVERY slot of the buffer (mp_vector_round_kernel over m * maxnzr entries), the ELLPACK padding included, which no kernel wrote:
+     * leftovers of earlier allocations there can keep its scaling loop busy for minutes.  A fresh process hands out zeroed memory; this makes it so always. */
+    cudaMemset(dbuf.digits, 0, sizeof(int) * RNS_MODULI_SIZE * cnt); cudaMemset(dbuf.sign, 0, sizeof(int) * cnt); cudaMemset(dbuf.exp, 0, sizeof(int) * cnt);
+    cudaMemset(dbuf.eval, 0, sizeof(er_float_t) * 2 * cnt);
     cuda::mp_collection_host2device(das, (mp_float_ptr) as, cnt);
     upload(dx, x, n); cuda::mp_array_init(dy, m);
     int *dptr = nullptr, *didx = nullptr;
