@@ -165,7 +165,6 @@ def test_spmv_two_stage_matches_the_reference_sequence(pkg, N, m, n, per_row, fu
         r1 = ref.gpu_spmv_2st(0, m, n, nnz, irp, ja, vals, x)
         assert diff_fields(got, r1, ("digits", "sign", "exp")).size == 0
         r2 = ref.gpu_spmv_2st(1, m, n, maxnzr, None, eja.reshape(-1), evals.reshape(-1), x)
-        print("reference ELL call: kernels %.3f ms, wall %.3f s" % (ref.last_kernel_ms, ref.last_wall_s))
         assert diff_fields(got, r2, ("digits", "sign", "exp")).size == 0
     ctx.close()
 
