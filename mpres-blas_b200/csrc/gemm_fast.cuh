@@ -382,8 +382,8 @@ inline int gemm_fast_flat(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
     if (!c->attr_align) { cudaFuncSetAttribute(k_align_small<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) align_small_smem(false)); c->attr_align = true; }
     // ---- stage 1: the rank's column block of B first (it has to travel), then its rows of A ----
     {
-        const unsigned gB = (unsigned) std::min<long long>((nb / kASo) * (k_p / kASl), (long long) c->sm_count * MPRES_ALIGN_BLOCKS);
-        const unsigned gA = (unsigned) std::min<long long>((m_ps / kASo) * (k_p / kASl), (long long) c->sm_count * MPRES_ALIGN_BLOCKS);
+        const unsigned gB = (unsigned) std::min<long long>((nb / kASo) * (k_p / kASl), (long long) c->sm_count * align_small_blocks(false, false));
+        const unsigned gA = (unsigned) std::min<long long>((m_ps / kASo) * (k_p / kASl), (long long) c->sm_count * align_small_blocks(false, false));
         k_align_small<false><<<gB, 256, align_small_smem(false), st>>>(c->dconsts, Bown, soB, slB, nb, k, IB + col_own, QB + col_own * k_p, SB + col_own * k_p,
                                                                        nb, k_p, sel, n);
         ++launches;
@@ -711,8 +711,9 @@ inline int gemm_fast_full(mpres_ctx *c, bool ta, bool tb, int m, int n, int k, S
         c->attr_ext = true;
     }
     {
-        const unsigned gA = (unsigned) std::min<long long>((m_ps / kASo) * (k_p / kASl), (long long) c->sm_count * MPRES_ALIGN_BLOCKS);
-        const unsigned gB = (unsigned) std::min<long long>((nb_p / kASo) * (k_p / kASl), (long long) c->sm_count * MPRES_ALIGN_BLOCKS);
+        const int resident = align_small_blocks(c->align_mma != 0, slices > 1);
+        const unsigned gA = (unsigned) std::min<long long>((m_ps / kASo) * (k_p / kASl), (long long) c->sm_count * resident);
+        const unsigned gB = (unsigned) std::min<long long>((nb_p / kASo) * (k_p / kASl), (long long) c->sm_count * resident);
         // the rank's column block first: its package has to travel (the copies of the previous call have left the package by now: the
         // peers' flags of that call were raised behind them and every rank has passed this call's rendezvous; the wait is a safeguard)
         if (sh) for (int si = 0; si < sh->npush && si < W - 1; ++si) CUDA_TRY(cudaStreamWaitEvent(st, sh->ev_push[si], 0));

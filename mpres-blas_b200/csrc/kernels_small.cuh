@@ -74,6 +74,16 @@ __device__ __forceinline__ void slice_extract(unsigned (&x)[N], int sh, int widt
     }
 }
 
+// 16 bytes of a digit row of which only the leading residues are read: fetch 64 bytes of the line, not 128 (see the cp.async of the first quad)
+__device__ __forceinline__ int4 ldg_row16(const int4 *p) {
+    int4 v;
+    asm volatile("ld.global.nc.L2::64B.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+#ifdef MPRES_ALIGN_UNROLL
+constexpr int kAlignUnroll = MPRES_ALIGN_UNROLL;      // A/B knob: unroll factor of the loop over the one-byte moduli (quads)
+#endif
 // NW: words of the binary significand = reference residues read (>= n_in); CW = NW rounded up to a multiple of four
 // is the row pitch of the staged tables.  width > 0: only bits [slice width, (slice + 1) width) of the significand are converted.
 template <int NW, bool MMA>
@@ -152,6 +162,9 @@ __device__ __forceinline__ void align_small_entry(const int4 (&dg)[(NW + 3) / 4]
     // lives on -- staging the rows in shared memory shrank it and cost 5x)
     const unsigned *mrow = (const unsigned *) (pws + (size_t) srow * 64);
     const int nq4 = width > 0 ? (((width + 31) >> 5) + 3) >> 2 : CW / 4;      // word quads that can be non-zero (a slice is short)
+#ifdef MPRES_ALIGN_UNROLL
+#pragma unroll kAlignUnroll
+#endif
     for (int jg = 0; 4 * jg < P; ++jg) {
         const unsigned mult4 = __ldg(mrow + jg);
 #pragma unroll
@@ -184,7 +197,7 @@ __device__ __forceinline__ void align_small_dispatch(const int *dig, const int4 
     int4 dg[(NW + 3) / 4];
     dg[0] = d0;                                   // prefetched with the entry's other fields
 #pragma unroll
-    for (int g = 1; g < (NW + 3) / 4; ++g) dg[g] = (4 * g < nin) ? __ldg((const int4 *) dig + g) : make_int4(0, 0, 0, 0);
+    for (int g = 1; g < (NW + 3) / 4; ++g) dg[g] = (4 * g < nin) ? ldg_row16((const int4 *) dig + g) : make_int4(0, 0, 0, 0);
     align_small_entry<NW, MMA>(dg, nin, P, srow, s_mi, s_negmp, s_m, s_bmu, s_w, s_rcpm, s_cw, s_ppm, pws, out, xrow, slice, width);
 }
 
@@ -198,11 +211,15 @@ __host__ __device__ constexpr size_t align_small_smem_base() {   // output tile,
 }
 constexpr int kAXPitch = 96;      // bytes per operand row (conflict-free 64-bit fragment loads)
 #ifndef MPRES_ALIGN_BLOCKS
-#define MPRES_ALIGN_BLOCKS 3
+#define MPRES_ALIGN_BLOCKS 4
 #endif
+// resident blocks per SM the alignment kernel is compiled for (and its persistent grid is sized by).  Measured on B200 (round 2): the plain
+// instantiation gains 3-5 % from four blocks of 64 registers (config 3: 2 x 1.04 -> 2 x 0.99 ms); the sliced one loses 30 % (17.9 -> 23.6 ms at
+// 4096^3 / 424-bit full-precision inputs: its slice extraction spills), and the tensor-core variant's shared memory allows three at most
+__host__ __device__ constexpr int align_small_blocks(bool mma, bool sliced) { return (mma || sliced) ? 3 : MPRES_ALIGN_BLOCKS; }
 // SLICED: the instantiation for significands cut into pieces (kept apart: the default one is tuned to its register budget)
 template <bool MMA, bool SLICED = false>
-__global__ void __launch_bounds__(256, MPRES_ALIGN_BLOCKS) k_align_small(const DevConsts *Cp, SoA X, long long so, long long sl, int outer, int inner,
+__global__ void __launch_bounds__(256, align_small_blocks(MMA, SLICED)) k_align_small(const DevConsts *Cp, SoA X, long long so, long long sl, int outer, int inner,
                                                         const OuterInfo *info, uint8_t *planes, int16_t *shifts,
                                                         long long outer_p, long long inner_p, const int *sel, long long plane_rows = 0) {
     extern __shared__ __align__(16) uint8_t as_smem[];
@@ -258,7 +275,9 @@ __global__ void __launch_bounds__(256, MPRES_ALIGN_BLOCKS) k_align_small(const D
     };
     auto cp_async = [](void *dst, const void *src, auto bytes) {
         const unsigned sa = (unsigned) __cvta_generic_to_shared(dst);
-        if (decltype(bytes)::value == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(src));
+        // (.L2::64B: a 16-byte request into an otherwise untouched 128-byte digit row costs a full line of DRAM time by default and half of it with
+        // this prefetch size -- tools/row_read_probe.cu, profiles/r02_row_read_probe.json; cudaLimitMaxL2FetchGranularity changes nothing)
+        if (decltype(bytes)::value == 16) asm volatile("cp.async.cg.shared.global.L2::64B [%0], [%1], 16;\n" ::"r"(sa), "l"(src));
         else if (decltype(bytes)::value == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(src));
         else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(src));
     };
