@@ -101,37 +101,48 @@ def read_ncu_traffic(workload, kernel):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs"""
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs.  One query process per rank streams lines for the whole
+    run (its first line takes ~0.1 s, longer than a short timed region) and every line is stamped on arrival; `window(t0, t1)` summarises
+    the samples taken between two host times.  bench.py brackets the timed region with it; when that region is shorter than the sampling
+    period and holds no sample, the same loop is repeated UNTIMED for a few periods and its samples are reported (`window` says so)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
-        self.idx, self.rows, self.proc = gpu_index, [], None
+    def __init__(self, gpu_index, period_ms=25):
+        self.idx, self.rows, self.proc, self.period = gpu_index, [], None, period_ms
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", str(self.period)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
+        return self
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
-    def stop(self):
+    def close(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+            self.proc = None
+
+    def window(self, t0, t1, what="timed region"):
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.002 * self.period)            # a line arriving just after t1 was sampled inside the window
         sm, mx, reasons, pw = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for t, r in list(self.rows):
+            if not (t0 <= t <= t1 + 0.001 * self.period):
+                continue
             try:
                 sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
                 for nme, v in zip(names, r[4:8]):
@@ -140,7 +151,24 @@ class ClockSampler:
             except Exception:
                 continue
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w": statistics.median(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w": statistics.median(pw) if pw else None, "samples": len(sm), "window": what, "reasons": sorted(reasons)}
+
+
+def clocks_under_load(env, t0, t1, step, ms_step, steps):
+    """clocks of the timed region [t0, t1]; if it held fewer than three samples, of an untimed repeat of the same loop (the same number of steps on every rank)"""
+    sampler = env.sampler
+    c = sampler.window(t0, t1)
+    none = env.max_over_ranks(0.0 if c.get("samples", 0) >= 3 else 1.0) > 0   # any rank with fewer than three samples: all repeat (the sharded step is collective)
+    if none and sampler.proc:
+        reps = max(steps, int(12 * sampler.period / max(ms_step, 1e-3)) + 1)
+        env.barrier()
+        r0 = time.time()
+        for _ in range(reps):
+            step()
+        env.barrier()
+        c = sampler.window(r0, time.time(), "untimed repeat of the timed loop (%d steps, same load): the timed region (%.1f ms) is shorter than the %d ms sampling period"
+                           % (reps, ms_step * steps, sampler.period))
+    return c
 
 
 # ---- CPU legs (the reference's own host code through oracle/_ref, or the C port where no _ref binary exists) -------------------------
@@ -317,6 +345,9 @@ class Env:
         if not torch.cuda.is_available():
             raise SystemExit("bench.py needs a CUDA device: there is no CPU path in this library")
         torch.cuda.set_device(self.local_rank)
+        self.sampler = ClockSampler(self.local_rank).start()
+        import atexit
+        atexit.register(self.sampler.close)
         if self.world > 1:
             import torch.distributed as dist
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
@@ -465,20 +496,20 @@ def run_vec(env, workload, steps, warmup, want_e2e=True, want_cpu=True, e2e_step
             return {"verified_entries": len(pick) * world, "verified_mismatches": int(bad),
                     "against": "%d sampled outputs per rank recomputed in REFERENCE_ORDER mode (digits, sign, exponent)" % len(pick)}
 
+    ctx.set_profiling(True)
     for _ in range(max(3, warmup)):
         step()
     env.barrier()
-    ctx.set_profiling(True)
-    sampler = ClockSampler(env.local_rank); sampler.start()
     launches0 = ctx.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     env.barrier()
+    t_host0 = time.time()
     e0.record()
     for _ in range(steps):
         step()
     e1.record()
     env.barrier()
-    clocks = sampler.stop()
+    t_host1 = time.time()
     ms_total = e0.elapsed_time(e1)
     launches = ctx.launch_count - launches0
     fallback = ctx.last_fallback_count()
@@ -488,6 +519,7 @@ def run_vec(env, workload, steps, warmup, want_e2e=True, want_cpu=True, e2e_step
         stage_ms = None
     ctx.set_profiling(False)
     ms_step = env.max_over_ranks(ms_total) / steps
+    clocks = clocks_under_load(env, t_host0, t_host1, step, ms_step, steps)
     value = flops / (ms_step * 1e-3) / 1e9
     ver = verify() if verify else None
     e2e = None
@@ -608,26 +640,25 @@ def run_gemm(env, workload, steps, warmup, full_precision=False, want_e2e=True, 
             parallel.broadcast_arrays(dist, B.tensors(), 0)
         pkg.mp_gemm(ctx, pkg.mblas_no_trans, pkg.mblas_no_trans, mr, n, k, alpha, A, mr, B, k, beta, Cb, mr, None, stream)
 
+    ctx.set_profiling(True)                               # (on during the warm-up too: the same load as the timed steps)
     for _ in range(max(3, warmup)):
         step()
     env.barrier()
-    ctx.set_profiling(True)
-    sampler = ClockSampler(env.local_rank)
-    sampler.start()
     launches0 = ctx.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     env.barrier()
     use_profiler_range = os.environ.get("MPRES_BENCH_PROFILER_RANGE") == "1"   # ncu --profile-from-start off
     if use_profiler_range:
         torch.cuda.profiler.start()
+    t_host0 = time.time()
     e0.record()
     for _ in range(steps):
         step()
     e1.record()
     env.barrier()
+    t_host1 = time.time()
     if use_profiler_range:
         torch.cuda.profiler.stop()
-    clocks = sampler.stop()
     ms_total = e0.elapsed_time(e1)
     launches = ctx.launch_count - launches0
     fallback = ctx.last_fallback_count()
@@ -641,6 +672,7 @@ def run_gemm(env, workload, steps, warmup, full_precision=False, want_e2e=True, 
     kern_ms = ctx.last_kernel_ms()
     ctx.set_profiling(False)
     ms_step = env.max_over_ranks(ms_total) / steps
+    clocks = clocks_under_load(env, t_host0, t_host1, step, ms_step, steps)
     value = 2.0 * m * n * k / (ms_step * 1e-3) / 1e9
 
     # ---- sampled check of the last step's C against the reference-order k-loop (src/blas/gemm.cuh:39-58 semantics) on this rank's rows ----
