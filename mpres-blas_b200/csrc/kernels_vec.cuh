@@ -382,59 +382,113 @@ __global__ void __launch_bounds__(256) k_mv_acc_t(const DevConsts *Cp, SoA M, lo
     auto cp16 = [](unsigned dst, const void *src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src)); };
     auto cp4 = [](unsigned dst, const void *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst), "l"(src)); };
 
-    auto load = [&](int ch, int st) {
-        const unsigned S = smem0 + st * stageBytes;
-        const long long r0 = rbeg + (long long) ch * RS;
-        const int nr = (int) min((long long) RS, rend - r0);   // valid rows of this chunk
-        const long long doff = (long long) ch * RS * N;
+    // Loader state: the chunks are requested in order, so every source pointer is a running one (this thread's first item of the NEXT chunk to
+    // load) advanced by a constant per chunk.  Computing the addresses from the chunk index inside the lambda cost ~45 instructions per pair of
+    // copies -- 44 % of the kernel's instructions at 16384 x 16384 / 16 moduli (ncu source view) -- against the ~40 of the arithmetic on that pair.
+    // Full chunks whose eight source runs are 16-byte aligned travel as eight bulk copies (cp.async.bulk, the TMA unit) issued by ONE thread and
+    // tracked by the stage's mbarrier: every array of a column's rows is one contiguous run, and the per-thread 16-byte copies below spent more
+    // instructions on issuing the loads than the arithmetic on using them.  The last (partial) chunk of a split, unaligned views and the
+    // single-entry vector of the ABS variants (vs = 0) keep the per-thread copies.
+    __shared__ __align__(8) unsigned long long s_bar[STAGES];
+    const bool bulk_ok = vs == 1 && quadsM && quadsV &&
+                         ((((size_t) M.digits) | ((size_t) V.digits) | ((size_t) M.eval) | ((size_t) V.eval)) & 15) == 0;
+    if (t == 0) {
+#pragma unroll
+        for (int sgi = 0; sgi < STAGES; ++sgi)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned) __cvta_generic_to_shared(&s_bar[sgi])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    auto bulk = [](unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+    };
+    const long long chunkM = (long long) RS * N, chunkV = chunkM * vs;          // ints of digits per chunk
+    const int uM = 4 * T, uV = 4 * T * vs;                                      // ints between this thread's rows u and u + 1
+    const int *ldM = gM, *ldV = gV;
+    const Er *ldEM = M.eval + (mbase + rbeg + lenM) + t, *ldEV = V.eval + (rbeg + t) * vs + lenV;
+    const int *ldXM = M.exp + mbase + rbeg + 4 * t, *ldSM = M.sign + mbase + rbeg + 4 * t;
+    const int *ldXV = V.exp + (rbeg + 4 * t) * vs, *ldSV = V.sign + (rbeg + 4 * t) * vs;
+    long long ld_left = rend - rbeg;                                            // rows not yet requested
+    const unsigned sdig = smem0 + t * 16;
+    auto load = [&](int st) {
+        const unsigned so = st * stageBytes;
+        const int nr = (int) min((long long) RS, ld_left);   // valid rows of this chunk
+        if (bulk_ok && nr == RS) {
+            if (t == 0) {
+                const unsigned bar = (unsigned) __cvta_generic_to_shared(&s_bar[st]), S = smem0 + so;
+                const unsigned bd = (unsigned) RS * (unsigned) N * 4u, be = (unsigned) RS * 16u, bx = (unsigned) RS * 4u;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // the stage was last touched through the generic proxy
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2 * bd + 2 * be + 4 * bx) : "memory");
+                bulk(S, ldM - 4 * t, bd, bar);
+                bulk(S + oDigV, ldV - 4 * t, bd, bar);
+                bulk(S + oUppM, ldEM - t, be, bar);
+                bulk(S + oUppV, ldEV - t, be, bar);
+                bulk(S + oExpM, ldXM - 4 * t, bx, bar);
+                bulk(S + oSgnM, ldSM - 4 * t, bx, bar);
+                bulk(S + oExpV, ldXV - 4 * t, bx, bar);
+                bulk(S + oSgnV, ldSV - 4 * t, bx, bar);
+            }
+            ldM += chunkM; ldV += chunkV; ldEM += RS; ldEV += RS * vs; ldXM += RS; ldSM += RS; ldXV += RS * vs; ldSV += RS * vs;
+            ld_left -= RS;
+            return;
+        }
 #pragma unroll
         for (int u = 0; u < RT; ++u) {
             if (rl + (u << lgRB) < nr) {                // 16-byte chunk t + T u: row rl + RB u, moduli 4 q4 ..
-                cp16(S + (t + T * u) * 16, gM + doff + 4 * T * u);
-                cp16(S + oDigV + (t + T * u) * 16, gV + (doff + 4 * T * u) * vs);
+                cp16(sdig + so + T * u * 16, ldM + u * uM);
+                cp16(sdig + so + oDigV + T * u * 16, ldV + u * uV);
             }
         }
-        for (int e = t; e < RS; e += T) {
-            if (e < nr) {
-                cp16(S + oUppM + e * 16, M.eval + (mbase + r0 + e + lenM));
-                cp16(S + oUppV + e * 16, V.eval + ((r0 + e) * vs + lenV));
-            }
-        }
-        for (int e = t; e < (RS >> 2); e += T) {   // exponents and signs, four rows per item
-            const int e4 = 4 * e;
-            if (e4 < nr) {
-                const long long row = r0 + e4;
-                const bool full = e4 + 3 < nr;
-                if (quadsM && full) {
-                    cp16(S + oExpM + e * 16, M.exp + mbase + row);
-                    cp16(S + oSgnM + e * 16, M.sign + mbase + row);
-                } else {
-                    for (int k = 0; k < 4 && e4 + k < nr; ++k) { cp4(S + oExpM + e * 16 + 4 * k, M.exp + mbase + row + k); cp4(S + oSgnM + e * 16 + 4 * k, M.sign + mbase + row + k); }
-                }
-                if (quadsV && full) {
-                    cp16(S + oExpV + e * 16, V.exp + row);
-                    cp16(S + oSgnV + e * 16, V.sign + row);
-                } else {
-                    for (int k = 0; k < 4 && e4 + k < nr; ++k) { cp4(S + oExpV + e * 16 + 4 * k, V.exp + (row + k) * vs); cp4(S + oSgnV + e * 16 + 4 * k, V.sign + (row + k) * vs); }
+        {
+            const Er *em = ldEM, *ev = ldEV;
+            for (int e = t; e < RS; e += T, em += T, ev += T * vs) {
+                if (e < nr) {
+                    cp16(smem0 + so + oUppM + e * 16, em);
+                    cp16(smem0 + so + oUppV + e * 16, ev);
                 }
             }
         }
+        {
+            const int *xm = ldXM, *sm = ldSM, *xv = ldXV, *sv = ldSV;
+            for (int e = t; e < (RS >> 2); e += T, xm += 4 * T, sm += 4 * T, xv += 4 * T * vs, sv += 4 * T * vs) {   // exponents and signs, four rows per item
+                const int e4 = 4 * e;
+                if (e4 < nr) {
+                    const bool full = e4 + 3 < nr;
+                    const unsigned S = smem0 + so;
+                    if (quadsM && full) {
+                        cp16(S + oExpM + e * 16, xm);
+                        cp16(S + oSgnM + e * 16, sm);
+                    } else {
+                        for (int k = 0; k < 4 && e4 + k < nr; ++k) { cp4(S + oExpM + e * 16 + 4 * k, xm + k); cp4(S + oSgnM + e * 16 + 4 * k, sm + k); }
+                    }
+                    if (quadsV && full) {
+                        cp16(S + oExpV + e * 16, xv);
+                        cp16(S + oSgnV + e * 16, sv);
+                    } else {
+                        for (int k = 0; k < 4 && e4 + k < nr; ++k) { cp4(S + oExpV + e * 16 + 4 * k, xv + k * vs); cp4(S + oSgnV + e * 16 + 4 * k, sv + k * vs); }
+                    }
+                }
+            }
+        }
+        ldM += chunkM; ldV += chunkV; ldEM += RS; ldEV += RS * vs; ldXM += RS; ldSM += RS; ldXV += RS * vs; ldSV += RS * vs;
+        ld_left -= RS;
     };
 
     acc_t acc[4] = {0, 0, 0, 0};
     int mylab = kVecNone, pending = 0;
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
-        if (s < nchunks) load(s, s);
+        if (s < nchunks) load(s);
         cp_async_commit();
     }
     for (int ch = 0; ch < nchunks; ++ch) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
-        if (ch + STAGES - 1 < nchunks) load(ch + STAGES - 1, (ch + STAGES - 1) % STAGES);
+        if (ch + STAGES - 1 < nchunks) load((ch + STAGES - 1) % STAGES);
         cp_async_commit();
         unsigned char *S = vsm + (ch % STAGES) * stageBytes;
         const int nr = (int) min((long long) RS, rend - (rbeg + (long long) ch * RS));
+        if (bulk_ok && nr == RS)          // every earlier chunk of this stage was a bulk one too (only a split's last chunk can be partial)
+            ptx::mbar_wait((uint64_t *) &s_bar[ch % STAGES], (unsigned) ((ch / STAGES) & 1));
         {   // phase A: one term per thread and pass; block-wide minimum exponent and window top
             const int *expM = (const int *) (S + oExpM), *sgnM = (const int *) (S + oSgnM), *expV = (const int *) (S + oExpV), *sgnV = (const int *) (S + oSgnV);
             const Er *uppM = (const Er *) (S + oUppM), *uppV = (const Er *) (S + oUppV);
