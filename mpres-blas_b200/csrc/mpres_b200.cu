@@ -158,12 +158,6 @@ int mpres_init_moduli(mpres_ctx **out, const int *moduli, int n, int device) {
     if (e == cudaSuccess) e = cudaHostAlloc(&c->h_sel, 8 * sizeof(int), cudaHostAllocDefault);
     if (e != cudaSuccess) { cudaGetLastError(); mpres_finalize(c); return (int) e; }
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
-    // MPRES_L2_FETCH=32|64|128: largest L2 fetch granularity of the device (a hint).  The alignment kernels read 16 bytes out of every 128-byte digit row:
-    // with the default granularity the DRAM traffic of k_align_small is 3.8 x its algorithmic bytes
-    if (const char *env = getenv("MPRES_L2_FETCH")) {
-        const int g2 = atoi(env);
-        if (g2 == 32 || g2 == 64 || g2 == 128) { cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t) g2); cudaGetLastError(); }
-    }
     *out = c;
     return 0;
 }
