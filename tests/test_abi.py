@@ -44,6 +44,14 @@ def test_no_cpu_fallback(pkg):
     assert ctx.lib.mpres_gemm(ctx.h, 111, 111, 1, 1, 1, ctypes.byref(arr), ctypes.byref(arr), 1, ctypes.byref(arr), 1,
                               ctypes.byref(arr), ctypes.byref(arr), 1, None, None) == -100
     assert ctx.lib.mpres_dot(ctx.h, 1, ctypes.byref(arr), 1, ctypes.byref(arr), 1, ctypes.byref(arr), None, None) == -100
+    # the round-2 entry points too (norms, sparse product, conversions, division, solver, host GEMM, sharding)
+    assert ctx.lib.mpres_asum(ctx.h, 1, ctypes.byref(arr), 1, ctypes.byref(arr), None) == -100
+    assert ctx.lib.mpres_norm(ctx.h, 171, 1, ctypes.byref(arr), 1, ctypes.byref(arr), None) == -100
+    assert ctx.lib.mpres_div(ctx.h, ctypes.byref(arr), ctypes.byref(arr), ctypes.byref(arr), None) == -100
+    # the workspace budget is host state: settable and readable without a device
+    assert ctx.workspace_bytes() == 0 and ctx.workspace_fallbacks() == 0
+    ctx.set_workspace_limit(1 << 30)
+    ctx.set_workspace_limit(0)
     ctx.close()
     if not torch.cuda.is_available():
         with pytest.raises(pkg.MpresError):

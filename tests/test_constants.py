@@ -63,6 +63,8 @@ def test_bad_moduli_rejected(pkg):
         pkg.Context(moduli=[15, 21, 1000003], device=-1)    # not coprime
     with pytest.raises(pkg.MpresError):
         pkg.Context(7, -1)                                  # no such predefined set
+    with pytest.raises(pkg.MpresError):
+        pkg.Context(moduli=[1000003, 1000033, 1000037], device=-1)   # odd count: the reference's mp_float_t gets padding there, records would not line up
 
 
 def test_small_modulus_base(pkg):
