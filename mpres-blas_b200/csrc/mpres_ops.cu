@@ -613,25 +613,31 @@ int mpres_cg_csr(mpres_ctx *c, int n, int nnz, const int *irp, const int *ja, co
     const int N = c->hc.N;
     mpres_array_t r, p, q, z, sc, Mv;                     // sc: rho, rhop, alpha, beta, pq, nrm as six one-element views of one array
     mpres_collection_t Am;
-    memset(&z, 0, sizeof(z)); memset(&Mv, 0, sizeof(Mv));
+    memset(&r, 0, sizeof(r)); memset(&p, 0, sizeof(p)); memset(&q, 0, sizeof(q)); memset(&z, 0, sizeof(z)); memset(&sc, 0, sizeof(sc)); memset(&Mv, 0, sizeof(Mv));
+    memset(&Am, 0, sizeof(Am));
+    double *d_nrm = nullptr;
+    auto cleanup = [&]() {                                   // every exit: nothing of this call stays allocated (clearing a never-allocated array is a no-op)
+        cudaStreamSynchronize(st);
+        mpres_array_clear(c, &r); mpres_array_clear(c, &p); mpres_array_clear(c, &q); mpres_array_clear(c, &sc); mpres_collection_clear(c, &Am);
+        mpres_array_clear(c, &z); mpres_array_clear(c, &Mv);
+        cudaFree(d_nrm);
+    };
     int rc;
     if ((rc = mpres_array_init(c, &r, n)) || (rc = mpres_array_init(c, &p, n)) || (rc = mpres_array_init(c, &q, n)) || (rc = mpres_array_init(c, &sc, 6)) ||
-        (rc = mpres_collection_init(c, &Am, nnz ? nnz : 1))) return rc;
-    if (M && ((rc = mpres_array_init(c, &z, n)) || (rc = mpres_array_init(c, &Mv, n)))) return rc;
+        (rc = mpres_collection_init(c, &Am, nnz ? nnz : 1)) || (M && ((rc = mpres_array_init(c, &z, n)) || (rc = mpres_array_init(c, &Mv, n))))) {
+        cleanup();
+        return rc;
+    }
+    {
+        const cudaError_t e = cudaMalloc(&d_nrm, sizeof(double));
+        if (e != cudaSuccess) { d_nrm = nullptr; cudaGetLastError(); cleanup(); return (int) e; }
+    }
     auto scalar = [&](int i) {                               // element i of sc as a length-1 array (same allocated length: same offset of the upper bounds)
         mpres_array_t v = sc;
         v.digits += (size_t) i * N; v.sign += i; v.exp += i; v.eval += i;
         return v;
     };
     mpres_array_t rho = scalar(0), rhop = scalar(1), alpha = scalar(2), beta = scalar(3), pq = scalar(4), nrm = scalar(5);
-    double *d_nrm = nullptr;
-    CUDA_TRY(cudaMalloc(&d_nrm, sizeof(double)));
-    auto cleanup = [&]() {
-        cudaStreamSynchronize(st);
-        mpres_array_clear(c, &r); mpres_array_clear(c, &p); mpres_array_clear(c, &q); mpres_array_clear(c, &sc); mpres_collection_clear(c, &Am);
-        if (M) { mpres_array_clear(c, &z); mpres_array_clear(c, &Mv); }
-        cudaFree(d_nrm);
-    };
     auto grid = [&](long long items, int G_) { return (unsigned) std::max<long long>(1, std::min<long long>((items * G_ + 127) / 128, (long long) c->sm_count * 16)); };
     // the matrix (and the preconditioner) in multiple precision, exactly
     {
@@ -692,9 +698,9 @@ int mpres_cg_csr(mpres_ctx *c, int n, int nnz, const int *irp, const int *ja, co
         if (resvec) resvec[k] = norm0 > 0 ? normk / norm0 : 0.0;
     }
     if (iters) *iters = k;
-    CUDA_TRY(cudaGetLastError());
+    const cudaError_t last = cudaGetLastError();
     cleanup();
-    return 0;
+    return (int) last;
 }
 
 int mpres_array_get_d(mpres_ctx *c, double *dst, const mpres_array_t *src, size_t offset, size_t n, mpres_stream_t stream) {
